@@ -1,0 +1,176 @@
+/*
+ * wicca_b200.h - C ABI of libwicca_b200.so, the B200 (sm_100a) implementation of
+ * the WICCA HaarCoder hot path.
+ *
+ * The reference (Todmount/wicca) is pure Python and has no FFI; the interface
+ * each entry point replaces is the Python call it is bound under (see
+ * INTEGRATION.md for the ctypes stub a reference maintainer would add):
+ *
+ *   wicca_haar_icon_u8            HaarCoder.get_small_copy        wicca/wavelet_coder.py:50-67
+ *                                   incl. validate_image          wicca/validation.py:80-101
+ *                                   and   get_padded_copy         wicca/data_loader.py:66-117
+ *   wicca_haar_icons_multi_u8     the per-depth loop that calls it wicca/classifying_tools.py:546-551, :317
+ *   wicca_batch_icons_u8          the per-image loop               wicca/classifying_tools.py:312-321
+ *   wicca_icon_resize_norm_f32    cv2.resize(icon) + np.stack      wicca/classifying_tools.py:318, :323
+ *                                   + preprocess_input / cast      wicca/classifying_tools.py:286-287
+ *   wicca_haar_forward_f32 / wicca_haar_inverse_f32
+ *                                 extension: all sub-bands of the
+ *                                 transform whose LL is wavelet_coder.py:61-65
+ *
+ * Conventions
+ *   - plain C types only; images are uint8, HWC (channels interleaved), row
+ *     stride given in bytes; icons are uint8 HWC.
+ *   - return 0 on success, a negative WICCA_E* code for argument errors, a
+ *     positive value = cudaError_t for CUDA failures.  wicca_last_error()
+ *     returns a thread-local message for the last non-zero return.
+ *   - every entry point is re-entrant: concurrent calls from different host
+ *     threads (the reference calls the coder from a ThreadPoolExecutor,
+ *     classifying_tools.py:414-418) use separate streams and scratch buffers.
+ *   - there is no CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with a cudaError_t.
+ */
+#ifndef WICCA_B200_H
+#define WICCA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WICCA_API __attribute__((visibility("default")))
+
+/* argument errors (negative) */
+#define WICCA_EINVAL      (-1)  /* null pointer / non-positive size / bad stride            */
+#define WICCA_ECHANNELS   (-2)  /* channel count unsupported for this call                   */
+#define WICCA_EBORDER     (-3)  /* border type not one of cv2.BORDER_{CONSTANT,REPLICATE,REFLECT,WRAP,REFLECT_101} */
+#define WICCA_EDEPTH      (-4)  /* depth out of the supported range for this call            */
+#define WICCA_EDEVICE     (-5)  /* device ordinal out of range                               */
+#define WICCA_EALIGN      (-6)  /* device pointer / pitch alignment not met (device-pointer entry points) */
+#define WICCA_ENOMEM      (-7)  /* host allocation failed                                    */
+#define WICCA_ESTATE      (-8)  /* plan / handle used incorrectly                            */
+
+/* OpenCV border codes accepted by cv2.copyMakeBorder (data_loader.py:116); bit 16 (BORDER_ISOLATED) is ignored */
+#define WICCA_BORDER_CONSTANT    0
+#define WICCA_BORDER_REPLICATE   1
+#define WICCA_BORDER_REFLECT     2
+#define WICCA_BORDER_WRAP        3
+#define WICCA_BORDER_REFLECT_101 4
+
+/* preprocess_input modes (keras imagenet_utils; classifying_tools.py:286) */
+#define WICCA_NORM_IDENTITY 0   /* cast only            (EfficientNet)                     */
+#define WICCA_NORM_TF       1   /* x/127.5 - 1          (MobileNetV2, NASNet, Inception*, Xception) */
+#define WICCA_NORM_CAFFE    2   /* RGB->BGR, - mean     (VGG, ResNet)                      */
+#define WICCA_NORM_TORCH    3   /* x/255, (x-mean)/std  (DenseNet)                         */
+
+#define WICCA_MAX_FUSED_DEPTH 6   /* levels produced by the one-pass tiled kernel            */
+#define WICCA_MAX_DEPTH       16  /* deepest transform accepted (levels > 8 are done in fp32 like the reference) */
+
+typedef struct wicca_timing {
+    float h2d_ms;      /* host->device copies (CUDA events)                 */
+    float kernel_ms;   /* kernels only                                      */
+    float d2h_ms;      /* device->host copies                               */
+    float total_ms;    /* first enqueue to last completion, on the device   */
+} wicca_timing;
+
+/* ---- library / device ------------------------------------------------- */
+WICCA_API const char* wicca_version(void);
+WICCA_API const char* wicca_last_error(void);
+WICCA_API int         wicca_device_count(void);           /* 0 when no CUDA device is usable */
+WICCA_API int         wicca_shutdown(void);               /* frees every cached stream / buffer */
+
+/* Row pitch (bytes, multiple of 128) the library uses for device-resident images of width W. */
+WICCA_API int64_t wicca_pitch_bytes(int W, int C);
+/* Icon extent at a depth: ceil(H / 2^depth), ceil(W / 2^depth) (depth <= 0: H, W). */
+WICCA_API int     wicca_icon_dim(int n, int depth);
+
+/* Page-locked host memory for inputs/outputs that should be DMA'd without a bounce copy. */
+WICCA_API int wicca_host_alloc(void** ptr, size_t bytes);
+WICCA_API int wicca_host_free(void* ptr);
+
+/* ---- HaarCoder.get_small_copy  (host buffers in, host buffers out) ----- */
+/* dst must hold wicca_icon_dim(H,depth) * wicca_icon_dim(W,depth) * C bytes (tight HWC).
+ * depth <= 0 copies the image (reference behaviour).  t may be NULL. */
+WICCA_API int wicca_haar_icon_u8(const uint8_t* src, int H, int W, int C, int64_t src_row_stride,
+                                 int depth, int border_type, double border_const,
+                                 uint8_t* dst, int device, wicca_timing* t);
+
+/* Several depths from ONE upload and (for depths 1..6, C == 3) ONE pass over the image. */
+WICCA_API int wicca_haar_icons_multi_u8(const uint8_t* src, int H, int W, int C, int64_t src_row_stride,
+                                        const int* depths, int n_depths,
+                                        int border_type, double border_const,
+                                        uint8_t* const* dsts, int device, wicca_timing* t);
+
+/* ---- device-resident variants (benchmark / tensor bridge) -------------- */
+/* d_src: device pointer, rows src_pitch bytes apart.  d_dsts[i]: device pointer, rows
+ * dst_pitches[i] bytes apart.  The one-pass kernel is used when C == 3, all depths are in
+ * 1..6, d_src is 16-byte aligned and src_pitch is a multiple of 16, each dst is 8-byte
+ * aligned with a pitch that is a multiple of 8; otherwise the general kernel runs.
+ * stream is a cudaStream_t (NULL = legacy default stream); the call only enqueues. */
+WICCA_API int wicca_haar_icons_multi_dev(const uint8_t* d_src, int H, int W, int C, int64_t src_pitch,
+                                         const int* depths, int n_depths,
+                                         int border_type, double border_const,
+                                         uint8_t* const* d_dsts, const int64_t* dst_pitches,
+                                         int device, void* stream);
+
+/* ---- batch plans: many device-resident images, one launch -------------- */
+typedef struct wicca_plan wicca_plan;
+/* All images share C, depths and border.  Icons are allocated by the plan. */
+WICCA_API int wicca_plan_create(int device, int n_images, const uint8_t* const* d_srcs,
+                                const int* Hs, const int* Ws, const int64_t* src_pitches, int C,
+                                const int* depths, int n_depths, int border_type, double border_const,
+                                wicca_plan** plan);
+WICCA_API int wicca_plan_launch(wicca_plan* plan, void* stream);
+/* Device pointer / extents of one icon produced by the plan. */
+WICCA_API int wicca_plan_icon(const wicca_plan* plan, int image, int depth_index,
+                              uint8_t** d_icon, int* h, int* w, int64_t* pitch);
+/* Copy one icon to a tight host buffer (synchronous). */
+WICCA_API int wicca_plan_read_icon(const wicca_plan* plan, int image, int depth_index, uint8_t* dst);
+/* Number of kernel launches one wicca_plan_launch issues, and the algorithmic bytes it moves. */
+WICCA_API int wicca_plan_info(const wicca_plan* plan, int* launches, int64_t* bytes_read, int64_t* bytes_written);
+WICCA_API int wicca_plan_destroy(wicca_plan* plan);
+
+/* ---- sharded host batch: images are independent units ------------------ */
+/* srcs[i]: host image i, (Hs[i], Ws[i], C) uint8 with row stride strides[i] (0 = tight).
+ * dsts[i * n_depths + k]: tight host icon of image i at depths[k].
+ * Image i runs on devices[i % n_devices] (devices == NULL: ordinals 0..n_devices-1); each
+ * device has its own worker thread, streams and double-buffered upload slots, so H2D of
+ * image i+1 overlaps the kernel of image i.  No inter-GPU traffic.  t (nullable) receives the
+ * SUM over images of the per-stage device times. */
+WICCA_API int wicca_batch_icons_u8(const uint8_t* const* srcs, const int* Hs, const int* Ws,
+                                   const int64_t* strides, int n_images, int C,
+                                   const int* depths, int n_depths,
+                                   int border_type, double border_const,
+                                   uint8_t* const* dsts,
+                                   const int* devices, int n_devices, wicca_timing* t);
+
+/* ---- extension: full sub-band transform -------- */
+/* Coefficient layout ("pyramid in place"): one float32 HWC plane of the padded size
+ * (Hp, Wp, C), Hp = ceil(H/2^depth)*2^depth.  After level l the LL_l block occupies
+ * [0,Hp/2^l) x [0,Wp/2^l); HL_l (high-pass along x) sits to its right, LH_l (high-pass along y)
+ * below it, HH_l diagonally - the classic Mallat arrangement. */
+WICCA_API int wicca_haar_forward_f32(const uint8_t* src, int H, int W, int C, int64_t src_row_stride,
+                                     int depth, int border_type, double border_const,
+                                     float* coeffs /* host, Hp*Wp*C */, int device, wicca_timing* t);
+WICCA_API int wicca_haar_inverse_f32(const float* coeffs /* host, Hp*Wp*C */, int Hp, int Wp, int C,
+                                     int depth, float* image /* host, Hp*Wp*C */, int device, wicca_timing* t);
+/* Device-resident versions: d_coeffs/d_image are tight (Hp, Wp, C) float32 device planes;
+ * d_work is a scratch plane of the same size (ping-pong for levels >= 2). */
+WICCA_API int wicca_haar_forward_dev(const uint8_t* d_src, int H, int W, int C, int64_t src_pitch,
+                                     int depth, int border_type, double border_const,
+                                     float* d_coeffs, float* d_work, int device, void* stream);
+WICCA_API int wicca_haar_inverse_dev(const float* d_coeffs, int Hp, int Wp, int C, int depth,
+                                     float* d_image, float* d_work, int device, void* stream);
+
+/* ---- epilogue: icon -> INTER_AREA resize -> preprocess_input ----------- */
+/* icons[i]: host uint8 HWC icon i (hs[i], ws[i], 3), tight.  dst: host float32 (n, out_h, out_w, 3).
+ * dst_u8 (nullable): the intermediate uint8 batch exactly as cv2.resize would return it. */
+WICCA_API int wicca_icon_resize_norm_f32(const uint8_t* const* icons, const int* hs, const int* ws, int n,
+                                         int out_h, int out_w, int norm_mode,
+                                         float* dst, uint8_t* dst_u8, int device, wicca_timing* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WICCA_B200_H */

@@ -1,0 +1,98 @@
+// emul_icon.cpp - CPU replay of the one-pass icon kernel (test infrastructure).
+//
+// Compiles wicca_b200/csrc/haar_math.cuh as plain C++ and walks every work item / lane exactly
+// as haar_icon_tma_kernel does: a 24 KB "stage" is filled the way the TMA box load would fill it
+// (zero beyond the tensor extent, pad bytes of the pitched image included), each of the 32 lanes
+// runs make_chunk_src / reduce_lane, the level 5/6 warp shuffles are replayed with the same xor
+// pattern, and emit_tail stores the results.  What is NOT covered: mbarrier/TMA mechanics.
+//
+// Build:  g++ -O2 -shared -fPIC -I/usr/local/cuda/include -Iwicca_b200/csrc tests/cpu_emul/emul_icon.cpp
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "haar_math.cuh"
+
+using namespace wicca;
+
+extern "C" {
+
+// src: tight (H, W, 3) uint8.  mask bit (d-1) requests depth d.  outs[d-1]: tight icon buffers
+// (may be NULL when not requested).  Returns 0, or a positive code when a guard byte around an
+// icon was overwritten (out-of-bounds store).
+int emul_fused_icons(const uint8_t* src, int H, int W, int border_type, int border_const, unsigned mask,
+                     uint8_t** outs) {
+    const int64_t pitch = ((int64_t)W * 3 + 127) / 128 * 128;
+    std::vector<uint8_t> img((size_t)pitch * H + 64, 0xA5);      // pad bytes are garbage on purpose
+    for (int y = 0; y < H; ++y) memcpy(&img[(size_t)y * pitch], src + (size_t)y * W * 3, (size_t)W * 3);
+
+    IconImage im;
+    memset(&im, 0, sizeof im);
+    icon_image_geometry(&im, img.data(), H, W, pitch, 0);
+    std::vector<std::vector<uint8_t>> icons(kMaxFused);
+    const size_t guard = 256;
+    for (int d = 1; d <= kMaxFused; ++d) {
+        if (!(mask & (1u << (d - 1)))) continue;
+        const int r = 1 << d;
+        const int h = (H + r - 1) >> d, w = (W + r - 1) >> d;
+        const int64_t ip = ((int64_t)w * 3 + 127) / 128 * 128;
+        icons[d - 1].assign((size_t)ip * h + 2 * guard, 0xEE);
+        icon_image_add_level(&im, d, icons[d - 1].data() + guard, ip);
+    }
+    const int Wa = W & ~(kChunkPx - 1);
+    const int npx = im.Wp_max - Wa;
+    std::vector<uint8_t> strip;
+    if (npx > 0) {
+        strip.assign((size_t)H * kStripPitch, 0x5A);
+        for (int y = 0; y < H; ++y)
+            for (int px = 0; px < npx; ++px) strip_pixel(im, strip.data(), y, px, border_type, border_const);
+    }
+    const uint32_t fill = (uint32_t)border_const * 0x01010101u;
+    const IconSink sk = make_sink(im);
+    std::vector<uint8_t> stage(kStageBytes);
+    for (int iy = 0; iy < im.items_y; ++iy)
+        for (int ix = 0; ix < im.items_x; ++ix) {
+            // TMA box: (kStageRowBytes/4) uint32 x kItemH rows at element (ix*96, iy*64) of the
+            // (pitch/4 x H) tensor; out-of-range elements are zero-filled.
+            for (int r = 0; r < kItemH; ++r)
+                for (int b = 0; b < kStageRowBytes; ++b) {
+                    const int y = iy * kItemH + r;
+                    const int64_t xb = (int64_t)ix * kStageRowBytes + b;
+                    stage[(size_t)r * kStageRowBytes + b] = (y < H && xb < pitch) ? img[(size_t)y * pitch + xb] : 0;
+                }
+            uint32_t acc4[32][3], v1[32][3], s5[32][3], u1[32][3], s6[32][3];
+            ChunkSrc cs[32];
+            for (int lane = 0; lane < 32; ++lane) {
+                cs[lane] = make_chunk_src(im, strip.empty() ? nullptr : strip.data(), stage.data(), ix, iy, lane & 7,
+                                          lane >> 3, border_type, fill);
+                reduce_lane(cs[lane], sk, acc4[lane]);
+            }
+            for (int c = 0; c < 3; ++c) {
+                for (int l = 0; l < 32; ++l) v1[l][c] = acc4[l][c] + acc4[l ^ 1][c];
+                for (int l = 0; l < 32; ++l) s5[l][c] = v1[l][c] + v1[l ^ 8][c];
+                for (int l = 0; l < 32; ++l) u1[l][c] = s5[l][c] + s5[l ^ 2][c];
+                for (int l = 0; l < 32; ++l) s6[l][c] = u1[l][c] + u1[l ^ 16][c];
+            }
+            for (int lane = 0; lane < 32; ++lane)
+                emit_tail(sk, cs[lane].x0, cs[lane].y0, lane & 7, lane >> 3, acc4[lane], s5[lane], s6[lane]);
+        }
+    int bad = 0;
+    for (int d = 1; d <= kMaxFused; ++d) {
+        if (!(mask & (1u << (d - 1)))) continue;
+        const int h = im.icon_h[d - 1], w = im.icon_w[d - 1];
+        const int64_t ip = im.icon_pitch[d - 1];
+        const std::vector<uint8_t>& buf = icons[d - 1];
+        for (size_t i = 0; i < guard; ++i)
+            if (buf[i] != 0xEE || buf[buf.size() - 1 - i] != 0xEE) bad = 100 + d;
+        for (int y = 0; y < h; ++y) {
+            for (int64_t b = (int64_t)w * 3; b < ip; ++b)
+                if (buf[guard + (size_t)y * ip + b] != 0xEE) bad = 200 + d;     // wrote into the row padding
+            if (outs[d - 1]) memcpy(outs[d - 1] + (size_t)y * w * 3, &buf[guard + (size_t)y * ip], (size_t)w * 3);
+        }
+    }
+    return bad;
+}
+
+}  // extern "C"

@@ -1,0 +1,316 @@
+// haar_icon.cu - Haar LL "icon" kernels for sm_100a.
+//
+// Replaces the body of HaarCoder.get_small_copy (wicca/wavelet_coder.py:56-67) including the
+// padding of get_padded_copy (wicca/data_loader.py:107-117), which is never materialised.
+//
+//   haar_icon_tma_kernel   one HBM pass over a pitched RGB image produces the icons of ANY
+//                          subset of depths 1..6.  Persistent CTAs; a producer lane streams
+//                          128 px x 64 row tiles (24 KB) into a shared-memory ring with TMA
+//                          (cp.async.bulk.tensor + mbarrier), consumer warps reduce one tile
+//                          each: levels 1-4 in registers (packed 16-bit lanes), levels 5-6
+//                          with warp shuffles.  HBM-bound: ~3 B/px read, <= 1 B/px written.
+//   edge_strip_kernel      tiny pre-pass: materialises the border-extended right strip
+//                          (<= 79 px per row) so the hot kernel never evaluates the border
+//                          rule per pixel.
+//   haar_icon_generic_kernel  any C, any alignment, depth <= 8: one thread per output element.
+//   haar_level_f32_kernel  one further level in fp32, for depths > 8 (the reference's fp32
+//                          arithmetic stops being exact there, so it is replayed literally).
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+
+#include "haar_math.cuh"
+#include "icon_types.h"
+#include "kernels.h"
+
+namespace wicca {
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers (mbarrier + TMA)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// Tensor maps are read through the tensormap proxy; they were written by the host (cudaMemcpy),
+// so an acquire fence at system scope is required before the first use from global memory.
+__device__ __forceinline__ void fence_tensormap_acquire(const CUtensorMap* tmap) {
+    asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar,
+                                            uint64_t cache_policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(smem_dst)),
+        "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)), "l"(cache_policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// ------------------------------------------------------------------------------------------
+// The one-pass kernel
+// ------------------------------------------------------------------------------------------
+template <int kStages, int kConsumerWarps>
+__global__ void __launch_bounds__(32 * (1 + kConsumerWarps), 1)
+haar_icon_tma_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* __restrict__ strips, int n_images,
+                     int total_items, int border_type, int border_const) {
+    static_assert(kConsumerWarps <= kStages, "a stage must be released before its barrier phase is reused");
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* stages = smem_raw;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            int img = 0;
+            bool fresh = true;
+            int k = 0;
+            for (int g = blockIdx.x; g < total_items; g += gridDim.x, ++k) {
+                const int s = k % kStages;
+                const uint32_t ph = (uint32_t)(k / kStages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                while (img + 1 < n_images && g >= imgs[img + 1].item_base) { ++img; fresh = true; }
+                const IconImage* im = &imgs[img];
+                if (fresh) { fence_tensormap_acquire(&im->tmap); fresh = false; }
+                const int local = g - im->item_base;
+                const int iy = local / im->items_x;
+                const int ix = local - iy * im->items_x;
+                mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                tma_load_2d(stages + (size_t)s * kStageBytes, &im->tmap, ix * (kStageRowBytes / 4), iy * kItemH,
+                            &full_bar[s], pol);
+            }
+        }
+        return;
+    }
+
+    // ------------------------------- consumers ---------------------------------
+    const int cw = warp - 1;
+    const int cx = lane & 7;    // chunk column inside the item (16 px each)
+    const int ry = lane >> 3;   // row group inside the item (16 rows each)
+    const uint32_t fill = (uint32_t)border_const * 0x01010101u;
+    int img = 0;
+
+    for (int k = cw;; k += kConsumerWarps) {
+        const int g = blockIdx.x + k * gridDim.x;
+        if (g >= total_items) break;
+        const int s = k % kStages;
+        const uint32_t ph = (uint32_t)(k / kStages) & 1u;
+        while (img + 1 < n_images && g >= imgs[img + 1].item_base) ++img;
+        const IconImage& im = imgs[img];
+        const int local = g - im.item_base;
+        const int iy = local / im.items_x;
+        const int ix = local - iy * im.items_x;
+
+        const ChunkSrc cs = make_chunk_src(im, strips[img], stages + (size_t)s * kStageBytes, ix, iy, cx, ry,
+                                           border_type, fill);
+        const IconSink sk = make_sink(im);
+        const int x0 = cs.x0, y0 = cs.y0;
+
+        mbar_wait(&full_bar[s], ph);
+
+        uint32_t acc4[3];
+        reduce_lane(cs, sk, acc4);
+
+        // the stage is no longer needed: hand it back to the producer before the tail
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+
+        // levels 5 and 6: 2x2 and 4x4 lane groups (cx bit 0 / ry bit 0, then cx bit 1 / ry bit 1)
+        uint32_t s5[3], s6[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            uint32_t v = acc4[c] + __shfl_xor_sync(0xFFFFFFFFu, acc4[c], 1);
+            v += __shfl_xor_sync(0xFFFFFFFFu, v, 8);
+            s5[c] = v;
+            uint32_t u = v + __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+            u += __shfl_xor_sync(0xFFFFFFFFu, u, 16);
+            s6[c] = u;
+        }
+        emit_tail(sk, x0, y0, cx, ry, acc4, s5, s6);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Right-edge strip: strip[y][ (x - Wa)*3 + c ] = padded_image[y][x][c] for x in [Wa, Wa + strip_px)
+// ------------------------------------------------------------------------------------------
+__global__ void edge_strip_kernel(const IconImage* __restrict__ imgs, uint8_t* const* __restrict__ strips,
+                                  int border_type, int border_const) {
+    const IconImage& im = imgs[blockIdx.y];
+    uint8_t* strip = strips[blockIdx.y];
+    if (strip == nullptr) return;
+    const int npx = im.Wp_max - (im.W & ~(kChunkPx - 1));   // <= 78
+    if (npx <= 0) return;
+    const int total = im.H * npx;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int y = i / npx;
+        strip_pixel(im, strip, y, i - y * npx, border_type, border_const);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// General kernel: thread per output element, exact integer block sum (depth <= 8)
+// ------------------------------------------------------------------------------------------
+__global__ void haar_icon_generic_kernel(GenericIconArgs a) {
+    const int r = 1 << a.depth;
+    const int64_t n = (int64_t)a.out_h * a.out_w * a.C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % a.C);
+        const int64_t t = i / a.C;
+        const int ox = (int)(t % a.out_w);
+        const int oy = (int)(t / a.out_w);
+        uint32_t sum = 0;
+        for (int dy = 0; dy < r; ++dy) {
+            const int ym = border_index(oy * r + dy, a.H, a.border_type);
+            if (ym < 0) { sum += (uint32_t)a.border_const * (uint32_t)r; continue; }
+            const uint8_t* row = a.src + (int64_t)ym * a.pitch + c;
+            const int xb = ox * r;
+            if (xb + r <= a.W) {
+                for (int dx = 0; dx < r; ++dx) sum += row[(int64_t)(xb + dx) * a.C];
+            } else {
+                for (int dx = 0; dx < r; ++dx) {
+                    const int xm = border_index(xb + dx, a.W, a.border_type);
+                    sum += (xm < 0) ? (uint32_t)a.border_const : (uint32_t)row[(int64_t)xm * a.C];
+                }
+            }
+        }
+        if (a.dst_u8 != nullptr) {
+            a.dst_u8[(int64_t)oy * a.dst_pitch + (int64_t)ox * a.C + c] = (uint8_t)(sum >> (2 * a.depth));
+        } else {
+            // exact: sum < 2^24 for depth <= 8, and the scale is a power of two
+            a.dst_f32[i] = __uint2float_rn(sum) * (1.0f / (float)(1u << (2 * a.depth)));
+        }
+    }
+}
+
+// One more level in fp32, literally wavelet_coder.py:62-65: (even_row + odd_row), then
+// (even_col + odd_col) * 0.25.  in: (2*out_h, 2*out_w, C) tight fp32.
+__global__ void haar_level_f32_kernel(const float* __restrict__ in, float* __restrict__ out, uint8_t* out_u8,
+                                      int out_h, int out_w, int C) {
+    const int64_t n = (int64_t)out_h * out_w * C;
+    const int64_t in_row = (int64_t)2 * out_w * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t t = i / C;
+        const int ox = (int)(t % out_w);
+        const int oy = (int)(t / out_w);
+        const float* p = in + (int64_t)(2 * oy) * in_row + (int64_t)(2 * ox) * C + c;
+        const float s0 = __fadd_rn(p[0], p[in_row]);          // sums[:, even]
+        const float s1 = __fadd_rn(p[C], p[in_row + C]);      // sums[:, odd]
+        const float v = __fmul_rn(__fadd_rn(s0, s1), 0.25f);
+        if (out_u8 != nullptr) {
+            const float cl = fminf(fmaxf(v, 0.0f), 255.0f);   // np.clip, then astype(uint8) truncates
+            out_u8[i] = (uint8_t)cl;
+        } else {
+            out[i] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Launchers
+// ------------------------------------------------------------------------------------------
+template <int S, int NCW>
+static cudaError_t launch_tma_variant(const IconImage* d_imgs, const uint8_t* const* d_strips, int n_images,
+                                      int total_items, int border_type, int border_const, int grid,
+                                      cudaStream_t stream) {
+    const size_t smem = (size_t)S * kStageBytes + 2 * S * sizeof(uint64_t);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(haar_icon_tma_kernel<S, NCW>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured_dev = dev;
+    }
+    haar_icon_tma_kernel<S, NCW><<<grid, 32 * (1 + NCW), smem, stream>>>(d_imgs, d_strips, n_images, total_items,
+                                                                         border_type, border_const);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_icon_tma(const IconImage* d_imgs, const uint8_t* const* d_strips, int n_images, int total_items,
+                            int border_type, int border_const, int sm_count, int variant, cudaStream_t stream) {
+    if (total_items <= 0) return cudaSuccess;
+    const int grid = total_items < sm_count ? total_items : sm_count;
+    switch (variant) {
+        case 1: return launch_tma_variant<9, 6>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, stream);
+        case 2: return launch_tma_variant<9, 9>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, stream);
+        case 3: return launch_tma_variant<6, 6>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, stream);
+        case 4: return launch_tma_variant<8, 4>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, stream);
+        default: return launch_tma_variant<8, 8>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, stream);
+    }
+}
+
+cudaError_t launch_edge_strips(const IconImage* d_imgs, uint8_t* const* d_strips, int n_images, int max_rows,
+                               int border_type, int border_const, cudaStream_t stream) {
+    if (n_images <= 0) return cudaSuccess;
+    int bx = (max_rows * 80 + 255) / 256;
+    if (bx < 1) bx = 1;
+    if (bx > 64) bx = 64;
+    edge_strip_kernel<<<dim3(bx, n_images), 256, 0, stream>>>(d_imgs, d_strips, border_type, border_const);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_icon_generic(const GenericIconArgs& a, cudaStream_t stream) {
+    const int64_t n = (int64_t)a.out_h * a.out_w * a.C;
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    haar_icon_generic_kernel<<<(int)blocks, 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_level_f32(const float* in, float* out, uint8_t* out_u8, int out_h, int out_w, int C,
+                             cudaStream_t stream) {
+    const int64_t n = (int64_t)out_h * out_w * C;
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    haar_level_f32_kernel<<<(int)blocks, 256, 0, stream>>>(in, out, out_u8, out_h, out_w, C);
+    return cudaGetLastError();
+}
+
+}  // namespace wicca

@@ -1,0 +1,409 @@
+// haar_math.cuh - register-level arithmetic of the one-pass Haar icon kernel.
+//
+// Everything here is __host__ __device__ so the exact code the GPU runs can be
+// replayed lane by lane on the CPU (tests/cpu_emul/emul_icon.cu) and compared
+// with the oracle without a GPU.
+//
+// Model.  One thread owns a "chunk": 16 RGB pixels = 48 bytes = 12 words of one
+// image row, and walks 16 rows of it two at a time.  The reference computes, per
+// level, (even_row + odd_row) then (even_col + odd_col) * 0.25 in fp32
+// (wicca/wavelet_coder.py:61-65) and truncates once at the end (:67).  Those
+// fp32 values are exact, so level-d output = (sum of the 2^d x 2^d block) >> 2d.
+// We therefore carry exact integer block sums up the pyramid:
+//   s1 (2x2 sums, <= 1020), s2 (4x4, <= 4080), s3 (8x8, <= 16320) live in packed
+//   16-bit lanes (two values per register); s4..s6 in 32-bit registers.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include "icon_types.h"
+
+#if defined(__CUDACC__)
+#define WHD __host__ __device__ __forceinline__
+#else
+#define WHD inline
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+#endif
+
+namespace wicca {
+
+// PRMT: result byte i = byte sel.nibble[i] of the 8-byte pool {a (0..3), b (4..7)}.
+WHD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    uint64_t pool = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        uint32_t n = (sel >> (4 * i)) & 0x7;
+        r |= (uint32_t)((pool >> (8 * n)) & 0xFF) << (8 * i);
+    }
+    return r;
+#endif
+}
+
+// (x & m) | (y & ~m): one LOP3 on the device.
+WHD uint32_t bitsel(uint32_t m, uint32_t x, uint32_t y) { return (x & m) | (y & ~m); }
+
+// ---------------------------------------------------------------------------
+// Level 1 of one row pair.
+// In : A[12], B[12] - the 48 bytes of rows 2i and 2i+1 of the chunk.
+// Out: T[c*4 + j] = ( s1(j, c) , s1(j+4, c) ) packed lo/hi, for c in 0..2, j in 0..3,
+//      where s1(q, c) = sum over the 2 rows of pixel 2q and 2q+1, channel c.
+// ---------------------------------------------------------------------------
+WHD void level1_rowpair(const uint32_t (&A)[12], const uint32_t (&B)[12], uint32_t (&T)[12]) {
+    // vertical add, widening bytes to 16-bit lanes:
+    //   E[k] = (byte0, byte2) of word k, O[k] = (byte1, byte3) of word k
+    uint32_t E[12], O[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        E[k] = (A[k] & 0x00FF00FFu) + (B[k] & 0x00FF00FFu);
+        O[k] = prmt(A[k], 0u, 0x4341u) + prmt(B[k], 0u, 0x4341u);
+    }
+    // G[b] = ( V(b) , V(b+24) ) for byte position b in 0..23 of the chunk row, V = vertical sum
+    uint32_t G[24];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        G[4 * k + 0] = prmt(E[k], E[k + 6], 0x5410u);
+        G[4 * k + 2] = prmt(E[k], E[k + 6], 0x7632u);
+        G[4 * k + 1] = prmt(O[k], O[k + 6], 0x5410u);
+        G[4 * k + 3] = prmt(O[k], O[k + 6], 0x7632u);
+    }
+    // horizontal pair: byte b of pixel 2q pairs with byte b+3 of pixel 2q+1
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) T[c * 4 + j] = G[6 * j + c] + G[6 * j + c + 3];
+}
+
+// pack two lane-registers into 4 bytes: ( x.lo>>S, y.lo>>S, x.hi>>S, y.hi>>S ), values < 2^(8+S)
+template <int S>
+WHD uint32_t pack2(uint32_t x, uint32_t y) {
+    return bitsel(0x00FF00FFu, x >> S, y << (8 - S));
+}
+
+// Level-1 icon bytes of one row pair: 8 pixels x 3 channels = 24 bytes = W[6].
+WHD void icon1_words(const uint32_t (&T)[12], uint32_t (&W)[6]) {
+    // output byte 3q+c = s1(q,c) >> 2 ; T index = c*4 + (q & 3), lane = q >> 2
+    // word n (q in 0..3) takes entries L[4n..4n+3] of (q,c) = (0,0)(0,1)(0,2)(1,0)(1,1)(1,2)(2,0)...
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+        const int b0 = 4 * n, b1 = 4 * n + 1, b2 = 4 * n + 2, b3 = 4 * n + 3;
+        uint32_t P1 = pack2<2>(T[(b0 % 3) * 4 + b0 / 3], T[(b1 % 3) * 4 + b1 / 3]);
+        uint32_t P2 = pack2<2>(T[(b2 % 3) * 4 + b2 / 3], T[(b3 % 3) * 4 + b3 / 3]);
+        W[n]     = prmt(P1, P2, 0x5410u);   // lo lanes: pixels 0..3
+        W[n + 3] = prmt(P1, P2, 0x7632u);   // hi lanes: pixels 4..7
+    }
+}
+
+// Level-2 partial of one row pair: U[c*2+h] = T[c][2h] + T[c][2h+1]
+//   U[c*2+0] = ( s2row(0,c), s2row(2,c) ), U[c*2+1] = ( s2row(1,c), s2row(3,c) )
+WHD void level2_accumulate(const uint32_t (&T)[12], uint32_t (&acc2)[6]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        acc2[c * 2 + 0] += T[c * 4 + 0] + T[c * 4 + 1];
+        acc2[c * 2 + 1] += T[c * 4 + 2] + T[c * 4 + 3];
+    }
+}
+
+// Level-2 icon bytes (4 pixels x 3 channels = 12 bytes) from complete 4x4 sums.
+WHD void icon2_words(const uint32_t (&acc2)[6], uint32_t (&W)[3]) {
+    uint32_t PA = pack2<4>(acc2[0], acc2[2]);   // s2(0,0) s2(0,1) | s2(2,0) s2(2,1)
+    uint32_t PB = pack2<4>(acc2[4], acc2[1]);   // s2(0,2) s2(1,0) | s2(2,2) s2(3,0)
+    uint32_t PC = pack2<4>(acc2[3], acc2[5]);   // s2(1,1) s2(1,2) | s2(3,1) s2(3,2)
+    W[0] = prmt(PA, PB, 0x5410u);
+    W[1] = prmt(PC, PA, 0x7610u);
+    W[2] = prmt(PB, PC, 0x7632u);
+}
+
+// Level 3: acc3[c] += ( s3row(0,c), s3row(1,c) ) from complete level-2 sums.
+WHD void level3_accumulate(const uint32_t (&acc2)[6], uint32_t (&acc3)[3]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc3[c] += acc2[c * 2 + 0] + acc2[c * 2 + 1];
+}
+
+// Level-3 icon bytes: 2 pixels x 3 channels = 6 bytes, returned as three 16-bit values.
+WHD void icon3_halves(const uint32_t (&acc3)[3], uint32_t (&Hh)[3]) {
+    const uint32_t p0c0 = (acc3[0] & 0xFFFFu) >> 6, p1c0 = acc3[0] >> 22;
+    const uint32_t p0c1 = (acc3[1] & 0xFFFFu) >> 6, p1c1 = acc3[1] >> 22;
+    const uint32_t p0c2 = (acc3[2] & 0xFFFFu) >> 6, p1c2 = acc3[2] >> 22;
+    Hh[0] = p0c0 | (p0c1 << 8);
+    Hh[1] = p0c2 | (p1c0 << 8);
+    Hh[2] = p1c1 | (p1c2 << 8);
+}
+
+// Level 4: acc4[c] += lo + hi of the complete level-3 sums (32-bit from here on).
+WHD void level4_accumulate(const uint32_t (&acc3)[3], uint32_t (&acc4)[3]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc4[c] += (acc3[c] & 0xFFFFu) + (acc3[c] >> 16);
+}
+
+// ---------------------------------------------------------------------------
+// Output side.  IconSink = where the (up to six) icons of the current image live.
+// ---------------------------------------------------------------------------
+struct IconSink {
+    uint8_t* icon[6];      // index = depth-1; nullptr = level not requested
+    int64_t pitch[6];
+    int h[6], w[6];        // icon extents: ceil(H / 2^d), ceil(W / 2^d)
+};
+
+WHD uint32_t word_byte(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
+
+// Store NW words = NW*4/3 pixels at pixel ox0 of an icon row; whole-group vector stores when the
+// group lies inside the row, bytewise clipping at the right edge otherwise.
+template <int NW>
+WHD void store_px_group(uint8_t* row, int ox0, int icon_w, const uint32_t (&W)[NW]) {
+    constexpr int NPX = NW * 4 / 3;
+    uint8_t* p = row + (int64_t)ox0 * 3;
+    if (ox0 + NPX <= icon_w) {
+        if (NW == 6) {                       // 24 B, 8-byte aligned (ox0 multiple of 8)
+            uint2* q = reinterpret_cast<uint2*>(p);
+            uint2 v0, v1, v2;
+            v0.x = W[0]; v0.y = W[1]; v1.x = W[2]; v1.y = W[3]; v2.x = W[4 % NW]; v2.y = W[5 % NW];
+            q[0] = v0; q[1] = v1; q[2] = v2;
+        } else {                             // 12 B, 4-byte aligned (ox0 multiple of 4)
+            uint32_t* q = reinterpret_cast<uint32_t*>(p);
+#pragma unroll
+            for (int k = 0; k < NW; ++k) q[k] = W[k];
+        }
+    } else {
+        const int nb = (icon_w - ox0) * 3;
+#pragma unroll
+        for (int t = 0; t < NW * 4; ++t)
+            if (t < nb) p[t] = (uint8_t)word_byte(W[t >> 2], t & 3);
+    }
+}
+
+// Reduce one chunk (16 px x 16 rows at pixel x0, row y0): emits levels 1..3 to the sink and
+// returns the three 16x16 channel sums in acc4.  `load(r, A)` fills A[12] with the 48 bytes of
+// chunk row r (0..15), border-extended.
+template <class Loader>
+WHD void reduce_chunk(Loader& load, const IconSink& sk, int x0, int y0, uint32_t (&acc4)[3]) {
+    acc4[0] = acc4[1] = acc4[2] = 0u;
+#pragma unroll 1
+    for (int h8 = 0; h8 < 2; ++h8) {                 // two 8-row groups
+        uint32_t acc3[3] = {0u, 0u, 0u};
+#pragma unroll
+        for (int q4 = 0; q4 < 2; ++q4) {             // two 4-row groups
+            uint32_t acc2[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int p2 = 0; p2 < 2; ++p2) {         // two row pairs
+                const int r = h8 * 8 + q4 * 4 + p2 * 2;
+                uint32_t A[12], B[12], T[12];
+                load(r, A);
+                load(r + 1, B);
+                level1_rowpair(A, B, T);
+                if (sk.icon[0] != nullptr) {
+                    const int oy = (y0 + r) >> 1, ox0 = x0 >> 1;
+                    if (oy < sk.h[0] && ox0 < sk.w[0]) {
+                        uint32_t Wd[6];
+                        icon1_words(T, Wd);
+                        store_px_group<6>(sk.icon[0] + (int64_t)oy * sk.pitch[0], ox0, sk.w[0], Wd);
+                    }
+                }
+                level2_accumulate(T, acc2);
+            }
+            if (sk.icon[1] != nullptr) {
+                const int oy = (y0 + h8 * 8 + q4 * 4) >> 2, ox0 = x0 >> 2;
+                if (oy < sk.h[1] && ox0 < sk.w[1]) {
+                    uint32_t Wd[3];
+                    icon2_words(acc2, Wd);
+                    store_px_group<3>(sk.icon[1] + (int64_t)oy * sk.pitch[1], ox0, sk.w[1], Wd);
+                }
+            }
+            level3_accumulate(acc2, acc3);
+        }
+        if (sk.icon[2] != nullptr) {
+            const int oy = (y0 + h8 * 8) >> 3, ox0 = x0 >> 3;
+            if (oy < sk.h[2] && ox0 < sk.w[2]) {
+                uint32_t Hh[3];
+                icon3_halves(acc3, Hh);
+                uint8_t* p = sk.icon[2] + (int64_t)oy * sk.pitch[2] + (int64_t)ox0 * 3;
+                if (ox0 + 2 <= sk.w[2]) {            // 6 B, 2-byte aligned (ox0 multiple of 2)
+                    uint16_t* q = reinterpret_cast<uint16_t*>(p);
+                    q[0] = (uint16_t)Hh[0]; q[1] = (uint16_t)Hh[1]; q[2] = (uint16_t)Hh[2];
+                } else {                             // only the first pixel is inside the icon
+                    p[0] = (uint8_t)(Hh[0] & 0xFFu); p[1] = (uint8_t)(Hh[0] >> 8); p[2] = (uint8_t)(Hh[1] & 0xFFu);
+                }
+            }
+        }
+        level4_accumulate(acc3, acc4);
+    }
+}
+
+// Levels 4..6 of one lane.  cx = chunk column (0..7), ry = row group (0..3) inside the 128x64
+// item; s5 / s6 = the 32x32 / 64x64 sums of the lane's 2x2 / 4x4 lane group.
+WHD void emit_tail(const IconSink& sk, int x0, int y0, int cx, int ry, const uint32_t (&acc4)[3],
+                   const uint32_t (&s5)[3], const uint32_t (&s6)[3]) {
+    if (sk.icon[3] != nullptr) {
+        const int oy = y0 >> 4, ox = x0 >> 4;
+        if (oy < sk.h[3] && ox < sk.w[3]) {
+            uint8_t* p = sk.icon[3] + (int64_t)oy * sk.pitch[3] + (int64_t)ox * 3;
+            p[0] = (uint8_t)(acc4[0] >> 8); p[1] = (uint8_t)(acc4[1] >> 8); p[2] = (uint8_t)(acc4[2] >> 8);
+        }
+    }
+    if (sk.icon[4] != nullptr && (cx & 1) == 0 && (ry & 1) == 0) {
+        const int oy = y0 >> 5, ox = x0 >> 5;
+        if (oy < sk.h[4] && ox < sk.w[4]) {
+            uint8_t* p = sk.icon[4] + (int64_t)oy * sk.pitch[4] + (int64_t)ox * 3;
+            p[0] = (uint8_t)(s5[0] >> 10); p[1] = (uint8_t)(s5[1] >> 10); p[2] = (uint8_t)(s5[2] >> 10);
+        }
+    }
+    if (sk.icon[5] != nullptr && (cx & 3) == 0 && ry == 0) {
+        const int oy = y0 >> 6, ox = x0 >> 6;
+        if (oy < sk.h[5] && ox < sk.w[5]) {
+            uint8_t* p = sk.icon[5] + (int64_t)oy * sk.pitch[5] + (int64_t)ox * 3;
+            p[0] = (uint8_t)(s6[0] >> 12); p[1] = (uint8_t)(s6[1] >> 12); p[2] = (uint8_t)(s6[2] >> 12);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// cv::borderInterpolate for p >= 0 (padding is bottom/right only,
+// wicca/data_loader.py:107-117).  Returns -1 for BORDER_CONSTANT.
+// ---------------------------------------------------------------------------
+WHD int border_index(int p, int n, int border_type) {
+    if (p < n) return p;
+    switch (border_type) {
+        case 1: return n - 1;                               // REPLICATE
+        case 2:                                             // REFLECT      fedcba|abcdefgh|hgfedcb
+        case 4: {                                           // REFLECT_101  gfedcb|abcdefgh|gfedcba
+            if (n == 1) return 0;
+            const int delta = (border_type == 4) ? 1 : 0;
+            do {
+                if (p < 0) p = -p - 1 + delta;
+                else       p = n - 1 - (p - n) - delta;
+            } while ((unsigned)p >= (unsigned)n);
+            return p;
+        }
+        case 3: return p % n;                               // WRAP
+        default: return -1;                                 // CONSTANT
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Input side: where the 48 bytes of a chunk row come from.
+//   kSmem  - interior chunk: rows < H from the TMA-filled shared-memory stage, border rows
+//            (y >= H) from the mapped image row in global memory;
+//   kStrip - chunk that touches or lies right of column W: every row from the pre-built
+//            border-extended right strip (edge_strip_kernel);
+//   kDead  - chunk beyond the padded extent of the deepest requested level: zeros.
+// ---------------------------------------------------------------------------
+enum ChunkMode : int { kDead = 0, kSmem = 1, kStrip = 2 };
+
+struct ChunkSrc {
+    int mode;
+    const uint8_t* smem;      // chunk origin inside the stage (row stride kStageRowBytes)
+    const uint8_t* gcol;      // kSmem: image + x0*3 ; kStrip: strip + (x0 - Wa)*3   (row 0)
+    int64_t gpitch;           // row pitch of gcol's plane
+    int x0, y0, H, Hp_max;
+    int border_type;
+    uint32_t fill;            // border constant replicated in 4 bytes
+};
+
+WHD void words_from(const uint4& a, const uint4& b, const uint4& c, uint32_t (&A)[12]) {
+    A[0] = a.x; A[1] = a.y; A[2] = a.z; A[3] = a.w;
+    A[4] = b.x; A[5] = b.y; A[6] = b.z; A[7] = b.w;
+    A[8] = c.x; A[9] = c.y; A[10] = c.z; A[11] = c.w;
+}
+
+// 48 bytes from the shared-memory stage (16-byte aligned)
+WHD void load48_stage(const uint8_t* p, uint32_t (&A)[12]) {
+#if defined(__CUDA_ARCH__)
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    words_from(q[0], q[1], q[2], A);
+#else
+    memcpy(A, p, 48);
+#endif
+}
+
+// 48 bytes from global memory (16-byte aligned), read-only path
+WHD void load48_global(const uint8_t* p, uint32_t (&A)[12]) {
+#if defined(__CUDA_ARCH__)
+    uint4 a, b, c;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p));
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p + 16));
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "l"(p + 32));
+    words_from(a, b, c, A);
+#else
+    memcpy(A, p, 48);
+#endif
+}
+
+// Geometry of lane (cx, ry) of work item (ix, iy) of image `im`.
+WHD ChunkSrc make_chunk_src(const IconImage& im, const uint8_t* strip, const uint8_t* stage, int ix, int iy, int cx,
+                            int ry, int border_type, uint32_t fill) {
+    ChunkSrc cs;
+    cs.x0 = ix * kItemW + cx * kChunkPx;
+    cs.y0 = iy * kItemH + ry * 16;
+    cs.smem = stage + (ry * 16) * kStageRowBytes + cx * (kChunkPx * 3);
+    cs.H = im.H; cs.Hp_max = im.Hp_max;
+    cs.border_type = border_type; cs.fill = fill;
+    const int Wa = im.W & ~(kChunkPx - 1);      // first pixel of the chunk that straddles W
+    if (cs.x0 >= im.Wp_max || cs.y0 >= im.Hp_max) {
+        cs.mode = kDead; cs.gcol = nullptr; cs.gpitch = 0;
+    } else if (cs.x0 + kChunkPx <= im.W) {
+        cs.mode = kSmem; cs.gcol = im.src + (int64_t)cs.x0 * 3; cs.gpitch = im.pitch;
+    } else {
+        cs.mode = kStrip; cs.gcol = strip + (int64_t)(cs.x0 - Wa) * 3; cs.gpitch = kStripPitch;
+    }
+    return cs;
+}
+
+WHD bool chunk_is_interior(const ChunkSrc& cs) { return cs.mode == kSmem && cs.y0 + 16 <= cs.H; }
+
+// General row loader (any mode, any row).
+WHD void load_chunk_row(const ChunkSrc& cs, int r, uint32_t (&A)[12]) {
+    const int y = cs.y0 + r;
+    if (cs.mode == kSmem && y < cs.H) { load48_stage(cs.smem + r * kStageRowBytes, A); return; }
+    if (cs.mode == kDead || y >= cs.Hp_max) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) A[k] = 0u;
+        return;
+    }
+    const int ym = border_index(y, cs.H, cs.border_type);
+    if (ym < 0) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) A[k] = cs.fill;
+        return;
+    }
+    load48_global(cs.gcol + (int64_t)ym * cs.gpitch, A);
+}
+
+// One lane's share of a work item up to level 4.
+WHD void reduce_lane(const ChunkSrc& cs, const IconSink& sk, uint32_t (&acc4)[3]) {
+    if (chunk_is_interior(cs)) {
+        const uint8_t* sm = cs.smem;
+        auto loader = [sm](int r, uint32_t (&A)[12]) { load48_stage(sm + r * kStageRowBytes, A); };
+        reduce_chunk(loader, sk, cs.x0, cs.y0, acc4);
+    } else {
+        auto loader = [&cs](int r, uint32_t (&A)[12]) { load_chunk_row(cs, r, A); };
+        reduce_chunk(loader, sk, cs.x0, cs.y0, acc4);
+    }
+}
+
+WHD IconSink make_sink(const IconImage& im) {
+    IconSink sk;
+#pragma unroll
+    for (int l = 0; l < kMaxFused; ++l) {
+        sk.icon[l] = im.icon[l]; sk.pitch[l] = im.icon_pitch[l]; sk.h[l] = im.icon_h[l]; sk.w[l] = im.icon_w[l];
+    }
+    return sk;
+}
+
+// Right-edge strip element: strip[y][(x - Wa)*3 + c] = padded_image[y][x][c], x = Wa + px.
+WHD void strip_pixel(const IconImage& im, uint8_t* strip, int y, int px, int border_type, int border_const) {
+    const int Wa = im.W & ~(kChunkPx - 1);
+    const int xm = border_index(Wa + px, im.W, border_type);
+    uint8_t* d = strip + (int64_t)y * kStripPitch + px * 3;
+    if (xm < 0) {
+        d[0] = d[1] = d[2] = (uint8_t)border_const;
+    } else {
+        const uint8_t* s = im.src + (int64_t)y * im.pitch + (int64_t)xm * 3;
+        d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+    }
+}
+
+
+}  // namespace wicca

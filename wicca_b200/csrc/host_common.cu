@@ -1,0 +1,234 @@
+// host_common.cu - error strings, device/context pool, TMA descriptor encoding.
+#include "host_common.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "icon_types.h"
+
+namespace wicca {
+
+std::string& last_error_ref() {
+    static thread_local std::string s;
+    return s;
+}
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s): %s [%s]", (int)e, cudaGetErrorName(e), cudaGetErrorString(e), what);
+    last_error_ref() = buf;
+    cudaGetLastError();   // clear the sticky-less error state
+    return (int)e;
+}
+
+int saturate_u8(double v) {
+    if (!(v == v)) return 0;
+    double r = nearbyint(v);   // default rounding mode: half to even, like cvRound
+    if (r < 0) return 0;
+    if (r > 255) return 255;
+    return (int)r;
+}
+
+bool border_valid(int border_type) {
+    const int b = border_base(border_type);
+    return b >= 0 && b <= 4;
+}
+
+cudaError_t DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { p = nullptr; return e; }
+    cap = want;
+    return cudaSuccess;
+}
+void DevBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+
+cudaError_t PinBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) { p = nullptr; return e; }
+    cap = want;
+    return cudaSuccess;
+}
+void PinBuf::release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+
+cudaError_t Ctx::init(int dev) {
+    device = dev;
+    cudaError_t e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return e;
+    for (auto& x : ev) {
+        e = cudaEventCreate(&x);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+void Ctx::destroy() {
+    if (device < 0) return;
+    cudaSetDevice(device);
+    d_src.release(); d_icons.release(); d_desc.release(); d_strip.release();
+    d_f32a.release(); d_f32b.release(); d_misc.release();
+    h_desc.release(); h_bounce.release();
+    for (auto& x : ev) if (x) { cudaEventDestroy(x); x = nullptr; }
+    if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+    device = -1;
+}
+
+namespace {
+struct Pool {
+    std::mutex mu;
+    std::vector<Ctx*> idle;
+    std::vector<Ctx*> all;
+};
+std::mutex g_mu;
+int g_ndev = -2;                    // -2: not probed
+std::vector<DeviceInfo> g_info;
+std::vector<Pool*> g_pools;
+
+void probe_locked() {
+    if (g_ndev != -2) return;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    g_ndev = n;
+    g_info.assign(n, DeviceInfo());
+    g_pools.assign(n, nullptr);
+    for (int i = 0; i < n; ++i) g_pools[i] = new Pool();
+}
+}  // namespace
+
+int device_count_cached() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    probe_locked();
+    return g_ndev;
+}
+
+int check_device(int device) {
+    const int n = device_count_cached();
+    if (n <= 0) {
+        int m = 0;
+        cudaError_t e = cudaGetDeviceCount(&m);
+        if (e == cudaSuccess) e = cudaErrorNoDevice;
+        return cuda_fail(e, "no usable CUDA device (libwicca_b200 has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(WICCA_EDEVICE, "device ordinal %d out of range (0..%d)", device, n - 1);
+    return 0;
+}
+
+const DeviceInfo& device_info(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceInfo& di = g_info[device];
+    if (!di.ok) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+        di.sm_count = v > 0 ? v : 148;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        di.smem_optin = (size_t)v;
+        di.ok = true;
+    }
+    return di;
+}
+
+int acquire_ctx(int device, Ctx** out) {
+    int rc = check_device(device);
+    if (rc) return rc;
+    WICCA_CUDA(cudaSetDevice(device));
+    Pool* pool = g_pools[device];
+    {
+        std::lock_guard<std::mutex> lk(pool->mu);
+        if (!pool->idle.empty()) {
+            *out = pool->idle.back();
+            pool->idle.pop_back();
+            return 0;
+        }
+    }
+    Ctx* c = new Ctx();
+    cudaError_t e = c->init(device);
+    if (e != cudaSuccess) { c->destroy(); delete c; return cuda_fail(e, "context init"); }
+    {
+        std::lock_guard<std::mutex> lk(pool->mu);
+        pool->all.push_back(c);
+    }
+    *out = c;
+    return 0;
+}
+
+void release_ctx(Ctx* c) {
+    if (!c || c->device < 0) return;
+    Pool* pool = g_pools[c->device];
+    std::lock_guard<std::mutex> lk(pool->mu);
+    pool->idle.push_back(c);
+}
+
+void destroy_all_ctx() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ndev <= 0) return;
+    for (Pool* pool : g_pools) {
+        if (!pool) continue;
+        std::lock_guard<std::mutex> lk2(pool->mu);
+        for (Ctx* c : pool->all) { c->destroy(); delete c; }
+        pool->all.clear();
+        pool->idle.clear();
+    }
+}
+
+// ---- TMA descriptor ---------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+        else cudaGetLastError();
+    });
+    return fn;
+}
+
+int encode_image_tmap(CUtensorMap* tm, const void* d_src, int H, int64_t pitch) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail((int)cudaErrorNotSupported, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)(pitch / 4), (cuuint64_t)H};
+    cuuint64_t gstride[1] = {(cuuint64_t)pitch};
+    cuuint32_t box[2] = {(cuuint32_t)(kStageRowBytes / 4), (cuuint32_t)kItemH};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(d_src), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail((int)cudaErrorInvalidValue, "cuTensorMapEncodeTiled failed with CUresult %d (H=%d pitch=%lld)", (int)r, H,
+                    (long long)pitch);
+    return 0;
+}
+
+int icon_variant_from_env() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("WICCA_ICON_VARIANT");
+        v = e ? atoi(e) : 0;
+        if (v < 0) v = 0;
+    }
+    return v;
+}
+
+}  // namespace wicca

@@ -1,0 +1,85 @@
+// host_common.h - host-side plumbing shared by the C-ABI translation units (internal).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/wicca_b200.h"
+
+namespace wicca {
+
+// ---- thread-local error string --------------------------------------------------------
+std::string& last_error_ref();
+int fail(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define WICCA_CUDA(call)                                          \
+    do {                                                          \
+        cudaError_t _e = (call);                                  \
+        if (_e != cudaSuccess) return ::wicca::cuda_fail(_e, #call); \
+    } while (0)
+
+// ---- small helpers ---------------------------------------------------------------------
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int icon_dim(int n, int depth) { return depth <= 0 ? n : (int)(((int64_t)n + ((int64_t)1 << depth) - 1) >> depth); }
+int saturate_u8(double v);                 // cv::saturate_cast<uchar>(double)
+bool border_valid(int border_type);        // after masking BORDER_ISOLATED
+inline int border_base(int border_type) { return border_type & ~16; }
+
+// ---- grow-only buffers ------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes);     // keeps contents only if no growth is needed
+    void release();
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes);
+    void release();
+};
+
+// ---- per-call context: one stream + scratch, leased from a per-device pool --------------
+struct Ctx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};                // start, h2d done, kernels done, d2h done, spare x2
+    DevBuf d_src, d_icons, d_desc, d_strip, d_f32a, d_f32b, d_misc;
+    PinBuf h_desc, h_bounce;
+    cudaError_t init(int dev);
+    void destroy();
+};
+
+struct DeviceInfo {
+    bool ok = false;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+};
+
+int device_count_cached();
+int check_device(int device);                       // 0 or WICCA_EDEVICE / cuda error
+const DeviceInfo& device_info(int device);
+int acquire_ctx(int device, Ctx** out);             // sets the calling thread's current device
+void release_ctx(Ctx* c);
+void destroy_all_ctx();
+
+struct CtxLease {
+    Ctx* c = nullptr;
+    ~CtxLease() { if (c) release_ctx(c); }
+};
+
+// ---- TMA descriptor ---------------------------------------------------------------------
+// 2-D uint32 view (pitch/4 x H) of a pitched byte image, box (kStageRowBytes/4) x kItemH.
+int encode_image_tmap(CUtensorMap* tm, const void* d_src, int H, int64_t pitch);
+
+int icon_variant_from_env();
+
+}  // namespace wicca
