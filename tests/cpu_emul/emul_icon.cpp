@@ -51,6 +51,7 @@ int emul_fused_icons(const uint8_t* src, int H, int W, int border_type, int bord
     }
     const uint32_t fill = (uint32_t)border_const * 0x01010101u;
     const IconSink sk = make_sink(im);
+    const ImageGeom geo = make_geom(im);
     std::vector<uint8_t> stage(kStageBytes);
     for (int iy = 0; iy < im.items_y; ++iy)
         for (int ix = 0; ix < im.items_x; ++ix) {
@@ -65,7 +66,7 @@ int emul_fused_icons(const uint8_t* src, int H, int W, int border_type, int bord
             uint32_t acc4[32][3], v1[32][3], s5[32][3], u1[32][3], s6[32][3];
             ChunkSrc cs[32];
             for (int lane = 0; lane < 32; ++lane) {
-                cs[lane] = make_chunk_src(im, strip.empty() ? nullptr : strip.data(), stage.data(), ix, iy, lane & 7,
+                cs[lane] = make_chunk_src(geo, strip.empty() ? nullptr : strip.data(), stage.data(), ix, iy, lane & 7,
                                           lane >> 3, border_type, fill);
                 reduce_lane(cs[lane], sk, acc4[lane]);
             }

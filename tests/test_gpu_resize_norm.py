@@ -1,0 +1,70 @@
+"""Epilogue rows A5/A6: icon -> INTER_AREA resize -> preprocess_input, against the oracle
+(which is pinned on cv2 outputs) and, when cv2 is importable, against cv2 itself."""
+import numpy as np
+import pytest
+
+from oracle import resize_oracle as ro
+from tests.golden.make_golden import gen_input
+from wicca_b200 import HaarCoder
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def coder():
+    return HaarCoder()
+
+
+def test_resize_goldens_bit_exact(coder, resize_golden):
+    cases, outs = resize_golden
+    for (seed, sh, sw, dw, dh), exp in zip(cases, outs):
+        src = gen_input("noise", 1000 + seed, sh, sw, 3)
+        f32, u8 = coder.icons_to_batch([src], (dw, dh), "identity", return_uint8=True)
+        assert u8.shape == (1, dh, dw, 3) and np.array_equal(u8[0], exp), (seed, sh, sw, dw, dh)
+        assert np.array_equal(f32[0], exp.astype(np.float32))
+
+
+@pytest.mark.parametrize("target", [224, 331])
+def test_headline_icon_sizes_all_regimes(coder, target):
+    """Icon sizes of the (6393, 8284) image at depths 2..6 -> 224 / 331 (depth 1 is in the slow test)."""
+    sizes = [(1599, 2071), (800, 1036), (400, 518), (200, 259), (100, 130)]
+    icons = [gen_input("noise", 50 + i, h, w, 3) for i, (h, w) in enumerate(sizes)]
+    f32, u8 = coder.icons_to_batch(icons, (target, target), "tf", return_uint8=True)
+    assert f32.shape == (len(sizes), target, target, 3) and f32.dtype == np.float32
+    for i, ic in enumerate(icons):
+        exp = ro.resize_area(ic, target, target)
+        assert np.array_equal(u8[i], exp), (sizes[i], target, ro.regime(ic.shape[1], ic.shape[0], target, target))
+    exp_f = ro.preprocess_input(u8, "tf")
+    assert np.allclose(f32, exp_f, rtol=1e-5, atol=0) and np.array_equal(f32, exp_f)
+
+
+@pytest.mark.parametrize("mode", ["identity", "tf", "caffe", "torch"])
+def test_preprocess_modes(coder, mode):
+    icons = [gen_input("noise", 70 + i, 300 + 10 * i, 410 + 7 * i, 3) for i in range(4)]
+    f32, u8 = coder.icons_to_batch(icons, (240, 240), mode, return_uint8=True)
+    exp = ro.preprocess_input(u8, mode)
+    # tolerance stated by north_star: <= 1e-5 relative; the implementation is in fact bit-exact
+    assert np.allclose(f32, exp, rtol=1e-5, atol=1e-6)
+    assert np.array_equal(f32, exp)
+
+
+def test_live_cv2_when_available(coder):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(11)
+    icons = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in [(448, 448), (672, 672), (224, 224), (57, 91),
+                                                                           (3197 // 2, 4142 // 2), (299, 299)]]
+    for t in (224, 299):
+        _, u8 = coder.icons_to_batch(icons, (t, t), "identity", return_uint8=True)
+        for i, ic in enumerate(icons):
+            assert np.array_equal(u8[i], cv2.resize(ic, (t, t), interpolation=cv2.INTER_AREA)), (ic.shape, t)
+
+
+def test_end_to_end_icon_then_batch(coder):
+    """configs[3]: HaarCoder icons -> resize -> normalise, batch of images."""
+    from oracle import haar_oracle as ho
+    imgs = [gen_input("noise", 90 + i, 1200 + 13 * i, 1600 + 7 * i, 3) for i in range(6)]
+    for depth in (1, 3):
+        icons = [coder.get_small_copy(im, depth) for im in imgs]
+        batch = coder.icons_to_batch(icons, (224, 224), "tf")
+        exp = ro.preprocess_input(np.stack([ro.resize_area(ho.haar_icon_blocksum(im, depth), 224, 224) for im in imgs]), "tf")
+        assert np.array_equal(batch, exp)

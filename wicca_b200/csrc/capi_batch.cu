@@ -1,0 +1,126 @@
+// capi_batch.cu - sharded host batch: images are independent units (the per-image loop of
+// wicca/classifying_tools.py:312-321), so image i goes to devices[i % n_devices] and nothing
+// crosses between GPUs.  One worker thread per device; two upload slots (stream + buffers) per
+// worker so the H2D copy of image j+1 overlaps the kernel and icon D2H of image j.
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "host_common.h"
+
+using namespace wicca;
+
+namespace {
+
+struct BatchArgs {
+    const uint8_t* const* srcs; const int* Hs; const int* Ws; const int64_t* strides;
+    int n_images, C; const int* depths; int n_depths; int border_type, bconst;
+    uint8_t* const* dsts;
+};
+
+struct WorkerResult {
+    int rc = 0;
+    std::string msg;
+    double h2d = 0, kernel = 0, d2h = 0, total = 0;
+};
+
+void add_times(WorkerResult& r, Ctx& c) {
+    float a = 0, b = 0, d = 0, e = 0;
+    cudaEventElapsedTime(&a, c.ev[0], c.ev[1]);
+    cudaEventElapsedTime(&b, c.ev[1], c.ev[2]);
+    cudaEventElapsedTime(&d, c.ev[2], c.ev[3]);
+    cudaEventElapsedTime(&e, c.ev[0], c.ev[3]);
+    r.h2d += a; r.kernel += b; r.d2h += d; r.total += e;
+}
+
+int worker_body(const BatchArgs& a, int device, int first, int step, WorkerResult& res) {
+    CtxLease slot[2];
+    bool busy[2] = {false, false};
+    for (int s = 0; s < 2; ++s) {
+        int rc = acquire_ctx(device, &slot[s].c);
+        if (rc) return rc;
+    }
+    int j = 0;
+    for (int i = first; i < a.n_images; i += step, ++j) {
+        const int H = a.Hs[i], W = a.Ws[i];
+        const int64_t rowb = (int64_t)W * a.C;
+        const int64_t stride = (a.strides && a.strides[i]) ? a.strides[i] : rowb;
+        uint8_t* const* dsts = a.dsts + (size_t)i * a.n_depths;
+        bool device_work = false;
+        for (int k = 0; k < a.n_depths; ++k) {
+            if (a.depths[k] <= 0) {
+                for (int y = 0; y < H; ++y) memcpy(dsts[k] + (size_t)y * rowb, a.srcs[i] + (size_t)y * stride, (size_t)rowb);
+            } else {
+                device_work = true;
+            }
+        }
+        if (!device_work) continue;
+        Ctx& c = *slot[j & 1].c;
+        if (busy[j & 1]) {
+            WICCA_CUDA(cudaStreamSynchronize(c.stream));
+            add_times(res, c);
+        }
+        const int64_t pitch = wicca_pitch_bytes(W, a.C);
+        WICCA_CUDA(c.d_src.reserve((size_t)pitch * H + 256));
+        WICCA_CUDA(cudaEventRecord(c.ev[0], c.stream));
+        WICCA_CUDA(cudaMemcpy2DAsync(c.d_src.p, (size_t)pitch, a.srcs[i], (size_t)stride, (size_t)rowb, (size_t)H,
+                                     cudaMemcpyHostToDevice, c.stream));
+        WICCA_CUDA(cudaEventRecord(c.ev[1], c.stream));
+        int rc = icons_from_resident(c, H, W, a.C, pitch, a.depths, a.n_depths, a.border_type, a.bconst, dsts);
+        if (rc) { cudaStreamSynchronize(c.stream); return rc; }
+        busy[j & 1] = true;
+    }
+    for (int s = 0; s < 2; ++s)
+        if (busy[s]) {
+            WICCA_CUDA(cudaStreamSynchronize(slot[s].c->stream));
+            add_times(res, *slot[s].c);
+        }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int wicca_batch_icons_u8(const uint8_t* const* srcs, const int* Hs, const int* Ws, const int64_t* strides,
+                                    int n_images, int C, const int* depths, int n_depths, int border_type,
+                                    double border_const, uint8_t* const* dsts, const int* devices, int n_devices,
+                                    wicca_timing* t) {
+    if (t) memset(t, 0, sizeof(*t));
+    if (n_images < 0) return fail(WICCA_EINVAL, "negative image count");
+    if (n_images == 0) return 0;
+    if (!srcs || !Hs || !Ws || !dsts) return fail(WICCA_EINVAL, "null array");
+    if (n_devices <= 0) return fail(WICCA_EDEVICE, "need at least one device");
+    for (int i = 0; i < n_images; ++i) {
+        int rc = validate_icon_args(srcs[i], Hs[i], Ws[i], C, depths, n_depths, border_type);
+        if (rc) return rc;
+        const int64_t rowb = (int64_t)Ws[i] * C;
+        if (strides && strides[i] && strides[i] < rowb) return fail(WICCA_EINVAL, "strides[%d] < W*C", i);
+        for (int k = 0; k < n_depths; ++k)
+            if (!dsts[(size_t)i * n_depths + k]) return fail(WICCA_EINVAL, "dsts[%d][%d] is NULL", i, k);
+    }
+    std::vector<int> devs(n_devices);
+    for (int k = 0; k < n_devices; ++k) {
+        devs[k] = devices ? devices[k] : k;
+        int rc = check_device(devs[k]);
+        if (rc) return rc;
+    }
+    BatchArgs a{srcs, Hs, Ws, strides, n_images, C, depths, n_depths, border_type, saturate_u8(border_const), dsts};
+    const int nw = n_devices < n_images ? n_devices : n_images;
+    std::vector<WorkerResult> results(nw);
+    std::vector<std::thread> threads;
+    for (int k = 0; k < nw; ++k)
+        threads.emplace_back([&, k] {
+            results[k].rc = worker_body(a, devs[k], k, nw, results[k]);
+            if (results[k].rc) results[k].msg = last_error_ref();
+        });
+    for (auto& th : threads) th.join();
+    wicca_timing sum = {0, 0, 0, 0};
+    for (auto& r : results) {
+        if (r.rc) { last_error_ref() = r.msg; return r.rc; }
+        sum.h2d_ms += (float)r.h2d; sum.kernel_ms += (float)r.kernel; sum.d2h_ms += (float)r.d2h; sum.total_ms += (float)r.total;
+    }
+    if (t) *t = sum;
+    return 0;
+}

@@ -29,7 +29,7 @@ bool needs_padding(int H, int W, int depth) {
 
 // Common argument validation of the icon entry points.  Mirrors the order of checks of the
 // reference: validate_image (validation.py:94-99) then get_padded_copy (data_loader.py:93-117).
-int validate_icon_args(const void* src, int H, int W, int C, const int* depths, int n_depths, int border_type) {
+int validate_icon_args_impl(const void* src, int H, int W, int C, const int* depths, int n_depths, int border_type) {
     if (!src) return fail(WICCA_EINVAL, "image pointer is NULL");
     if (H <= 0 || W <= 0 || C <= 0) return fail(WICCA_EINVAL, "image is empty (H=%d W=%d C=%d)", H, W, C);
     if (!depths || n_depths <= 0) return fail(WICCA_EINVAL, "no depths given");
@@ -116,6 +116,10 @@ void fill_timing(wicca_timing* t, Ctx& c) {
 }  // namespace
 
 namespace wicca {
+
+int validate_icon_args(const void* src, int H, int W, int C, const int* depths, int n_depths, int border_type) {
+    return validate_icon_args_impl(src, H, W, C, depths, n_depths, border_type);
+}
 
 // Shared by the one-shot host call and the batch workers: image already on the device in
 // c.d_src (pitched); computes every requested depth > 0 and copies the icons to the host

@@ -105,21 +105,30 @@ haar_icon_tma_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* _
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
             const uint64_t pol = policy_evict_first();
-            int img = 0;
-            bool fresh = true;
+            // Per-image fields live in registers and are refreshed only when the item index crosses
+            // into the next image: the issue loop has no dependent global loads.
+            int img = -1, base = 0, next_base = 0, items_x = 1;
+            const CUtensorMap* tmap = nullptr;
             int k = 0;
             for (int g = blockIdx.x; g < total_items; g += gridDim.x, ++k) {
+                if (g >= next_base) {
+                    do {
+                        ++img;
+                        next_base = (img + 1 < n_images) ? imgs[img + 1].item_base : 0x7FFFFFFF;
+                    } while (g >= next_base);
+                    base = imgs[img].item_base;
+                    items_x = imgs[img].items_x;
+                    tmap = &imgs[img].tmap;
+                    fence_tensormap_acquire(tmap);
+                }
+                const int local = g - base;
+                const int iy = local / items_x;
+                const int ix = local - iy * items_x;
                 const int s = k % kStages;
                 const uint32_t ph = (uint32_t)(k / kStages) & 1u;
                 mbar_wait(&empty_bar[s], ph ^ 1u);
-                while (img + 1 < n_images && g >= imgs[img + 1].item_base) { ++img; fresh = true; }
-                const IconImage* im = &imgs[img];
-                if (fresh) { fence_tensormap_acquire(&im->tmap); fresh = false; }
-                const int local = g - im->item_base;
-                const int iy = local / im->items_x;
-                const int ix = local - iy * im->items_x;
                 mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-                tma_load_2d(stages + (size_t)s * kStageBytes, &im->tmap, ix * (kStageRowBytes / 4), iy * kItemH,
+                tma_load_2d(stages + (size_t)s * kStageBytes, tmap, ix * (kStageRowBytes / 4), iy * kItemH,
                             &full_bar[s], pol);
             }
         }
@@ -131,22 +140,33 @@ haar_icon_tma_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* _
     const int cx = lane & 7;    // chunk column inside the item (16 px each)
     const int ry = lane >> 3;   // row group inside the item (16 rows each)
     const uint32_t fill = (uint32_t)border_const * 0x01010101u;
-    int img = 0;
+    int img = -1, base = 0, next_base = 0;
+    ImageGeom geo;
+    IconSink sk;
+    const uint8_t* strip = nullptr;
 
     for (int k = cw;; k += kConsumerWarps) {
         const int g = blockIdx.x + k * gridDim.x;
         if (g >= total_items) break;
         const int s = k % kStages;
         const uint32_t ph = (uint32_t)(k / kStages) & 1u;
-        while (img + 1 < n_images && g >= imgs[img + 1].item_base) ++img;
-        const IconImage& im = imgs[img];
-        const int local = g - im.item_base;
-        const int iy = local / im.items_x;
-        const int ix = local - iy * im.items_x;
+        if (g >= next_base) {            // warp-uniform: entered a new image, refresh the cached descriptor
+            do {
+                ++img;
+                next_base = (img + 1 < n_images) ? imgs[img + 1].item_base : 0x7FFFFFFF;
+            } while (g >= next_base);
+            const IconImage& im = imgs[img];
+            base = im.item_base;
+            geo = make_geom(im);
+            sk = make_sink(im);
+            strip = strips[img];
+        }
+        const int local = g - base;
+        const int iy = local / geo.items_x;
+        const int ix = local - iy * geo.items_x;
 
-        const ChunkSrc cs = make_chunk_src(im, strips[img], stages + (size_t)s * kStageBytes, ix, iy, cx, ry,
-                                           border_type, fill);
-        const IconSink sk = make_sink(im);
+        const ChunkSrc cs = make_chunk_src(geo, strip, stages + (size_t)s * kStageBytes, ix, iy, cx, ry, border_type,
+                                           fill);
         const int x0 = cs.x0, y0 = cs.y0;
 
         mbar_wait(&full_bar[s], ph);

@@ -331,8 +331,21 @@ WHD void load48_global(const uint8_t* p, uint32_t (&A)[12]) {
 #endif
 }
 
+// The per-image fields the consumers need (kept in registers across work items).
+struct ImageGeom {
+    const uint8_t* src;
+    int64_t pitch;
+    int H, W, Hp_max, Wp_max, items_x;
+};
+WHD ImageGeom make_geom(const IconImage& im) {
+    ImageGeom g;
+    g.src = im.src; g.pitch = im.pitch; g.H = im.H; g.W = im.W;
+    g.Hp_max = im.Hp_max; g.Wp_max = im.Wp_max; g.items_x = im.items_x;
+    return g;
+}
+
 // Geometry of lane (cx, ry) of work item (ix, iy) of image `im`.
-WHD ChunkSrc make_chunk_src(const IconImage& im, const uint8_t* strip, const uint8_t* stage, int ix, int iy, int cx,
+WHD ChunkSrc make_chunk_src(const ImageGeom& im, const uint8_t* strip, const uint8_t* stage, int ix, int iy, int cx,
                             int ry, int border_type, uint32_t fill) {
     ChunkSrc cs;
     cs.x0 = ix * kItemW + cx * kChunkPx;

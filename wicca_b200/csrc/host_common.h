@@ -82,4 +82,10 @@ int encode_image_tmap(CUtensorMap* tm, const void* d_src, int H, int64_t pitch);
 
 int icon_variant_from_env();
 
+// capi_icon.cu: image already resident in c.d_src (pitched); enqueue every depth > 0 on c.stream and
+// the D2H copies of the icons; records c.ev[2] (kernels done) and c.ev[3] (D2H done).
+int icons_from_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int* depths, int n_depths, int border_type,
+                        int bconst, uint8_t* const* dsts);
+int validate_icon_args(const void* src, int H, int W, int C, const int* depths, int n_depths, int border_type);
+
 }  // namespace wicca

@@ -16,21 +16,30 @@ cudaError_t launch_icon_generic(const GenericIconArgs& a, cudaStream_t stream);
 cudaError_t launch_level_f32(const float* in, float* out, uint8_t* out_u8, int out_h, int out_w, int C,
                              cudaStream_t stream);
 
-// haar_subband.cu
-cudaError_t launch_forward_level1_u8(const uint8_t* src, int64_t pitch, int H, int W, int C, int Hp, int Wp,
-                                     int border_type, int border_const, float* coeffs, cudaStream_t stream);
-cudaError_t launch_forward_level_f32(const float* ll_in, int64_t in_row_elems, float* coeffs, int64_t co_row_elems,
-                                     int out_h, int out_w, int C, cudaStream_t stream);
-cudaError_t launch_inverse_level_f32(const float* coeffs, int64_t co_row_elems, const float* ll_in,
-                                     int64_t ll_row_elems, float* out, int64_t out_row_elems, int h, int w, int C,
-                                     cudaStream_t stream);
+// haar_subband.cu   (d_work: scratch of >= Hp*Wp*C*5/16 floats)
+cudaError_t launch_forward(const uint8_t* d_src, int64_t pitch, int H, int W, int C, int Hp, int Wp, int depth,
+                           int border_type, int border_const, float* d_coeffs, float* d_work, cudaStream_t stream);
+cudaError_t launch_inverse(const float* d_coeffs, int Hp, int Wp, int C, int depth, float* d_image, float* d_work,
+                           cudaStream_t stream);
 
 // resize_norm.cu
-struct ResizeTap { int dst; int src; float w; };
-cudaError_t launch_resize_area_generic(const uint8_t* const* d_icons, const int* d_hs, const int* d_ws, int n,
-                                       const ResizeTap* d_xtabs, const int* d_xtab_off, const ResizeTap* d_ytabs,
-                                       const int* d_ytab_off, int out_h, int out_w, int norm_mode, float* d_out,
-                                       uint8_t* d_out_u8, float* d_hbuf, const int64_t* d_hbuf_off,
-                                       cudaStream_t stream);
+struct ResizeJob {           // one icon of a batch
+    const uint8_t* src;      // device, tight (sh, sw, 3)
+    int sh, sw;
+    int regime;              // 0 = same size (copy), 1 = integer-factor area, 2 = general area, 3 = bilinear "area mode"
+    int isx, isy;            // regime 1: integer scale factors
+    int xoff, yoff;          // regime 2: offsets into the CSR row-pointer arrays (out_w+1 / out_h+1 entries)
+                             // regime 3: offsets into the bilinear tap arrays (out_w / out_h entries)
+};
+struct AreaTap { int src; float w; };
+struct LinTap { int i0, i1, c0, c1; };
+struct ResizeTables {
+    const ResizeJob* jobs;
+    const int* rowptr;       // concatenated CSR row pointers (absolute indices into taps)
+    const AreaTap* taps;
+    const LinTap* lin;
+};
+cudaError_t launch_resize_norm(const ResizeTables& t, int n, int out_h, int out_w, int norm_mode, float* d_out,
+                               uint8_t* d_out_u8, cudaStream_t stream);
 
 }  // namespace wicca

@@ -1,0 +1,107 @@
+// resize_norm.cu - classifier-input epilogue: icon (uint8 HWC) -> cv2.resize(..., INTER_AREA)
+// (wicca/classifying_tools.py:318) -> np.stack (:323) -> preprocess_input + float32 cast
+// (:286-287), one thread per output element, bit-exact with OpenCV's three 8-bit code paths
+// (restated in oracle/resize_oracle.py):
+//   regime 1  integer factors     : integer block sum; 2x2 -> (s+2)>>2, else rint(float(s) * (1/area))
+//   regime 2  general area        : fp32 taps, accumulated in OpenCV's order (x taps inside each
+//                                   source row, then beta * row over the y taps), rint, saturate
+//   regime 3  any axis upscaled   : 2-tap bilinear in 11-bit fixed point ("area mode" taps)
+// No FMA contraction anywhere: OpenCV's scalar code multiplies and adds separately.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace wicca {
+
+__device__ __forceinline__ float norm_value(float v, int c, int mode) {
+    switch (mode) {
+        case 1: return __fsub_rn(__fdiv_rn(v, 127.5f), 1.0f);                                   // "tf"
+        case 3: {                                                                               // "torch"
+            const float mean = (c == 0) ? 0.485f : (c == 1) ? 0.456f : 0.406f;
+            const float sd = (c == 0) ? 0.229f : (c == 1) ? 0.224f : 0.225f;
+            return __fdiv_rn(__fsub_rn(__fdiv_rn(v, 255.0f), mean), sd);
+        }
+        default: return v;                                                                      // identity
+    }
+}
+
+__device__ __forceinline__ uint8_t sat_rint_u8(float x) {
+    const float r = rintf(x);                       // round half to even, like cvRound
+    return (uint8_t)fminf(fmaxf(r, 0.0f), 255.0f);
+}
+
+__global__ void resize_norm_kernel(ResizeTables t, int n, int out_h, int out_w, int norm_mode, float* __restrict__ out,
+                                   uint8_t* __restrict__ out_u8) {
+    const int64_t per = (int64_t)out_h * out_w * 3;
+    const int64_t total = per * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int img = (int)(i / per);
+        int64_t r = i - (int64_t)img * per;
+        const int c = (int)(r % 3);
+        r /= 3;
+        const int dx = (int)(r % out_w);
+        const int dy = (int)(r / out_w);
+        const ResizeJob j = t.jobs[img];
+        const int64_t srow = (int64_t)j.sw * 3;
+        const uint8_t* s = j.src + c;
+        uint8_t v;
+        if (j.regime == 0) {
+            v = s[(int64_t)dy * srow + (int64_t)dx * 3];
+        } else if (j.regime == 1) {
+            uint32_t sum = 0;
+            for (int yy = 0; yy < j.isy; ++yy) {
+                const uint8_t* p = s + (int64_t)(dy * j.isy + yy) * srow + (int64_t)(dx * j.isx) * 3;
+                for (int xx = 0; xx < j.isx; ++xx) sum += p[xx * 3];
+            }
+            if (j.isx == 2 && j.isy == 2) v = (uint8_t)((sum + 2) >> 2);
+            else v = sat_rint_u8(__fmul_rn((float)sum, 1.0f / (float)(j.isx * j.isy)));
+        } else if (j.regime == 2) {
+            const int xb = t.rowptr[j.xoff + dx], xe = t.rowptr[j.xoff + dx + 1];
+            const int yb = t.rowptr[j.yoff + dy], ye = t.rowptr[j.yoff + dy + 1];
+            float acc = 0.0f;
+            for (int ky = yb; ky < ye; ++ky) {
+                const AreaTap ty = t.taps[ky];
+                const uint8_t* p = s + (int64_t)ty.src * srow;
+                float h = 0.0f;
+                for (int kx = xb; kx < xe; ++kx) {
+                    const AreaTap tx = t.taps[kx];
+                    h = __fadd_rn(h, __fmul_rn((float)p[(int64_t)tx.src * 3], tx.w));
+                }
+                const float bh = __fmul_rn(ty.w, h);
+                acc = (ky == yb) ? bh : __fadd_rn(acc, bh);
+            }
+            v = sat_rint_u8(acc);
+        } else {
+            const LinTap tx = t.lin[j.xoff + dx];
+            const LinTap ty = t.lin[j.yoff + dy];
+            const uint8_t* p0 = s + (int64_t)ty.i0 * srow;
+            const uint8_t* p1 = s + (int64_t)ty.i1 * srow;
+            const int r0 = ((int)p0[(int64_t)tx.i0 * 3] * tx.c0 + (int)p0[(int64_t)tx.i1 * 3] * tx.c1) >> 4;
+            const int r1 = ((int)p1[(int64_t)tx.i0 * 3] * tx.c0 + (int)p1[(int64_t)tx.i1 * 3] * tx.c1) >> 4;
+            int o = (((ty.c0 * r0) >> 16) + ((ty.c1 * r1) >> 16) + 2) >> 2;
+            o = o < 0 ? 0 : (o > 255 ? 255 : o);
+            v = (uint8_t)o;
+        }
+        if (out_u8) out_u8[i] = v;
+        if (norm_mode == 2) {
+            // "caffe": RGB -> BGR then subtract the BGR means: output channel (2 - c) takes this value
+            const float mean = (c == 0) ? 123.68f : (c == 1) ? 116.779f : 103.939f;
+            out[i - c + (2 - c)] = __fsub_rn((float)v, mean);
+        } else {
+            out[i] = norm_value((float)v, c, norm_mode);
+        }
+    }
+}
+
+cudaError_t launch_resize_norm(const ResizeTables& t, int n, int out_h, int out_w, int norm_mode, float* d_out,
+                               uint8_t* d_out_u8, cudaStream_t stream) {
+    const int64_t total = (int64_t)n * out_h * out_w * 3;
+    if (total <= 0) return cudaSuccess;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    resize_norm_kernel<<<(int)blocks, 256, 0, stream>>>(t, n, out_h, out_w, norm_mode, d_out, d_out_u8);
+    return cudaGetLastError();
+}
+
+}  // namespace wicca
