@@ -22,8 +22,10 @@ extern "C" {
 // src: tight (H, W, 3) uint8.  mask bit (d-1) requests depth d.  outs[d-1]: tight icon buffers
 // (may be NULL when not requested).  Returns 0, or a positive code when a guard byte around an
 // icon was overwritten (out-of-bounds store).
+// staged != 0 replays the TMA-store path (levels 1..3 assembled in a per-warp tile, then copied
+// to the icon with the hardware's clipping rule); staged == 0 the direct-store path.
 int emul_fused_icons(const uint8_t* src, int H, int W, int border_type, int border_const, unsigned mask,
-                     uint8_t** outs) {
+                     uint8_t** outs, int staged) {
     const int64_t pitch = ((int64_t)W * 3 + 127) / 128 * 128;
     std::vector<uint8_t> img((size_t)pitch * H + 64, 0xA5);      // pad bytes are garbage on purpose
     for (int y = 0; y < H; ++y) memcpy(&img[(size_t)y * pitch], src + (size_t)y * W * 3, (size_t)W * 3);
@@ -65,10 +67,33 @@ int emul_fused_icons(const uint8_t* src, int H, int W, int border_type, int bord
                 }
             uint32_t acc4[32][3], v1[32][3], s5[32][3], u1[32][3], s6[32][3];
             ChunkSrc cs[32];
+            std::vector<uint8_t> tile(kOutStageBytes, 0xCD);
             for (int lane = 0; lane < 32; ++lane) {
                 cs[lane] = make_chunk_src(geo, strip.empty() ? nullptr : strip.data(), stage.data(), ix, iy, lane & 7,
                                           lane >> 3, border_type, fill);
-                reduce_lane(cs[lane], sk, acc4[lane]);
+                if (staged) {
+                    const StagedEmit em{tile.data(), lane & 7, lane >> 3, mask & 7u};
+                    reduce_lane(cs[lane], em, acc4[lane]);
+                } else {
+                    const DirectEmit em{sk, cs[lane].x0, cs[lane].y0};
+                    reduce_lane(cs[lane], em, acc4[lane]);
+                }
+            }
+            if (staged) {
+                // TMA store of a (box_w bytes x box_h rows) tile at byte x / row y, clipped to the tensor
+                const int box_w[3] = {kOut1Row, kOut2Row, kOut3Row}, box_h[3] = {32, 16, 8};
+                const int off[3] = {kOut1Off, kOut2Off, kOut3Off};
+                for (int l = 0; l < 3; ++l) {
+                    if (!(mask & (1u << l))) continue;
+                    const int64_t wb = (int64_t)im.icon_w[l] * 3;
+                    for (int r = 0; r < box_h[l]; ++r)
+                        for (int b = 0; b < box_w[l]; ++b) {
+                            const int64_t gx = (int64_t)ix * box_w[l] + b;
+                            const int gy = iy * box_h[l] + r;
+                            if (gx < wb && gy < im.icon_h[l])
+                                im.icon[l][(int64_t)gy * im.icon_pitch[l] + gx] = tile[off[l] + r * box_w[l] + b];
+                        }
+                }
             }
             for (int c = 0; c < 3; ++c) {
                 for (int l = 0; l < 32; ++l) v1[l][c] = acc4[l][c] + acc4[l ^ 1][c];

@@ -19,7 +19,7 @@ def main():
     n_img = int(os.environ.get("N_IMG", "30"))
     H, W = 6393, 8284
     variants = [int(v) for v in os.environ.get("VARIANTS", "0,1,2,3,4").split(",")]
-    depth_sets = [[1, 2, 3, 4, 5, 6], [1], [2], [3], [6]]
+    depth_sets = json.loads(os.environ.get("DEPTH_SETS", "[[1,2,3,4,5,6],[1],[3],[6]]"))
     dev = torch.device("cuda:0")
     pitch = pitch_bytes(W, 3)
     g = torch.Generator(device=dev); g.manual_seed(0)

@@ -54,7 +54,17 @@ int fill_icon_image(IconImage* im, const uint8_t* d_src, int H, int W, int64_t p
     int rc = encode_image_tmap(&im->tmap, d_src, H, pitch);
     if (rc) return rc;
     icon_image_geometry(im, d_src, H, W, pitch, item_base);
-    for (int i = 0; i < n_outs; ++i) icon_image_add_level(im, outs[i].depth, outs[i].d_ptr, outs[i].pitch);
+    for (int i = 0; i < n_outs; ++i) {
+        icon_image_add_level(im, outs[i].depth, outs[i].d_ptr, outs[i].pitch);
+        const int d = outs[i].depth;
+        if (d <= 3) {   // levels 1..3 leave the kernel through TMA store
+            static const int box_w[3] = {kOut1Row, kOut2Row, kOut3Row};
+            static const int box_h[3] = {32, 16, 8};
+            rc = encode_icon_tmap(&im->omap[d - 1], outs[i].d_ptr, outs[i].h, (int64_t)outs[i].w * 3, outs[i].pitch,
+                                  box_w[d - 1], box_h[d - 1]);
+            if (rc) return rc;
+        }
+    }
     return 0;
 }
 
@@ -298,7 +308,7 @@ int wicca_haar_icons_multi_dev(const uint8_t* d_src, int H, int W, int C, int64_
         if (dst_pitches[i] < (int64_t)w * C) return fail(WICCA_EINVAL, "dst_pitches[%d] too small", i);
         bool dup = false;
         for (auto& o : fo) dup |= (o.depth == d);
-        if (can_fuse && d <= kMaxFused && !dup && ((uintptr_t)d_dsts[i] % 8) == 0 && (dst_pitches[i] % 8) == 0) {
+        if (can_fuse && d <= kMaxFused && !dup && ((uintptr_t)d_dsts[i] % 16) == 0 && (dst_pitches[i] % 16) == 0) {
             IconOut o;
             o.depth = d; o.h = icon_dim(H, d); o.w = w; o.d_ptr = d_dsts[i]; o.pitch = dst_pitches[i];
             fo.push_back(o);

@@ -70,6 +70,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)), "l"(cache_policy)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(x),
+                 "r"(y), "r"(smem_u32(smem_src))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -78,14 +87,19 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 // ------------------------------------------------------------------------------------------
 // The one-pass kernel
 // ------------------------------------------------------------------------------------------
-template <int kStages, int kConsumerWarps>
+// kStaged: levels 1..3 are assembled as dense tiles in shared memory and written with TMA
+// store (full-line writes, hardware clipping); otherwise straight register->global stores.
+// debug: 0 = normal, 1 = consumers skip the arithmetic (load path only), 2 = arithmetic but no
+// level 1..3 output (developer instrumentation for tools/bench_variants.py).
+template <int kStages, int kConsumerWarps, bool kStaged>
 __global__ void __launch_bounds__(32 * (1 + kConsumerWarps), 1)
 haar_icon_tma_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* __restrict__ strips, int n_images,
-                     int total_items, int border_type, int border_const) {
+                     int total_items, int border_type, int border_const, int debug) {
     static_assert(kConsumerWarps <= kStages, "a stage must be released before its barrier phase is reused");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* stages = smem_raw;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageBytes);
+    uint8_t* out_tiles = smem_raw + (size_t)kStages * kStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_tiles + (kStaged ? (size_t)kConsumerWarps * kOutStageBytes : 0));
     uint64_t* empty_bar = full_bar + kStages;
 
     const int warp = threadIdx.x >> 5;
@@ -140,10 +154,14 @@ haar_icon_tma_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* _
     const int cx = lane & 7;    // chunk column inside the item (16 px each)
     const int ry = lane >> 3;   // row group inside the item (16 rows each)
     const uint32_t fill = (uint32_t)border_const * 0x01010101u;
+    uint8_t* tile = out_tiles + (size_t)cw * kOutStageBytes;
     int img = -1, base = 0, next_base = 0;
     ImageGeom geo;
     IconSink sk;
     const uint8_t* strip = nullptr;
+    const CUtensorMap* omap = nullptr;
+    unsigned mask = 0;
+    uint32_t sink_word = 0;
 
     for (int k = cw;; k += kConsumerWarps) {
         const int g = blockIdx.x + k * gridDim.x;
@@ -160,6 +178,20 @@ haar_icon_tma_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* _
             geo = make_geom(im);
             sk = make_sink(im);
             strip = strips[img];
+            omap = im.omap;
+            mask = 0;
+#pragma unroll
+            for (int l = 0; l < 3; ++l) mask |= (sk.icon[l] != nullptr ? 1u : 0u) << l;
+            if (debug == 2) {
+                mask = 0;
+#pragma unroll
+                for (int l = 0; l < 3; ++l) sk.icon[l] = nullptr;
+            }
+            if (kStaged && lane == 0) {
+#pragma unroll
+                for (int l = 0; l < 3; ++l)
+                    if ((mask >> l) & 1u) fence_tensormap_acquire(&omap[l]);
+            }
         }
         const int local = g - base;
         const int iy = local / geo.items_x;
@@ -169,14 +201,40 @@ haar_icon_tma_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* _
                                            fill);
         const int x0 = cs.x0, y0 = cs.y0;
 
+        if (kStaged) {
+            // the previous item's TMA stores must have finished READING this warp's tile
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+        }
+
         mbar_wait(&full_bar[s], ph);
 
         uint32_t acc4[3];
-        reduce_lane(cs, sk, acc4);
+        if (debug == 1) {
+            sink_word ^= *reinterpret_cast<const uint32_t*>(cs.smem);
+            acc4[0] = acc4[1] = acc4[2] = 0u;
+        } else if (kStaged) {
+            const StagedEmit em{tile, cx, ry, mask};
+            reduce_lane(cs, em, acc4);
+        } else {
+            const DirectEmit em{sk, x0, y0};
+            reduce_lane(cs, em, acc4);
+        }
 
         // the stage is no longer needed: hand it back to the producer before the tail
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
+
+        if (kStaged && mask != 0u && debug != 1) {
+            fence_proxy_async_smem();        // generic-proxy tile writes -> visible to the TMA (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+                if (mask & 1u) tma_store_2d(&omap[0], tile + kOut1Off, ix * kOut1Row, iy * 32);
+                if (mask & 2u) tma_store_2d(&omap[1], tile + kOut2Off, ix * kOut2Row, iy * 16);
+                if (mask & 4u) tma_store_2d(&omap[2], tile + kOut3Off, ix * kOut3Row, iy * 8);
+                bulk_commit();
+            }
+        }
 
         // levels 5 and 6: 2x2 and 4x4 lane groups (cx bit 0 / ry bit 0, then cx bit 1 / ry bit 1)
         uint32_t s5[3], s6[3];
@@ -189,8 +247,10 @@ haar_icon_tma_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* _
             u += __shfl_xor_sync(0xFFFFFFFFu, u, 16);
             s6[c] = u;
         }
-        emit_tail(sk, x0, y0, cx, ry, acc4, s5, s6);
+        if (debug != 1) emit_tail(sk, x0, y0, cx, ry, acc4, s5, s6);
     }
+    if (kStaged && lane == 0) bulk_wait0();      // all TMA stores of this warp are complete
+    if (debug == 1 && sink_word == 0x9E3779B9u && sk.icon[5] != nullptr) sk.icon[5][0] = (uint8_t)sink_word;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -272,36 +332,47 @@ __global__ void haar_level_f32_kernel(const float* __restrict__ in, float* __res
 // ------------------------------------------------------------------------------------------
 // Launchers
 // ------------------------------------------------------------------------------------------
-template <int S, int NCW>
+template <int S, int NCW, bool STAGED>
 static cudaError_t launch_tma_variant(const IconImage* d_imgs, const uint8_t* const* d_strips, int n_images,
-                                      int total_items, int border_type, int border_const, int grid,
+                                      int total_items, int border_type, int border_const, int grid, int debug,
                                       cudaStream_t stream) {
-    const size_t smem = (size_t)S * kStageBytes + 2 * S * sizeof(uint64_t);
+    const size_t smem = (size_t)S * kStageBytes + (STAGED ? (size_t)NCW * kOutStageBytes : 0) + 2 * S * sizeof(uint64_t);
     static thread_local int configured_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (configured_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(haar_icon_tma_kernel<S, NCW>,
+        cudaError_t e = cudaFuncSetAttribute(haar_icon_tma_kernel<S, NCW, STAGED>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured_dev = dev;
     }
-    haar_icon_tma_kernel<S, NCW><<<grid, 32 * (1 + NCW), smem, stream>>>(d_imgs, d_strips, n_images, total_items,
-                                                                         border_type, border_const);
+    haar_icon_tma_kernel<S, NCW, STAGED><<<grid, 32 * (1 + NCW), smem, stream>>>(d_imgs, d_strips, n_images, total_items,
+                                                                                 border_type, border_const, debug);
     return cudaGetLastError();
 }
 
+// variant: 0 = default.  1x = TMA-store output tiles, 0x = direct stores; see the switch.
 cudaError_t launch_icon_tma(const IconImage* d_imgs, const uint8_t* const* d_strips, int n_images, int total_items,
                             int border_type, int border_const, int sm_count, int variant, cudaStream_t stream) {
     if (total_items <= 0) return cudaSuccess;
     const int grid = total_items < sm_count ? total_items : sm_count;
+    const int debug = variant / 100;
+    variant %= 100;
+#define WICCA_V(S, N, ST) \
+    return launch_tma_variant<S, N, ST>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, stream)
     switch (variant) {
-        case 1: return launch_tma_variant<9, 6>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, stream);
-        case 2: return launch_tma_variant<9, 9>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, stream);
-        case 3: return launch_tma_variant<6, 6>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, stream);
-        case 4: return launch_tma_variant<8, 4>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, stream);
-        default: return launch_tma_variant<8, 8>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, stream);
+        case 1: WICCA_V(9, 6, false);
+        case 2: WICCA_V(9, 9, false);
+        case 3: WICCA_V(6, 6, false);
+        case 4: WICCA_V(8, 4, false);
+        case 5: WICCA_V(8, 8, false);
+        case 11: WICCA_V(7, 5, true);
+        case 12: WICCA_V(6, 6, true);
+        case 13: WICCA_V(7, 4, true);
+        case 14: WICCA_V(5, 5, true);
+        default: WICCA_V(7, 7, true);
     }
+#undef WICCA_V
 }
 
 cudaError_t launch_edge_strips(const IconImage* d_imgs, uint8_t* const* d_strips, int n_images, int max_rows,

@@ -58,8 +58,10 @@ WHD void level1_rowpair(const uint32_t (&A)[12], const uint32_t (&B)[12], uint32
     uint32_t E[12], O[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) {
-        E[k] = (A[k] & 0x00FF00FFu) + (B[k] & 0x00FF00FFu);
         O[k] = prmt(A[k], 0u, 0x4341u) + prmt(B[k], 0u, 0x4341u);
+        // A = E_A + (O_A << 8) exactly, so the even-byte sums fall out of one wrap-around
+        // subtract (an IMAD on the FMA pipe) instead of two maskings on the ALU pipe.
+        E[k] = A[k] + B[k] - (O[k] << 8);
     }
     // G[b] = ( V(b) , V(b+24) ) for byte position b in 0..23 of the chunk row, V = vertical sum
     uint32_t G[24];
@@ -175,12 +177,67 @@ WHD void store_px_group(uint8_t* row, int ox0, int icon_w, const uint32_t (&W)[N
     }
 }
 
-// Reduce one chunk (16 px x 16 rows at pixel x0, row y0): emits levels 1..3 to the sink and
-// returns the three 16x16 channel sums in acc4.  `load(r, A)` fills A[12] with the 48 bytes of
-// chunk row r (0..15), border-extended.
-template <class Loader>
-WHD void reduce_chunk(Loader& load, const IconSink& sk, int x0, int y0, uint32_t (&acc4)[3]) {
+// ---------------------------------------------------------------------------
+// Emitters for levels 1..3 (r = chunk row 0..15 at which the group starts).
+//   DirectEmit : global stores straight from registers, clipped at the icon's right/bottom edge.
+//   StagedEmit : dense per-warp tiles in shared memory (L1 32 x 192 B, L2 16 x 96 B, L3 8 x 48 B)
+//                that one lane then hands to TMA store, which clips in hardware.
+// ---------------------------------------------------------------------------
+
+struct DirectEmit {
+    const IconSink& sk;
+    int x0, y0;
+    WHD bool want(int l) const { return sk.icon[l] != nullptr; }
+    WHD void icon1(int r, const uint32_t (&W)[6]) const {
+        const int oy = (y0 + r) >> 1, ox0 = x0 >> 1;
+        if (oy < sk.h[0] && ox0 < sk.w[0]) store_px_group<6>(sk.icon[0] + (int64_t)oy * sk.pitch[0], ox0, sk.w[0], W);
+    }
+    WHD void icon2(int r, const uint32_t (&W)[3]) const {
+        const int oy = (y0 + r) >> 2, ox0 = x0 >> 2;
+        if (oy < sk.h[1] && ox0 < sk.w[1]) store_px_group<3>(sk.icon[1] + (int64_t)oy * sk.pitch[1], ox0, sk.w[1], W);
+    }
+    WHD void icon3(int r, const uint32_t (&Hh)[3]) const {
+        const int oy = (y0 + r) >> 3, ox0 = x0 >> 3;
+        if (oy < sk.h[2] && ox0 < sk.w[2]) {
+            uint8_t* p = sk.icon[2] + (int64_t)oy * sk.pitch[2] + (int64_t)ox0 * 3;
+            if (ox0 + 2 <= sk.w[2]) {            // 6 B, 2-byte aligned (ox0 multiple of 2)
+                uint16_t* q = reinterpret_cast<uint16_t*>(p);
+                q[0] = (uint16_t)Hh[0]; q[1] = (uint16_t)Hh[1]; q[2] = (uint16_t)Hh[2];
+            } else {                             // only the first pixel is inside the icon
+                p[0] = (uint8_t)(Hh[0] & 0xFFu); p[1] = (uint8_t)(Hh[0] >> 8); p[2] = (uint8_t)(Hh[1] & 0xFFu);
+            }
+        }
+    }
+};
+
+struct StagedEmit {
+    uint8_t* tile;          // this warp's kOutStageBytes staging area
+    int cx, ry;             // lane position inside the item
+    unsigned mask;          // bit l set = level l+1 requested
+    WHD bool want(int l) const { return (mask >> l) & 1u; }
+    WHD void icon1(int r, const uint32_t (&W)[6]) const {
+        uint2* q = reinterpret_cast<uint2*>(tile + kOut1Off + (ry * 8 + (r >> 1)) * kOut1Row + cx * 24);
+        uint2 v0, v1, v2;
+        v0.x = W[0]; v0.y = W[1]; v1.x = W[2]; v1.y = W[3]; v2.x = W[4]; v2.y = W[5];
+        q[0] = v0; q[1] = v1; q[2] = v2;
+    }
+    WHD void icon2(int r, const uint32_t (&W)[3]) const {
+        uint32_t* q = reinterpret_cast<uint32_t*>(tile + kOut2Off + (ry * 4 + (r >> 2)) * kOut2Row + cx * 12);
+        q[0] = W[0]; q[1] = W[1]; q[2] = W[2];
+    }
+    WHD void icon3(int r, const uint32_t (&Hh)[3]) const {
+        uint16_t* q = reinterpret_cast<uint16_t*>(tile + kOut3Off + (ry * 2 + (r >> 3)) * kOut3Row + cx * 6);
+        q[0] = (uint16_t)Hh[0]; q[1] = (uint16_t)Hh[1]; q[2] = (uint16_t)Hh[2];
+    }
+};
+
+// Reduce one chunk (16 px x 16 rows): emits levels 1..3 through `em` and returns the three 16x16
+// channel sums in acc4.  `load(r, A)` fills A[12] with the 48 bytes of chunk row r (0..15),
+// border-extended.
+template <class Loader, class Emit>
+WHD void reduce_chunk(Loader& load, const Emit& em, uint32_t (&acc4)[3]) {
     acc4[0] = acc4[1] = acc4[2] = 0u;
+    const bool want1 = em.want(0), want2 = em.want(1), want3 = em.want(2);
 #pragma unroll 1
     for (int h8 = 0; h8 < 2; ++h8) {                 // two 8-row groups
         uint32_t acc3[3] = {0u, 0u, 0u};
@@ -194,39 +251,24 @@ WHD void reduce_chunk(Loader& load, const IconSink& sk, int x0, int y0, uint32_t
                 load(r, A);
                 load(r + 1, B);
                 level1_rowpair(A, B, T);
-                if (sk.icon[0] != nullptr) {
-                    const int oy = (y0 + r) >> 1, ox0 = x0 >> 1;
-                    if (oy < sk.h[0] && ox0 < sk.w[0]) {
-                        uint32_t Wd[6];
-                        icon1_words(T, Wd);
-                        store_px_group<6>(sk.icon[0] + (int64_t)oy * sk.pitch[0], ox0, sk.w[0], Wd);
-                    }
+                if (want1) {
+                    uint32_t Wd[6];
+                    icon1_words(T, Wd);
+                    em.icon1(r, Wd);
                 }
                 level2_accumulate(T, acc2);
             }
-            if (sk.icon[1] != nullptr) {
-                const int oy = (y0 + h8 * 8 + q4 * 4) >> 2, ox0 = x0 >> 2;
-                if (oy < sk.h[1] && ox0 < sk.w[1]) {
-                    uint32_t Wd[3];
-                    icon2_words(acc2, Wd);
-                    store_px_group<3>(sk.icon[1] + (int64_t)oy * sk.pitch[1], ox0, sk.w[1], Wd);
-                }
+            if (want2) {
+                uint32_t Wd[3];
+                icon2_words(acc2, Wd);
+                em.icon2(h8 * 8 + q4 * 4, Wd);
             }
             level3_accumulate(acc2, acc3);
         }
-        if (sk.icon[2] != nullptr) {
-            const int oy = (y0 + h8 * 8) >> 3, ox0 = x0 >> 3;
-            if (oy < sk.h[2] && ox0 < sk.w[2]) {
-                uint32_t Hh[3];
-                icon3_halves(acc3, Hh);
-                uint8_t* p = sk.icon[2] + (int64_t)oy * sk.pitch[2] + (int64_t)ox0 * 3;
-                if (ox0 + 2 <= sk.w[2]) {            // 6 B, 2-byte aligned (ox0 multiple of 2)
-                    uint16_t* q = reinterpret_cast<uint16_t*>(p);
-                    q[0] = (uint16_t)Hh[0]; q[1] = (uint16_t)Hh[1]; q[2] = (uint16_t)Hh[2];
-                } else {                             // only the first pixel is inside the icon
-                    p[0] = (uint8_t)(Hh[0] & 0xFFu); p[1] = (uint8_t)(Hh[0] >> 8); p[2] = (uint8_t)(Hh[1] & 0xFFu);
-                }
-            }
+        if (want3) {
+            uint32_t Hh[3];
+            icon3_halves(acc3, Hh);
+            em.icon3(h8 * 8, Hh);
         }
         level4_accumulate(acc3, acc4);
     }
@@ -385,14 +427,15 @@ WHD void load_chunk_row(const ChunkSrc& cs, int r, uint32_t (&A)[12]) {
 }
 
 // One lane's share of a work item up to level 4.
-WHD void reduce_lane(const ChunkSrc& cs, const IconSink& sk, uint32_t (&acc4)[3]) {
+template <class Emit>
+WHD void reduce_lane(const ChunkSrc& cs, const Emit& em, uint32_t (&acc4)[3]) {
     if (chunk_is_interior(cs)) {
         const uint8_t* sm = cs.smem;
         auto loader = [sm](int r, uint32_t (&A)[12]) { load48_stage(sm + r * kStageRowBytes, A); };
-        reduce_chunk(loader, sk, cs.x0, cs.y0, acc4);
+        reduce_chunk(loader, em, acc4);
     } else {
         auto loader = [&cs](int r, uint32_t (&A)[12]) { load_chunk_row(cs, r, A); };
-        reduce_chunk(loader, sk, cs.x0, cs.y0, acc4);
+        reduce_chunk(loader, em, acc4);
     }
 }
 

@@ -221,14 +221,27 @@ int encode_image_tmap(CUtensorMap* tm, const void* d_src, int H, int64_t pitch) 
     return 0;
 }
 
+// uint8 view (w_bytes x h) of a pitched icon, box box_w x box_h bytes/rows: target of TMA store.
+int encode_icon_tmap(CUtensorMap* tm, const void* d_icon, int h, int64_t w_bytes, int64_t pitch, int box_w, int box_h) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail((int)cudaErrorNotSupported, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)w_bytes, (cuuint64_t)h};
+    cuuint64_t gstride[1] = {(cuuint64_t)pitch};
+    cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(d_icon), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail((int)cudaErrorInvalidValue, "cuTensorMapEncodeTiled (icon) failed with CUresult %d (h=%d w=%lld pitch=%lld)",
+                    (int)r, h, (long long)w_bytes, (long long)pitch);
+    return 0;
+}
+
 int icon_variant_from_env() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("WICCA_ICON_VARIANT");
-        v = e ? atoi(e) : 0;
-        if (v < 0) v = 0;
-    }
-    return v;
+    const char* e = getenv("WICCA_ICON_VARIANT");   // developer knob, see haar_icon.cu launch_icon_tma
+    const int v = e ? atoi(e) : 0;
+    return v < 0 ? 0 : v;
 }
 
 }  // namespace wicca

@@ -80,6 +80,8 @@ struct CtxLease {
 // 2-D uint32 view (pitch/4 x H) of a pitched byte image, box (kStageRowBytes/4) x kItemH.
 int encode_image_tmap(CUtensorMap* tm, const void* d_src, int H, int64_t pitch);
 
+int encode_icon_tmap(CUtensorMap* tm, const void* d_icon, int h, int64_t w_bytes, int64_t pitch, int box_w, int box_h);
+
 int icon_variant_from_env();
 
 // capi_icon.cu: image already resident in c.d_src (pitched); enqueue every depth > 0 on c.stream and

@@ -11,11 +11,16 @@ constexpr int kItemH = 64;            // rows per work item = 2^kMaxFused
 constexpr int kChunkPx = 16;          // pixels per lane per row
 constexpr int kStageRowBytes = kItemW * 3;            // 384
 constexpr int kStageBytes = kStageRowBytes * kItemH;  // 24576
+// per-warp output tiles of levels 1..3 (dense, handed to TMA store)
+constexpr int kOut1Row = 192, kOut2Row = 96, kOut3Row = 48;            // bytes per tile row
+constexpr int kOut1Off = 0, kOut2Off = 32 * kOut1Row, kOut3Off = kOut2Off + 16 * kOut2Row;   // 0, 6144, 7680
+constexpr int kOutStageBytes = 8192;
 constexpr int kStripPitch = 256;      // bytes per row of the right-edge strip (<= 78 px * 3)
 
 // One image of a launch.  Lives in global memory (array indexed by image).
 struct alignas(128) IconImage {
     CUtensorMap tmap;            // 2-D uint32 view of the pitched image, box 96 x 64
+    CUtensorMap omap[3];         // uint8 views of the level 1..3 icons (boxes 192x32, 96x16, 48x8) for TMA store
     const uint8_t* src;          // device, 16-byte aligned
     int64_t pitch;               // bytes, multiple of 16
     int H, W;
