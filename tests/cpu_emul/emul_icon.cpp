@@ -49,7 +49,7 @@ int emul_fused_icons(const uint8_t* src, int H, int W, int border_type, int bord
     if (npx > 0) {
         strip.assign((size_t)H * kStripPitch, 0x5A);
         for (int y = 0; y < H; ++y)
-            for (int px = 0; px < npx; ++px) strip_pixel(im, strip.data(), y, px, border_type, border_const);
+            for (int j = 0; j < (npx * 3 + 3) / 4; ++j) strip_word(im, strip.data(), y, j, border_type, border_const);
     }
     const uint32_t fill = (uint32_t)border_const * 0x01010101u;
     const IconSink sk = make_sink(im);
@@ -65,18 +65,63 @@ int emul_fused_icons(const uint8_t* src, int H, int W, int border_type, int bord
                     const int64_t xb = (int64_t)ix * kStageRowBytes + b;
                     stage[(size_t)r * kStageRowBytes + b] = (y < H && xb < pitch) ? img[(size_t)y * pitch + xb] : 0;
                 }
+            if (staged == 2) {
+                // two warps per item: half 0 = rows 0..31, half 1 = rows 32..63; 8 rows per lane
+                uint32_t s6half[2][32][3];
+                ChunkSrc hcs[2][32];
+                uint32_t hs4[2][32][3], hs5[2][32][3];
+                for (int half = 0; half < 2; ++half) {
+                    std::vector<uint8_t> tile(kHalfStageBytes, 0xCD);
+                    uint32_t acc[32][3], a1[32][3], b1[32][3];
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int cx = lane & 7, ry = lane >> 3;
+                        hcs[half][lane] = make_chunk_src(geo, strip.empty() ? nullptr : strip.data(), stage.data(), ix, iy,
+                                                         cx, half * 32 + ry * 8, 8, border_type, fill);
+                        const StagedEmit em = staged_emit_half(tile.data(), cx, ry, mask & 7u);
+                        reduce_lane<8>(hcs[half][lane], em, acc[lane]);
+                    }
+                    const int box_w[3] = {kOut1Row, kOut2Row, kOut3Row}, box_h[3] = {16, 8, 4};
+                    const int off[3] = {kHalf1Off, kHalf2Off, kHalf3Off};
+                    for (int l = 0; l < 3; ++l) {
+                        if (!(mask & (1u << l))) continue;
+                        const int64_t wb = (int64_t)im.icon_w[l] * 3;
+                        for (int r = 0; r < box_h[l]; ++r)
+                            for (int b = 0; b < box_w[l]; ++b) {
+                                const int64_t gx = (int64_t)ix * box_w[l] + b;
+                                const int gy = iy * (2 * box_h[l]) + half * box_h[l] + r;
+                                if (gx < wb && gy < im.icon_h[l])
+                                    im.icon[l][(int64_t)gy * im.icon_pitch[l] + gx] = tile[off[l] + r * box_w[l] + b];
+                            }
+                    }
+                    for (int c = 0; c < 3; ++c) {
+                        for (int l = 0; l < 32; ++l) hs4[half][l][c] = acc[l][c] + acc[l ^ 8][c];
+                        for (int l = 0; l < 32; ++l) a1[l][c] = hs4[half][l][c] + hs4[half][l ^ 1][c];
+                        for (int l = 0; l < 32; ++l) hs5[half][l][c] = a1[l][c] + a1[l ^ 16][c];
+                        for (int l = 0; l < 32; ++l) b1[l][c] = hs5[half][l][c] + hs5[half][l ^ 2][c];
+                        for (int l = 0; l < 32; ++l) s6half[half][l][c] = b1[l][c];
+                    }
+                }
+                for (int half = 0; half < 2; ++half)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        uint32_t s6v[3];
+                        for (int c = 0; c < 3; ++c) s6v[c] = s6half[0][lane][c] + s6half[1][lane][c];
+                        emit_tail_half(sk, hcs[half][lane].x0, hcs[half][lane].y0, lane & 7, lane >> 3, half == 0,
+                                       hs4[half][lane], hs5[half][lane], s6v);
+                    }
+                continue;
+            }
             uint32_t acc4[32][3], v1[32][3], s5[32][3], u1[32][3], s6[32][3];
             ChunkSrc cs[32];
             std::vector<uint8_t> tile(kOutStageBytes, 0xCD);
             for (int lane = 0; lane < 32; ++lane) {
                 cs[lane] = make_chunk_src(geo, strip.empty() ? nullptr : strip.data(), stage.data(), ix, iy, lane & 7,
-                                          lane >> 3, border_type, fill);
+                                          (lane >> 3) * 16, 16, border_type, fill);
                 if (staged) {
-                    const StagedEmit em{tile.data(), lane & 7, lane >> 3, mask & 7u};
-                    reduce_lane(cs[lane], em, acc4[lane]);
+                    const StagedEmit em = staged_emit_full(tile.data(), lane & 7, lane >> 3, mask & 7u);
+                    reduce_lane<16>(cs[lane], em, acc4[lane]);
                 } else {
                     const DirectEmit em{sk, cs[lane].x0, cs[lane].y0};
-                    reduce_lane(cs[lane], em, acc4[lane]);
+                    reduce_lane<16>(cs[lane], em, acc4[lane]);
                 }
             }
             if (staged) {

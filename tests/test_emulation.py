@@ -44,7 +44,7 @@ SHAPES = [(1, 1), (1, 2), (2, 1), (3, 5), (5, 7), (16, 16), (17, 33), (64, 64), 
           (127, 255), (128, 256), (200, 259), (130, 517), (129, 257), (70, 300)]
 
 
-@pytest.mark.parametrize("staged", [1, 0])
+@pytest.mark.parametrize("staged", [2, 1, 0])
 @pytest.mark.parametrize("border", [1, 0, 2, 3, 4])
 def test_emulated_kernel_matches_oracle(emul, border, staged):
     rng = np.random.default_rng(border)
@@ -60,6 +60,7 @@ def test_emulated_kernel_matches_oracle(emul, border, staged):
 @pytest.mark.parametrize("kind", ["full", "trunc", "zeros", "hramp", "vramp"])
 def test_emulated_kernel_adversarial(emul, kind):
     img = gen_input(kind, 5, 139, 301, 3)
-    outs = emul(img, 1, 0, [1, 2, 3, 4, 5, 6])
-    for d, got in outs.items():
-        assert np.array_equal(got, ho.haar_icon_blocksum(img, d, 1, 0)), (kind, d)
+    for staged in (2, 1, 0):
+        outs = emul(img, 1, 0, [1, 2, 3, 4, 5, 6], staged)
+        for d, got in outs.items():
+            assert np.array_equal(got, ho.haar_icon_blocksum(img, d, 1, 0)), (kind, d, staged)

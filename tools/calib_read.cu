@@ -77,6 +77,49 @@ read_tma(const __grid_constant__ CUtensorMap tmap, int boxes_x, int boxes_y, int
     }
 }
 
+// read 384x64 boxes and write a 192x32 box (the level-1 icon's share) per item with TMA store, no arithmetic
+__global__ void __launch_bounds__(64, 1)
+read_write_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap omap, int boxes_x, int boxes_y, int stages, int contiguous, uint32_t* sink) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int stage_bytes = 24576;
+    uint64_t* full = (uint64_t*)(smem + (size_t)stages * stage_bytes);
+    uint64_t* empty = full + stages;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int total = boxes_x * boxes_y;
+    const int per = (total + gridDim.x - 1) / gridDim.x;
+    const int g0 = contiguous ? blockIdx.x * per : blockIdx.x;
+    const int g1 = contiguous ? min(total, g0 + per) : total;
+    const int gs = contiguous ? 1 : gridDim.x;
+    if (threadIdx.x == 0) {
+        int k = 0;
+        for (int g = g0; g < g1; g += gs, ++k) {
+            const int s = k % stages; const uint32_t ph = (k / stages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            const int by = g / boxes_x, bx = g - by * boxes_x;
+            mbar_expect(&full[s], stage_bytes);
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(smem_u32(smem + (size_t)s * stage_bytes)), "l"(&tmap), "r"(bx * 48), "r"(by * 64), "r"(smem_u32(&full[s])) : "memory");
+        }
+    } else if (threadIdx.x == 32) {
+        int k = 0;
+        for (int g = g0; g < g1; g += gs, ++k) {
+            const int s = k % stages; const uint32_t ph = (k / stages) & 1;
+            mbar_wait(&full[s], ph);
+            const int by = g / boxes_x, bx = g - by * boxes_x;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&omap), "r"(bx * 192), "r"(by * 32), "r"(smem_u32(smem + (size_t)s * stage_bytes)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_arrive(&empty[s]);
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int main() {
@@ -123,6 +166,29 @@ int main() {
                 timeit([&] { read_tma<<<148, 64, smem>>>(tm, bx, by, sh.w_bytes / esz, sh.h, stage_bytes, stages, hint, sink); }, nm);
             }
         }
+    }
+    {   // read + quarter-size write, strided vs contiguous item assignment
+        uint8_t* o; const int64_t opitch = 12544; const int64_t orows = rows / 2;
+        CK(cudaMalloc(&o, (size_t)opitch * orows));
+        CUtensorMap tm, om;
+        cuuint64_t gdim[2] = {(cuuint64_t)(pitch / 8), (cuuint64_t)rows};
+        cuuint64_t gstr[1] = {(cuuint64_t)pitch};
+        cuuint32_t box[2] = {48, 64};
+        cuuint32_t es[2] = {1, 1};
+        enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, d, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        cuuint64_t odim[2] = {(cuuint64_t)12426, (cuuint64_t)orows};
+        cuuint64_t ostr[1] = {(cuuint64_t)opitch};
+        cuuint32_t obox[2] = {192, 32};
+        CUresult r = enc(&om, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, o, odim, ostr, obox, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) printf("out encode failed %d\n", (int)r);
+        CK(cudaFuncSetAttribute(read_write_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        for (int contiguous : {0, 1})
+            for (int stages : {4, 8}) {
+                char nm[96]; snprintf(nm, sizeof nm, "tma read 384x64 + store 192x32, %d st, contig=%d", stages, contiguous);
+                const size_t smem = (size_t)24576 * stages + 2 * stages * 8;
+                timeit([&] { read_write_tma<<<148, 64, smem>>>(tm, om, 65, (int)((rows + 63) / 64), stages, contiguous, sink); }, nm);
+            }
+        printf("(GB/s above counts READ bytes only; add 25%% for the stores)\n");
     }
     // two CTAs per SM, smaller rings
     for (int stages : {2, 4}) {

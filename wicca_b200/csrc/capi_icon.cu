@@ -63,6 +63,9 @@ int fill_icon_image(IconImage* im, const uint8_t* d_src, int H, int W, int64_t p
             rc = encode_icon_tmap(&im->omap[d - 1], outs[i].d_ptr, outs[i].h, (int64_t)outs[i].w * 3, outs[i].pitch,
                                   box_w[d - 1], box_h[d - 1]);
             if (rc) return rc;
+            rc = encode_icon_tmap(&im->hmap[d - 1], outs[i].d_ptr, outs[i].h, (int64_t)outs[i].w * 3, outs[i].pitch,
+                                  box_w[d - 1], box_h[d - 1] / 2);
+            if (rc) return rc;
         }
     }
     return 0;

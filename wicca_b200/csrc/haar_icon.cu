@@ -95,7 +95,10 @@ template <int kStages, int kConsumerWarps, bool kStaged>
 __global__ void __launch_bounds__(32 * (1 + kConsumerWarps), 1)
 haar_icon_tma_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* __restrict__ strips, int n_images,
                      int total_items, int border_type, int border_const, int debug) {
-    static_assert(kConsumerWarps <= kStages, "a stage must be released before its barrier phase is reused");
+    // Item k uses stage k % kStages and consumer warp k % kConsumerWarps.  A parity wait can only be
+    // one phase ahead of the barrier, so the warp that waits for item k + kStages must be the one
+    // that consumed item k: kStages has to be a multiple of kConsumerWarps.
+    static_assert(kStages % kConsumerWarps == 0, "kStages must be a multiple of kConsumerWarps");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* stages = smem_raw;
     uint8_t* out_tiles = smem_raw + (size_t)kStages * kStageBytes;
@@ -197,8 +200,8 @@ haar_icon_tma_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* _
         const int iy = local / geo.items_x;
         const int ix = local - iy * geo.items_x;
 
-        const ChunkSrc cs = make_chunk_src(geo, strip, stages + (size_t)s * kStageBytes, ix, iy, cx, ry, border_type,
-                                           fill);
+        const ChunkSrc cs = make_chunk_src(geo, strip, stages + (size_t)s * kStageBytes, ix, iy, cx, ry * 16, 16,
+                                           border_type, fill);
         const int x0 = cs.x0, y0 = cs.y0;
 
         if (kStaged) {
@@ -214,11 +217,11 @@ haar_icon_tma_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* _
             sink_word ^= *reinterpret_cast<const uint32_t*>(cs.smem);
             acc4[0] = acc4[1] = acc4[2] = 0u;
         } else if (kStaged) {
-            const StagedEmit em{tile, cx, ry, mask};
-            reduce_lane(cs, em, acc4);
+            const StagedEmit em = staged_emit_full(tile, cx, ry, mask);
+            reduce_lane<16>(cs, em, acc4);
         } else {
             const DirectEmit em{sk, x0, y0};
-            reduce_lane(cs, em, acc4);
+            reduce_lane<16>(cs, em, acc4);
         }
 
         // the stage is no longer needed: hand it back to the producer before the tail
@@ -254,6 +257,178 @@ haar_icon_tma_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* _
 }
 
 // ------------------------------------------------------------------------------------------
+// Two consumer warps per stage: warp pair p owns stage p; the upper warp reduces rows 0..31 of the
+// 128 x 64 item, the lower warp rows 32..63 (8 rows per lane), so a stage is held half as long and
+// twice as many warps hide each other's latencies.  Levels 1..5 are complete inside a warp; the
+// two 64 x 32 partial sums of level 6 meet through a small shared-memory mailbox.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <int kStages>
+__global__ void __launch_bounds__(32 * (1 + 2 * kStages), 1)
+haar_icon_tma2_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* __restrict__ strips, int n_images,
+                      int total_items, int border_type, int border_const, int debug) {
+    static_assert(kStages <= 15, "one named barrier per warp pair");
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* stages = smem_raw;
+    uint8_t* out_tiles = smem_raw + (size_t)kStages * kStageBytes;
+    uint32_t* mailbox = reinterpret_cast<uint32_t*>(out_tiles + (size_t)2 * kStages * kHalfStageBytes);   // [pair][2][8]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(mailbox + kStages * 16);
+    uint64_t* empty_bar = full_bar + kStages;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 2);       // both warps of the pair release the stage
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            int img = -1, base = 0, next_base = 0, items_x = 1;
+            const CUtensorMap* tmap = nullptr;
+            int k = 0;
+            for (int g = blockIdx.x; g < total_items; g += gridDim.x, ++k) {
+                if (g >= next_base) {
+                    do {
+                        ++img;
+                        next_base = (img + 1 < n_images) ? imgs[img + 1].item_base : 0x7FFFFFFF;
+                    } while (g >= next_base);
+                    base = imgs[img].item_base;
+                    items_x = imgs[img].items_x;
+                    tmap = &imgs[img].tmap;
+                    fence_tensormap_acquire(tmap);
+                }
+                const int local = g - base;
+                const int iy = local / items_x;
+                const int ix = local - iy * items_x;
+                const int s = k % kStages;
+                const uint32_t ph = (uint32_t)(k / kStages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                tma_load_2d(stages + (size_t)s * kStageBytes, tmap, ix * (kStageRowBytes / 4), iy * kItemH,
+                            &full_bar[s], pol);
+            }
+        }
+        return;
+    }
+
+    const int cw = warp - 1;
+    const int pair = cw >> 1;          // == stage index
+    const int half = cw & 1;           // 0: rows 0..31 of the item, 1: rows 32..63
+    const int cx = lane & 7;
+    const int ry = lane >> 3;          // 8-row group inside the half
+    const uint32_t fill = (uint32_t)border_const * 0x01010101u;
+    uint8_t* tile = out_tiles + (size_t)cw * kHalfStageBytes;
+    uint32_t* box = mailbox + pair * 16;
+    int img = -1, base = 0, next_base = 0;
+    ImageGeom geo;
+    IconSink sk;
+    const uint8_t* strip = nullptr;
+    const CUtensorMap* hmap = nullptr;
+    unsigned mask = 0;
+    uint32_t sink_word = 0;
+
+    for (int k = pair;; k += kStages) {
+        const int g = blockIdx.x + k * gridDim.x;
+        if (g >= total_items) break;
+        const uint32_t ph = (uint32_t)(k / kStages) & 1u;
+        if (g >= next_base) {
+            do {
+                ++img;
+                next_base = (img + 1 < n_images) ? imgs[img + 1].item_base : 0x7FFFFFFF;
+            } while (g >= next_base);
+            const IconImage& im = imgs[img];
+            base = im.item_base;
+            geo = make_geom(im);
+            sk = make_sink(im);
+            strip = strips[img];
+            hmap = im.hmap;
+            mask = 0;
+#pragma unroll
+            for (int l = 0; l < 3; ++l) mask |= (sk.icon[l] != nullptr ? 1u : 0u) << l;
+            if (debug == 2) {
+                mask = 0;
+#pragma unroll
+                for (int l = 0; l < 3; ++l) sk.icon[l] = nullptr;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int l = 0; l < 3; ++l)
+                    if ((mask >> l) & 1u) fence_tensormap_acquire(&hmap[l]);
+            }
+        }
+        const int local = g - base;
+        const int iy = local / geo.items_x;
+        const int ix = local - iy * geo.items_x;
+        const ChunkSrc cs = make_chunk_src(geo, strip, stages + (size_t)pair * kStageBytes, ix, iy, cx,
+                                           half * 32 + ry * 8, 8, border_type, fill);
+
+        if (lane == 0) bulk_wait_read0();     // previous TMA stores have finished reading the tile
+        __syncwarp();
+
+        mbar_wait(&full_bar[pair], ph);
+
+        uint32_t acc[3];
+        if (debug == 1) {
+            sink_word ^= *reinterpret_cast<const uint32_t*>(cs.smem);
+            acc[0] = acc[1] = acc[2] = 0u;
+        } else {
+            const StagedEmit em = staged_emit_half(tile, cx, ry, mask);
+            reduce_lane<8>(cs, em, acc);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[pair]);
+
+        if (mask != 0u && debug != 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if (mask & 1u) tma_store_2d(&hmap[0], tile + kHalf1Off, ix * kOut1Row, iy * 32 + half * 16);
+                if (mask & 2u) tma_store_2d(&hmap[1], tile + kHalf2Off, ix * kOut2Row, iy * 16 + half * 8);
+                if (mask & 4u) tma_store_2d(&hmap[2], tile + kHalf3Off, ix * kOut3Row, iy * 8 + half * 4);
+                bulk_commit();
+            }
+        }
+
+        // level 4: two 8-row groups; level 5: two chunk columns x two 16-row groups; level 6 partial:
+        // two 32-px blocks (this warp's 32 rows), completed through the pair's mailbox
+        uint32_t s4[3], s5[3], s6[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t a = acc[c] + __shfl_xor_sync(0xFFFFFFFFu, acc[c], 8);
+            s4[c] = a;
+            uint32_t b = a + __shfl_xor_sync(0xFFFFFFFFu, a, 1);
+            b += __shfl_xor_sync(0xFFFFFFFFu, b, 16);
+            s5[c] = b;
+            s6[c] = b + __shfl_xor_sync(0xFFFFFFFFu, b, 2);
+        }
+        if (sk.icon[5] != nullptr && debug != 1) {
+            uint32_t* slot = box + (k / kStages & 1) * 8;        // double-buffered per item parity
+            if (half == 1 && (cx & 3) == 0 && ry == 0) {
+                uint32_t* q = slot + (cx >> 2) * 3;
+                q[0] = s6[0]; q[1] = s6[1]; q[2] = s6[2];
+            }
+            pair_barrier(1 + pair);
+            if (half == 0 && (cx & 3) == 0 && ry == 0) {
+                const uint32_t* q = slot + (cx >> 2) * 3;
+                s6[0] += q[0]; s6[1] += q[1]; s6[2] += q[2];
+            }
+        }
+        if (debug != 1) emit_tail_half(sk, cs.x0, cs.y0, cx, ry, half == 0, s4, s5, s6);
+    }
+    if (lane == 0) bulk_wait0();
+    if (debug == 1 && sink_word == 0x9E3779B9u && sk.icon[5] != nullptr) sk.icon[5][0] = (uint8_t)sink_word;
+}
+
+// ------------------------------------------------------------------------------------------
 // Right-edge strip: strip[y][ (x - Wa)*3 + c ] = padded_image[y][x][c] for x in [Wa, Wa + strip_px)
 // ------------------------------------------------------------------------------------------
 __global__ void edge_strip_kernel(const IconImage* __restrict__ imgs, uint8_t* const* __restrict__ strips,
@@ -263,10 +438,11 @@ __global__ void edge_strip_kernel(const IconImage* __restrict__ imgs, uint8_t* c
     if (strip == nullptr) return;
     const int npx = im.Wp_max - (im.W & ~(kChunkPx - 1));   // <= 78
     if (npx <= 0) return;
-    const int total = im.H * npx;
+    const int words = (npx * 3 + 3) >> 2;                   // <= 59
+    const int total = im.H * words;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int y = i / npx;
-        strip_pixel(im, strip, y, i - y * npx, border_type, border_const);
+        const int y = i / words;
+        strip_word(im, strip, y, i - y * words, border_type, border_const);
     }
 }
 
@@ -351,6 +527,25 @@ static cudaError_t launch_tma_variant(const IconImage* d_imgs, const uint8_t* co
     return cudaGetLastError();
 }
 
+template <int S>
+static cudaError_t launch_tma2_variant(const IconImage* d_imgs, const uint8_t* const* d_strips, int n_images,
+                                       int total_items, int border_type, int border_const, int grid, int debug,
+                                       cudaStream_t stream) {
+    const size_t smem = (size_t)S * kStageBytes + (size_t)2 * S * kHalfStageBytes + (size_t)S * 16 * sizeof(uint32_t) +
+                        2 * S * sizeof(uint64_t);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(haar_icon_tma2_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured_dev = dev;
+    }
+    haar_icon_tma2_kernel<S><<<grid, 32 * (1 + 2 * S), smem, stream>>>(d_imgs, d_strips, n_images, total_items, border_type,
+                                                                      border_const, debug);
+    return cudaGetLastError();
+}
+
 // variant: 0 = default.  1x = TMA-store output tiles, 0x = direct stores; see the switch.
 cudaError_t launch_icon_tma(const IconImage* d_imgs, const uint8_t* const* d_strips, int n_images, int total_items,
                             int border_type, int border_const, int sm_count, int variant, cudaStream_t stream) {
@@ -361,14 +556,18 @@ cudaError_t launch_icon_tma(const IconImage* d_imgs, const uint8_t* const* d_str
 #define WICCA_V(S, N, ST) \
     return launch_tma_variant<S, N, ST>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, stream)
     switch (variant) {
-        case 1: WICCA_V(9, 6, false);
+        case 20: return launch_tma2_variant<7>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, stream);
+        case 21: return launch_tma2_variant<6>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, stream);
+        case 22: return launch_tma2_variant<5>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, stream);
+        case 23: return launch_tma2_variant<4>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, stream);
+        case 1: WICCA_V(9, 3, false);
         case 2: WICCA_V(9, 9, false);
         case 3: WICCA_V(6, 6, false);
         case 4: WICCA_V(8, 4, false);
         case 5: WICCA_V(8, 8, false);
-        case 11: WICCA_V(7, 5, true);
+        case 11: WICCA_V(8, 4, true);
         case 12: WICCA_V(6, 6, true);
-        case 13: WICCA_V(7, 4, true);
+        case 13: WICCA_V(6, 3, true);
         case 14: WICCA_V(5, 5, true);
         default: WICCA_V(7, 7, true);
     }
@@ -378,9 +577,9 @@ cudaError_t launch_icon_tma(const IconImage* d_imgs, const uint8_t* const* d_str
 cudaError_t launch_edge_strips(const IconImage* d_imgs, uint8_t* const* d_strips, int n_images, int max_rows,
                                int border_type, int border_const, cudaStream_t stream) {
     if (n_images <= 0) return cudaSuccess;
-    int bx = (max_rows * 80 + 255) / 256;
+    int bx = (max_rows * 60 + 255) / 256;
     if (bx < 1) bx = 1;
-    if (bx > 64) bx = 64;
+    if (bx > 1024) bx = 1024;
     edge_strip_kernel<<<dim3(bx, n_images), 256, 0, stream>>>(d_imgs, d_strips, border_type, border_const);
     return cudaGetLastError();
 }

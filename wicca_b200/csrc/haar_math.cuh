@@ -211,35 +211,53 @@ struct DirectEmit {
 };
 
 struct StagedEmit {
-    uint8_t* tile;          // this warp's kOutStageBytes staging area
-    int cx, ry;             // lane position inside the item
-    unsigned mask;          // bit l set = level l+1 requested
+    uint8_t* t1; uint8_t* t2; uint8_t* t3;   // this lane's first row inside the warp's L1 / L2 / L3 tile, at its column
+    unsigned mask;                           // bit l set = level l+1 requested
     WHD bool want(int l) const { return (mask >> l) & 1u; }
     WHD void icon1(int r, const uint32_t (&W)[6]) const {
-        uint2* q = reinterpret_cast<uint2*>(tile + kOut1Off + (ry * 8 + (r >> 1)) * kOut1Row + cx * 24);
+        uint2* q = reinterpret_cast<uint2*>(t1 + (r >> 1) * kOut1Row);
         uint2 v0, v1, v2;
         v0.x = W[0]; v0.y = W[1]; v1.x = W[2]; v1.y = W[3]; v2.x = W[4]; v2.y = W[5];
         q[0] = v0; q[1] = v1; q[2] = v2;
     }
     WHD void icon2(int r, const uint32_t (&W)[3]) const {
-        uint32_t* q = reinterpret_cast<uint32_t*>(tile + kOut2Off + (ry * 4 + (r >> 2)) * kOut2Row + cx * 12);
+        uint32_t* q = reinterpret_cast<uint32_t*>(t2 + (r >> 2) * kOut2Row);
         q[0] = W[0]; q[1] = W[1]; q[2] = W[2];
     }
     WHD void icon3(int r, const uint32_t (&Hh)[3]) const {
-        uint16_t* q = reinterpret_cast<uint16_t*>(tile + kOut3Off + (ry * 2 + (r >> 3)) * kOut3Row + cx * 6);
+        uint16_t* q = reinterpret_cast<uint16_t*>(t3 + (r >> 3) * kOut3Row);
         q[0] = (uint16_t)Hh[0]; q[1] = (uint16_t)Hh[1]; q[2] = (uint16_t)Hh[2];
     }
 };
+// Lane (cx, ry) of a warp that owns a whole 128 x 64 item (16 rows per lane, tiles 32/16/8 rows).
+WHD StagedEmit staged_emit_full(uint8_t* tile, int cx, int ry, unsigned mask) {
+    StagedEmit e;
+    e.t1 = tile + kOut1Off + (ry * 8) * kOut1Row + cx * 24;
+    e.t2 = tile + kOut2Off + (ry * 4) * kOut2Row + cx * 12;
+    e.t3 = tile + kOut3Off + (ry * 2) * kOut3Row + cx * 6;
+    e.mask = mask;
+    return e;
+}
+// Lane (cx, ry) of a warp that owns half an item, 128 x 32 (8 rows per lane, tiles 16/8/4 rows).
+WHD StagedEmit staged_emit_half(uint8_t* tile, int cx, int ry, unsigned mask) {
+    StagedEmit e;
+    e.t1 = tile + kHalf1Off + (ry * 4) * kOut1Row + cx * 24;
+    e.t2 = tile + kHalf2Off + (ry * 2) * kOut2Row + cx * 12;
+    e.t3 = tile + kHalf3Off + ry * kOut3Row + cx * 6;
+    e.mask = mask;
+    return e;
+}
 
-// Reduce one chunk (16 px x 16 rows): emits levels 1..3 through `em` and returns the three 16x16
-// channel sums in acc4.  `load(r, A)` fills A[12] with the 48 bytes of chunk row r (0..15),
-// border-extended.
-template <class Loader, class Emit>
+// Reduce one chunk (16 px x kRows rows, kRows = 8 or 16): emits levels 1..3 through `em` and
+// returns the three 16 x kRows channel sums in acc4.  `load(r, A)` fills A[12] with the 48 bytes
+// of chunk row r (0..kRows-1), border-extended.
+template <int kRows, class Loader, class Emit>
 WHD void reduce_chunk(Loader& load, const Emit& em, uint32_t (&acc4)[3]) {
+    static_assert(kRows == 8 || kRows == 16, "a lane owns 8 or 16 rows");
     acc4[0] = acc4[1] = acc4[2] = 0u;
     const bool want1 = em.want(0), want2 = em.want(1), want3 = em.want(2);
 #pragma unroll 1
-    for (int h8 = 0; h8 < 2; ++h8) {                 // two 8-row groups
+    for (int h8 = 0; h8 < kRows / 8; ++h8) {         // 8-row groups
         uint32_t acc3[3] = {0u, 0u, 0u};
 #pragma unroll
         for (int q4 = 0; q4 < 2; ++q4) {             // two 4-row groups
@@ -301,6 +319,34 @@ WHD void emit_tail(const IconSink& sk, int x0, int y0, int cx, int ry, const uin
     }
 }
 
+// Levels 4..6 when a warp owns half an item (128 x 32; lane = cx + 8*ry owns rows ry*8..ry*8+7).
+//   s4 = 16x16 sums (lanes ry even), s5 = 32x32 sums (cx even, ry == 0),
+//   s6 = 64x64 sums, valid on the UPPER warp of the pair for lanes cx in {0, 4}, ry == 0.
+WHD void emit_tail_half(const IconSink& sk, int x0, int y0, int cx, int ry, bool upper, const uint32_t (&s4)[3],
+                        const uint32_t (&s5)[3], const uint32_t (&s6)[3]) {
+    if (sk.icon[3] != nullptr && (ry & 1) == 0) {
+        const int oy = y0 >> 4, ox = x0 >> 4;
+        if (oy < sk.h[3] && ox < sk.w[3]) {
+            uint8_t* p = sk.icon[3] + (int64_t)oy * sk.pitch[3] + (int64_t)ox * 3;
+            p[0] = (uint8_t)(s4[0] >> 8); p[1] = (uint8_t)(s4[1] >> 8); p[2] = (uint8_t)(s4[2] >> 8);
+        }
+    }
+    if (sk.icon[4] != nullptr && (cx & 1) == 0 && ry == 0) {
+        const int oy = y0 >> 5, ox = x0 >> 5;
+        if (oy < sk.h[4] && ox < sk.w[4]) {
+            uint8_t* p = sk.icon[4] + (int64_t)oy * sk.pitch[4] + (int64_t)ox * 3;
+            p[0] = (uint8_t)(s5[0] >> 10); p[1] = (uint8_t)(s5[1] >> 10); p[2] = (uint8_t)(s5[2] >> 10);
+        }
+    }
+    if (sk.icon[5] != nullptr && upper && (cx & 3) == 0 && ry == 0) {
+        const int oy = y0 >> 6, ox = x0 >> 6;
+        if (oy < sk.h[5] && ox < sk.w[5]) {
+            uint8_t* p = sk.icon[5] + (int64_t)oy * sk.pitch[5] + (int64_t)ox * 3;
+            p[0] = (uint8_t)(s6[0] >> 12); p[1] = (uint8_t)(s6[1] >> 12); p[2] = (uint8_t)(s6[2] >> 12);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // cv::borderInterpolate for p >= 0 (padding is bottom/right only,
 // wicca/data_loader.py:107-117).  Returns -1 for BORDER_CONSTANT.
@@ -339,7 +385,7 @@ struct ChunkSrc {
     const uint8_t* smem;      // chunk origin inside the stage (row stride kStageRowBytes)
     const uint8_t* gcol;      // kSmem: image + x0*3 ; kStrip: strip + (x0 - Wa)*3   (row 0)
     int64_t gpitch;           // row pitch of gcol's plane
-    int x0, y0, H, Hp_max;
+    int x0, y0, rows, H, Hp_max;     // rows = rows owned by the lane (8 or 16)
     int border_type;
     uint32_t fill;            // border constant replicated in 4 bytes
 };
@@ -387,12 +433,14 @@ WHD ImageGeom make_geom(const IconImage& im) {
 }
 
 // Geometry of lane (cx, ry) of work item (ix, iy) of image `im`.
+// row0 = first row of the lane inside the item, rows = how many rows it owns.
 WHD ChunkSrc make_chunk_src(const ImageGeom& im, const uint8_t* strip, const uint8_t* stage, int ix, int iy, int cx,
-                            int ry, int border_type, uint32_t fill) {
+                            int row0, int rows, int border_type, uint32_t fill) {
     ChunkSrc cs;
     cs.x0 = ix * kItemW + cx * kChunkPx;
-    cs.y0 = iy * kItemH + ry * 16;
-    cs.smem = stage + (ry * 16) * kStageRowBytes + cx * (kChunkPx * 3);
+    cs.y0 = iy * kItemH + row0;
+    cs.rows = rows;
+    cs.smem = stage + row0 * kStageRowBytes + cx * (kChunkPx * 3);
     cs.H = im.H; cs.Hp_max = im.Hp_max;
     cs.border_type = border_type; cs.fill = fill;
     const int Wa = im.W & ~(kChunkPx - 1);      // first pixel of the chunk that straddles W
@@ -406,7 +454,7 @@ WHD ChunkSrc make_chunk_src(const ImageGeom& im, const uint8_t* strip, const uin
     return cs;
 }
 
-WHD bool chunk_is_interior(const ChunkSrc& cs) { return cs.mode == kSmem && cs.y0 + 16 <= cs.H; }
+WHD bool chunk_is_interior(const ChunkSrc& cs) { return cs.mode == kSmem && cs.y0 + cs.rows <= cs.H; }
 
 // General row loader (any mode, any row).
 WHD void load_chunk_row(const ChunkSrc& cs, int r, uint32_t (&A)[12]) {
@@ -427,15 +475,15 @@ WHD void load_chunk_row(const ChunkSrc& cs, int r, uint32_t (&A)[12]) {
 }
 
 // One lane's share of a work item up to level 4.
-template <class Emit>
+template <int kRows, class Emit>
 WHD void reduce_lane(const ChunkSrc& cs, const Emit& em, uint32_t (&acc4)[3]) {
     if (chunk_is_interior(cs)) {
         const uint8_t* sm = cs.smem;
         auto loader = [sm](int r, uint32_t (&A)[12]) { load48_stage(sm + r * kStageRowBytes, A); };
-        reduce_chunk(loader, em, acc4);
+        reduce_chunk<kRows>(loader, em, acc4);
     } else {
         auto loader = [&cs](int r, uint32_t (&A)[12]) { load_chunk_row(cs, r, A); };
-        reduce_chunk(loader, em, acc4);
+        reduce_chunk<kRows>(loader, em, acc4);
     }
 }
 
@@ -448,17 +496,25 @@ WHD IconSink make_sink(const IconImage& im) {
     return sk;
 }
 
-// Right-edge strip element: strip[y][(x - Wa)*3 + c] = padded_image[y][x][c], x = Wa + px.
-WHD void strip_pixel(const IconImage& im, uint8_t* strip, int y, int px, int border_type, int border_const) {
+// Right-edge strip: strip[y][(x - Wa)*3 + c] = padded_image[y][x][c] for x in [Wa, Wp_max), Wa = W & ~15.
+// One call writes the 4 bytes of word j (0..kStripPitch/4-1) of strip row y.
+WHD void strip_word(const IconImage& im, uint8_t* strip, int y, int j, int border_type, int border_const) {
     const int Wa = im.W & ~(kChunkPx - 1);
-    const int xm = border_index(Wa + px, im.W, border_type);
-    uint8_t* d = strip + (int64_t)y * kStripPitch + px * 3;
-    if (xm < 0) {
-        d[0] = d[1] = d[2] = (uint8_t)border_const;
-    } else {
-        const uint8_t* s = im.src + (int64_t)y * im.pitch + (int64_t)xm * 3;
-        d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+    const int npx = im.Wp_max - Wa;
+    const uint8_t* row = im.src + (int64_t)y * im.pitch;
+    uint32_t w = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int b = 4 * j + t;
+        const int px = b / 3, c = b - 3 * px;
+        uint32_t v = 0;
+        if (px < npx) {
+            const int xm = border_index(Wa + px, im.W, border_type);
+            v = (xm < 0) ? (uint32_t)border_const : (uint32_t)row[(int64_t)xm * 3 + c];
+        }
+        w |= v << (8 * t);
     }
+    *reinterpret_cast<uint32_t*>(strip + (int64_t)y * kStripPitch + 4 * j) = w;
 }
 
 
