@@ -46,7 +46,7 @@ int emul_fused_icons(const uint8_t* src, int H, int W, int border_type, int bord
     const int Wa = W & ~(kChunkPx - 1);
     const int npx = im.Wp_max - Wa;
     std::vector<uint8_t> strip;
-    if (npx > 0) {
+    if (npx > 0 && border_type >= 2) {      // REPLICATE / CONSTANT never touch the strip
         strip.assign((size_t)H * kStripPitch, 0x5A);
         for (int y = 0; y < H; ++y)
             for (int j = 0; j < (npx * 3 + 3) / 4; ++j) strip_word(im, strip.data(), y, j, border_type, border_const);

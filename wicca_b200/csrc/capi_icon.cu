@@ -72,6 +72,9 @@ int fill_icon_image(IconImage* im, const uint8_t* d_src, int H, int W, int64_t p
 }
 
 int strip_px(int W, int Wp_max) { return Wp_max - (W & ~(kChunkPx - 1)); }
+// REPLICATE and CONSTANT borders are resolved from the shared-memory stage; only the mirroring /
+// wrapping borders need the pre-built right strip.
+bool border_needs_strip(int border_type) { const int b = border_base(border_type); return b == 2 || b == 3 || b == 4; }
 
 int64_t icon_pitch_for(int w, int C) { return align_up((int64_t)w * C, 128); }
 
@@ -180,7 +183,7 @@ int icons_from_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int* d
         if (rc) return rc;
         uint8_t** h_strip = (uint8_t**)((uint8_t*)c.h_desc.p + sizeof(IconImage));
         *h_strip = nullptr;
-        if (strip_px(W, him->Wp_max) > 0) {
+        if (border_needs_strip(border_type) && strip_px(W, him->Wp_max) > 0) {
             WICCA_CUDA(c.d_strip.reserve((size_t)H * kStripPitch));
             *h_strip = (uint8_t*)c.d_strip.p;
         }
@@ -335,7 +338,7 @@ int wicca_haar_icons_multi_dev(const uint8_t* d_src, int H, int W, int C, int64_
         rc = fill_icon_image(&him, d_src, H, W, src_pitch, fo.data(), (int)fo.size(), 0);
         if (rc) return rc;
         uint8_t* strip = nullptr;
-        if (strip_px(W, him.Wp_max) > 0) {
+        if (border_needs_strip(border_type) && strip_px(W, him.Wp_max) > 0) {
             WICCA_CUDA(c.d_strip.reserve((size_t)H * kStripPitch));
             strip = (uint8_t*)c.d_strip.p;
         }
@@ -453,7 +456,7 @@ int wicca_plan_create(int device, int n_images, const uint8_t* const* d_srcs, co
             if (rc) return cleanup(rc);
             base += p->h_imgs[i].items_x * p->h_imgs[i].items_y;
             p->max_rows = std::max(p->max_rows, Hs[i]);
-            if (strip_px(Ws[i], p->h_imgs[i].Wp_max) > 0) strip_bytes += (size_t)Hs[i] * kStripPitch;
+            if (border_needs_strip(border_type) && strip_px(Ws[i], p->h_imgs[i].Wp_max) > 0) strip_bytes += (size_t)Hs[i] * kStripPitch;
         }
         p->total_items = base;
         if (strip_bytes) {
@@ -461,7 +464,7 @@ int wicca_plan_create(int device, int n_images, const uint8_t* const* d_srcs, co
             if (e != cudaSuccess) return cleanup(cuda_fail(e, "strip allocation"));
             size_t so = 0;
             for (int i = 0; i < n_images; ++i)
-                if (strip_px(Ws[i], p->h_imgs[i].Wp_max) > 0) {
+                if (border_needs_strip(border_type) && strip_px(Ws[i], p->h_imgs[i].Wp_max) > 0) {
                     strip_ptrs[i] = (uint8_t*)p->d_strips.p + so;
                     so += (size_t)Hs[i] * kStripPitch;
                     p->need_strips = true;

@@ -87,6 +87,13 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 // ------------------------------------------------------------------------------------------
 // The one-pass kernel
 // ------------------------------------------------------------------------------------------
+// Work item of a CTA's k-th turn.  run_len consecutive turns take horizontally adjacent items, so
+// the narrow output rows of neighbouring items reach L2 together and merge into full lines.
+__device__ __forceinline__ int item_index(int k, int run_len) {
+    const int u = k / run_len;
+    return (u * (int)gridDim.x + (int)blockIdx.x) * run_len + (k - u * run_len);
+}
+
 // kStaged: levels 1..3 are assembled as dense tiles in shared memory and written with TMA
 // store (full-line writes, hardware clipping); otherwise straight register->global stores.
 // debug: 0 = normal, 1 = consumers skip the arithmetic (load path only), 2 = arithmetic but no
@@ -94,7 +101,7 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 template <int kStages, int kConsumerWarps, bool kStaged>
 __global__ void __launch_bounds__(32 * (1 + kConsumerWarps), 1)
 haar_icon_tma_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* __restrict__ strips, int n_images,
-                     int total_items, int border_type, int border_const, int debug) {
+                     int total_items, int border_type, int border_const, int debug, int run_len) {
     // Item k uses stage k % kStages and consumer warp k % kConsumerWarps.  A parity wait can only be
     // one phase ahead of the barrier, so the warp that waits for item k + kStages must be the one
     // that consumed item k: kStages has to be a multiple of kConsumerWarps.
@@ -127,7 +134,9 @@ haar_icon_tma_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* _
             int img = -1, base = 0, next_base = 0, items_x = 1;
             const CUtensorMap* tmap = nullptr;
             int k = 0;
-            for (int g = blockIdx.x; g < total_items; g += gridDim.x, ++k) {
+            for (;; ++k) {
+                const int g = item_index(k, run_len);
+                if (g >= total_items) break;
                 if (g >= next_base) {
                     do {
                         ++img;
@@ -167,7 +176,7 @@ haar_icon_tma_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* _
     uint32_t sink_word = 0;
 
     for (int k = cw;; k += kConsumerWarps) {
-        const int g = blockIdx.x + k * gridDim.x;
+        const int g = item_index(k, run_len);
         if (g >= total_items) break;
         const int s = k % kStages;
         const uint32_t ph = (uint32_t)(k / kStages) & 1u;
@@ -267,7 +276,9 @@ __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0
 template <int kStages>
 __global__ void __launch_bounds__(32 * (1 + 2 * kStages), 1)
 haar_icon_tma2_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* __restrict__ strips, int n_images,
-                      int total_items, int border_type, int border_const, int debug) {
+                      int total_items, int border_type, int border_const, int debug_flags, int run_len) {
+    const int debug = debug_flags & 3;
+    const bool no_fence = (debug_flags & 4) != 0;   // developer experiment only
     static_assert(kStages <= 15, "one named barrier per warp pair");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* stages = smem_raw;
@@ -295,7 +306,9 @@ haar_icon_tma2_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* 
             int img = -1, base = 0, next_base = 0, items_x = 1;
             const CUtensorMap* tmap = nullptr;
             int k = 0;
-            for (int g = blockIdx.x; g < total_items; g += gridDim.x, ++k) {
+            for (;; ++k) {
+                const int g = item_index(k, run_len);
+                if (g >= total_items) break;
                 if (g >= next_base) {
                     do {
                         ++img;
@@ -304,7 +317,7 @@ haar_icon_tma2_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* 
                     base = imgs[img].item_base;
                     items_x = imgs[img].items_x;
                     tmap = &imgs[img].tmap;
-                    fence_tensormap_acquire(tmap);
+                    if (!no_fence) fence_tensormap_acquire(tmap);
                 }
                 const int local = g - base;
                 const int iy = local / items_x;
@@ -337,7 +350,7 @@ haar_icon_tma2_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* 
     uint32_t sink_word = 0;
 
     for (int k = pair;; k += kStages) {
-        const int g = blockIdx.x + k * gridDim.x;
+        const int g = item_index(k, run_len);
         if (g >= total_items) break;
         const uint32_t ph = (uint32_t)(k / kStages) & 1u;
         if (g >= next_base) {
@@ -362,7 +375,7 @@ haar_icon_tma2_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* 
             if (lane == 0) {
 #pragma unroll
                 for (int l = 0; l < 3; ++l)
-                    if ((mask >> l) & 1u) fence_tensormap_acquire(&hmap[l]);
+                    if (((mask >> l) & 1u) && !no_fence) fence_tensormap_acquire(&hmap[l]);
             }
         }
         const int local = g - base;
@@ -511,7 +524,7 @@ __global__ void haar_level_f32_kernel(const float* __restrict__ in, float* __res
 template <int S, int NCW, bool STAGED>
 static cudaError_t launch_tma_variant(const IconImage* d_imgs, const uint8_t* const* d_strips, int n_images,
                                       int total_items, int border_type, int border_const, int grid, int debug,
-                                      cudaStream_t stream) {
+                                      int run_len, cudaStream_t stream) {
     const size_t smem = (size_t)S * kStageBytes + (STAGED ? (size_t)NCW * kOutStageBytes : 0) + 2 * S * sizeof(uint64_t);
     static thread_local int configured_dev = -1;
     int dev = 0;
@@ -523,14 +536,14 @@ static cudaError_t launch_tma_variant(const IconImage* d_imgs, const uint8_t* co
         configured_dev = dev;
     }
     haar_icon_tma_kernel<S, NCW, STAGED><<<grid, 32 * (1 + NCW), smem, stream>>>(d_imgs, d_strips, n_images, total_items,
-                                                                                 border_type, border_const, debug);
+                                                                                 border_type, border_const, debug, run_len);
     return cudaGetLastError();
 }
 
 template <int S>
 static cudaError_t launch_tma2_variant(const IconImage* d_imgs, const uint8_t* const* d_strips, int n_images,
                                        int total_items, int border_type, int border_const, int grid, int debug,
-                                       cudaStream_t stream) {
+                                       int run_len, cudaStream_t stream) {
     const size_t smem = (size_t)S * kStageBytes + (size_t)2 * S * kHalfStageBytes + (size_t)S * 16 * sizeof(uint32_t) +
                         2 * S * sizeof(uint64_t);
     static thread_local int configured_dev = -1;
@@ -542,7 +555,7 @@ static cudaError_t launch_tma2_variant(const IconImage* d_imgs, const uint8_t* c
         configured_dev = dev;
     }
     haar_icon_tma2_kernel<S><<<grid, 32 * (1 + 2 * S), smem, stream>>>(d_imgs, d_strips, n_images, total_items, border_type,
-                                                                      border_const, debug);
+                                                                      border_const, debug, run_len);
     return cudaGetLastError();
 }
 
@@ -551,15 +564,18 @@ cudaError_t launch_icon_tma(const IconImage* d_imgs, const uint8_t* const* d_str
                             int border_type, int border_const, int sm_count, int variant, cudaStream_t stream) {
     if (total_items <= 0) return cudaSuccess;
     const int grid = total_items < sm_count ? total_items : sm_count;
-    const int debug = variant / 100;
+    // developer knobs: variant = kernel shape, + 100 * debug flags, + 1000 * log2(run length)
+    int run_len = 1 << ((variant / 1000) % 10);
+    if ((int64_t)run_len * grid > total_items) run_len = 1;
+    const int debug = (variant / 100) % 10;
     variant %= 100;
 #define WICCA_V(S, N, ST) \
-    return launch_tma_variant<S, N, ST>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, stream)
+    return launch_tma_variant<S, N, ST>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, run_len, stream)
     switch (variant) {
-        case 20: return launch_tma2_variant<7>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, stream);
-        case 21: return launch_tma2_variant<6>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, stream);
-        case 22: return launch_tma2_variant<5>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, stream);
-        case 23: return launch_tma2_variant<4>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, stream);
+        case 20: return launch_tma2_variant<7>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, run_len, stream);
+        case 21: return launch_tma2_variant<6>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, run_len, stream);
+        case 22: return launch_tma2_variant<5>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, run_len, stream);
+        case 23: return launch_tma2_variant<4>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, run_len, stream);
         case 1: WICCA_V(9, 3, false);
         case 2: WICCA_V(9, 9, false);
         case 3: WICCA_V(6, 6, false);

@@ -374,11 +374,14 @@ WHD int border_index(int p, int n, int border_type) {
 // Input side: where the 48 bytes of a chunk row come from.
 //   kSmem  - interior chunk: rows < H from the TMA-filled shared-memory stage, border rows
 //            (y >= H) from the mapped image row in global memory;
-//   kStrip - chunk that touches or lies right of column W: every row from the pre-built
+//            (y >= H) from the stage too for REPLICATE (row H-1 is always in the same band);
+//   kEdge  - chunk that touches or lies right of column W, border REPLICATE or CONSTANT: valid
+//            bytes from the stage, the rest patched with pixel W-1 (same stage) / the constant;
+//   kStrip - same position, border REFLECT / WRAP / REFLECT_101: every row from the pre-built
 //            border-extended right strip (edge_strip_kernel);
 //   kDead  - chunk beyond the padded extent of the deepest requested level: zeros.
 // ---------------------------------------------------------------------------
-enum ChunkMode : int { kDead = 0, kSmem = 1, kStrip = 2 };
+enum ChunkMode : int { kDead = 0, kSmem = 1, kStrip = 2, kEdge = 3 };
 
 struct ChunkSrc {
     int mode;
@@ -386,6 +389,8 @@ struct ChunkSrc {
     const uint8_t* gcol;      // kSmem: image + x0*3 ; kStrip: strip + (x0 - Wa)*3   (row 0)
     int64_t gpitch;           // row pitch of gcol's plane
     int x0, y0, rows, H, Hp_max;     // rows = rows owned by the lane (8 or 16)
+    int nvalid;               // kEdge: pixels of the chunk that are inside the image (0..15)
+    int rep_off;              // kEdge: byte offset of pixel W-1 relative to the chunk's row start (may be < 0)
     int border_type;
     uint32_t fill;            // border constant replicated in 4 bytes
 };
@@ -443,11 +448,16 @@ WHD ChunkSrc make_chunk_src(const ImageGeom& im, const uint8_t* strip, const uin
     cs.smem = stage + row0 * kStageRowBytes + cx * (kChunkPx * 3);
     cs.H = im.H; cs.Hp_max = im.Hp_max;
     cs.border_type = border_type; cs.fill = fill;
+    cs.nvalid = 0; cs.rep_off = 0;
     const int Wa = im.W & ~(kChunkPx - 1);      // first pixel of the chunk that straddles W
     if (cs.x0 >= im.Wp_max || cs.y0 >= im.Hp_max) {
         cs.mode = kDead; cs.gcol = nullptr; cs.gpitch = 0;
     } else if (cs.x0 + kChunkPx <= im.W) {
         cs.mode = kSmem; cs.gcol = im.src + (int64_t)cs.x0 * 3; cs.gpitch = im.pitch;
+    } else if (border_type == 1 || border_type == 0) {
+        cs.mode = kEdge; cs.gcol = nullptr; cs.gpitch = 0;
+        cs.nvalid = im.W > cs.x0 ? im.W - cs.x0 : 0;
+        cs.rep_off = (im.W - 1 - cs.x0) * 3;
     } else {
         cs.mode = kStrip; cs.gcol = strip + (int64_t)(cs.x0 - Wa) * 3; cs.gpitch = kStripPitch;
     }
@@ -463,6 +473,39 @@ WHD void load_chunk_row(const ChunkSrc& cs, int r, uint32_t (&A)[12]) {
     if (cs.mode == kDead || y >= cs.Hp_max) {
 #pragma unroll
         for (int k = 0; k < 12; ++k) A[k] = 0u;
+        return;
+    }
+    if (cs.border_type == 0 && y >= cs.H) {              // CONSTANT: rows below the image
+#pragma unroll
+        for (int k = 0; k < 12; ++k) A[k] = cs.fill;
+        return;
+    }
+    // REPLICATE: rows below the image repeat row H-1, which lies in the same 64-row band (stage)
+    const int rr = (cs.border_type == 1 && y >= cs.H) ? r - (y - (cs.H - 1)) : r;
+    if (cs.mode == kSmem && cs.border_type == 1) { load48_stage(cs.smem + rr * kStageRowBytes, A); return; }
+    if (cs.mode == kEdge) {
+        const uint8_t* p = cs.smem + rr * kStageRowBytes;
+        if (cs.nvalid > 0) load48_stage(p, A);
+        else {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) A[k] = 0u;
+        }
+        uint32_t R[3];
+        if (cs.border_type == 1) {
+            const uint32_t c0 = p[cs.rep_off], c1 = p[cs.rep_off + 1], c2 = p[cs.rep_off + 2];
+            R[0] = c0 | (c1 << 8) | (c2 << 16) | (c0 << 24);
+            R[1] = c1 | (c2 << 8) | (c0 << 16) | (c1 << 24);
+            R[2] = c2 | (c0 << 8) | (c1 << 16) | (c2 << 24);
+        } else {
+            R[0] = R[1] = R[2] = cs.fill;
+        }
+        const int vb = cs.nvalid * 3;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const int nb = vb - 4 * k;
+            const uint32_t mask = nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
+            A[k] = bitsel(mask, A[k], R[k % 3]);
+        }
         return;
     }
     const int ym = border_index(y, cs.H, cs.border_type);
