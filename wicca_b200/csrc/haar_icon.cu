@@ -564,8 +564,17 @@ cudaError_t launch_icon_tma(const IconImage* d_imgs, const uint8_t* const* d_str
                             int border_type, int border_const, int sm_count, int variant, cudaStream_t stream) {
     if (total_items <= 0) return cudaSuccess;
     const int grid = total_items < sm_count ? total_items : sm_count;
-    // developer knobs: variant = kernel shape, + 100 * debug flags, + 1000 * log2(run length)
-    int run_len = 1 << ((variant / 1000) % 10);
+    // variant 0 (default): two warps per stage, 6 stages, runs of up to 16 horizontally adjacent
+    // items per CTA (shorter when the launch is small, to keep the CTAs balanced).
+    // developer knobs: variant = kernel shape, + 100 * debug flags, + 1000 * (1 + log2(run length)).
+    int run_len;
+    const int run_code = (variant / 1000) % 10;
+    if (run_code > 0) {
+        run_len = 1 << (run_code - 1);
+    } else {
+        run_len = 16;
+        while (run_len > 1 && (int64_t)8 * run_len * grid > total_items) run_len >>= 1;
+    }
     if ((int64_t)run_len * grid > total_items) run_len = 1;
     const int debug = (variant / 100) % 10;
     variant %= 100;
@@ -585,7 +594,8 @@ cudaError_t launch_icon_tma(const IconImage* d_imgs, const uint8_t* const* d_str
         case 12: WICCA_V(6, 6, true);
         case 13: WICCA_V(6, 3, true);
         case 14: WICCA_V(5, 5, true);
-        default: WICCA_V(7, 7, true);
+        case 10: WICCA_V(7, 7, true);
+        default: return launch_tma2_variant<6>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, run_len, stream);
     }
 #undef WICCA_V
 }
