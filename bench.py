@@ -190,6 +190,7 @@ def run_ours(args) -> int:
     dev = torch.device(f"cuda:{local}")
     distributed = world > 1
     if distributed:
+        os.environ["NCCL_DEBUG"] = os.environ.get("WICCA_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
