@@ -127,6 +127,12 @@ WICCA_API int wicca_plan_icon(const wicca_plan* plan, int image, int depth_index
                               uint8_t** d_icon, int* h, int* w, int64_t* pitch);
 /* Copy one icon to a tight host buffer (synchronous). */
 WICCA_API int wicca_plan_read_icon(const wicca_plan* plan, int image, int depth_index, uint8_t* dst);
+/* Fused epilogue on the icons the plan just produced (they never leave the device): for every image,
+ * cv2.resize(icon[depth_index], (out_w, out_h), INTER_AREA) -> preprocess_input(norm_mode) -> float32.
+ * d_dst: device (n_images, out_h, out_w, 3) float32; d_dst_u8 (nullable): the uint8 batch cv2 would
+ * return.  Enqueue after wicca_plan_launch on the same stream.  (classifying_tools.py:318,323,286-287) */
+WICCA_API int wicca_plan_resize_norm(wicca_plan* plan, int depth_index, int out_h, int out_w, int norm_mode,
+                                     float* d_dst, uint8_t* d_dst_u8, void* stream);
 /* Number of kernel launches one wicca_plan_launch issues, and the algorithmic bytes it moves. */
 WICCA_API int wicca_plan_info(const wicca_plan* plan, int* launches, int64_t* bytes_read, int64_t* bytes_written);
 WICCA_API int wicca_plan_destroy(wicca_plan* plan);

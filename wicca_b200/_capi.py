@@ -48,6 +48,7 @@ SIGNATURES = {
     "wicca_plan_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "wicca_plan_icon": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), c_intp, c_intp, c_i64p]),
     "wicca_plan_read_icon": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "wicca_plan_resize_norm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "wicca_plan_info": (C.c_int, [C.c_void_p, c_intp, c_i64p, c_i64p]),
     "wicca_plan_destroy": (C.c_int, [C.c_void_p]),
     "wicca_batch_icons_u8": (C.c_int, [C.POINTER(C.c_void_p), c_intp, c_intp, c_i64p, C.c_int, C.c_int, c_intp, C.c_int,

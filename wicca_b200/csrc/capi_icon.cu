@@ -9,6 +9,10 @@
 #include "host_common.h"
 #include "icon_types.h"
 #include "kernels.h"
+#include "resize_tables.h"
+
+#include <map>
+#include <tuple>
 
 using namespace wicca;
 
@@ -384,6 +388,10 @@ struct wicca_plan {
     bool need_strips = false;
     int launches = 0;
     int64_t bytes_read = 0, bytes_written = 0;
+    // resize/normalise epilogue: tap tables per (depth index, out_h, out_w), built on first use
+    struct Epilogue { DevBuf d_tables; ResizeTableBlob blob; };
+    std::map<std::tuple<int, int, int>, Epilogue*> epilogues;
+    std::mutex epi_mu;
 };
 
 int wicca_plan_create(int device, int n_images, const uint8_t* const* d_srcs, const int* Hs, const int* Ws,
@@ -547,9 +555,44 @@ int wicca_plan_info(const wicca_plan* p, int* launches, int64_t* bytes_read, int
     return 0;
 }
 
+int wicca_plan_resize_norm(wicca_plan* p, int depth_index, int out_h, int out_w, int norm_mode, float* d_dst,
+                           uint8_t* d_dst_u8, void* stream_v) {
+    if (!p || !d_dst) return fail(WICCA_ESTATE, "plan or destination is NULL");
+    if (depth_index < 0 || depth_index >= p->n_depths) return fail(WICCA_EINVAL, "depth index out of range");
+    if (out_h <= 0 || out_w <= 0 || norm_mode < 0 || norm_mode > 3) return fail(WICCA_EINVAL, "bad target size / mode");
+    if (p->C != 3) return fail(WICCA_ECHANNELS, "the resize/normalise epilogue needs 3-channel icons");
+    WICCA_CUDA(cudaSetDevice(p->device));
+    wicca_plan::Epilogue* ep = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(p->epi_mu);
+        auto key = std::make_tuple(depth_index, out_h, out_w);
+        auto it = p->epilogues.find(key);
+        if (it == p->epilogues.end()) {
+            std::vector<ResizeSrc> srcs(p->n);
+            for (int i = 0; i < p->n; ++i) {
+                const IconOut& o = p->outs[(size_t)i * p->n_depths + depth_index];
+                srcs[i] = {o.d_ptr, o.h, o.w, o.pitch};
+            }
+            ep = new wicca_plan::Epilogue();
+            ep->blob = build_resize_tables(srcs, out_h, out_w);
+            cudaError_t e = ep->d_tables.reserve(ep->blob.bytes.size());
+            if (e == cudaSuccess) e = cudaMemcpy(ep->d_tables.p, ep->blob.bytes.data(), ep->blob.bytes.size(), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { ep->d_tables.release(); delete ep; return cuda_fail(e, "epilogue table upload"); }
+            p->epilogues[key] = ep;
+        } else {
+            ep = it->second;
+        }
+    }
+    cudaError_t e = launch_resize_norm(ep->blob.view(ep->d_tables.p), p->n, out_h, out_w, norm_mode, d_dst, d_dst_u8,
+                                       (cudaStream_t)stream_v);
+    if (e != cudaSuccess) return cuda_fail(e, "resize/normalise kernel");
+    return 0;
+}
+
 int wicca_plan_destroy(wicca_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
+    for (auto& kv : p->epilogues) { kv.second->d_tables.release(); delete kv.second; }
     p->d_imgs.release(); p->d_strip_ptrs.release(); p->d_strips.release(); p->d_icons.release();
     delete p;
     return 0;

@@ -24,7 +24,8 @@ cudaError_t launch_inverse(const float* d_coeffs, int Hp, int Wp, int C, int dep
 
 // resize_norm.cu
 struct ResizeJob {           // one icon of a batch
-    const uint8_t* src;      // device, tight (sh, sw, 3)
+    const uint8_t* src;      // device, (sh, sw, 3) uint8, rows `pitch` bytes apart
+    int64_t pitch;
     int sh, sw;
     int regime;              // 0 = same size (copy), 1 = integer-factor area, 2 = general area, 3 = bilinear "area mode"
     int isx, isy;            // regime 1: integer scale factors

@@ -43,7 +43,7 @@ __global__ void resize_norm_kernel(ResizeTables t, int n, int out_h, int out_w, 
         const int dx = (int)(r % out_w);
         const int dy = (int)(r / out_w);
         const ResizeJob j = t.jobs[img];
-        const int64_t srow = (int64_t)j.sw * 3;
+        const int64_t srow = j.pitch;
         const uint8_t* s = j.src + c;
         uint8_t v;
         if (j.regime == 0) {

@@ -1,0 +1,116 @@
+// resize_tables.h - host-side construction of the INTER_AREA tap tables exactly as OpenCV builds
+// them (double arithmetic for the geometry, float32 taps), shared by the host-buffer entry point
+// and the device-resident plan epilogue.  See oracle/resize_oracle.py for the restated algorithm.
+#pragma once
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "host_common.h"
+#include "kernels.h"
+
+namespace wicca {
+
+struct ResizeSrc { const uint8_t* d_ptr; int h, w; int64_t pitch; };
+
+struct ResizeTableBlob {
+    std::vector<uint8_t> bytes;          // [jobs][rowptr][taps][lin], 256-byte aligned sections
+    size_t o_jobs = 0, o_rp = 0, o_tp = 0, o_ln = 0;
+    ResizeTables view(const void* device_base) const {
+        const uint8_t* b = (const uint8_t*)device_base;
+        ResizeTables t;
+        t.jobs = (const ResizeJob*)(b + o_jobs);
+        t.rowptr = (const int*)(b + o_rp);
+        t.taps = (const AreaTap*)(b + o_tp);
+        t.lin = (const LinTap*)(b + o_ln);
+        return t;
+    }
+};
+
+// computeResizeAreaTab: CSR list of (src index, fp32 weight) per destination index.
+inline void area_tab(int ssize, int dsize, double scale, std::vector<int>& rowptr, std::vector<AreaTap>& taps) {
+    for (int dx = 0; dx < dsize; ++dx) {
+        rowptr.push_back((int)taps.size());
+        const double fsx1 = dx * scale;
+        const double fsx2 = fsx1 + scale;
+        const double cell = fmin(scale, ssize - fsx1);
+        int sx1 = (int)ceil(fsx1);
+        int sx2 = (int)floor(fsx2);
+        if (sx2 > ssize - 1) sx2 = ssize - 1;
+        if (sx1 > sx2) sx1 = sx2;
+        if (sx1 - fsx1 > 1e-3) taps.push_back({sx1 - 1, (float)((sx1 - fsx1) / cell)});
+        for (int s = sx1; s < sx2; ++s) taps.push_back({s, (float)(1.0 / cell)});
+        if (fsx2 - sx2 > 1e-3) taps.push_back({sx2, (float)(fmin(fmin(fsx2 - sx2, 1.0), cell) / cell)});
+    }
+    rowptr.push_back((int)taps.size());
+}
+
+// INTER_LINEAR tap computation in "area mode" (used by INTER_AREA when an axis is upscaled).
+inline void linear_tab(int ssize, int dsize, double inv, double scale, std::vector<LinTap>& lin) {
+    for (int d = 0; d < dsize; ++d) {
+        int s = (int)floor(d * scale);
+        float f = (float)((d + 1) - (s + 1) * inv);
+        f = f <= 0 ? 0.f : f - floorf(f);
+        if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+        LinTap t;
+        t.i0 = s;
+        t.i1 = (s + 1 < ssize) ? s + 1 : ssize - 1;
+        t.c0 = (int)nearbyintf((1.f - f) * 2048.f);
+        t.c1 = (int)nearbyintf(f * 2048.f);
+        lin.push_back(t);
+    }
+}
+
+inline ResizeTableBlob build_resize_tables(const std::vector<ResizeSrc>& srcs, int out_h, int out_w) {
+    std::vector<ResizeJob> jobs(srcs.size());
+    std::vector<int> rowptr;
+    std::vector<AreaTap> taps;
+    std::vector<LinTap> lin;
+    for (size_t i = 0; i < srcs.size(); ++i) {
+        ResizeJob& j = jobs[i];
+        memset(&j, 0, sizeof j);
+        j.src = srcs[i].d_ptr; j.pitch = srcs[i].pitch; j.sh = srcs[i].h; j.sw = srcs[i].w;
+        const double inv_x = (double)out_w / j.sw, inv_y = (double)out_h / j.sh;
+        const double sx = 1.0 / inv_x, sy = 1.0 / inv_y;      // OpenCV: scale = 1/inv, not ssize/dsize
+        if (j.sw == out_w && j.sh == out_h) {
+            j.regime = 0;
+        } else if (sx >= 1 && sy >= 1) {
+            const int isx = (int)nearbyint(sx), isy = (int)nearbyint(sy);
+            if (fabs(sx - isx) < 2.220446049250313e-16 && fabs(sy - isy) < 2.220446049250313e-16) {
+                j.regime = 1; j.isx = isx; j.isy = isy;
+            } else {
+                j.regime = 2;
+                std::vector<int> rp; std::vector<AreaTap> tp;
+                area_tab(j.sw, out_w, sx, rp, tp);
+                j.xoff = (int)rowptr.size();
+                for (int v : rp) rowptr.push_back(v + (int)taps.size());
+                taps.insert(taps.end(), tp.begin(), tp.end());
+                rp.clear(); tp.clear();
+                area_tab(j.sh, out_h, sy, rp, tp);
+                j.yoff = (int)rowptr.size();
+                for (int v : rp) rowptr.push_back(v + (int)taps.size());
+                taps.insert(taps.end(), tp.begin(), tp.end());
+            }
+        } else {
+            j.regime = 3;
+            j.xoff = (int)lin.size();
+            linear_tab(j.sw, out_w, inv_x, sx, lin);
+            j.yoff = (int)lin.size();
+            linear_tab(j.sh, out_h, inv_y, sy, lin);
+        }
+    }
+    ResizeTableBlob b;
+    b.o_jobs = 0;
+    b.o_rp = (size_t)align_up((int64_t)(b.o_jobs + jobs.size() * sizeof(ResizeJob)), 256);
+    b.o_tp = (size_t)align_up((int64_t)(b.o_rp + rowptr.size() * sizeof(int)), 256);
+    b.o_ln = (size_t)align_up((int64_t)(b.o_tp + taps.size() * sizeof(AreaTap)), 256);
+    b.bytes.assign(b.o_ln + lin.size() * sizeof(LinTap) + 256, 0);
+    memcpy(b.bytes.data() + b.o_jobs, jobs.data(), jobs.size() * sizeof(ResizeJob));
+    if (!rowptr.empty()) memcpy(b.bytes.data() + b.o_rp, rowptr.data(), rowptr.size() * sizeof(int));
+    if (!taps.empty()) memcpy(b.bytes.data() + b.o_tp, taps.data(), taps.size() * sizeof(AreaTap));
+    if (!lin.empty()) memcpy(b.bytes.data() + b.o_ln, lin.data(), lin.size() * sizeof(LinTap));
+    return b;
+}
+
+}  // namespace wicca

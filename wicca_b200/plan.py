@@ -47,6 +47,13 @@ class IconPlan:
         _capi.check(self._lib.wicca_plan_read_icon(self._h, image, depth_index, out.ctypes.data), "wicca_plan_read_icon")
         return out
 
+    def resize_norm(self, depth_index: int, out_h: int, out_w: int, norm_mode: int, d_dst: int, d_dst_u8: int = 0,
+                    stream: int = 0) -> None:
+        """Fused epilogue on the plan's icons (device pointers in, nothing leaves the GPU)."""
+        _capi.check(self._lib.wicca_plan_resize_norm(self._h, depth_index, out_h, out_w, norm_mode, C.c_void_p(d_dst),
+                                                     C.c_void_p(d_dst_u8) if d_dst_u8 else None, C.c_void_p(stream)),
+                    "wicca_plan_resize_norm")
+
     def info(self) -> dict:
         launches, br, bw = C.c_int(), C.c_int64(), C.c_int64()
         _capi.check(self._lib.wicca_plan_info(self._h, C.byref(launches), C.byref(br), C.byref(bw)), "wicca_plan_info")
