@@ -1,0 +1,168 @@
+#!/usr/bin/env python3
+"""Per-row measurements for SURVEY.md section 8 (everything except the headline line, which is bench.py):
+single-depth icons, full sub-band forward/inverse (configs[2]), fused resize+normalise epilogue
+(configs[3]) and the sharded host batch with pinned ingest (configs[4]).  Device times are CUDA
+events around K back-to-back launches; one JSON line per measurement."""
+import ctypes as C
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+
+import numpy as np
+import torch
+
+from wicca_b200 import HaarCoder, _capi
+from wicca_b200.plan import IconPlan, pitch_bytes
+
+PEAK = 6544.7
+try:
+    PEAK = float(json.loads((Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+except Exception:  # noqa: BLE001
+    pass
+H, W = 6393, 8284
+dev = torch.device("cuda:0")
+lib = _capi.load()
+stream = torch.cuda.current_stream().cuda_stream
+
+
+def timed(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def row_icons():
+    n = 30
+    pitch = pitch_bytes(W, 3)
+    g = torch.Generator(device=dev); g.manual_seed(0)
+    imgs = [torch.randint(0, 256, (H, pitch), dtype=torch.uint8, device=dev, generator=g) for _ in range(n)]
+    for ds in ([1], [2], [3], [4], [5], [6], [2, 3, 4, 5, 6], [1, 2, 3, 4, 5, 6]):
+        plan = IconPlan(0, [t.data_ptr() for t in imgs], [H] * n, [W] * n, [pitch] * n, ds)
+        info = plan.info()
+        ms = timed(lambda: plan.launch(stream), reps=20)
+        byt = info["bytes_read"] + info["bytes_written"]
+        emit(row="A3 icon", config=f"30 x ({H},{W},3), depths {ds}, device-resident, one launch", ms=ms,
+             MP_per_s=n * H * W / ms / 1e3, GBps=byt / ms / 1e6, frac_of_measured_peak=byt / ms / 1e6 / PEAK,
+             algorithmic_bytes=byt)
+        if ds == [1, 2, 3, 4, 5, 6]:
+            # fused epilogue on the resident icons (configs[3])
+            for target in (224, 331):
+                out = torch.empty((n, target, target, 3), dtype=torch.float32, device=dev)
+                for k, d in enumerate(ds):
+                    _, ih, iw, _ = plan.icon_info(0, k)
+                    ms_e = timed(lambda: plan.resize_norm(k, target, target, 1, out.data_ptr(), 0, stream), reps=5, warm=2)
+                    byt_e = n * (ih * iw * 3 + target * target * 3 * 4)
+                    emit(row="A5+A6 epilogue", config=f"30 icons of depth {d} ({ih}x{iw}) -> {target}x{target} tf, device-resident",
+                         ms=ms_e, GBps=byt_e / ms_e / 1e6, frac_of_measured_peak=byt_e / ms_e / 1e6 / PEAK,
+                         algorithmic_bytes=byt_e, batches_of_30_per_s=1e3 / ms_e)
+                # icon + epilogue for one depth, as a classifier would consume it (depth 3, both sizes)
+            plan3 = IconPlan(0, [t.data_ptr() for t in imgs], [H] * n, [W] * n, [pitch] * n, [3])
+            out = torch.empty((n, 224, 224, 3), dtype=torch.float32, device=dev)
+            ms_f = timed(lambda: (plan3.launch(stream), plan3.resize_norm(0, 224, 224, 1, out.data_ptr(), 0, stream)), reps=10)
+            emit(row="A3+A5+A6 fused", config="30 images -> depth-3 icon -> 224x224 tf batch, device-resident", ms=ms_f,
+                 MP_per_s=n * H * W / ms_f / 1e3)
+            plan3.close()
+        plan.close()
+    del imgs
+    torch.cuda.empty_cache()
+
+
+def row_subbands():
+    S = 16384
+    pitch = pitch_bytes(S, 3)
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    img = torch.randint(0, 256, (S, pitch), dtype=torch.uint8, device=dev, generator=g)
+    coeffs = torch.empty((S, S, 3), dtype=torch.float32, device=dev)
+    work = torch.empty((S * S * 3 * 5 // 16 + 64,), dtype=torch.float32, device=dev)
+    rec = torch.empty((S, S, 3), dtype=torch.float32, device=dev)
+    for depth in (1, 3, 6):
+        def fwd():
+            _capi.check(lib.wicca_haar_forward_dev(img.data_ptr(), S, S, 3, pitch, depth, 1, 0.0, coeffs.data_ptr(),
+                                                   work.data_ptr(), 0, C.c_void_p(stream)), "forward_dev")
+
+        def inv():
+            _capi.check(lib.wicca_haar_inverse_dev(coeffs.data_ptr(), S, S, 3, depth, rec.data_ptr(), work.data_ptr(), 0,
+                                                   C.c_void_p(stream)), "inverse_dev")
+        ms_f = timed(fwd, reps=5, warm=2)
+        ms_i = timed(inv, reps=5, warm=2)
+        fwd(); inv(); torch.cuda.synchronize()
+        err = float((rec[:, :, :] - img[:, : S * 3].reshape(S, S, 3).float()).abs().max().item())
+        px = S * S
+        emit(row="A4 forward", config=f"{S}x{S}x3 u8 -> fp32 Mallat plane, depth {depth}", ms=ms_f, MP_per_s=px / ms_f / 1e3,
+             GBps=15 * px / ms_f / 1e6, frac_of_measured_peak=15 * px / ms_f / 1e6 / PEAK, algorithmic_bytes=15 * px)
+        emit(row="A4 inverse", config=f"{S}x{S}x3 fp32 plane -> fp32 image, depth {depth}", ms=ms_i, MP_per_s=px / ms_i / 1e3,
+             GBps=24 * px / ms_i / 1e6, frac_of_measured_peak=24 * px / ms_i / 1e6 / PEAK, algorithmic_bytes=24 * px,
+             round_trip_max_abs_error=err)
+    del img, coeffs, work, rec
+    torch.cuda.empty_cache()
+
+
+def row_batch():
+    """configs[4]: 130 ragged ~52 MP images, depths 2-6, pinned host ingest, all visible GPUs."""
+    ndev = lib.wicca_device_count()
+    n, distinct = 130, 13
+    rng = np.random.default_rng(0)
+    shapes = [(H + int(rng.integers(-256, 257)), W + int(rng.integers(-256, 257))) for _ in range(distinct)]
+    ptrs, arrs = [], []
+    for (h, w) in shapes:
+        p = C.c_void_p()
+        _capi.check(lib.wicca_host_alloc(C.byref(p), h * w * 3), "host_alloc")
+        a = np.ctypeslib.as_array((C.c_uint8 * (h * w * 3)).from_address(p.value)).reshape(h, w, 3)
+        a[:] = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ptrs.append(p); arrs.append(a)
+    coder = HaarCoder()
+    images = [arrs[i % distinct] for i in range(n)]
+    depths = [2, 3, 4, 5, 6]
+    for devices in ([0], list(range(ndev))) if ndev > 1 else ([0],):
+        coder.get_small_copies_batch(images[:4], depths, devices=devices)          # warm-up
+        t0 = time.perf_counter()
+        out = coder.get_small_copies_batch(images, depths, devices=devices)
+        dt = time.perf_counter() - t0
+        mp = sum(a.shape[0] * a.shape[1] for a in images) / 1e6
+        byt = sum(a.nbytes for a in images)
+        emit(row="(e) sharded host batch", config=f"130 ragged ~52 MP images, depths 2-6, pinned host -> icons on host, {len(devices)} GPU(s)",
+             s=dt, MP_per_s=mp / dt, h2d_GBps=byt / dt / 1e9, stage_ms_sum=coder.last_timing)
+    from oracle import haar_oracle as ho
+    assert np.array_equal(out[5][1], ho.haar_icon_blocksum(images[5], 3))
+    for p in ptrs:
+        lib.wicca_host_free(p)
+
+
+def cpu_side():
+    from oracle import haar_oracle as ho, resize_oracle as ro
+    img = ho.synthetic_image(0, 4096, 4096, 3)
+    t0 = time.perf_counter(); ho.haar_icon_fp32(img, 3); t1 = time.perf_counter()
+    emit(row="CPU oracle", config="configs[0]: 4096x4096x3 depth 3, NumPy port, 1 core", s=t1 - t0, MP_per_s=16.777 / (t1 - t0))
+    t0 = time.perf_counter(); co = ho.haar_forward(img, 3); t1 = time.perf_counter(); ho.haar_inverse(co); t2 = time.perf_counter()
+    emit(row="CPU oracle", config="A4 forward / inverse 4096x4096x3 depth 3, NumPy, 1 core", forward_s=t1 - t0, inverse_s=t2 - t1,
+         forward_MP_per_s=16.777 / (t1 - t0), inverse_MP_per_s=16.777 / (t2 - t1))
+    icon = ho.synthetic_image(1, 800, 1036, 3)
+    t0 = time.perf_counter(); ro.preprocess_input(ro.resize_area(icon, 224, 224)[None], "tf"); t1 = time.perf_counter()
+    emit(row="CPU oracle", config="A5+A6 one 800x1036 icon -> 224 tf (NumPy restatement; cv2 itself takes ~4 ms)", s=t1 - t0)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["icons", "subbands", "batch", "cpu"]
+    if "icons" in which:
+        row_icons()
+    if "subbands" in which:
+        row_subbands()
+    if "batch" in which:
+        row_batch()
+    if "cpu" in which:
+        cpu_side()
