@@ -106,7 +106,9 @@ WICCA_API int wicca_haar_icons_multi_u8(const uint8_t* src, int H, int W, int C,
 /* d_src: device pointer, rows src_pitch bytes apart.  d_dsts[i]: device pointer, rows
  * dst_pitches[i] bytes apart.  The one-pass kernel is used when C == 3, all depths are in
  * 1..6, d_src is 16-byte aligned and src_pitch is a multiple of 16, each dst is 16-byte
- * aligned with a pitch that is a multiple of 16; otherwise the general kernel runs.
+ * aligned with a pitch that is a multiple of 16; otherwise the general kernel runs.  On the one-pass
+ * path the padding bytes of a destination row between w*C and the next 16-byte boundary (always inside
+ * the row's pitch) may be overwritten - TMA store clips at 16-byte granularity; nothing else is touched.
  * stream is a cudaStream_t (NULL = legacy default stream); the call only enqueues. */
 WICCA_API int wicca_haar_icons_multi_dev(const uint8_t* d_src, int H, int W, int C, int64_t src_pitch,
                                          const int* depths, int n_depths,
