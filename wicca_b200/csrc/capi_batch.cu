@@ -61,6 +61,7 @@ int worker_body(const BatchArgs& a, int device, int first, int step, WorkerResul
         Ctx& c = *slot[j & 1].c;
         if (busy[j & 1]) {
             WICCA_CUDA(cudaStreamSynchronize(c.stream));
+            c.flush_pending();
             add_times(res, c);
         }
         const int64_t pitch = wicca_pitch_bytes(W, a.C);
@@ -70,12 +71,13 @@ int worker_body(const BatchArgs& a, int device, int first, int step, WorkerResul
                                      cudaMemcpyHostToDevice, c.stream));
         WICCA_CUDA(cudaEventRecord(c.ev[1], c.stream));
         int rc = icons_from_resident(c, H, W, a.C, pitch, a.depths, a.n_depths, a.border_type, a.bconst, dsts);
-        if (rc) { cudaStreamSynchronize(c.stream); return rc; }
+        if (rc) { cudaStreamSynchronize(c.stream); c.pending.clear(); return rc; }
         busy[j & 1] = true;
     }
     for (int s = 0; s < 2; ++s)
         if (busy[s]) {
             WICCA_CUDA(cudaStreamSynchronize(slot[s].c->stream));
+            slot[s].c->flush_pending();
             add_times(res, *slot[s].c);
         }
     return 0;

@@ -209,10 +209,29 @@ int icons_from_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int* d
         if (rc) return rc;
     }
     WICCA_CUDA(cudaEventRecord(c.ev[2], c.stream));
+    // D2H: straight into page-locked destinations; pageable ones go through the pinned bounce buffer
+    // (a pageable cudaMemcpyAsync would block the host until the whole stream has drained).
+    size_t bounce = 0;
+    std::vector<char> direct(n_depths, 1);
+    for (int i = 0; i < n_depths; ++i) {
+        if (depths[i] <= 0) continue;
+        if (!is_pinned_host(dsts[i])) { direct[i] = 0; bounce += (size_t)outs[i].w * C * outs[i].h; }
+    }
+    if (bounce) {
+        c.flush_pending();                           // never reallocate under copies that are still owed
+        WICCA_CUDA(c.h_bounce.reserve(bounce));
+    }
+    size_t boff = 0;
     for (int i = 0; i < n_depths; ++i) {
         if (depths[i] <= 0) continue;
         const size_t rowb = (size_t)outs[i].w * C;
-        WICCA_CUDA(cudaMemcpy2DAsync(dsts[i], rowb, outs[i].d_ptr, (size_t)outs[i].pitch, rowb, (size_t)outs[i].h,
+        uint8_t* target = dsts[i];
+        if (!direct[i]) {
+            target = (uint8_t*)c.h_bounce.p + boff;
+            c.pending.push_back({dsts[i], target, rowb * outs[i].h});
+            boff += rowb * outs[i].h;
+        }
+        WICCA_CUDA(cudaMemcpy2DAsync(target, rowb, outs[i].d_ptr, (size_t)outs[i].pitch, rowb, (size_t)outs[i].h,
                                      cudaMemcpyDeviceToHost, c.stream));
     }
     WICCA_CUDA(cudaEventRecord(c.ev[3], c.stream));
@@ -281,8 +300,10 @@ int wicca_haar_icons_multi_u8(const uint8_t* src, int H, int W, int C, int64_t s
     WICCA_CUDA(cudaEventRecord(c.ev[1], c.stream));
     rc = icons_from_resident(c, H, W, C, pitch, depths, n_depths, border_type, bconst, dsts);
     cudaError_t se = cudaStreamSynchronize(c.stream);
+    if (rc || se != cudaSuccess) c.pending.clear();
     if (rc) return rc;
     if (se != cudaSuccess) return cuda_fail(se, "stream synchronize");
+    c.flush_pending();
     fill_timing(t, c);
     return 0;
 }

@@ -78,6 +78,17 @@ cudaError_t Ctx::init(int dev) {
     return cudaSuccess;
 }
 
+void Ctx::flush_pending() {
+    for (const Pending& q : pending) memcpy(q.dst, q.src, q.bytes);
+    pending.clear();
+}
+
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 void Ctx::destroy() {
     if (device < 0) return;
     cudaSetDevice(device);
@@ -170,6 +181,7 @@ int acquire_ctx(int device, Ctx** out) {
 
 void release_ctx(Ctx* c) {
     if (!c || c->device < 0) return;
+    c->pending.clear();          // copies still owed belong to a call that failed: never replay them later
     Pool* pool = g_pools[c->device];
     std::lock_guard<std::mutex> lk(pool->mu);
     pool->idle.push_back(c);

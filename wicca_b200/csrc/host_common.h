@@ -54,6 +54,11 @@ struct Ctx {
     cudaEvent_t ev[6] = {};                // start, h2d done, kernels done, d2h done, spare x2
     DevBuf d_src, d_icons, d_desc, d_strip, d_f32a, d_f32b, d_misc;
     PinBuf h_desc, h_bounce;
+    // Results bound for pageable host memory are DMA'd into h_bounce (so the copy is truly
+    // asynchronous) and moved to their destination after the stream has been synchronised.
+    struct Pending { void* dst; const void* src; size_t bytes; };
+    std::vector<Pending> pending;
+    void flush_pending();                  // call after cudaStreamSynchronize(stream)
     cudaError_t init(int dev);
     void destroy();
 };
@@ -81,6 +86,8 @@ struct CtxLease {
 int encode_image_tmap(CUtensorMap* tm, const void* d_src, int H, int64_t pitch);
 
 int encode_icon_tmap(CUtensorMap* tm, const void* d_icon, int h, int64_t w_bytes, int64_t pitch, int box_w, int box_h);
+
+bool is_pinned_host(const void* p);
 
 int icon_variant_from_env();
 
