@@ -99,139 +99,197 @@ __global__ void inverse_level_f32_kernel(const float* __restrict__ ll, int64_t l
 // Fused tile kernels: all levels 1..min(depth, 6) of one 64 x 64-pixel tile in one pass.
 // Forward: the uint8 tile is read once (3 B/px), every coefficient is written once (12 B/px);
 // the shrinking LL pyramid stays in shared memory.  Inverse: every coefficient is read once,
-// the image is written once.  Consecutive threads own consecutive (x, c) elements of a sub-band
-// row, so every global access is a run of whole 32-byte sectors.
+// the image is written once.  One thread owns one 2 x 2 block with all its channels, and
+// consecutive threads own consecutive blocks of a row, so a warp reads/writes runs of whole
+// sectors; the channel count is a template parameter and every index is a shift.
 // ------------------------------------------------------------------------------------------
 constexpr int kTile = 64;
 constexpr int kTileThreads = 256;
 
 struct TileGeom {
-    int Hp, Wp, C;              // padded extents (multiples of 2^depth), channels (1..4)
+    int Hp, Wp;                 // padded extents (multiples of 2^depth)
     int levels;                 // levels done inside the tile: min(depth, 6)
     int tiles_x, tiles_y;
     float* plane; int64_t pl_stride;      // Mallat plane
     float* ll; int64_t ll_stride;         // where LL_levels lives (the plane itself when depth <= 6)
 };
 
-__global__ void __launch_bounds__(kTileThreads)
-forward_tile_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int W, int border_type, int border_const,
-                    TileGeom g) {
-    __shared__ __align__(16) uint8_t s_u8[kTile * kTile * 4];
-    __shared__ float s_a[32 * 32 * 4];
-    __shared__ float s_b[16 * 16 * 4];
-    const int C = g.C;
-    const int row_bytes = kTile * C;
-    const bool vec_ok = ((uintptr_t)src % 16 == 0) && (pitch % 16 == 0);
-    const int n_tiles = g.tiles_x * g.tiles_y;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
-        const int y0 = ty * kTile, x0 = tx * kTile;
-        // ---- load the tile (border-extended) into shared memory
-        if (vec_ok && y0 + kTile <= H && x0 + kTile <= W) {
-            const int per_row = row_bytes / 16;                       // 4*C uint4 per row
-            for (int i = threadIdx.x; i < kTile * per_row; i += kTileThreads) {
-                const int r = i / per_row, q = i - r * per_row;
-                const uint4 v = *reinterpret_cast<const uint4*>(src + (int64_t)(y0 + r) * pitch + (int64_t)x0 * C + q * 16);
-                *reinterpret_cast<uint4*>(s_u8 + r * row_bytes + q * 16) = v;
-            }
-        } else {
-            for (int i = threadIdx.x; i < kTile * row_bytes; i += kTileThreads) {
-                const int r = i / row_bytes, b = i - r * row_bytes;
-                const int px = b / C, c = b - px * C;
-                uint8_t v = 0;
-                if (y0 + r < g.Hp && x0 + px < g.Wp) {
-                    const int ym = border_index(y0 + r, H, border_type), xm = border_index(x0 + px, W, border_type);
-                    v = (ym < 0 || xm < 0) ? (uint8_t)border_const : src[(int64_t)ym * pitch + (int64_t)xm * C + c];
-                }
-                s_u8[i] = v;
-            }
-        }
-        __syncthreads();
-        // ---- levels
-        const float* in_f = nullptr;
-        for (int l = 1; l <= g.levels; ++l) {
-            const int n = kTile >> l;                       // blocks per tile side at this level
-            const int hl = g.Hp >> l, wl = g.Wp >> l;       // sub-band extents
-            const int in_row = 2 * n * C;                   // elements per row of this level's input
-            float* out_f = (l & 1) ? s_a : s_b;
-            const bool last = (l == g.levels);
-            for (int e = threadIdx.x; e < n * n * C; e += kTileThreads) {
-                const int by = e / (n * C), r = e - by * (n * C);
-                const int bx = r / C, c = r - bx * C;
-                float a, b, cc, d;
-                if (l == 1) {
-                    const uint8_t* p = s_u8 + (2 * by) * row_bytes + (2 * bx) * C + c;
-                    a = (float)p[0]; b = (float)p[C]; cc = (float)p[row_bytes]; d = (float)p[row_bytes + C];
-                } else {
-                    const float* p = in_f + (2 * by) * in_row + (2 * bx) * C + c;
-                    a = p[0]; b = p[C]; cc = p[in_row]; d = p[in_row + C];
-                }
-                const float rs0 = __fadd_rn(a, cc), rs1 = __fadd_rn(b, d);
-                const float rd0 = __fsub_rn(a, cc), rd1 = __fsub_rn(b, d);
-                const float vll = __fmul_rn(__fadd_rn(rs0, rs1), 0.25f);
-                const int gy = ty * n + by, gx = tx * n + bx;
-                if (gy < hl && gx < wl) {
-                    const int64_t ecol = (int64_t)gx * C + c;
-                    g.plane[(int64_t)gy * g.pl_stride + (int64_t)wl * C + ecol] = __fmul_rn(__fsub_rn(rs0, rs1), 0.25f);
-                    g.plane[(int64_t)(gy + hl) * g.pl_stride + ecol] = __fmul_rn(__fadd_rn(rd0, rd1), 0.25f);
-                    g.plane[(int64_t)(gy + hl) * g.pl_stride + (int64_t)wl * C + ecol] = __fmul_rn(__fsub_rn(rd0, rd1), 0.25f);
-                    if (last) g.ll[(int64_t)gy * g.ll_stride + ecol] = vll;
-                }
-                if (!last) out_f[by * (n * C) + r] = vll;
-            }
-            __syncthreads();
-            in_f = out_f;
-        }
+template <int C>
+__device__ __forceinline__ void analyse(const float (&a)[C], const float (&b)[C], const float (&cc)[C],
+                                        const float (&d)[C], float (&ll)[C], float (&hl)[C], float (&lh)[C],
+                                        float (&hh)[C]) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float rs0 = __fadd_rn(a[c], cc[c]), rs1 = __fadd_rn(b[c], d[c]);
+        const float rd0 = __fsub_rn(a[c], cc[c]), rd1 = __fsub_rn(b[c], d[c]);
+        ll[c] = __fmul_rn(__fadd_rn(rs0, rs1), 0.25f);
+        hl[c] = __fmul_rn(__fsub_rn(rs0, rs1), 0.25f);
+        lh[c] = __fmul_rn(__fadd_rn(rd0, rd1), 0.25f);
+        hh[c] = __fmul_rn(__fsub_rn(rd0, rd1), 0.25f);
     }
 }
 
-__global__ void __launch_bounds__(kTileThreads)
-inverse_tile_kernel(TileGeom g, float* __restrict__ out, int64_t out_stride) {
-    extern __shared__ __align__(16) float s_dyn[];          // final 64 x 64 x C tile
-    __shared__ float s_a[32 * 32 * 4];
-    __shared__ float s_b[16 * 16 * 4];
-    const int C = g.C;
-    const int n_tiles = g.tiles_x * g.tiles_y;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
-        const float* in_f = nullptr;
-        for (int l = g.levels; l >= 1; --l) {
-            const int n = kTile >> l;                       // LL_l tile is n x n
-            const int hl = g.Hp >> l, wl = g.Wp >> l;
-            float* out_f = (l == 1) ? s_dyn : (((l - 1) & 1) ? s_a : s_b);
-            const int out_row = 2 * n * C;
-            for (int e = threadIdx.x; e < n * n * C; e += kTileThreads) {
-                const int by = e / (n * C), r = e - by * (n * C);
-                const int bx = r / C, c = r - bx * C;
-                const int gy = ty * n + by, gx = tx * n + bx;
-                float vll = 0.f, vhl = 0.f, vlh = 0.f, vhh = 0.f;
-                if (gy < hl && gx < wl) {
-                    const int64_t ecol = (int64_t)gx * C + c;
-                    vll = (l == g.levels) ? g.ll[(int64_t)gy * g.ll_stride + ecol] : in_f[by * (n * C) + r];
-                    vhl = g.plane[(int64_t)gy * g.pl_stride + (int64_t)wl * C + ecol];
-                    vlh = g.plane[(int64_t)(gy + hl) * g.pl_stride + ecol];
-                    vhh = g.plane[(int64_t)(gy + hl) * g.pl_stride + (int64_t)wl * C + ecol];
-                }
-                const float s0 = __fadd_rn(vll, vhl), s1 = __fsub_rn(vll, vhl);
-                const float d0 = __fadd_rn(vlh, vhh), d1 = __fsub_rn(vlh, vhh);
-                float* q = out_f + (2 * by) * out_row + (2 * bx) * C + c;
-                q[0] = __fadd_rn(s0, d0);
-                q[C] = __fadd_rn(s1, d1);
-                q[out_row] = __fsub_rn(s0, d0);
-                q[out_row + C] = __fsub_rn(s1, d1);
-            }
-            __syncthreads();
-            in_f = out_f;
+// 2*C consecutive bytes (two horizontally adjacent pixels) -> floats, with the widest loads the
+// alignment allows (p is 4-byte aligned when `wide`).
+template <int C>
+__device__ __forceinline__ void load_pixel_pair(const uint8_t* p, bool wide, float (&a)[C], float (&b)[C]) {
+    uint8_t v[2 * C];
+    if (wide && (2 * C) % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < 2 * C / 4; ++k) {
+            const uint32_t w = reinterpret_cast<const uint32_t*>(p)[k];
+            v[4 * k] = (uint8_t)w; v[4 * k + 1] = (uint8_t)(w >> 8); v[4 * k + 2] = (uint8_t)(w >> 16); v[4 * k + 3] = (uint8_t)(w >> 24);
         }
-        // ---- write the reconstructed 64 x 64 x C tile, whole rows of consecutive floats
-        const int row_f = kTile * C;
-        for (int i = threadIdx.x; i < kTile * row_f; i += kTileThreads) {
-            const int r = i / row_f, b = i - r * row_f;
-            const int y = ty * kTile + r, xf = tx * row_f + b;
-            if (y < g.Hp && xf < g.Wp * C) out[(int64_t)y * out_stride + xf] = s_dyn[i];
+    } else if (wide) {                       // 2*C is even: 16-bit loads (p is even because x is even)
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const uint16_t w = reinterpret_cast<const uint16_t*>(p)[k];
+            v[2 * k] = (uint8_t)w; v[2 * k + 1] = (uint8_t)(w >> 8);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 2 * C; ++k) v[k] = p[k];
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) { a[c] = (float)v[c]; b[c] = (float)v[C + c]; }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kTileThreads)
+forward_tile_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int W, int border_type, int border_const,
+                    TileGeom g) {
+    __shared__ float s_a[32 * 32 * C];
+    __shared__ float s_b[16 * 16 * C];
+    const int tile = blockIdx.x;
+    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+    const int y0 = ty * kTile, x0 = tx * kTile;
+    const bool interior = (y0 + kTile <= H) && (x0 + kTile <= W);
+    const float fc = (float)border_const;
+    const bool wide = ((uintptr_t)src % 4 == 0) && (pitch % 4 == 0);      // x0*C and 2*bx*C are multiples of 2*C
+    const float* in_f = nullptr;
+#pragma unroll
+    for (int l = 1; l <= 6; ++l) {
+        if (l > g.levels) break;
+        const int sh = 6 - l;                           // log2(blocks per tile side)
+        const int n = 1 << sh;
+        const int hl_ = g.Hp >> l, wl_ = g.Wp >> l;     // sub-band extents
+        float* out_f = (l & 1) ? s_a : s_b;
+        const bool last = (l == g.levels);
+        for (int blk = threadIdx.x; blk < n * n; blk += kTileThreads) {
+            const int by = blk >> sh, bx = blk & (n - 1);
+            float a[C], b[C], cc[C], d[C];
+            if (l == 1) {
+                if (interior) {
+                    const uint8_t* p = src + (int64_t)(y0 + 2 * by) * pitch + (int64_t)(x0 + 2 * bx) * C;
+                    load_pixel_pair<C>(p, wide, a, b);
+                    load_pixel_pair<C>(p + pitch, wide, cc, d);
+                } else {
+                    const int ya = border_index(y0 + 2 * by, H, border_type), yb = border_index(y0 + 2 * by + 1, H, border_type);
+                    const int xa = border_index(x0 + 2 * bx, W, border_type), xb = border_index(x0 + 2 * bx + 1, W, border_type);
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        a[c] = (ya < 0 || xa < 0) ? fc : (float)src[(int64_t)ya * pitch + (int64_t)xa * C + c];
+                        b[c] = (ya < 0 || xb < 0) ? fc : (float)src[(int64_t)ya * pitch + (int64_t)xb * C + c];
+                        cc[c] = (yb < 0 || xa < 0) ? fc : (float)src[(int64_t)yb * pitch + (int64_t)xa * C + c];
+                        d[c] = (yb < 0 || xb < 0) ? fc : (float)src[(int64_t)yb * pitch + (int64_t)xb * C + c];
+                    }
+                }
+            } else {
+                const int in_row = 2 * n * C;
+                const float* p = in_f + (2 * by) * in_row + (2 * bx) * C;
+#pragma unroll
+                for (int c = 0; c < C; ++c) { a[c] = p[c]; b[c] = p[C + c]; cc[c] = p[in_row + c]; d[c] = p[in_row + C + c]; }
+            }
+            float vll[C], vhl[C], vlh[C], vhh[C];
+            analyse<C>(a, b, cc, d, vll, vhl, vlh, vhh);
+            const int gy = ty * n + by, gx = tx * n + bx;
+            if (gy < hl_ && gx < wl_) {
+                float* q_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(wl_ + gx) * C;
+                float* q_lh = g.plane + (int64_t)(gy + hl_) * g.pl_stride + (int64_t)gx * C;
+                float* q_hh = q_lh + (int64_t)wl_ * C;
+#pragma unroll
+                for (int c = 0; c < C; ++c) { q_hl[c] = vhl[c]; q_lh[c] = vlh[c]; q_hh[c] = vhh[c]; }
+                if (last) {
+                    float* q_ll = g.ll + (int64_t)gy * g.ll_stride + (int64_t)gx * C;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) q_ll[c] = vll[c];
+                }
+            }
+            if (!last) {
+                float* q = out_f + (by * n + bx) * C;
+#pragma unroll
+                for (int c = 0; c < C; ++c) q[c] = vll[c];
+            }
         }
         __syncthreads();
+        in_f = out_f;
     }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kTileThreads)
+inverse_tile_kernel(TileGeom g, float* __restrict__ out, int64_t out_stride) {
+    __shared__ float s_a[32 * 32 * C];
+    __shared__ float s_b[16 * 16 * C];
+    const int tile = blockIdx.x;
+    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+    const float* in_f = nullptr;
+    for (int l = g.levels; l >= 1; --l) {
+        const int sh = 6 - l;
+        const int n = 1 << sh;                          // LL_l tile is n x n
+        const int hl_ = g.Hp >> l, wl_ = g.Wp >> l;
+        float* out_f = ((l - 1) & 1) ? s_a : s_b;
+        for (int blk = threadIdx.x; blk < n * n; blk += kTileThreads) {
+            const int by = blk >> sh, bx = blk & (n - 1);
+            const int gy = ty * n + by, gx = tx * n + bx;
+            const bool inside = gy < hl_ && gx < wl_;
+            float vll[C], vhl[C], vlh[C], vhh[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) vll[c] = vhl[c] = vlh[c] = vhh[c] = 0.f;
+            if (inside) {
+                const float* q_ll = (l == g.levels) ? g.ll + (int64_t)gy * g.ll_stride + (int64_t)gx * C
+                                                    : in_f + (by * n + bx) * C;
+                const float* q_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(wl_ + gx) * C;
+                const float* q_lh = g.plane + (int64_t)(gy + hl_) * g.pl_stride + (int64_t)gx * C;
+                const float* q_hh = q_lh + (int64_t)wl_ * C;
+#pragma unroll
+                for (int c = 0; c < C; ++c) { vll[c] = q_ll[c]; vhl[c] = q_hl[c]; vlh[c] = q_lh[c]; vhh[c] = q_hh[c]; }
+            }
+            float a[C], b[C], cc[C], d[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float s0 = __fadd_rn(vll[c], vhl[c]), s1 = __fsub_rn(vll[c], vhl[c]);
+                const float d0 = __fadd_rn(vlh[c], vhh[c]), d1 = __fsub_rn(vlh[c], vhh[c]);
+                a[c] = __fadd_rn(s0, d0); b[c] = __fadd_rn(s1, d1); cc[c] = __fsub_rn(s0, d0); d[c] = __fsub_rn(s1, d1);
+            }
+            if (l == 1) {
+                if (inside) {       // 2 rows x 2 pixels x C consecutive floats per thread, consecutive threads adjacent
+                    float* q = out + (int64_t)(2 * gy) * out_stride + (int64_t)(2 * gx) * C;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) { q[c] = a[c]; q[C + c] = b[c]; q[out_stride + c] = cc[c]; q[out_stride + C + c] = d[c]; }
+                }
+            } else {
+                const int out_row = 2 * n * C;
+                float* q = out_f + (2 * by) * out_row + (2 * bx) * C;
+#pragma unroll
+                for (int c = 0; c < C; ++c) { q[c] = a[c]; q[C + c] = b[c]; q[out_row + c] = cc[c]; q[out_row + C + c] = d[c]; }
+            }
+        }
+        __syncthreads();
+        in_f = out_f;
+    }
+}
+
+template <int C>
+static cudaError_t launch_forward_tiles(const uint8_t* d_src, int64_t pitch, int H, int W, int border_type,
+                                        int border_const, const TileGeom& g, cudaStream_t stream) {
+    forward_tile_kernel<C><<<g.tiles_x * g.tiles_y, kTileThreads, 0, stream>>>(d_src, pitch, H, W, border_type, border_const, g);
+    return cudaGetLastError();
+}
+template <int C>
+static cudaError_t launch_inverse_tiles(const TileGeom& g, float* out, int64_t out_stride, cudaStream_t stream) {
+    inverse_tile_kernel<C><<<g.tiles_x * g.tiles_y, kTileThreads, 0, stream>>>(g, out, out_stride);
+    return cudaGetLastError();
 }
 
 static int grid_for(int64_t n) {
@@ -253,15 +311,18 @@ cudaError_t launch_forward(const uint8_t* d_src, int64_t pitch, int H, int W, in
     if (C <= 4) {
         // levels 1..min(depth,6) in one pass per 64 x 64 tile
         TileGeom g;
-        g.Hp = Hp; g.Wp = Wp; g.C = C; g.levels = depth < 6 ? depth : 6;
+        g.Hp = Hp; g.Wp = Wp; g.levels = depth < 6 ? depth : 6;
         g.tiles_x = (Wp + kTile - 1) / kTile; g.tiles_y = (Hp + kTile - 1) / kTile;
         g.plane = d_coeffs; g.pl_stride = pl_stride;
         if (depth <= 6) { g.ll = d_coeffs; g.ll_stride = pl_stride; }
         else { g.ll = (g.levels & 1) ? workA : workB; g.ll_stride = (int64_t)(Wp >> g.levels) * C; }
-        const int64_t tiles = (int64_t)g.tiles_x * g.tiles_y;
-        const int grid = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
-        forward_tile_kernel<<<grid, kTileThreads, 0, stream>>>(d_src, pitch, H, W, border_type, border_const, g);
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e;
+        switch (C) {
+            case 1: e = launch_forward_tiles<1>(d_src, pitch, H, W, border_type, border_const, g, stream); break;
+            case 2: e = launch_forward_tiles<2>(d_src, pitch, H, W, border_type, border_const, g, stream); break;
+            case 3: e = launch_forward_tiles<3>(d_src, pitch, H, W, border_type, border_const, g, stream); break;
+            default: e = launch_forward_tiles<4>(d_src, pitch, H, W, border_type, border_const, g, stream); break;
+        }
         if (e != cudaSuccess) return e;
         in = g.ll; in_stride = g.ll_stride;
         first = g.levels + 1;
@@ -305,23 +366,17 @@ cudaError_t launch_inverse(const float* d_coeffs, int Hp, int Wp, int C, int dep
     }
     if (fused_levels > 0) {
         TileGeom g;
-        g.Hp = Hp; g.Wp = Wp; g.C = C; g.levels = fused_levels;
+        g.Hp = Hp; g.Wp = Wp; g.levels = fused_levels;
         g.tiles_x = (Wp + kTile - 1) / kTile; g.tiles_y = (Hp + kTile - 1) / kTile;
         g.plane = const_cast<float*>(d_coeffs); g.pl_stride = pl_stride;
         g.ll = const_cast<float*>(ll); g.ll_stride = ll_stride;
-        const size_t smem = (size_t)kTile * kTile * C * sizeof(float);
-        static thread_local int configured_dev = -1;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (configured_dev != dev) {
-            cudaError_t e = cudaFuncSetAttribute(inverse_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            if (e != cudaSuccess) return e;
-            configured_dev = dev;
+        cudaError_t e;
+        switch (C) {
+            case 1: e = launch_inverse_tiles<1>(g, d_image, pl_stride, stream); break;
+            case 2: e = launch_inverse_tiles<2>(g, d_image, pl_stride, stream); break;
+            case 3: e = launch_inverse_tiles<3>(g, d_image, pl_stride, stream); break;
+            default: e = launch_inverse_tiles<4>(g, d_image, pl_stride, stream); break;
         }
-        const int64_t tiles = (int64_t)g.tiles_x * g.tiles_y;
-        const int grid = (int)(tiles < 148 * 3 ? tiles : 148 * 3);
-        inverse_tile_kernel<<<grid, kTileThreads, smem, stream>>>(g, d_image, pl_stride);
-        cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
