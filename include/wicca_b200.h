@@ -178,6 +178,13 @@ WICCA_API int wicca_icon_resize_norm_f32(const uint8_t* const* icons, const int*
                                          int out_h, int out_w, int norm_mode,
                                          float* dst, uint8_t* dst_u8, int device, wicca_timing* t);
 
+/* Device-resident variant for sources that already live in HBM - icons, or the full-size source images of
+ * the reference's other branch, cv2.resize(image, shape, interpolation) (classifying_tools.py:315).
+ * d_srcs[i]: device uint8 (hs[i], ws[i], 3), rows pitches[i] bytes apart.  Enqueues on `stream`. */
+WICCA_API int wicca_resize_norm_dev(const uint8_t* const* d_srcs, const int* hs, const int* ws, const int64_t* pitches,
+                                    int n, int out_h, int out_w, int norm_mode, float* d_dst, uint8_t* d_dst_u8,
+                                    int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,3 +68,28 @@ def test_end_to_end_icon_then_batch(coder):
         batch = coder.icons_to_batch(icons, (224, 224), "tf")
         exp = ro.preprocess_input(np.stack([ro.resize_area(ho.haar_icon_blocksum(im, depth), 224, 224) for im in imgs]), "tf")
         assert np.array_equal(batch, exp)
+
+
+def test_source_image_branch_n1(coder):
+    """Row N1: the reference also resizes the full source image (classifying_tools.py:315); the same
+    kernel handles it (scale ~ 9-14 here), host and device-resident entry points."""
+    import ctypes as C
+    import torch
+    from wicca_b200 import _capi
+    from wicca_b200.plan import to_device_pitched
+    imgs = [gen_input("noise", 600 + i, 2000 + 31 * i, 3100 - 17 * i, 3) for i in range(3)]
+    exp = np.stack([ro.resize_area(im, 224, 224) for im in imgs])
+    f32, u8 = coder.icons_to_batch(imgs, (224, 224), "caffe", return_uint8=True)
+    assert np.array_equal(u8, exp) and np.array_equal(f32, ro.preprocess_input(exp, "caffe"))
+    dev = [to_device_pitched(im) for im in imgs]
+    out = torch.empty((3, 224, 224, 3), dtype=torch.float32, device="cuda:0")
+    out8 = torch.empty((3, 224, 224, 3), dtype=torch.uint8, device="cuda:0")
+    n = len(imgs)
+    rc = _capi.load().wicca_resize_norm_dev((C.c_void_p * n)(*[t.data_ptr() for t in dev]), (C.c_int * n)(*[im.shape[0] for im in imgs]),
+                                            (C.c_int * n)(*[im.shape[1] for im in imgs]), (C.c_int64 * n)(*[t.shape[1] for t in dev]),
+                                            n, 224, 224, 1, out.data_ptr(), out8.data_ptr(), 0,
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _capi.check(rc, "wicca_resize_norm_dev")
+    torch.cuda.synchronize()
+    assert np.array_equal(out8.cpu().numpy(), exp)
+    assert np.array_equal(out.cpu().numpy(), ro.preprocess_input(exp, "tf"))

@@ -60,6 +60,15 @@ def row_icons():
              MP_per_s=n * H * W / ms / 1e3, GBps=byt / ms / 1e6, frac_of_measured_peak=byt / ms / 1e6 / PEAK,
              algorithmic_bytes=byt)
         if ds == [1, 2, 3, 4, 5, 6]:
+            # row N1: the source-image branch, cv2.resize(image, (224, 224), INTER_AREA), on the resident images
+            out_s = torch.empty((n, 224, 224, 3), dtype=torch.float32, device=dev)
+            ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in imgs])
+            def src_resize():
+                _capi.check(lib.wicca_resize_norm_dev(ptrs, (C.c_int * n)(*[H] * n), (C.c_int * n)(*[W] * n), (C.c_int64 * n)(*[pitch] * n),
+                                                      n, 224, 224, 1, out_s.data_ptr(), None, 0, C.c_void_p(stream)), "resize_norm_dev")
+            ms_s = timed(src_resize, reps=3, warm=1)
+            emit(row="N1 source-image resize", config=f"30 x ({H},{W},3) -> 224x224 tf, device-resident", ms=ms_s,
+                 MP_per_s=n * H * W / ms_s / 1e3, GBps=n * H * W * 3 / ms_s / 1e6, frac_of_measured_peak=n * H * W * 3 / ms_s / 1e6 / PEAK)
             # fused epilogue on the resident icons (configs[3])
             for target in (224, 331):
                 out = torch.empty((n, target, target, 3), dtype=torch.float32, device=dev)
@@ -143,6 +152,28 @@ def row_batch():
         lib.wicca_host_free(p)
 
 
+def row_oneshot():
+    """The call the reference's callers make: one get_small_copy on a host array (pageable vs pinned)."""
+    coder = HaarCoder()
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    p = C.c_void_p()
+    _capi.check(lib.wicca_host_alloc(C.byref(p), H * W * 3), "host_alloc")
+    pin = np.ctypeslib.as_array((C.c_uint8 * (H * W * 3)).from_address(p.value)).reshape(H, W, 3)
+    pin[:] = img
+    for name, arr in (("pageable", img), ("pinned", pin)):
+        for d in (3, [1, 2, 3, 4, 5, 6]):
+            f = (lambda: coder.get_small_copy(arr, d)) if isinstance(d, int) else (lambda: coder.get_small_copies(arr, d))
+            f(); f()
+            ts = []
+            for _ in range(5):
+                t0 = time.perf_counter(); f(); ts.append(time.perf_counter() - t0)
+            emit(row="A3 one-shot host call", config=f"get_small_copy/ies(({H},{W},3) {name} ndarray, depth {d})", ms=1e3 * min(ts),
+                 MP_per_s=H * W / 1e6 / min(ts), stage_ms=coder.last_timing)
+    del pin
+    lib.wicca_host_free(p)
+
+
 def cpu_side():
     from oracle import haar_oracle as ho, resize_oracle as ro
     img = ho.synthetic_image(0, 4096, 4096, 3)
@@ -157,12 +188,14 @@ def cpu_side():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["icons", "subbands", "batch", "cpu"]
+    which = sys.argv[1:] or ["icons", "subbands", "batch", "oneshot", "cpu"]
     if "icons" in which:
         row_icons()
     if "subbands" in which:
         row_subbands()
     if "batch" in which:
         row_batch()
+    if "oneshot" in which:
+        row_oneshot()
     if "cpu" in which:
         cpu_side()

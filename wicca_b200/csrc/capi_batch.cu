@@ -67,10 +67,10 @@ int worker_body(const BatchArgs& a, int device, int first, int step, WorkerResul
         const int64_t pitch = wicca_pitch_bytes(W, a.C);
         WICCA_CUDA(c.d_src.reserve((size_t)pitch * H + 256));
         WICCA_CUDA(cudaEventRecord(c.ev[0], c.stream));
-        WICCA_CUDA(cudaMemcpy2DAsync(c.d_src.p, (size_t)pitch, a.srcs[i], (size_t)stride, (size_t)rowb, (size_t)H,
-                                     cudaMemcpyHostToDevice, c.stream));
+        int rc = upload_image_async(c, a.srcs[i], H, rowb, stride, pitch);
+        if (rc) { cudaStreamSynchronize(c.stream); c.pending.clear(); return rc; }
         WICCA_CUDA(cudaEventRecord(c.ev[1], c.stream));
-        int rc = icons_from_resident(c, H, W, a.C, pitch, a.depths, a.n_depths, a.border_type, a.bconst, dsts);
+        rc = icons_from_resident(c, H, W, a.C, pitch, a.depths, a.n_depths, a.border_type, a.bconst, dsts);
         if (rc) { cudaStreamSynchronize(c.stream); c.pending.clear(); return rc; }
         busy[j & 1] = true;
     }

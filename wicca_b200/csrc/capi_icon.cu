@@ -295,8 +295,8 @@ int wicca_haar_icons_multi_u8(const uint8_t* src, int H, int W, int C, int64_t s
     const int64_t pitch = wicca_pitch_bytes(W, C);
     WICCA_CUDA(c.d_src.reserve((size_t)pitch * H + 256));
     WICCA_CUDA(cudaEventRecord(c.ev[0], c.stream));
-    WICCA_CUDA(cudaMemcpy2DAsync(c.d_src.p, (size_t)pitch, src, (size_t)src_row_stride, (size_t)rowb, (size_t)H,
-                                 cudaMemcpyHostToDevice, c.stream));
+    rc = upload_image_async(c, src, H, rowb, src_row_stride, pitch);
+    if (rc) { cudaStreamSynchronize(c.stream); return rc; }
     WICCA_CUDA(cudaEventRecord(c.ev[1], c.stream));
     rc = icons_from_resident(c, H, W, C, pitch, depths, n_depths, border_type, bconst, dsts);
     cudaError_t se = cudaStreamSynchronize(c.stream);

@@ -63,3 +63,33 @@ extern "C" int wicca_icon_resize_norm_f32(const uint8_t* const* icons, const int
     }
     return 0;
 }
+
+// Device-resident variant: the sources already live in HBM (icons, or full source images for the
+// reference's `cv2.resize(image, shape, interpolation)` branch, classifying_tools.py:315).
+extern "C" int wicca_resize_norm_dev(const uint8_t* const* d_srcs, const int* hs, const int* ws, const int64_t* pitches,
+                                     int n, int out_h, int out_w, int norm_mode, float* d_dst, uint8_t* d_dst_u8,
+                                     int device, void* stream_v) {
+    if (n < 0 || out_h <= 0 || out_w <= 0) return fail(WICCA_EINVAL, "bad batch/target size");
+    if (norm_mode < 0 || norm_mode > 3) return fail(WICCA_EINVAL, "unknown normalisation mode %d", norm_mode);
+    if (n == 0) return 0;
+    if (!d_srcs || !hs || !ws || !pitches || !d_dst) return fail(WICCA_EINVAL, "null pointer");
+    std::vector<ResizeSrc> srcs(n);
+    for (int i = 0; i < n; ++i) {
+        if (!d_srcs[i] || hs[i] <= 0 || ws[i] <= 0 || pitches[i] < (int64_t)ws[i] * 3) return fail(WICCA_EINVAL, "image %d is malformed", i);
+        srcs[i] = {d_srcs[i], hs[i], ws[i], pitches[i]};
+    }
+    int rc = check_device(device);
+    if (rc) return rc;
+    WICCA_CUDA(cudaSetDevice(device));
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const ResizeTableBlob blob = build_resize_tables(srcs, out_h, out_w);
+    void* d_tables = nullptr;
+    WICCA_CUDA(cudaMallocAsync(&d_tables, blob.bytes.size(), stream));          // stream-ordered scratch
+    // pageable source: staged by the runtime before the call returns, so `blob` may go out of scope
+    cudaError_t e = cudaMemcpyAsync(d_tables, blob.bytes.data(), blob.bytes.size(), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = launch_resize_norm(blob.view(d_tables), n, out_h, out_w, norm_mode, d_dst, d_dst_u8, stream);
+    cudaError_t e2 = cudaFreeAsync(d_tables, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "resize/normalise kernel");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFreeAsync");
+    return 0;
+}

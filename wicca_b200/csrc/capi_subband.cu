@@ -72,8 +72,8 @@ int wicca_haar_forward_f32(const uint8_t* src, int H, int W, int C, int64_t src_
     WICCA_CUDA(c.d_f32a.reserve(plane_bytes));
     WICCA_CUDA(c.d_f32b.reserve(work_floats(Hp, Wp, C) * sizeof(float)));
     WICCA_CUDA(cudaEventRecord(c.ev[0], c.stream));
-    WICCA_CUDA(cudaMemcpy2DAsync(c.d_src.p, (size_t)pitch, src, (size_t)src_row_stride, (size_t)rowb, (size_t)H,
-                                 cudaMemcpyHostToDevice, c.stream));
+    rc = upload_image_async(c, src, H, rowb, src_row_stride, pitch);
+    if (rc) { cudaStreamSynchronize(c.stream); return rc; }
     WICCA_CUDA(cudaEventRecord(c.ev[1], c.stream));
     cudaError_t e = launch_forward((const uint8_t*)c.d_src.p, pitch, H, W, C, Hp, Wp, depth, border_base(border_type),
                                    saturate_u8(border_const), (float*)c.d_f32a.p, (float*)c.d_f32b.p, c.stream);

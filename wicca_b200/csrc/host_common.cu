@@ -7,6 +7,8 @@
 
 #include "icon_types.h"
 
+#include <thread>
+
 namespace wicca {
 
 std::string& last_error_ref() {
@@ -94,7 +96,7 @@ void Ctx::destroy() {
     cudaSetDevice(device);
     d_src.release(); d_icons.release(); d_desc.release(); d_strip.release();
     d_f32a.release(); d_f32b.release(); d_misc.release();
-    h_desc.release(); h_bounce.release();
+    h_desc.release(); h_bounce.release(); h_in.release();
     for (auto& x : ev) if (x) { cudaEventDestroy(x); x = nullptr; }
     if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
     device = -1;
@@ -197,6 +199,43 @@ void destroy_all_ctx() {
         pool->all.clear();
         pool->idle.clear();
     }
+}
+
+int upload_image_async(Ctx& c, const uint8_t* src, int H, int64_t row_bytes, int64_t stride, int64_t pitch) {
+    const size_t total = (size_t)row_bytes * H;
+    if (total < ((size_t)4 << 20) || is_pinned_host(src)) {
+        WICCA_CUDA(cudaMemcpy2DAsync(c.d_src.p, (size_t)pitch, src, (size_t)stride, (size_t)row_bytes, (size_t)H,
+                                     cudaMemcpyHostToDevice, c.stream));
+        return 0;
+    }
+    WICCA_CUDA(c.h_in.reserve(total));
+    int rows_per_band = (int)(((size_t)8 << 20) / (size_t)row_bytes);
+    if (rows_per_band < 1) rows_per_band = 1;
+    const int n_bands = (H + rows_per_band - 1) / rows_per_band;
+    unsigned hw = std::thread::hardware_concurrency();
+    int n_threads = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
+    if (n_threads > n_bands) n_threads = n_bands;
+    std::vector<cudaError_t> errs(n_threads, cudaSuccess);
+    auto work = [&](int t) {
+        if (cudaSetDevice(c.device) != cudaSuccess) { errs[t] = cudaGetLastError(); return; }
+        for (int b = t; b < n_bands; b += n_threads) {
+            const int r0 = b * rows_per_band;
+            const int nr = (r0 + rows_per_band <= H) ? rows_per_band : H - r0;
+            uint8_t* stage = (uint8_t*)c.h_in.p + (size_t)r0 * row_bytes;
+            if (stride == row_bytes) memcpy(stage, src + (size_t)r0 * stride, (size_t)nr * row_bytes);
+            else for (int y = 0; y < nr; ++y) memcpy(stage + (size_t)y * row_bytes, src + (size_t)(r0 + y) * stride, (size_t)row_bytes);
+            cudaError_t e = cudaMemcpy2DAsync((uint8_t*)c.d_src.p + (size_t)r0 * pitch, (size_t)pitch, stage, (size_t)row_bytes,
+                                              (size_t)row_bytes, (size_t)nr, cudaMemcpyHostToDevice, c.stream);
+            if (e != cudaSuccess) { errs[t] = e; return; }
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int t = 1; t < n_threads; ++t) threads.emplace_back(work, t);
+    work(0);
+    for (auto& th : threads) th.join();
+    for (cudaError_t e : errs)
+        if (e != cudaSuccess) return cuda_fail(e, "staged image upload");
+    return 0;
 }
 
 // ---- TMA descriptor ---------------------------------------------------------------------

@@ -53,7 +53,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};                // start, h2d done, kernels done, d2h done, spare x2
     DevBuf d_src, d_icons, d_desc, d_strip, d_f32a, d_f32b, d_misc;
-    PinBuf h_desc, h_bounce;
+    PinBuf h_desc, h_bounce, h_in;
     // Results bound for pageable host memory are DMA'd into h_bounce (so the copy is truly
     // asynchronous) and moved to their destination after the stream has been synchronised.
     struct Pending { void* dst; const void* src; size_t bytes; };
@@ -88,6 +88,12 @@ int encode_image_tmap(CUtensorMap* tm, const void* d_src, int H, int64_t pitch);
 int encode_icon_tmap(CUtensorMap* tm, const void* d_icon, int h, int64_t w_bytes, int64_t pitch, int box_w, int box_h);
 
 bool is_pinned_host(const void* p);
+
+// Host image (rows `stride` bytes apart) -> c.d_src (rows `pitch` bytes apart), asynchronously on c.stream.
+// Page-locked sources are DMA'd directly; pageable ones are staged band by band through the pinned
+// buffer c.h_in by a few helper threads, so the CPU copy of band k+1 overlaps the DMA of band k.
+// c.d_src must already be reserved.
+int upload_image_async(Ctx& c, const uint8_t* src, int H, int64_t row_bytes, int64_t stride, int64_t pitch);
 
 int icon_variant_from_env();
 
