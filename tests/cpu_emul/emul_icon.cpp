@@ -1,10 +1,12 @@
 // emul_icon.cpp - CPU replay of the one-pass icon kernel (test infrastructure).
 //
 // Compiles wicca_b200/csrc/haar_math.cuh as plain C++ and walks every work item / lane exactly
-// as haar_icon_tma_kernel does: a 24 KB "stage" is filled the way the TMA box load would fill it
-// (zero beyond the tensor extent, pad bytes of the pitched image included), each of the 32 lanes
-// runs make_chunk_src / reduce_lane, the level 5/6 warp shuffles are replayed with the same xor
-// pattern, and emit_tail stores the results.  What is NOT covered: mbarrier/TMA mechanics.
+// as haar_icon_tma2_kernel does: a 24 KB "stage" is filled the way the TMA box load would fill it
+// (zero beyond the tensor extent, pad bytes of the pitched image included); for each of the two
+// warps of the pair, each of the 32 lanes runs make_chunk_src / reduce_lane into the warp's
+// output tile, the tile is copied to the icons with TMA store's clipping rule, the level 4/5/6
+// shuffles and the mailbox add are replayed with the same xor pattern, and emit_tail_half stores
+// the results.  What is NOT covered: mbarrier/TMA mechanics.
 //
 // Build:  g++ -O2 -shared -fPIC -I/usr/local/cuda/include -Iwicca_b200/csrc tests/cpu_emul/emul_icon.cpp
 #include <stdint.h>
@@ -22,10 +24,8 @@ extern "C" {
 // src: tight (H, W, 3) uint8.  mask bit (d-1) requests depth d.  outs[d-1]: tight icon buffers
 // (may be NULL when not requested).  Returns 0, or a positive code when a guard byte around an
 // icon was overwritten (out-of-bounds store).
-// staged != 0 replays the TMA-store path (levels 1..3 assembled in a per-warp tile, then copied
-// to the icon with the hardware's clipping rule); staged == 0 the direct-store path.
 int emul_fused_icons(const uint8_t* src, int H, int W, int border_type, int border_const, unsigned mask,
-                     uint8_t** outs, int staged) {
+                     uint8_t** outs) {
     const int64_t pitch = ((int64_t)W * 3 + 127) / 128 * 128;
     std::vector<uint8_t> img((size_t)pitch * H + 64, 0xA5);      // pad bytes are garbage on purpose
     for (int y = 0; y < H; ++y) memcpy(&img[(size_t)y * pitch], src + (size_t)y * W * 3, (size_t)W * 3);
@@ -65,89 +65,49 @@ int emul_fused_icons(const uint8_t* src, int H, int W, int border_type, int bord
                     const int64_t xb = (int64_t)ix * kStageRowBytes + b;
                     stage[(size_t)r * kStageRowBytes + b] = (y < H && xb < pitch) ? img[(size_t)y * pitch + xb] : 0;
                 }
-            if (staged == 2) {
-                // two warps per item: half 0 = rows 0..31, half 1 = rows 32..63; 8 rows per lane
-                uint32_t s6half[2][32][3];
-                ChunkSrc hcs[2][32];
-                uint32_t hs4[2][32][3], hs5[2][32][3];
-                for (int half = 0; half < 2; ++half) {
-                    std::vector<uint8_t> tile(kHalfStageBytes, 0xCD);
-                    uint32_t acc[32][3], a1[32][3], b1[32][3];
-                    for (int lane = 0; lane < 32; ++lane) {
-                        const int cx = lane & 7, ry = lane >> 3;
-                        hcs[half][lane] = make_chunk_src(geo, strip.empty() ? nullptr : strip.data(), stage.data(), ix, iy,
-                                                         cx, half * 32 + ry * 8, 8, border_type, fill);
-                        const StagedEmit em = staged_emit_half(tile.data(), cx, ry, mask & 7u);
-                        reduce_lane<8>(hcs[half][lane], em, acc[lane]);
-                    }
-                    const int box_w[3] = {kOut1Row, kOut2Row, kOut3Row}, box_h[3] = {16, 8, 4};
-                    const int off[3] = {kHalf1Off, kHalf2Off, kHalf3Off};
-                    for (int l = 0; l < 3; ++l) {
-                        if (!(mask & (1u << l))) continue;
-                        const int64_t wb = (int64_t)im.icon_w[l] * 3;
-                        for (int r = 0; r < box_h[l]; ++r)
-                            for (int b = 0; b < box_w[l]; ++b) {
-                                const int64_t gx = (int64_t)ix * box_w[l] + b;
-                                const int gy = iy * (2 * box_h[l]) + half * box_h[l] + r;
-                                if (gx < wb && gy < im.icon_h[l])
-                                    im.icon[l][(int64_t)gy * im.icon_pitch[l] + gx] = tile[off[l] + r * box_w[l] + b];
-                            }
-                    }
-                    for (int c = 0; c < 3; ++c) {
-                        for (int l = 0; l < 32; ++l) hs4[half][l][c] = acc[l][c] + acc[l ^ 8][c];
-                        for (int l = 0; l < 32; ++l) a1[l][c] = hs4[half][l][c] + hs4[half][l ^ 1][c];
-                        for (int l = 0; l < 32; ++l) hs5[half][l][c] = a1[l][c] + a1[l ^ 16][c];
-                        for (int l = 0; l < 32; ++l) b1[l][c] = hs5[half][l][c] + hs5[half][l ^ 2][c];
-                        for (int l = 0; l < 32; ++l) s6half[half][l][c] = b1[l][c];
-                    }
+
+            // two warps per item: half 0 = rows 0..31, half 1 = rows 32..63; 8 rows per lane
+            uint32_t s6half[2][32][3];
+            ChunkSrc hcs[2][32];
+            uint32_t hs4[2][32][3], hs5[2][32][3];
+            for (int half = 0; half < 2; ++half) {
+                std::vector<uint8_t> tile(kHalfStageBytes, 0xCD);
+                uint32_t acc[32][3], a1[32][3], b1[32][3];
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int cx = lane & 7, ry = lane >> 3;
+                    hcs[half][lane] = make_chunk_src(geo, strip.empty() ? nullptr : strip.data(), stage.data(), ix, iy,
+                                                     cx, half * 32 + ry * 8, 8, border_type, fill);
+                    const StagedEmit em = staged_emit_half(tile.data(), cx, ry, mask & 7u);
+                    reduce_lane(hcs[half][lane], em, acc[lane]);
                 }
-                for (int half = 0; half < 2; ++half)
-                    for (int lane = 0; lane < 32; ++lane) {
-                        uint32_t s6v[3];
-                        for (int c = 0; c < 3; ++c) s6v[c] = s6half[0][lane][c] + s6half[1][lane][c];
-                        emit_tail_half(sk, hcs[half][lane].x0, hcs[half][lane].y0, lane & 7, lane >> 3, half == 0,
-                                       hs4[half][lane], hs5[half][lane], s6v);
-                    }
-                continue;
-            }
-            uint32_t acc4[32][3], v1[32][3], s5[32][3], u1[32][3], s6[32][3];
-            ChunkSrc cs[32];
-            std::vector<uint8_t> tile(kOutStageBytes, 0xCD);
-            for (int lane = 0; lane < 32; ++lane) {
-                cs[lane] = make_chunk_src(geo, strip.empty() ? nullptr : strip.data(), stage.data(), ix, iy, lane & 7,
-                                          (lane >> 3) * 16, 16, border_type, fill);
-                if (staged) {
-                    const StagedEmit em = staged_emit_full(tile.data(), lane & 7, lane >> 3, mask & 7u);
-                    reduce_lane<16>(cs[lane], em, acc4[lane]);
-                } else {
-                    const DirectEmit em{sk, cs[lane].x0, cs[lane].y0};
-                    reduce_lane<16>(cs[lane], em, acc4[lane]);
-                }
-            }
-            if (staged) {
-                // TMA store of a (box_w bytes x box_h rows) tile at byte x / row y, clipped to the tensor
-                const int box_w[3] = {kOut1Row, kOut2Row, kOut3Row}, box_h[3] = {32, 16, 8};
-                const int off[3] = {kOut1Off, kOut2Off, kOut3Off};
+                const int box_w[3] = {kOut1Row, kOut2Row, kOut3Row}, box_h[3] = {16, 8, 4};
+                const int off[3] = {kHalf1Off, kHalf2Off, kHalf3Off};
                 for (int l = 0; l < 3; ++l) {
                     if (!(mask & (1u << l))) continue;
                     const int64_t wb = (int64_t)im.icon_w[l] * 3;
                     for (int r = 0; r < box_h[l]; ++r)
                         for (int b = 0; b < box_w[l]; ++b) {
                             const int64_t gx = (int64_t)ix * box_w[l] + b;
-                            const int gy = iy * box_h[l] + r;
+                            const int gy = iy * (2 * box_h[l]) + half * box_h[l] + r;
                             if (gx < wb && gy < im.icon_h[l])
                                 im.icon[l][(int64_t)gy * im.icon_pitch[l] + gx] = tile[off[l] + r * box_w[l] + b];
                         }
                 }
+                for (int c = 0; c < 3; ++c) {
+                    for (int l = 0; l < 32; ++l) hs4[half][l][c] = acc[l][c] + acc[l ^ 8][c];
+                    for (int l = 0; l < 32; ++l) a1[l][c] = hs4[half][l][c] + hs4[half][l ^ 1][c];
+                    for (int l = 0; l < 32; ++l) hs5[half][l][c] = a1[l][c] + a1[l ^ 16][c];
+                    for (int l = 0; l < 32; ++l) b1[l][c] = hs5[half][l][c] + hs5[half][l ^ 2][c];
+                    for (int l = 0; l < 32; ++l) s6half[half][l][c] = b1[l][c];
+                }
             }
-            for (int c = 0; c < 3; ++c) {
-                for (int l = 0; l < 32; ++l) v1[l][c] = acc4[l][c] + acc4[l ^ 1][c];
-                for (int l = 0; l < 32; ++l) s5[l][c] = v1[l][c] + v1[l ^ 8][c];
-                for (int l = 0; l < 32; ++l) u1[l][c] = s5[l][c] + s5[l ^ 2][c];
-                for (int l = 0; l < 32; ++l) s6[l][c] = u1[l][c] + u1[l ^ 16][c];
-            }
-            for (int lane = 0; lane < 32; ++lane)
-                emit_tail(sk, cs[lane].x0, cs[lane].y0, lane & 7, lane >> 3, acc4[lane], s5[lane], s6[lane]);
+            for (int half = 0; half < 2; ++half)
+                for (int lane = 0; lane < 32; ++lane) {
+                    uint32_t s6v[3];
+                    for (int c = 0; c < 3; ++c) s6v[c] = s6half[0][lane][c] + s6half[1][lane][c];
+                    emit_tail_half(sk, hcs[half][lane].x0, hcs[half][lane].y0, lane & 7, lane >> 3, half == 0,
+                                   hs4[half][lane], hs5[half][lane], s6v);
+                }
         }
     int bad = 0;
     for (int d = 1; d <= kMaxFused; ++d) {

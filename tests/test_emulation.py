@@ -25,16 +25,16 @@ def emul():
                         f"-I{ROOT / 'wicca_b200' / 'csrc'}", str(src), "-o", str(so)], check=True)
     lib = ctypes.CDLL(str(so))
     lib.emul_fused_icons.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                     ctypes.c_uint, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
+                                     ctypes.c_uint, ctypes.POINTER(ctypes.c_void_p)]
 
-    def run(img, bt, bc, depths, staged=1):
+    def run(img, bt, bc, depths):
         h, w, _ = img.shape
         mask, outs, arr = 0, {}, (ctypes.c_void_p * 6)()
         for d in depths:
             mask |= 1 << (d - 1)
             outs[d] = np.full((-(-h // 2 ** d), -(-w // 2 ** d), 3), 0x77, np.uint8)
             arr[d - 1] = outs[d].ctypes.data
-        rc = lib.emul_fused_icons(img.ctypes.data, h, w, bt, bc, mask, arr, staged)
+        rc = lib.emul_fused_icons(img.ctypes.data, h, w, bt, bc, mask, arr)
         assert rc == 0, f"guard bytes overwritten (code {rc})"
         return outs
     return run
@@ -44,15 +44,14 @@ SHAPES = [(1, 1), (1, 2), (2, 1), (3, 5), (5, 7), (16, 16), (17, 33), (64, 64), 
           (127, 255), (128, 256), (200, 259), (130, 517), (129, 257), (70, 300)]
 
 
-@pytest.mark.parametrize("staged", [2, 1, 0])
 @pytest.mark.parametrize("border", [1, 0, 2, 3, 4])
-def test_emulated_kernel_matches_oracle(emul, border, staged):
+def test_emulated_kernel_matches_oracle(emul, border):
     rng = np.random.default_rng(border)
     for (h, w) in SHAPES:
         img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
         bc = int(rng.integers(0, 256))
         for depths in ([1, 2, 3, 4, 5, 6], [1], [3], [6], [2, 5]):
-            outs = emul(img, border, bc, depths, staged)
+            outs = emul(img, border, bc, depths)
             for d in depths:
                 assert np.array_equal(outs[d], ho.haar_icon_blocksum(img, d, border, bc)), (h, w, border, depths, d)
 
@@ -60,7 +59,6 @@ def test_emulated_kernel_matches_oracle(emul, border, staged):
 @pytest.mark.parametrize("kind", ["full", "trunc", "zeros", "hramp", "vramp"])
 def test_emulated_kernel_adversarial(emul, kind):
     img = gen_input(kind, 5, 139, 301, 3)
-    for staged in (2, 1, 0):
-        outs = emul(img, 1, 0, [1, 2, 3, 4, 5, 6], staged)
-        for d, got in outs.items():
-            assert np.array_equal(got, ho.haar_icon_blocksum(img, d, 1, 0)), (kind, d, staged)
+    outs = emul(img, 1, 0, [1, 2, 3, 4, 5, 6])
+    for d, got in outs.items():
+        assert np.array_equal(got, ho.haar_icon_blocksum(img, d, 1, 0)), (kind, d)

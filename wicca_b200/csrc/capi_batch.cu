@@ -4,6 +4,7 @@
 // worker so the H2D copy of image j+1 overlaps the kernel and icon D2H of image j.
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -43,6 +44,12 @@ int worker_body(const BatchArgs& a, int device, int first, int step, WorkerResul
         int rc = acquire_ctx(device, &slot[s].c);
         if (rc) return rc;
     }
+    // one allocation per slot, sized for the largest image of this worker (ragged batches would
+    // otherwise grow the buffer - and synchronise the device - several times)
+    size_t max_src = 0;
+    for (int i = first; i < a.n_images; i += step)
+        max_src = std::max(max_src, (size_t)wicca_pitch_bytes(a.Ws[i], a.C) * a.Hs[i] + 256);
+    for (int s = 0; s < 2; ++s) WICCA_CUDA(slot[s].c->d_src.reserve(max_src));
     int j = 0;
     for (int i = first; i < a.n_images; i += step, ++j) {
         const int H = a.Hs[i], W = a.Ws[i];

@@ -63,12 +63,9 @@ int fill_icon_image(IconImage* im, const uint8_t* d_src, int H, int W, int64_t p
         const int d = outs[i].depth;
         if (d <= 3) {   // levels 1..3 leave the kernel through TMA store
             static const int box_w[3] = {kOut1Row, kOut2Row, kOut3Row};
-            static const int box_h[3] = {32, 16, 8};
-            rc = encode_icon_tmap(&im->omap[d - 1], outs[i].d_ptr, outs[i].h, (int64_t)outs[i].w * 3, outs[i].pitch,
-                                  box_w[d - 1], box_h[d - 1]);
-            if (rc) return rc;
+            static const int box_h[3] = {16, 8, 4};
             rc = encode_icon_tmap(&im->hmap[d - 1], outs[i].d_ptr, outs[i].h, (int64_t)outs[i].w * 3, outs[i].pitch,
-                                  box_w[d - 1], box_h[d - 1] / 2);
+                                  box_w[d - 1], box_h[d - 1]);
             if (rc) return rc;
         }
     }

@@ -3,15 +3,16 @@
 // Replaces the body of HaarCoder.get_small_copy (wicca/wavelet_coder.py:56-67) including the
 // padding of get_padded_copy (wicca/data_loader.py:107-117), which is never materialised.
 //
-//   haar_icon_tma_kernel   one HBM pass over a pitched RGB image produces the icons of ANY
+//   haar_icon_tma2_kernel  one HBM pass over a pitched RGB image produces the icons of ANY
 //                          subset of depths 1..6.  Persistent CTAs; a producer lane streams
 //                          128 px x 64 row tiles (24 KB) into a shared-memory ring with TMA
-//                          (cp.async.bulk.tensor + mbarrier), consumer warps reduce one tile
-//                          each: levels 1-4 in registers (packed 16-bit lanes), levels 5-6
-//                          with warp shuffles.  HBM-bound: ~3 B/px read, <= 1 B/px written.
-//   edge_strip_kernel      tiny pre-pass: materialises the border-extended right strip
-//                          (<= 79 px per row) so the hot kernel never evaluates the border
-//                          rule per pixel.
+//                          (cp.async.bulk.tensor + mbarrier); two consumer warps per tile reduce
+//                          it: levels 1-3 in registers (packed 16-bit lanes) and out through
+//                          TMA store, levels 4-5 with warp shuffles, level 6 through a mailbox.
+//                          HBM-bound: 3 B/px read, <= 1 B/px written.
+//   edge_strip_kernel      tiny pre-pass, only for BORDER_REFLECT / REFLECT_101 / WRAP: materialises
+//                          the border-extended right strip (<= 78 px per row).  REPLICATE and
+//                          CONSTANT borders are patched from the shared-memory tile instead.
 //   haar_icon_generic_kernel  any C, any alignment, depth <= 8: one thread per output element.
 //   haar_level_f32_kernel  one further level in fp32, for depths > 8 (the reference's fp32
 //                          arithmetic stops being exact there, so it is replayed literally).
@@ -94,178 +95,9 @@ __device__ __forceinline__ int item_index(int k, int run_len) {
     return (u * (int)gridDim.x + (int)blockIdx.x) * run_len + (k - u * run_len);
 }
 
-// kStaged: levels 1..3 are assembled as dense tiles in shared memory and written with TMA
-// store (full-line writes, hardware clipping); otherwise straight register->global stores.
-// debug: 0 = normal, 1 = consumers skip the arithmetic (load path only), 2 = arithmetic but no
-// level 1..3 output (developer instrumentation for tools/bench_variants.py).
-template <int kStages, int kConsumerWarps, bool kStaged>
-__global__ void __launch_bounds__(32 * (1 + kConsumerWarps), 1)
-haar_icon_tma_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* __restrict__ strips, int n_images,
-                     int total_items, int border_type, int border_const, int debug, int run_len) {
-    // Item k uses stage k % kStages and consumer warp k % kConsumerWarps.  A parity wait can only be
-    // one phase ahead of the barrier, so the warp that waits for item k + kStages must be the one
-    // that consumed item k: kStages has to be a multiple of kConsumerWarps.
-    static_assert(kStages % kConsumerWarps == 0, "kStages must be a multiple of kConsumerWarps");
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint8_t* stages = smem_raw;
-    uint8_t* out_tiles = smem_raw + (size_t)kStages * kStageBytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_tiles + (kStaged ? (size_t)kConsumerWarps * kOutStageBytes : 0));
-    uint64_t* empty_bar = full_bar + kStages;
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        fence_mbar_init();
-    }
-    __syncthreads();
-
-    if (warp == 0) {
-        // ------------------------------ TMA producer ------------------------------
-        if (lane == 0) {
-            const uint64_t pol = policy_evict_first();
-            // Per-image fields live in registers and are refreshed only when the item index crosses
-            // into the next image: the issue loop has no dependent global loads.
-            int img = -1, base = 0, next_base = 0, items_x = 1;
-            const CUtensorMap* tmap = nullptr;
-            int k = 0;
-            for (;; ++k) {
-                const int g = item_index(k, run_len);
-                if (g >= total_items) break;
-                if (g >= next_base) {
-                    do {
-                        ++img;
-                        next_base = (img + 1 < n_images) ? imgs[img + 1].item_base : 0x7FFFFFFF;
-                    } while (g >= next_base);
-                    base = imgs[img].item_base;
-                    items_x = imgs[img].items_x;
-                    tmap = &imgs[img].tmap;
-                    fence_tensormap_acquire(tmap);
-                }
-                const int local = g - base;
-                const int iy = local / items_x;
-                const int ix = local - iy * items_x;
-                const int s = k % kStages;
-                const uint32_t ph = (uint32_t)(k / kStages) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-                tma_load_2d(stages + (size_t)s * kStageBytes, tmap, ix * (kStageRowBytes / 4), iy * kItemH,
-                            &full_bar[s], pol);
-            }
-        }
-        return;
-    }
-
-    // ------------------------------- consumers ---------------------------------
-    const int cw = warp - 1;
-    const int cx = lane & 7;    // chunk column inside the item (16 px each)
-    const int ry = lane >> 3;   // row group inside the item (16 rows each)
-    const uint32_t fill = (uint32_t)border_const * 0x01010101u;
-    uint8_t* tile = out_tiles + (size_t)cw * kOutStageBytes;
-    int img = -1, base = 0, next_base = 0;
-    ImageGeom geo;
-    IconSink sk;
-    const uint8_t* strip = nullptr;
-    const CUtensorMap* omap = nullptr;
-    unsigned mask = 0;
-    uint32_t sink_word = 0;
-
-    for (int k = cw;; k += kConsumerWarps) {
-        const int g = item_index(k, run_len);
-        if (g >= total_items) break;
-        const int s = k % kStages;
-        const uint32_t ph = (uint32_t)(k / kStages) & 1u;
-        if (g >= next_base) {            // warp-uniform: entered a new image, refresh the cached descriptor
-            do {
-                ++img;
-                next_base = (img + 1 < n_images) ? imgs[img + 1].item_base : 0x7FFFFFFF;
-            } while (g >= next_base);
-            const IconImage& im = imgs[img];
-            base = im.item_base;
-            geo = make_geom(im);
-            sk = make_sink(im);
-            strip = strips[img];
-            omap = im.omap;
-            mask = 0;
-#pragma unroll
-            for (int l = 0; l < 3; ++l) mask |= (sk.icon[l] != nullptr ? 1u : 0u) << l;
-            if (debug == 2) {
-                mask = 0;
-#pragma unroll
-                for (int l = 0; l < 3; ++l) sk.icon[l] = nullptr;
-            }
-            if (kStaged && lane == 0) {
-#pragma unroll
-                for (int l = 0; l < 3; ++l)
-                    if ((mask >> l) & 1u) fence_tensormap_acquire(&omap[l]);
-            }
-        }
-        const int local = g - base;
-        const int iy = local / geo.items_x;
-        const int ix = local - iy * geo.items_x;
-
-        const ChunkSrc cs = make_chunk_src(geo, strip, stages + (size_t)s * kStageBytes, ix, iy, cx, ry * 16, 16,
-                                           border_type, fill);
-        const int x0 = cs.x0, y0 = cs.y0;
-
-        if (kStaged) {
-            // the previous item's TMA stores must have finished READING this warp's tile
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
-        }
-
-        mbar_wait(&full_bar[s], ph);
-
-        uint32_t acc4[3];
-        if (debug == 1) {
-            sink_word ^= *reinterpret_cast<const uint32_t*>(cs.smem);
-            acc4[0] = acc4[1] = acc4[2] = 0u;
-        } else if (kStaged) {
-            const StagedEmit em = staged_emit_full(tile, cx, ry, mask);
-            reduce_lane<16>(cs, em, acc4);
-        } else {
-            const DirectEmit em{sk, x0, y0};
-            reduce_lane<16>(cs, em, acc4);
-        }
-
-        // the stage is no longer needed: hand it back to the producer before the tail
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
-
-        if (kStaged && mask != 0u && debug != 1) {
-            fence_proxy_async_smem();        // generic-proxy tile writes -> visible to the TMA (async proxy)
-            __syncwarp();
-            if (lane == 0) {
-                if (mask & 1u) tma_store_2d(&omap[0], tile + kOut1Off, ix * kOut1Row, iy * 32);
-                if (mask & 2u) tma_store_2d(&omap[1], tile + kOut2Off, ix * kOut2Row, iy * 16);
-                if (mask & 4u) tma_store_2d(&omap[2], tile + kOut3Off, ix * kOut3Row, iy * 8);
-                bulk_commit();
-            }
-        }
-
-        // levels 5 and 6: 2x2 and 4x4 lane groups (cx bit 0 / ry bit 0, then cx bit 1 / ry bit 1)
-        uint32_t s5[3], s6[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            uint32_t v = acc4[c] + __shfl_xor_sync(0xFFFFFFFFu, acc4[c], 1);
-            v += __shfl_xor_sync(0xFFFFFFFFu, v, 8);
-            s5[c] = v;
-            uint32_t u = v + __shfl_xor_sync(0xFFFFFFFFu, v, 2);
-            u += __shfl_xor_sync(0xFFFFFFFFu, u, 16);
-            s6[c] = u;
-        }
-        if (debug != 1) emit_tail(sk, x0, y0, cx, ry, acc4, s5, s6);
-    }
-    if (kStaged && lane == 0) bulk_wait0();      // all TMA stores of this warp are complete
-    if (debug == 1 && sink_word == 0x9E3779B9u && sk.icon[5] != nullptr) sk.icon[5][0] = (uint8_t)sink_word;
-}
-
 // ------------------------------------------------------------------------------------------
+// The one-pass kernel.  debug: 0 = normal; 1 = consumers skip the arithmetic (load path only);
+// 2 = arithmetic but no level 1..3 output (developer instrumentation, see tools/bench_variants.py).
 // Two consumer warps per stage: warp pair p owns stage p; the upper warp reduces rows 0..31 of the
 // 128 x 64 item, the lower warp rows 32..63 (8 rows per lane), so a stage is held half as long and
 // twice as many warps hide each other's latencies.  Levels 1..5 are complete inside a warp; the
@@ -276,9 +108,7 @@ __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0
 template <int kStages>
 __global__ void __launch_bounds__(32 * (1 + 2 * kStages), 1)
 haar_icon_tma2_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* __restrict__ strips, int n_images,
-                      int total_items, int border_type, int border_const, int debug_flags, int run_len) {
-    const int debug = debug_flags & 3;
-    const bool no_fence = (debug_flags & 4) != 0;   // developer experiment only
+                      int total_items, int border_type, int border_const, int debug, int run_len) {
     static_assert(kStages <= 15, "one named barrier per warp pair");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* stages = smem_raw;
@@ -317,7 +147,7 @@ haar_icon_tma2_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* 
                     base = imgs[img].item_base;
                     items_x = imgs[img].items_x;
                     tmap = &imgs[img].tmap;
-                    if (!no_fence) fence_tensormap_acquire(tmap);
+                    fence_tensormap_acquire(tmap);
                 }
                 const int local = g - base;
                 const int iy = local / items_x;
@@ -375,7 +205,7 @@ haar_icon_tma2_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* 
             if (lane == 0) {
 #pragma unroll
                 for (int l = 0; l < 3; ++l)
-                    if (((mask >> l) & 1u) && !no_fence) fence_tensormap_acquire(&hmap[l]);
+                    if ((mask >> l) & 1u) fence_tensormap_acquire(&hmap[l]);
             }
         }
         const int local = g - base;
@@ -395,7 +225,7 @@ haar_icon_tma2_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* 
             acc[0] = acc[1] = acc[2] = 0u;
         } else {
             const StagedEmit em = staged_emit_half(tile, cx, ry, mask);
-            reduce_lane<8>(cs, em, acc);
+            reduce_lane(cs, em, acc);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[pair]);
@@ -521,25 +351,6 @@ __global__ void haar_level_f32_kernel(const float* __restrict__ in, float* __res
 // ------------------------------------------------------------------------------------------
 // Launchers
 // ------------------------------------------------------------------------------------------
-template <int S, int NCW, bool STAGED>
-static cudaError_t launch_tma_variant(const IconImage* d_imgs, const uint8_t* const* d_strips, int n_images,
-                                      int total_items, int border_type, int border_const, int grid, int debug,
-                                      int run_len, cudaStream_t stream) {
-    const size_t smem = (size_t)S * kStageBytes + (STAGED ? (size_t)NCW * kOutStageBytes : 0) + 2 * S * sizeof(uint64_t);
-    static thread_local int configured_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (configured_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(haar_icon_tma_kernel<S, NCW, STAGED>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured_dev = dev;
-    }
-    haar_icon_tma_kernel<S, NCW, STAGED><<<grid, 32 * (1 + NCW), smem, stream>>>(d_imgs, d_strips, n_images, total_items,
-                                                                                 border_type, border_const, debug, run_len);
-    return cudaGetLastError();
-}
-
 template <int S>
 static cudaError_t launch_tma2_variant(const IconImage* d_imgs, const uint8_t* const* d_strips, int n_images,
                                        int total_items, int border_type, int border_const, int grid, int debug,
@@ -559,14 +370,13 @@ static cudaError_t launch_tma2_variant(const IconImage* d_imgs, const uint8_t* c
     return cudaGetLastError();
 }
 
-// variant: 0 = default.  1x = TMA-store output tiles, 0x = direct stores; see the switch.
+// variant 0 (default): 6 stages, runs of up to 16 horizontally adjacent items per CTA (shorter when
+// the launch is small, to keep the CTAs balanced).  Developer knobs (WICCA_ICON_VARIANT):
+// variant % 100 in {20,21,22,23} = 7/6/5/4 stages, + 100 * debug mode, + 1000 * (1 + log2(run length)).
 cudaError_t launch_icon_tma(const IconImage* d_imgs, const uint8_t* const* d_strips, int n_images, int total_items,
                             int border_type, int border_const, int sm_count, int variant, cudaStream_t stream) {
     if (total_items <= 0) return cudaSuccess;
     const int grid = total_items < sm_count ? total_items : sm_count;
-    // variant 0 (default): two warps per stage, 6 stages, runs of up to 16 horizontally adjacent
-    // items per CTA (shorter when the launch is small, to keep the CTAs balanced).
-    // developer knobs: variant = kernel shape, + 100 * debug flags, + 1000 * (1 + log2(run length)).
     int run_len;
     const int run_code = (variant / 1000) % 10;
     if (run_code > 0) {
@@ -577,27 +387,12 @@ cudaError_t launch_icon_tma(const IconImage* d_imgs, const uint8_t* const* d_str
     }
     if ((int64_t)run_len * grid > total_items) run_len = 1;
     const int debug = (variant / 100) % 10;
-    variant %= 100;
-#define WICCA_V(S, N, ST) \
-    return launch_tma_variant<S, N, ST>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, run_len, stream)
-    switch (variant) {
+    switch (variant % 100) {
         case 20: return launch_tma2_variant<7>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, run_len, stream);
-        case 21: return launch_tma2_variant<6>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, run_len, stream);
         case 22: return launch_tma2_variant<5>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, run_len, stream);
         case 23: return launch_tma2_variant<4>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, run_len, stream);
-        case 1: WICCA_V(9, 3, false);
-        case 2: WICCA_V(9, 9, false);
-        case 3: WICCA_V(6, 6, false);
-        case 4: WICCA_V(8, 4, false);
-        case 5: WICCA_V(8, 8, false);
-        case 11: WICCA_V(8, 4, true);
-        case 12: WICCA_V(6, 6, true);
-        case 13: WICCA_V(6, 3, true);
-        case 14: WICCA_V(5, 5, true);
-        case 10: WICCA_V(7, 7, true);
         default: return launch_tma2_variant<6>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, run_len, stream);
     }
-#undef WICCA_V
 }
 
 cudaError_t launch_edge_strips(const IconImage* d_imgs, uint8_t* const* d_strips, int n_images, int max_rows,

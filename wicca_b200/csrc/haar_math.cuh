@@ -1,11 +1,11 @@
 // haar_math.cuh - register-level arithmetic of the one-pass Haar icon kernel.
 //
 // Everything here is __host__ __device__ so the exact code the GPU runs can be
-// replayed lane by lane on the CPU (tests/cpu_emul/emul_icon.cu) and compared
+// replayed lane by lane on the CPU (tests/cpu_emul/emul_icon.cpp) and compared
 // with the oracle without a GPU.
 //
 // Model.  One thread owns a "chunk": 16 RGB pixels = 48 bytes = 12 words of one
-// image row, and walks 16 rows of it two at a time.  The reference computes, per
+// image row, and walks 8 rows of it two at a time.  The reference computes, per
 // level, (even_row + odd_row) then (even_col + odd_col) * 0.25 in fp32
 // (wicca/wavelet_coder.py:61-65) and truncates once at the end (:67).  Those
 // fp32 values are exact, so level-d output = (sum of the 2^d x 2^d block) >> 2d.
@@ -150,66 +150,11 @@ struct IconSink {
     int h[6], w[6];        // icon extents: ceil(H / 2^d), ceil(W / 2^d)
 };
 
-WHD uint32_t word_byte(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
-
-// Store NW words = NW*4/3 pixels at pixel ox0 of an icon row; whole-group vector stores when the
-// group lies inside the row, bytewise clipping at the right edge otherwise.
-template <int NW>
-WHD void store_px_group(uint8_t* row, int ox0, int icon_w, const uint32_t (&W)[NW]) {
-    constexpr int NPX = NW * 4 / 3;
-    uint8_t* p = row + (int64_t)ox0 * 3;
-    if (ox0 + NPX <= icon_w) {
-        if (NW == 6) {                       // 24 B, 8-byte aligned (ox0 multiple of 8)
-            uint2* q = reinterpret_cast<uint2*>(p);
-            uint2 v0, v1, v2;
-            v0.x = W[0]; v0.y = W[1]; v1.x = W[2]; v1.y = W[3]; v2.x = W[4 % NW]; v2.y = W[5 % NW];
-            q[0] = v0; q[1] = v1; q[2] = v2;
-        } else {                             // 12 B, 4-byte aligned (ox0 multiple of 4)
-            uint32_t* q = reinterpret_cast<uint32_t*>(p);
-#pragma unroll
-            for (int k = 0; k < NW; ++k) q[k] = W[k];
-        }
-    } else {
-        const int nb = (icon_w - ox0) * 3;
-#pragma unroll
-        for (int t = 0; t < NW * 4; ++t)
-            if (t < nb) p[t] = (uint8_t)word_byte(W[t >> 2], t & 3);
-    }
-}
-
 // ---------------------------------------------------------------------------
-// Emitters for levels 1..3 (r = chunk row 0..15 at which the group starts).
-//   DirectEmit : global stores straight from registers, clipped at the icon's right/bottom edge.
-//   StagedEmit : dense per-warp tiles in shared memory (L1 32 x 192 B, L2 16 x 96 B, L3 8 x 48 B)
-//                that one lane then hands to TMA store, which clips in hardware.
+// Emitter for levels 1..3: dense per-warp tiles in shared memory (a warp owns half an item,
+// 128 x 32 px: L1 16 x 192 B, L2 8 x 96 B, L3 4 x 48 B) that one lane then hands to TMA store,
+// which clips at the icon edge in hardware.  r = chunk row (0..7) at which the group starts.
 // ---------------------------------------------------------------------------
-
-struct DirectEmit {
-    const IconSink& sk;
-    int x0, y0;
-    WHD bool want(int l) const { return sk.icon[l] != nullptr; }
-    WHD void icon1(int r, const uint32_t (&W)[6]) const {
-        const int oy = (y0 + r) >> 1, ox0 = x0 >> 1;
-        if (oy < sk.h[0] && ox0 < sk.w[0]) store_px_group<6>(sk.icon[0] + (int64_t)oy * sk.pitch[0], ox0, sk.w[0], W);
-    }
-    WHD void icon2(int r, const uint32_t (&W)[3]) const {
-        const int oy = (y0 + r) >> 2, ox0 = x0 >> 2;
-        if (oy < sk.h[1] && ox0 < sk.w[1]) store_px_group<3>(sk.icon[1] + (int64_t)oy * sk.pitch[1], ox0, sk.w[1], W);
-    }
-    WHD void icon3(int r, const uint32_t (&Hh)[3]) const {
-        const int oy = (y0 + r) >> 3, ox0 = x0 >> 3;
-        if (oy < sk.h[2] && ox0 < sk.w[2]) {
-            uint8_t* p = sk.icon[2] + (int64_t)oy * sk.pitch[2] + (int64_t)ox0 * 3;
-            if (ox0 + 2 <= sk.w[2]) {            // 6 B, 2-byte aligned (ox0 multiple of 2)
-                uint16_t* q = reinterpret_cast<uint16_t*>(p);
-                q[0] = (uint16_t)Hh[0]; q[1] = (uint16_t)Hh[1]; q[2] = (uint16_t)Hh[2];
-            } else {                             // only the first pixel is inside the icon
-                p[0] = (uint8_t)(Hh[0] & 0xFFu); p[1] = (uint8_t)(Hh[0] >> 8); p[2] = (uint8_t)(Hh[1] & 0xFFu);
-            }
-        }
-    }
-};
-
 struct StagedEmit {
     uint8_t* t1; uint8_t* t2; uint8_t* t3;   // this lane's first row inside the warp's L1 / L2 / L3 tile, at its column
     unsigned mask;                           // bit l set = level l+1 requested
@@ -229,15 +174,6 @@ struct StagedEmit {
         q[0] = (uint16_t)Hh[0]; q[1] = (uint16_t)Hh[1]; q[2] = (uint16_t)Hh[2];
     }
 };
-// Lane (cx, ry) of a warp that owns a whole 128 x 64 item (16 rows per lane, tiles 32/16/8 rows).
-WHD StagedEmit staged_emit_full(uint8_t* tile, int cx, int ry, unsigned mask) {
-    StagedEmit e;
-    e.t1 = tile + kOut1Off + (ry * 8) * kOut1Row + cx * 24;
-    e.t2 = tile + kOut2Off + (ry * 4) * kOut2Row + cx * 12;
-    e.t3 = tile + kOut3Off + (ry * 2) * kOut3Row + cx * 6;
-    e.mask = mask;
-    return e;
-}
 // Lane (cx, ry) of a warp that owns half an item, 128 x 32 (8 rows per lane, tiles 16/8/4 rows).
 WHD StagedEmit staged_emit_half(uint8_t* tile, int cx, int ry, unsigned mask) {
     StagedEmit e;
@@ -248,75 +184,44 @@ WHD StagedEmit staged_emit_half(uint8_t* tile, int cx, int ry, unsigned mask) {
     return e;
 }
 
-// Reduce one chunk (16 px x kRows rows, kRows = 8 or 16): emits levels 1..3 through `em` and
-// returns the three 16 x kRows channel sums in acc4.  `load(r, A)` fills A[12] with the 48 bytes
-// of chunk row r (0..kRows-1), border-extended.
-template <int kRows, class Loader, class Emit>
-WHD void reduce_chunk(Loader& load, const Emit& em, uint32_t (&acc4)[3]) {
-    static_assert(kRows == 8 || kRows == 16, "a lane owns 8 or 16 rows");
-    acc4[0] = acc4[1] = acc4[2] = 0u;
+// Reduce one chunk (16 px x 8 rows): emits levels 1..3 through `em` and returns the three
+// 16 x 8 channel sums in acc.  `load(r, A)` fills A[12] with the 48 bytes of chunk row r
+// (0..7), border-extended.
+template <class Loader>
+WHD void reduce_chunk(Loader& load, const StagedEmit& em, uint32_t (&acc)[3]) {
     const bool want1 = em.want(0), want2 = em.want(1), want3 = em.want(2);
-#pragma unroll 1
-    for (int h8 = 0; h8 < kRows / 8; ++h8) {         // 8-row groups
-        uint32_t acc3[3] = {0u, 0u, 0u};
+    uint32_t acc3[3] = {0u, 0u, 0u};
 #pragma unroll
-        for (int q4 = 0; q4 < 2; ++q4) {             // two 4-row groups
-            uint32_t acc2[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+    for (int q4 = 0; q4 < 2; ++q4) {                 // two 4-row groups
+        uint32_t acc2[6] = {0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
-            for (int p2 = 0; p2 < 2; ++p2) {         // two row pairs
-                const int r = h8 * 8 + q4 * 4 + p2 * 2;
-                uint32_t A[12], B[12], T[12];
-                load(r, A);
-                load(r + 1, B);
-                level1_rowpair(A, B, T);
-                if (want1) {
-                    uint32_t Wd[6];
-                    icon1_words(T, Wd);
-                    em.icon1(r, Wd);
-                }
-                level2_accumulate(T, acc2);
+        for (int p2 = 0; p2 < 2; ++p2) {             // two row pairs
+            const int r = q4 * 4 + p2 * 2;
+            uint32_t A[12], B[12], T[12];
+            load(r, A);
+            load(r + 1, B);
+            level1_rowpair(A, B, T);
+            if (want1) {
+                uint32_t Wd[6];
+                icon1_words(T, Wd);
+                em.icon1(r, Wd);
             }
-            if (want2) {
-                uint32_t Wd[3];
-                icon2_words(acc2, Wd);
-                em.icon2(h8 * 8 + q4 * 4, Wd);
-            }
-            level3_accumulate(acc2, acc3);
+            level2_accumulate(T, acc2);
         }
-        if (want3) {
-            uint32_t Hh[3];
-            icon3_halves(acc3, Hh);
-            em.icon3(h8 * 8, Hh);
+        if (want2) {
+            uint32_t Wd[3];
+            icon2_words(acc2, Wd);
+            em.icon2(q4 * 4, Wd);
         }
-        level4_accumulate(acc3, acc4);
+        level3_accumulate(acc2, acc3);
     }
-}
-
-// Levels 4..6 of one lane.  cx = chunk column (0..7), ry = row group (0..3) inside the 128x64
-// item; s5 / s6 = the 32x32 / 64x64 sums of the lane's 2x2 / 4x4 lane group.
-WHD void emit_tail(const IconSink& sk, int x0, int y0, int cx, int ry, const uint32_t (&acc4)[3],
-                   const uint32_t (&s5)[3], const uint32_t (&s6)[3]) {
-    if (sk.icon[3] != nullptr) {
-        const int oy = y0 >> 4, ox = x0 >> 4;
-        if (oy < sk.h[3] && ox < sk.w[3]) {
-            uint8_t* p = sk.icon[3] + (int64_t)oy * sk.pitch[3] + (int64_t)ox * 3;
-            p[0] = (uint8_t)(acc4[0] >> 8); p[1] = (uint8_t)(acc4[1] >> 8); p[2] = (uint8_t)(acc4[2] >> 8);
-        }
+    if (want3) {
+        uint32_t Hh[3];
+        icon3_halves(acc3, Hh);
+        em.icon3(0, Hh);
     }
-    if (sk.icon[4] != nullptr && (cx & 1) == 0 && (ry & 1) == 0) {
-        const int oy = y0 >> 5, ox = x0 >> 5;
-        if (oy < sk.h[4] && ox < sk.w[4]) {
-            uint8_t* p = sk.icon[4] + (int64_t)oy * sk.pitch[4] + (int64_t)ox * 3;
-            p[0] = (uint8_t)(s5[0] >> 10); p[1] = (uint8_t)(s5[1] >> 10); p[2] = (uint8_t)(s5[2] >> 10);
-        }
-    }
-    if (sk.icon[5] != nullptr && (cx & 3) == 0 && ry == 0) {
-        const int oy = y0 >> 6, ox = x0 >> 6;
-        if (oy < sk.h[5] && ox < sk.w[5]) {
-            uint8_t* p = sk.icon[5] + (int64_t)oy * sk.pitch[5] + (int64_t)ox * 3;
-            p[0] = (uint8_t)(s6[0] >> 12); p[1] = (uint8_t)(s6[1] >> 12); p[2] = (uint8_t)(s6[2] >> 12);
-        }
-    }
+    acc[0] = acc[1] = acc[2] = 0u;
+    level4_accumulate(acc3, acc);
 }
 
 // Levels 4..6 when a warp owns half an item (128 x 32; lane = cx + 8*ry owns rows ry*8..ry*8+7).
@@ -388,7 +293,7 @@ struct ChunkSrc {
     const uint8_t* smem;      // chunk origin inside the stage (row stride kStageRowBytes)
     const uint8_t* gcol;      // kSmem: image + x0*3 ; kStrip: strip + (x0 - Wa)*3   (row 0)
     int64_t gpitch;           // row pitch of gcol's plane
-    int x0, y0, rows, H, Hp_max;     // rows = rows owned by the lane (8 or 16)
+    int x0, y0, rows, H, Hp_max;     // rows = rows owned by the lane (8)
     int nvalid;               // kEdge: pixels of the chunk that are inside the image (0..15)
     int rep_off;              // kEdge: byte offset of pixel W-1 relative to the chunk's row start (may be < 0)
     int border_type;
@@ -517,16 +422,15 @@ WHD void load_chunk_row(const ChunkSrc& cs, int r, uint32_t (&A)[12]) {
     load48_global(cs.gcol + (int64_t)ym * cs.gpitch, A);
 }
 
-// One lane's share of a work item up to level 4.
-template <int kRows, class Emit>
-WHD void reduce_lane(const ChunkSrc& cs, const Emit& em, uint32_t (&acc4)[3]) {
+// One lane's share of a work item: its 16 px x 8 rows, levels 1..3 emitted, 16 x 8 sums returned.
+WHD void reduce_lane(const ChunkSrc& cs, const StagedEmit& em, uint32_t (&acc)[3]) {
     if (chunk_is_interior(cs)) {
         const uint8_t* sm = cs.smem;
         auto loader = [sm](int r, uint32_t (&A)[12]) { load48_stage(sm + r * kStageRowBytes, A); };
-        reduce_chunk<kRows>(loader, em, acc4);
+        reduce_chunk(loader, em, acc);
     } else {
         auto loader = [&cs](int r, uint32_t (&A)[12]) { load_chunk_row(cs, r, A); };
-        reduce_chunk<kRows>(loader, em, acc4);
+        reduce_chunk(loader, em, acc);
     }
 }
 

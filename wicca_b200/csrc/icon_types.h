@@ -11,11 +11,9 @@ constexpr int kItemH = 64;            // rows per work item = 2^kMaxFused
 constexpr int kChunkPx = 16;          // pixels per lane per row
 constexpr int kStageRowBytes = kItemW * 3;            // 384
 constexpr int kStageBytes = kStageRowBytes * kItemH;  // 24576
-// per-warp output tiles of levels 1..3 (dense, handed to TMA store)
+// per-warp output tiles of levels 1..3 (dense, handed to TMA store); a warp owns half an item
+// (128 x 32 px): L1 16 x 192 B, L2 8 x 96 B, L3 4 x 48 B
 constexpr int kOut1Row = 192, kOut2Row = 96, kOut3Row = 48;            // bytes per tile row
-constexpr int kOut1Off = 0, kOut2Off = 32 * kOut1Row, kOut3Off = kOut2Off + 16 * kOut2Row;   // 0, 6144, 7680
-constexpr int kOutStageBytes = 8192;
-// half-item tiles (a warp owns 128 x 32): L1 16 x 192, L2 8 x 96, L3 4 x 48
 constexpr int kHalf1Off = 0, kHalf2Off = 16 * kOut1Row, kHalf3Off = kHalf2Off + 8 * kOut2Row;   // 0, 3072, 3840
 constexpr int kHalfStageBytes = 4096;
 constexpr int kStripPitch = 256;      // bytes per row of the right-edge strip (<= 78 px * 3)
@@ -23,8 +21,7 @@ constexpr int kStripPitch = 256;      // bytes per row of the right-edge strip (
 // One image of a launch.  Lives in global memory (array indexed by image).
 struct alignas(128) IconImage {
     CUtensorMap tmap;            // 2-D uint32 view of the pitched image, box 96 x 64
-    CUtensorMap omap[3];         // uint8 views of the level 1..3 icons (boxes 192x32, 96x16, 48x8) for TMA store
-    CUtensorMap hmap[3];         // same icons, half-height boxes (192x16, 96x8, 48x4): one warp owns half an item
+    CUtensorMap hmap[3];         // uint8 views of the level 1..3 icons for TMA store, boxes 192x16, 96x8, 48x4
     const uint8_t* src;          // device, 16-byte aligned
     int64_t pitch;               // bytes, multiple of 16
     int H, W;
