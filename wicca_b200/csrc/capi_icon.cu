@@ -77,6 +77,13 @@ int strip_px(int W, int Wp_max) { return Wp_max - (W & ~(kChunkPx - 1)); }
 // wrapping borders need the pre-built right strip.
 bool border_needs_strip(int border_type) { const int b = border_base(border_type); return b == 2 || b == 3 || b == 4; }
 
+// evict_first on the input stream helps only when the output stream is negligible (no level 1 or 2)
+int stream_hint_for(const IconOut* outs, int n) {
+    for (int i = 0; i < n; ++i)
+        if (outs[i].depth >= 1 && outs[i].depth <= 2) return 0;
+    return 1;
+}
+
 int64_t icon_pitch_for(int w, int C) { return align_up((int64_t)w * C, 128); }
 
 // Enqueue the general path for one depth (1..WICCA_MAX_DEPTH).  f32a/f32b: ping-pong scratch for
@@ -197,7 +204,8 @@ int icons_from_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int* d
             if (e != cudaSuccess) return cuda_fail(e, "edge strip kernel");
         }
         cudaError_t e = launch_icon_tma(d_im, d_strips, 1, him->items_x * him->items_y, border_base(border_type), bconst,
-                                        device_info(c.device).sm_count, icon_variant_from_env(), c.stream);
+                                        device_info(c.device).sm_count, icon_variant_from_env(),
+                                        stream_hint_for(fo.data(), (int)fo.size()), c.stream);
         if (e != cudaSuccess) return cuda_fail(e, "fused icon kernel");
     }
     for (int i : generic) {
@@ -375,7 +383,8 @@ int wicca_haar_icons_multi_dev(const uint8_t* d_src, int H, int W, int C, int64_
             if (e != cudaSuccess) return cuda_fail(e, "edge strip kernel");
         }
         cudaError_t e = launch_icon_tma(d_im, d_strips, 1, him.items_x * him.items_y, border_base(border_type), bconst,
-                                        device_info(device).sm_count, icon_variant_from_env(), stream);
+                                        device_info(device).sm_count, icon_variant_from_env(),
+                                        stream_hint_for(fo.data(), (int)fo.size()), stream);
         if (e != cudaSuccess) return cuda_fail(e, "fused icon kernel");
     }
     for (int i : generic) {
@@ -530,7 +539,7 @@ int wicca_plan_launch(wicca_plan* p, void* stream_v) {
             if (e != cudaSuccess) return cuda_fail(e, "edge strip kernel");
         }
         cudaError_t e = launch_icon_tma(d_im, d_strips, p->n, p->total_items, p->border, p->bconst, p->sm_count,
-                                        icon_variant_from_env(), stream);
+                                        icon_variant_from_env(), stream_hint_for(p->outs.data(), p->n_depths), stream);
         if (e != cudaSuccess) return cuda_fail(e, "fused icon kernel");
     } else {
         for (const auto& a : p->gen) {

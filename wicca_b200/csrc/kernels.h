@@ -8,8 +8,10 @@
 namespace wicca {
 
 // haar_icon.cu
+// stream_hint: 1 = mark the input L2::evict_first (use when no level <= 2 is written)
 cudaError_t launch_icon_tma(const IconImage* d_imgs, const uint8_t* const* d_strips, int n_images, int total_items,
-                            int border_type, int border_const, int sm_count, int variant, cudaStream_t stream);
+                            int border_type, int border_const, int sm_count, int variant, int stream_hint,
+                            cudaStream_t stream);
 cudaError_t launch_edge_strips(const IconImage* d_imgs, uint8_t* const* d_strips, int n_images, int max_rows,
                                int border_type, int border_const, cudaStream_t stream);
 cudaError_t launch_icon_generic(const GenericIconArgs& a, cudaStream_t stream);
