@@ -51,7 +51,7 @@ def _worker(rank, world, port, n_images, ret):
 
 def test_world_size_2_gloo_gather_in_order():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, 7, ret), nprocs=2, join=True)
     assert dict(ret) == {0: True, 1: True}

@@ -18,7 +18,7 @@ from wicca_b200.plan import IconPlan, pitch_bytes
 def main():
     n_img = int(os.environ.get("N_IMG", "30"))
     H, W = 6393, 8284
-    variants = [int(v) for v in os.environ.get("VARIANTS", "0,1,2,3,4").split(",")]
+    variants = [int(v) for v in os.environ.get("VARIANTS", "0,20,22,23").split(",")]
     depth_sets = json.loads(os.environ.get("DEPTH_SETS", "[[1,2,3,4,5,6],[1],[3],[6]]"))
     dev = torch.device("cuda:0")
     pitch = pitch_bytes(W, 3)

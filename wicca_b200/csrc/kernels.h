@@ -31,15 +31,17 @@ struct ResizeJob {           // one icon of a batch
     int sh, sw;
     int regime;              // 0 = same size (copy), 1 = integer-factor area, 2 = general area, 3 = bilinear "area mode"
     int isx, isy;            // regime 1: integer scale factors
-    int xoff, yoff;          // regime 2: offsets into the CSR row-pointer arrays (out_w+1 / out_h+1 entries)
-                             // regime 3: offsets into the bilinear tap arrays (out_w / out_h entries)
+    int xoff, yoff;          // regime 2: offsets into the AreaDesc array (out_w / out_h entries)
+                             // regime 3: offsets into the bilinear tap array (out_w / out_h entries)
 };
-struct AreaTap { int src; float w; };
+// computeResizeAreaTab for one destination index, in closed form: OpenCV's tap list is always
+// [left partial pixel] + n_full whole pixels of equal weight + [right partial pixel], in that order.
+// A missing partial tap has weight 0 (it is skipped, which is exact: x + 0 == x).
+struct AreaDesc { int s_left, s_first, n_full, s_right; float w_left, w_full, w_right; int pad; };
 struct LinTap { int i0, i1, c0, c1; };
 struct ResizeTables {
     const ResizeJob* jobs;
-    const int* rowptr;       // concatenated CSR row pointers (absolute indices into taps)
-    const AreaTap* taps;
+    const AreaDesc* area;
     const LinTap* lin;
 };
 cudaError_t launch_resize_norm(const ResizeTables& t, int n, int out_h, int out_w, int norm_mode, float* d_out,

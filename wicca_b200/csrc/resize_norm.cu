@@ -57,20 +57,23 @@ __global__ void resize_norm_kernel(ResizeTables t, int n, int out_h, int out_w, 
             if (j.isx == 2 && j.isy == 2) v = (uint8_t)((sum + 2) >> 2);
             else v = sat_rint_u8(__fmul_rn((float)sum, 1.0f / (float)(j.isx * j.isy)));
         } else if (j.regime == 2) {
-            const int xb = t.rowptr[j.xoff + dx], xe = t.rowptr[j.xoff + dx + 1];
-            const int yb = t.rowptr[j.yoff + dy], ye = t.rowptr[j.yoff + dy + 1];
-            float acc = 0.0f;
-            for (int ky = yb; ky < ye; ++ky) {
-                const AreaTap ty = t.taps[ky];
-                const uint8_t* p = s + (int64_t)ty.src * srow;
+            const AreaDesc ax = t.area[j.xoff + dx];
+            const AreaDesc ay = t.area[j.yoff + dy];
+            // one source row: buf = 0; buf += src * alpha over the x taps, in order (0 + x == x)
+            auto hrow = [&](int sy) -> float {
+                const uint8_t* p = s + (int64_t)sy * srow;
                 float h = 0.0f;
-                for (int kx = xb; kx < xe; ++kx) {
-                    const AreaTap tx = t.taps[kx];
-                    h = __fadd_rn(h, __fmul_rn((float)p[(int64_t)tx.src * 3], tx.w));
-                }
-                const float bh = __fmul_rn(ty.w, h);
-                acc = (ky == yb) ? bh : __fadd_rn(acc, bh);
-            }
+                if (ax.w_left != 0.0f) h = __fmul_rn((float)p[(int64_t)ax.s_left * 3], ax.w_left);
+                const uint8_t* q = p + (int64_t)ax.s_first * 3;
+                for (int kx = 0; kx < ax.n_full; ++kx) h = __fadd_rn(h, __fmul_rn((float)q[kx * 3], ax.w_full));
+                if (ax.w_right != 0.0f) h = __fadd_rn(h, __fmul_rn((float)p[(int64_t)ax.s_right * 3], ax.w_right));
+                return h;
+            };
+            // sum = beta * buf for the first y tap, sum += beta * buf for the others
+            float acc = 0.0f;
+            if (ay.w_left != 0.0f) acc = __fmul_rn(ay.w_left, hrow(ay.s_left));
+            for (int ky = 0; ky < ay.n_full; ++ky) acc = __fadd_rn(acc, __fmul_rn(ay.w_full, hrow(ay.s_first + ky)));
+            if (ay.w_right != 0.0f) acc = __fadd_rn(acc, __fmul_rn(ay.w_right, hrow(ay.s_right)));
             v = sat_rint_u8(acc);
         } else {
             const LinTap tx = t.lin[j.xoff + dx];

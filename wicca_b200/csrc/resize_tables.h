@@ -15,23 +15,21 @@ namespace wicca {
 struct ResizeSrc { const uint8_t* d_ptr; int h, w; int64_t pitch; };
 
 struct ResizeTableBlob {
-    std::vector<uint8_t> bytes;          // [jobs][rowptr][taps][lin], 256-byte aligned sections
-    size_t o_jobs = 0, o_rp = 0, o_tp = 0, o_ln = 0;
+    std::vector<uint8_t> bytes;          // [jobs][area][lin], 256-byte aligned sections
+    size_t o_jobs = 0, o_area = 0, o_ln = 0;
     ResizeTables view(const void* device_base) const {
         const uint8_t* b = (const uint8_t*)device_base;
         ResizeTables t;
         t.jobs = (const ResizeJob*)(b + o_jobs);
-        t.rowptr = (const int*)(b + o_rp);
-        t.taps = (const AreaTap*)(b + o_tp);
+        t.area = (const AreaDesc*)(b + o_area);
         t.lin = (const LinTap*)(b + o_ln);
         return t;
     }
 };
 
-// computeResizeAreaTab: CSR list of (src index, fp32 weight) per destination index.
-inline void area_tab(int ssize, int dsize, double scale, std::vector<int>& rowptr, std::vector<AreaTap>& taps) {
+// computeResizeAreaTab, one descriptor per destination index.
+inline void area_tab(int ssize, int dsize, double scale, std::vector<AreaDesc>& out) {
     for (int dx = 0; dx < dsize; ++dx) {
-        rowptr.push_back((int)taps.size());
         const double fsx1 = dx * scale;
         const double fsx2 = fsx1 + scale;
         const double cell = fmin(scale, ssize - fsx1);
@@ -39,11 +37,17 @@ inline void area_tab(int ssize, int dsize, double scale, std::vector<int>& rowpt
         int sx2 = (int)floor(fsx2);
         if (sx2 > ssize - 1) sx2 = ssize - 1;
         if (sx1 > sx2) sx1 = sx2;
-        if (sx1 - fsx1 > 1e-3) taps.push_back({sx1 - 1, (float)((sx1 - fsx1) / cell)});
-        for (int s = sx1; s < sx2; ++s) taps.push_back({s, (float)(1.0 / cell)});
-        if (fsx2 - sx2 > 1e-3) taps.push_back({sx2, (float)(fmin(fmin(fsx2 - sx2, 1.0), cell) / cell)});
+        AreaDesc d;
+        memset(&d, 0, sizeof d);
+        d.s_first = sx1;
+        d.n_full = sx2 - sx1;
+        d.w_full = (float)(1.0 / cell);
+        d.s_left = sx1 > 0 ? sx1 - 1 : 0;
+        d.s_right = sx2;
+        if (sx1 - fsx1 > 1e-3) d.w_left = (float)((sx1 - fsx1) / cell);
+        if (fsx2 - sx2 > 1e-3) d.w_right = (float)(fmin(fmin(fsx2 - sx2, 1.0), cell) / cell);
+        out.push_back(d);
     }
-    rowptr.push_back((int)taps.size());
 }
 
 // INTER_LINEAR tap computation in "area mode" (used by INTER_AREA when an axis is upscaled).
@@ -64,8 +68,7 @@ inline void linear_tab(int ssize, int dsize, double inv, double scale, std::vect
 
 inline ResizeTableBlob build_resize_tables(const std::vector<ResizeSrc>& srcs, int out_h, int out_w) {
     std::vector<ResizeJob> jobs(srcs.size());
-    std::vector<int> rowptr;
-    std::vector<AreaTap> taps;
+    std::vector<AreaDesc> area;
     std::vector<LinTap> lin;
     for (size_t i = 0; i < srcs.size(); ++i) {
         ResizeJob& j = jobs[i];
@@ -81,16 +84,10 @@ inline ResizeTableBlob build_resize_tables(const std::vector<ResizeSrc>& srcs, i
                 j.regime = 1; j.isx = isx; j.isy = isy;
             } else {
                 j.regime = 2;
-                std::vector<int> rp; std::vector<AreaTap> tp;
-                area_tab(j.sw, out_w, sx, rp, tp);
-                j.xoff = (int)rowptr.size();
-                for (int v : rp) rowptr.push_back(v + (int)taps.size());
-                taps.insert(taps.end(), tp.begin(), tp.end());
-                rp.clear(); tp.clear();
-                area_tab(j.sh, out_h, sy, rp, tp);
-                j.yoff = (int)rowptr.size();
-                for (int v : rp) rowptr.push_back(v + (int)taps.size());
-                taps.insert(taps.end(), tp.begin(), tp.end());
+                j.xoff = (int)area.size();
+                area_tab(j.sw, out_w, sx, area);
+                j.yoff = (int)area.size();
+                area_tab(j.sh, out_h, sy, area);
             }
         } else {
             j.regime = 3;
@@ -102,13 +99,11 @@ inline ResizeTableBlob build_resize_tables(const std::vector<ResizeSrc>& srcs, i
     }
     ResizeTableBlob b;
     b.o_jobs = 0;
-    b.o_rp = (size_t)align_up((int64_t)(b.o_jobs + jobs.size() * sizeof(ResizeJob)), 256);
-    b.o_tp = (size_t)align_up((int64_t)(b.o_rp + rowptr.size() * sizeof(int)), 256);
-    b.o_ln = (size_t)align_up((int64_t)(b.o_tp + taps.size() * sizeof(AreaTap)), 256);
+    b.o_area = (size_t)align_up((int64_t)(b.o_jobs + jobs.size() * sizeof(ResizeJob)), 256);
+    b.o_ln = (size_t)align_up((int64_t)(b.o_area + area.size() * sizeof(AreaDesc)), 256);
     b.bytes.assign(b.o_ln + lin.size() * sizeof(LinTap) + 256, 0);
     memcpy(b.bytes.data() + b.o_jobs, jobs.data(), jobs.size() * sizeof(ResizeJob));
-    if (!rowptr.empty()) memcpy(b.bytes.data() + b.o_rp, rowptr.data(), rowptr.size() * sizeof(int));
-    if (!taps.empty()) memcpy(b.bytes.data() + b.o_tp, taps.data(), taps.size() * sizeof(AreaTap));
+    if (!area.empty()) memcpy(b.bytes.data() + b.o_area, area.data(), area.size() * sizeof(AreaDesc));
     if (!lin.empty()) memcpy(b.bytes.data() + b.o_ln, lin.data(), lin.size() * sizeof(LinTap));
     return b;
 }
