@@ -190,7 +190,7 @@ def run_ours(args) -> int:
     dev = torch.device(f"cuda:{local}")
     distributed = world > 1
     if distributed:
-        os.environ["NCCL_DEBUG"] = os.environ.get("WICCA_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL logs to stdout by default: keep it to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -240,7 +240,7 @@ def run_ours(args) -> int:
     rng = np.random.default_rng(99 + rank)
     for i in range(n_host):
         p = C.c_void_p()
-        _capi.check(lib.wicca_host_alloc(C.byref(p), H * W * CH), "wicca_host_alloc")
+        _capi.check(lib.wicca_host_alloc_near(C.byref(p), H * W * CH, local), "wicca_host_alloc_near")
         arr = np.ctypeslib.as_array((C.c_uint8 * (H * W * CH)).from_address(p.value)).reshape(H, W, CH)
         arr[:] = rng.integers(0, 256, (H, W, CH), dtype=np.uint8)
         host_ptrs.append(p)
@@ -251,7 +251,7 @@ def run_ours(args) -> int:
     def pinned_array(shape):
         n = int(np.prod(shape))
         q = C.c_void_p()
-        _capi.check(lib.wicca_host_alloc(C.byref(q), n), "wicca_host_alloc")
+        _capi.check(lib.wicca_host_alloc_near(C.byref(q), n, local), "wicca_host_alloc_near")
         out_ptrs.append(q)
         return np.ctypeslib.as_array((C.c_uint8 * n).from_address(q.value)).reshape(shape)
 

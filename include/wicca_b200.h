@@ -87,6 +87,9 @@ WICCA_API int     wicca_icon_dim(int n, int depth);
 
 /* Page-locked host memory for inputs/outputs that should be DMA'd without a bounce copy. */
 WICCA_API int wicca_host_alloc(void** ptr, size_t bytes);
+/* Same, with the pages placed on the NUMA node of `device` (its PCIe root's local CPUs, from sysfs),
+ * so the DMA does not cross the socket interconnect.  device < 0: no placement. */
+WICCA_API int wicca_host_alloc_near(void** ptr, size_t bytes, int device);
 WICCA_API int wicca_host_free(void* ptr);
 
 /* ---- HaarCoder.get_small_copy  (host buffers in, host buffers out) ----- */

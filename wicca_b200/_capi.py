@@ -36,6 +36,7 @@ SIGNATURES = {
     "wicca_pitch_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "wicca_icon_dim": (C.c_int, [C.c_int, C.c_int]),
     "wicca_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "wicca_host_alloc_near": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]),
     "wicca_host_free": (C.c_int, [C.c_void_p]),
     "wicca_haar_icon_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double,
                                      C.c_void_p, C.c_int, C.POINTER(Timing)]),

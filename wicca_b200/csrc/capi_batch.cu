@@ -38,6 +38,7 @@ void add_times(WorkerResult& r, Ctx& c) {
 }
 
 int worker_body(const BatchArgs& a, int device, int first, int step, WorkerResult& res) {
+    ScopedAffinity bind(device);         // this worker (and the buffers it allocates) stays on the GPU's NUMA node
     CtxLease slot[2];
     bool busy[2] = {false, false};
     for (int s = 0; s < 2; ++s) {

@@ -2,11 +2,13 @@
 #include "host_common.h"
 
 #include <math.h>
+#include <ctype.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "icon_types.h"
 
+#include <sched.h>
 #include <thread>
 
 namespace wicca {
@@ -199,6 +201,67 @@ void destroy_all_ctx() {
         pool->all.clear();
         pool->idle.clear();
     }
+}
+
+// ---- NUMA locality ------------------------------------------------------------------------
+namespace {
+// Parses a sysfs cpulist ("0-15,64-79") into a cpu_set_t; returns the number of CPUs found.
+int parse_cpulist(const char* text, cpu_set_t* set) {
+    CPU_ZERO(set);
+    int n = 0;
+    const char* p = text;
+    while (*p) {
+        while (*p == ',' || *p == ' ' || *p == '\n') ++p;
+        if (!*p) break;
+        char* end = nullptr;
+        long a = strtol(p, &end, 10);
+        if (end == p) break;
+        long b = a;
+        p = end;
+        if (*p == '-') { b = strtol(p + 1, &end, 10); p = end; }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET((int)c, set); ++n; }
+    }
+    return n;
+}
+
+bool device_cpuset(int device, cpu_set_t* set) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return false; }
+    for (char* q = bus; *q; ++q) *q = (char)tolower(*q);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return false;
+    char text[1024] = {0};
+    const size_t got = fread(text, 1, sizeof text - 1, f);
+    fclose(f);
+    if (got == 0) return false;
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return false;
+    cpu_set_t local;
+    if (parse_cpulist(text, &local) == 0) return false;
+    CPU_AND(set, &local, &allowed);                 // stay inside the cgroup / taskset of the process
+    return CPU_COUNT(set) > 0;
+}
+}  // namespace
+
+ScopedAffinity::ScopedAffinity(int device) {
+    static_assert(sizeof(saved) >= sizeof(cpu_set_t), "affinity mask does not fit");
+    if (device < 0 || getenv("WICCA_NO_NUMA_BIND")) return;
+    cpu_set_t want;
+    if (!device_cpuset(device, &want)) return;
+    cpu_set_t old;
+    if (sched_getaffinity(0, sizeof old, &old) != 0) return;
+    if (sched_setaffinity(0, sizeof want, &want) != 0) return;
+    memcpy(saved, &old, sizeof old);
+    active = true;
+}
+
+ScopedAffinity::~ScopedAffinity() {
+    if (!active) return;
+    cpu_set_t old;
+    memcpy(&old, saved, sizeof old);
+    sched_setaffinity(0, sizeof old, &old);
 }
 
 int upload_image_async(Ctx& c, const uint8_t* src, int H, int64_t row_bytes, int64_t stride, int64_t pitch) {

@@ -89,6 +89,16 @@ int encode_icon_tmap(CUtensorMap* tm, const void* d_icon, int h, int64_t w_bytes
 
 bool is_pinned_host(const void* p);
 
+// NUMA locality: CPUs attached to the same socket / PCIe root as `device` (from sysfs; empty when unknown).
+// ScopedAffinity binds the calling thread to them for its lifetime, so that page-locked memory
+// allocated meanwhile lands on the GPU's own NUMA node and staging copies stay local.
+struct ScopedAffinity {
+    explicit ScopedAffinity(int device);
+    ~ScopedAffinity();
+    bool active = false;
+    unsigned long saved[16] = {};
+};
+
 // Host image (rows `stride` bytes apart) -> c.d_src (rows `pitch` bytes apart), asynchronously on c.stream.
 // Page-locked sources are DMA'd directly; pageable ones are staged band by band through the pinned
 // buffer c.h_in by a few helper threads, so the CPU copy of band k+1 overlaps the DMA of band k.
