@@ -190,7 +190,8 @@ def run_ours(args) -> int:
     dev = torch.device(f"cuda:{local}")
     distributed = world > 1
     if distributed:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL logs to stdout by default: keep it to the one JSON line
+        if not os.environ.get("WICCA_KEEP_NCCL_DEBUG"):
+            os.environ.pop("NCCL_DEBUG", None)      # NCCL prints its banner on stdout; keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():

@@ -95,3 +95,16 @@ def test_plan_fused_epilogue_config4():
                 assert np.array_equal(out8.cpu().numpy(), exp8), (target, d)
                 assert np.array_equal(out.cpu().numpy(), ro.preprocess_input(exp8, mode_name)), (target, d, mode_name)
     plan.close()
+
+
+def test_torch_bridge_cuda_tensor():
+    import torch
+    from wicca_b200.torch_bridge import icons_from_cuda_tensor
+    for (h, w) in [(640, 1024), (777, 1301)]:                 # aligned rows (direct) and unaligned rows (staged)
+        img = gen_input("noise", h * 3 + w, h, w, 3)
+        t = torch.from_numpy(img).cuda()
+        outs = icons_from_cuda_tensor(t, [1, 3, 6, 7], border_type=4)
+        torch.cuda.synchronize()
+        for d, o in zip([1, 3, 6, 7], outs):
+            assert o.shape == (-(-h // 2 ** d), -(-w // 2 ** d), 3)
+            assert np.array_equal(o.cpu().numpy(), ho.haar_icon_blocksum(img, d, 4)), (h, w, d)

@@ -356,31 +356,38 @@ int wicca_haar_icons_multi_dev(const uint8_t* d_src, int H, int W, int C, int64_
             f32_elems = std::max(f32_elems, level8_elems(H, W, C, d));
         }
     }
-    // Scratch (descriptor, strip, fp32 ping-pong) comes from a leased context; it stays leased
-    // until the work enqueued on the caller's stream has finished.
-    CtxLease L;
-    rc = acquire_ctx(device, &L.c);
-    if (rc) return rc;
-    Ctx& c = *L.c;
+    // Scratch (descriptor, strip, fp32 ping-pong) is stream-ordered memory: allocated and freed on the
+    // caller's stream, so the call only enqueues and never synchronises.
+    struct AsyncScratch {
+        cudaStream_t stream;
+        std::vector<void*> ptrs;
+        cudaError_t get(void** p, size_t bytes) {
+            cudaError_t e = cudaMallocAsync(p, bytes, stream);
+            if (e == cudaSuccess) ptrs.push_back(*p);
+            return e;
+        }
+        ~AsyncScratch() { for (void* p : ptrs) cudaFreeAsync(p, stream); }
+    } scratch{stream, {}};
+    float* f32a = nullptr;
+    float* f32b = nullptr;
     if (f32_elems) {
-        WICCA_CUDA(c.d_f32a.reserve(f32_elems * sizeof(float)));
-        WICCA_CUDA(c.d_f32b.reserve(f32_elems * sizeof(float) / 4 + 16));
+        WICCA_CUDA(scratch.get((void**)&f32a, f32_elems * sizeof(float)));
+        WICCA_CUDA(scratch.get((void**)&f32b, f32_elems * sizeof(float) / 4 + 16));
     }
     if (!fo.empty()) {
         IconImage him;
         rc = fill_icon_image(&him, d_src, H, W, src_pitch, fo.data(), (int)fo.size(), 0);
         if (rc) return rc;
         uint8_t* strip = nullptr;
-        if (border_needs_strip(border_type) && strip_px(W, him.Wp_max) > 0) {
-            WICCA_CUDA(c.d_strip.reserve((size_t)H * kStripPitch));
-            strip = (uint8_t*)c.d_strip.p;
-        }
-        WICCA_CUDA(c.d_desc.reserve(sizeof(IconImage) + 64));
-        // pageable source: the runtime stages it before returning, so the stack copy is safe
-        WICCA_CUDA(cudaMemcpyAsync(c.d_desc.p, &him, sizeof(IconImage), cudaMemcpyHostToDevice, stream));
-        WICCA_CUDA(cudaMemcpyAsync((uint8_t*)c.d_desc.p + sizeof(IconImage), &strip, sizeof(strip), cudaMemcpyHostToDevice, stream));
-        const IconImage* d_im = (const IconImage*)c.d_desc.p;
-        uint8_t* const* d_strips = (uint8_t* const*)((uint8_t*)c.d_desc.p + sizeof(IconImage));
+        if (border_needs_strip(border_type) && strip_px(W, him.Wp_max) > 0)
+            WICCA_CUDA(scratch.get((void**)&strip, (size_t)H * kStripPitch));
+        uint8_t* d_desc = nullptr;
+        WICCA_CUDA(scratch.get((void**)&d_desc, sizeof(IconImage) + 64));
+        // pageable sources: the runtime stages them before returning, so the stack copies are safe
+        WICCA_CUDA(cudaMemcpyAsync(d_desc, &him, sizeof(IconImage), cudaMemcpyHostToDevice, stream));
+        WICCA_CUDA(cudaMemcpyAsync(d_desc + sizeof(IconImage), &strip, sizeof(strip), cudaMemcpyHostToDevice, stream));
+        const IconImage* d_im = (const IconImage*)d_desc;
+        uint8_t* const* d_strips = (uint8_t* const*)(d_desc + sizeof(IconImage));
         if (strip) {
             cudaError_t e = launch_edge_strips(d_im, d_strips, 1, H, border_base(border_type), bconst, stream);
             if (e != cudaSuccess) return cuda_fail(e, "edge strip kernel");
@@ -391,13 +398,10 @@ int wicca_haar_icons_multi_dev(const uint8_t* d_src, int H, int W, int C, int64_
         if (e != cudaSuccess) return cuda_fail(e, "fused icon kernel");
     }
     for (int i : generic) {
-        rc = enqueue_generic(d_src, src_pitch, H, W, C, depths[i], border_type, bconst, d_dsts[i], dst_pitches[i],
-                             (float*)c.d_f32a.p, (float*)c.d_f32b.p, stream);
+        rc = enqueue_generic(d_src, src_pitch, H, W, C, depths[i], border_type, bconst, d_dsts[i], dst_pitches[i], f32a,
+                             f32b, stream);
         if (rc) return rc;
     }
-    // The scratch must outlive the enqueued work: wait for it before the lease ends.  (The plan
-    // API below owns its scratch and is the fully asynchronous path.)
-    WICCA_CUDA(cudaStreamSynchronize(stream));
     return 0;
 }
 
