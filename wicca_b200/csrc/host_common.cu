@@ -272,11 +272,14 @@ int upload_image_async(Ctx& c, const uint8_t* src, int H, int64_t row_bytes, int
         return 0;
     }
     WICCA_CUDA(c.h_in.reserve(total));
-    int rows_per_band = (int)(((size_t)8 << 20) / (size_t)row_bytes);
+    int rows_per_band = (int)(((size_t)4 << 20) / (size_t)row_bytes);
     if (rows_per_band < 1) rows_per_band = 1;
     const int n_bands = (H + rows_per_band - 1) / rows_per_band;
     unsigned hw = std::thread::hardware_concurrency();
-    int n_threads = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
+    int n_threads = (int)(hw / 2);                     // staging is a plain memcpy: bandwidth scales with cores
+    if (n_threads > 8) n_threads = 8;
+    if (n_threads < 1) n_threads = 1;
+    if (const char* e = getenv("WICCA_UPLOAD_THREADS")) n_threads = atoi(e) > 0 ? atoi(e) : n_threads;
     if (n_threads > n_bands) n_threads = n_bands;
     std::vector<cudaError_t> errs(n_threads, cudaSuccess);
     auto work = [&](int t) {
