@@ -181,6 +181,19 @@ WICCA_API int wicca_icon_resize_norm_f32(const uint8_t* const* icons, const int*
                                          int out_h, int out_w, int norm_mode,
                                          float* dst, uint8_t* dst_u8, int device, wicca_timing* t);
 
+/* Classifier-ready batches straight from host images: for every image i, icon = get_small_copy(image, depth),
+ * dst_icons[i] = preprocess(cv2.resize(icon, (out_w, out_h), INTER_AREA)) and, when dst_images is not NULL,
+ * dst_images[i] = preprocess(cv2.resize(image, (out_w, out_h), INTER_AREA)) - the body of
+ * ClassifierProcessor._get_img_batch (classifying_tools.py:312-323) plus preprocess_input and the float32
+ * cast (:286-287).  Both outputs are host float32 (n_images, out_h, out_w, 3); the icon never leaves the
+ * GPU.  3-channel images only; image i runs on devices[i % n_devices] with double-buffered uploads. */
+WICCA_API int wicca_batch_classifier_inputs_f32(const uint8_t* const* srcs, const int* Hs, const int* Ws,
+                                                const int64_t* strides, int n_images, int depth,
+                                                int border_type, double border_const,
+                                                int out_h, int out_w, int norm_mode,
+                                                float* dst_icons, float* dst_images,
+                                                const int* devices, int n_devices, wicca_timing* t);
+
 /* Device-resident variant for sources that already live in HBM - icons, or the full-size source images of
  * the reference's other branch, cv2.resize(image, shape, interpolation) (classifying_tools.py:315).
  * d_srcs[i]: device uint8 (hs[i], ws[i], 3), rows pitches[i] bytes apart.  Enqueues on `stream`. */

@@ -93,3 +93,22 @@ def test_source_image_branch_n1(coder):
     torch.cuda.synchronize()
     assert np.array_equal(out8.cpu().numpy(), exp)
     assert np.array_equal(out.cpu().numpy(), ro.preprocess_input(exp, "tf"))
+
+
+@pytest.mark.parametrize("depth,shape,mode", [(2, (224, 224), "tf"), (3, (331, 331), "caffe"), (5, (224, 224), "torch"),
+                                              (1, (240, 299), "identity")])
+def test_classifier_batches_one_call(coder, depth, shape, mode):
+    """The fused _get_img_batch + preprocess_input call: both branches, ragged images, all regimes."""
+    from oracle import haar_oracle as ho
+    rng = np.random.default_rng(depth)
+    imgs = [gen_input("noise", 700 + i, 1500 + int(rng.integers(-200, 200)), 2100 + int(rng.integers(-300, 300)), 3)
+            for i in range(5)]
+    batch_images, batch_icons = coder.classifier_batches(imgs, depth, shape, mode)
+    ow, oh = shape
+    assert batch_images.shape == batch_icons.shape == (5, oh, ow, 3) and batch_icons.dtype == np.float32
+    exp_icons = ro.preprocess_input(np.stack([ro.resize_area(ho.haar_icon_blocksum(im, depth), ow, oh) for im in imgs]), mode)
+    exp_images = ro.preprocess_input(np.stack([ro.resize_area(im, ow, oh) for im in imgs]), mode)
+    assert np.array_equal(batch_icons, exp_icons)
+    assert np.array_equal(batch_images, exp_images)
+    only_icons = coder.classifier_batches(imgs, depth, shape, mode, with_source=False)
+    assert only_icons[0] is None and np.array_equal(only_icons[1], exp_icons)

@@ -148,6 +148,15 @@ def row_batch():
              s=dt, MP_per_s=mp / dt, h2d_GBps=byt / dt / 1e9, stage_ms_sum=coder.last_timing)
     from oracle import haar_oracle as ho
     assert np.array_equal(out[5][1], ho.haar_icon_blocksum(images[5], 3))
+    # configs[3] end to end: host images -> (batch_images, batch_icons) float32 for a classifier, batch of 30
+    for depth, target in ((3, 224), (3, 331), (2, 224)):
+        coder.classifier_batches(images[:4], depth, (target, target), "tf")
+        t0 = time.perf_counter()
+        bi, bc = coder.classifier_batches(images[:30], depth, (target, target), "tf")
+        dt = time.perf_counter() - t0
+        mp = sum(a.shape[0] * a.shape[1] for a in images[:30]) / 1e6
+        emit(row="A3+A5+A6+N1 one call", config=f"30 pinned host images -> depth-{depth} icons + source -> two ({target},{target},3) tf batches",
+             s=dt, MP_per_s=mp / dt, batches_of_30_per_s=1 / dt, stage_ms_sum=coder.last_timing)
     for p in ptrs:
         lib.wicca_host_free(p)
 

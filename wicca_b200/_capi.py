@@ -62,6 +62,9 @@ SIGNATURES = {
                                          C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "wicca_haar_inverse_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_void_p]),
+    "wicca_batch_classifier_inputs_f32": (C.c_int, [C.POINTER(C.c_void_p), c_intp, c_intp, c_i64p, C.c_int, C.c_int, C.c_int,
+                                                    C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, c_intp,
+                                                    C.c_int, C.POINTER(Timing)]),
     "wicca_resize_norm_dev": (C.c_int, [C.POINTER(C.c_void_p), c_intp, c_intp, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "wicca_icon_resize_norm_f32": (C.c_int, [C.POINTER(C.c_void_p), c_intp, c_intp, C.c_int, C.c_int, C.c_int, C.c_int,

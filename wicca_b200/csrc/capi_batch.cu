@@ -11,6 +11,8 @@
 #include <vector>
 
 #include "host_common.h"
+#include "kernels.h"
+#include "resize_tables.h"
 
 using namespace wicca;
 
@@ -123,6 +125,132 @@ extern "C" int wicca_batch_icons_u8(const uint8_t* const* srcs, const int* Hs, c
     for (int k = 0; k < nw; ++k)
         threads.emplace_back([&, k] {
             results[k].rc = worker_body(a, devs[k], k, nw, results[k]);
+            if (results[k].rc) results[k].msg = last_error_ref();
+        });
+    for (auto& th : threads) th.join();
+    wicca_timing sum = {0, 0, 0, 0};
+    for (auto& r : results) {
+        if (r.rc) { last_error_ref() = r.msg; return r.rc; }
+        sum.h2d_ms += (float)r.h2d; sum.kernel_ms += (float)r.kernel; sum.d2h_ms += (float)r.d2h; sum.total_ms += (float)r.total;
+    }
+    if (t) *t = sum;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Classifier-ready batches straight from host images: the body of ClassifierProcessor._get_img_batch
+// (classifying_tools.py:312-323: resize(image), get_small_copy(image, depth), resize(icon), np.stack)
+// followed by preprocess_input + float32 cast (:286-287), with the icon never leaving the device.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct ClsArgs {
+    const uint8_t* const* srcs; const int* Hs; const int* Ws; const int64_t* strides; int n_images;
+    int depth, border_type, bconst, out_h, out_w, norm_mode;
+    float* dst_icons; float* dst_images;
+};
+
+int cls_worker(const ClsArgs& a, int device, int first, int step, WorkerResult& res) {
+    ScopedAffinity bind(device);
+    CtxLease slot[2];
+    bool busy[2] = {false, false};
+    for (int s = 0; s < 2; ++s) {
+        int rc = acquire_ctx(device, &slot[s].c);
+        if (rc) return rc;
+    }
+    size_t max_src = 0;
+    for (int i = first; i < a.n_images; i += step)
+        max_src = std::max(max_src, (size_t)wicca_pitch_bytes(a.Ws[i], 3) * a.Hs[i] + 256);
+    const size_t slot_elems = (size_t)a.out_h * a.out_w * 3;
+    const int n_out = a.dst_images ? 2 : 1;
+    for (int s = 0; s < 2; ++s) {
+        Ctx& c = *slot[s].c;
+        WICCA_CUDA(c.d_src.reserve(max_src));
+        WICCA_CUDA(c.d_f32a.reserve(slot_elems * sizeof(float) * n_out));
+        WICCA_CUDA(c.h_out.reserve(slot_elems * sizeof(float) * n_out));
+    }
+    int j = 0;
+    for (int i = first; i < a.n_images; i += step, ++j) {
+        Ctx& c = *slot[j & 1].c;
+        if (busy[j & 1]) {
+            WICCA_CUDA(cudaStreamSynchronize(c.stream));
+            c.flush_pending();
+            add_times(res, c);
+        }
+        const int H = a.Hs[i], W = a.Ws[i];
+        const int64_t rowb = (int64_t)W * 3;
+        const int64_t stride = (a.strides && a.strides[i]) ? a.strides[i] : rowb;
+        const int64_t pitch = wicca_pitch_bytes(W, 3);
+        WICCA_CUDA(cudaEventRecord(c.ev[0], c.stream));
+        int rc = upload_image_async(c, a.srcs[i], H, rowb, stride, pitch);
+        if (rc) { cudaStreamSynchronize(c.stream); c.pending.clear(); return rc; }
+        WICCA_CUDA(cudaEventRecord(c.ev[1], c.stream));
+        std::vector<IconOut> outs;
+        rc = enqueue_icons_resident(c, H, W, 3, pitch, &a.depth, 1, a.border_type, a.bconst, outs);
+        if (rc) { cudaStreamSynchronize(c.stream); c.pending.clear(); return rc; }
+        // tap tables for [icon] (+ [source image]); each resize launch handles one image into its slot
+        std::vector<ResizeSrc> rs;
+        rs.push_back({outs[0].d_ptr, outs[0].h, outs[0].w, outs[0].pitch});
+        if (a.dst_images) rs.push_back({(const uint8_t*)c.d_src.p, H, W, pitch});
+        const ResizeTableBlob blob = build_resize_tables(rs, a.out_h, a.out_w);
+        WICCA_CUDA(c.h_bounce.reserve(blob.bytes.size()));
+        WICCA_CUDA(c.d_misc.reserve(blob.bytes.size()));
+        memcpy(c.h_bounce.p, blob.bytes.data(), blob.bytes.size());
+        WICCA_CUDA(cudaMemcpyAsync(c.d_misc.p, c.h_bounce.p, blob.bytes.size(), cudaMemcpyHostToDevice, c.stream));
+        cudaError_t e = launch_resize_norm(blob.view(c.d_misc.p), n_out, a.out_h, a.out_w, a.norm_mode, (float*)c.d_f32a.p,
+                                           nullptr, c.stream);
+        if (e != cudaSuccess) { cudaStreamSynchronize(c.stream); return cuda_fail(e, "resize/normalise kernel"); }
+        WICCA_CUDA(cudaEventRecord(c.ev[2], c.stream));
+        // D2H through the slot's pinned buffer (the destination batch is usually pageable NumPy memory)
+        WICCA_CUDA(cudaMemcpyAsync(c.h_out.p, c.d_f32a.p, slot_elems * sizeof(float) * n_out, cudaMemcpyDeviceToHost, c.stream));
+        c.pending.push_back({a.dst_icons + (size_t)i * slot_elems, c.h_out.p, slot_elems * sizeof(float)});
+        if (a.dst_images)
+            c.pending.push_back({a.dst_images + (size_t)i * slot_elems, (const float*)c.h_out.p + slot_elems, slot_elems * sizeof(float)});
+        WICCA_CUDA(cudaEventRecord(c.ev[3], c.stream));
+        busy[j & 1] = true;
+    }
+    for (int s = 0; s < 2; ++s)
+        if (busy[s]) {
+            WICCA_CUDA(cudaStreamSynchronize(slot[s].c->stream));
+            slot[s].c->flush_pending();
+            add_times(res, *slot[s].c);
+        }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int wicca_batch_classifier_inputs_f32(const uint8_t* const* srcs, const int* Hs, const int* Ws,
+                                                 const int64_t* strides, int n_images, int depth, int border_type,
+                                                 double border_const, int out_h, int out_w, int norm_mode,
+                                                 float* dst_icons, float* dst_images, const int* devices, int n_devices,
+                                                 wicca_timing* t) {
+    if (t) memset(t, 0, sizeof(*t));
+    if (n_images < 0) return fail(WICCA_EINVAL, "negative image count");
+    if (n_images == 0) return 0;
+    if (!srcs || !Hs || !Ws || !dst_icons) return fail(WICCA_EINVAL, "null array");
+    if (depth < 1) return fail(WICCA_EDEPTH, "transform depth must be >= 1");
+    if (out_h <= 0 || out_w <= 0 || norm_mode < 0 || norm_mode > 3) return fail(WICCA_EINVAL, "bad target size / mode");
+    if (n_devices <= 0) return fail(WICCA_EDEVICE, "need at least one device");
+    for (int i = 0; i < n_images; ++i) {
+        int rc = validate_icon_args(srcs[i], Hs[i], Ws[i], 3, &depth, 1, border_type);
+        if (rc) return rc;
+        if (strides && strides[i] && strides[i] < (int64_t)Ws[i] * 3) return fail(WICCA_EINVAL, "strides[%d] < W*3", i);
+    }
+    std::vector<int> devs(n_devices);
+    for (int k = 0; k < n_devices; ++k) {
+        devs[k] = devices ? devices[k] : k;
+        int rc = check_device(devs[k]);
+        if (rc) return rc;
+    }
+    ClsArgs a{srcs, Hs, Ws, strides, n_images, depth, border_type, saturate_u8(border_const), out_h, out_w, norm_mode,
+              dst_icons, dst_images};
+    const int nw = n_devices < n_images ? n_devices : n_images;
+    std::vector<WorkerResult> results(nw);
+    std::vector<std::thread> threads;
+    for (int k = 0; k < nw; ++k)
+        threads.emplace_back([&, k] {
+            results[k].rc = cls_worker(a, devs[k], k, nw, results[k]);
             if (results[k].rc) results[k].msg = last_error_ref();
         });
     for (auto& th : threads) th.join();

@@ -18,13 +18,6 @@ using namespace wicca;
 
 namespace {
 
-struct IconOut {          // one requested depth of one image
-    int depth = 0;
-    int h = 0, w = 0;
-    uint8_t* d_ptr = nullptr;
-    int64_t pitch = 0;
-};
-
 bool needs_padding(int H, int W, int depth) {
     if (depth <= 0) return false;
     const int64_t r = (int64_t)1 << depth;
@@ -148,10 +141,10 @@ int validate_icon_args(const void* src, int H, int W, int C, const int* depths, 
 // Shared by the one-shot host call and the batch workers: image already on the device in
 // c.d_src (pitched); computes every requested depth > 0 and copies the icons to the host
 // destinations.  Enqueues on c.stream; records ev[2] after the kernels and ev[3] after D2H.
-int icons_from_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int* depths, int n_depths, int border_type,
-                        int bconst, uint8_t* const* dsts) {
+int enqueue_icons_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int* depths, int n_depths, int border_type,
+                           int bconst, std::vector<IconOut>& outs) {
     const uint8_t* d_src = (const uint8_t*)c.d_src.p;
-    std::vector<IconOut> outs(n_depths);
+    outs.assign(n_depths, IconOut());
     std::vector<int> fused, generic;
     const bool can_fuse = fused_eligible(d_src, pitch, C);
     size_t icon_bytes = 0, f32_elems = 0;
@@ -214,6 +207,14 @@ int icons_from_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int* d
         if (rc) return rc;
     }
     WICCA_CUDA(cudaEventRecord(c.ev[2], c.stream));
+    return 0;
+}
+
+int icons_from_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int* depths, int n_depths, int border_type,
+                        int bconst, uint8_t* const* dsts) {
+    std::vector<IconOut> outs;
+    int rc0 = enqueue_icons_resident(c, H, W, C, pitch, depths, n_depths, border_type, bconst, outs);
+    if (rc0) return rc0;
     // D2H: straight into page-locked destinations; pageable ones go through the pinned bounce buffer
     // (a pageable cudaMemcpyAsync would block the host until the whole stream has drained).
     size_t bounce = 0;

@@ -53,7 +53,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};                // start, h2d done, kernels done, d2h done, spare x2
     DevBuf d_src, d_icons, d_desc, d_strip, d_f32a, d_f32b, d_misc;
-    PinBuf h_desc, h_bounce, h_in;
+    PinBuf h_desc, h_bounce, h_in, h_out;
     // Results bound for pageable host memory are DMA'd into h_bounce (so the copy is truly
     // asynchronous) and moved to their destination after the stream has been synchronised.
     struct Pending { void* dst; const void* src; size_t bytes; };
@@ -107,8 +107,18 @@ int upload_image_async(Ctx& c, const uint8_t* src, int H, int64_t row_bytes, int
 
 int icon_variant_from_env();
 
-// capi_icon.cu: image already resident in c.d_src (pitched); enqueue every depth > 0 on c.stream and
-// the D2H copies of the icons; records c.ev[2] (kernels done) and c.ev[3] (D2H done).
+struct IconOut {          // one requested depth of one image
+    int depth = 0;
+    int h = 0, w = 0;
+    uint8_t* d_ptr = nullptr;   // device icon (rows `pitch` bytes apart)
+    int64_t pitch = 0;
+};
+
+// capi_icon.cu: image already resident in c.d_src (pitched).  enqueue_icons_resident launches the
+// kernels for every depth > 0 on c.stream (icons stay in c.d_icons, described by `outs`) and records
+// c.ev[2]; icons_from_resident additionally enqueues their D2H copies and records c.ev[3].
+int enqueue_icons_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int* depths, int n_depths, int border_type,
+                           int bconst, std::vector<IconOut>& outs);
 int icons_from_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int* depths, int n_depths, int border_type,
                         int bconst, uint8_t* const* dsts);
 int validate_icon_args(const void* src, int H, int W, int C, const int* depths, int n_depths, int border_type);

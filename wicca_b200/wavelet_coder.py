@@ -279,6 +279,52 @@ class HaarCoder(WaveletCoder):
         self._tls.timing = t.as_dict()
         return (out, out_u8) if return_uint8 else out
 
+    def classifier_batches(self, images: Sequence[np.ndarray], transform_depth: int, shape: tuple[int, int],
+                           mode: str = "tf", border_type: int = BORDER_REPLICATE, border_constant: int = 0,
+                           with_source: bool = True, devices: Sequence[int] | None = None):
+        """What ``ClassifierProcessor._get_img_batch`` + ``preprocess_input`` produce for one batch
+        (``classifying_tools.py:312-323`` and ``:286-287``), in one call: ``(batch_images, batch_icons)``
+        as float32 ``(B, h, w, 3)`` arrays, where ``batch_icons[i]`` comes from
+        ``get_small_copy(images[i], transform_depth)`` and ``batch_images[i]`` from ``images[i]`` itself,
+        both through ``cv2.resize(..., shape, INTER_AREA)`` and the ``mode`` normalisation.  The icon
+        never leaves the GPU.  ``batch_images`` is ``None`` when ``with_source`` is false."""
+        if mode not in NORM_MODES:
+            raise ValueError(f"unknown preprocess mode {mode!r}; expected one of {sorted(NORM_MODES)}")
+        depth = _as_depth(transform_depth)
+        if depth < 1:
+            raise ValueError("transform_depth must be >= 1")
+        ow, oh = int(shape[0]), int(shape[1])
+        if ow <= 0 or oh <= 0:
+            raise ValueError("target shape must be positive")
+        views = []
+        for img in images:
+            validate_image(img)
+            _check_layout(img, (depth,), border_type)
+            if img.ndim != 3 or img.shape[2] != 3:
+                raise ValueError("classifier batches need (H, W, 3) images")
+            views.append(_row_major_view(img))
+        n = len(views)
+        icons = np.empty((n, oh, ow, 3), dtype=np.float32)
+        srcs_out = np.empty((n, oh, ow, 3), dtype=np.float32) if with_source else None
+        if n == 0:
+            return srcs_out, icons
+        lib = _capi.load()
+        if devices is None:
+            devices = list(range(max(1, lib.wicca_device_count())))
+        srcs = (C.c_void_p * n)(*[v.ctypes.data for v, _ in views])
+        hs = (C.c_int * n)(*[v.shape[0] for v, _ in views])
+        ws = (C.c_int * n)(*[v.shape[1] for v, _ in views])
+        strides = (C.c_int64 * n)(*[s for _, s in views])
+        dev = (C.c_int * len(devices))(*[int(x) for x in devices])
+        t = _capi.Timing()
+        rc = lib.wicca_batch_classifier_inputs_f32(srcs, hs, ws, strides, n, depth, int(border_type), float(border_constant),
+                                                   oh, ow, NORM_MODES[mode], icons.ctypes.data,
+                                                   srcs_out.ctypes.data if with_source else None, dev, len(devices),
+                                                   C.byref(t))
+        _capi.check(rc, "wicca_batch_classifier_inputs_f32")
+        self._tls.timing = t.as_dict()
+        return srcs_out, icons
+
     @property
     def last_timing(self) -> dict | None:
         """Device-side stage times (ms) of this thread's last call."""
