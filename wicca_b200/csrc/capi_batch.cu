@@ -198,7 +198,7 @@ int cls_worker(const ClsArgs& a, int device, int first, int step, WorkerResult& 
         memcpy(c.h_bounce.p, blob.bytes.data(), blob.bytes.size());
         WICCA_CUDA(cudaMemcpyAsync(c.d_misc.p, c.h_bounce.p, blob.bytes.size(), cudaMemcpyHostToDevice, c.stream));
         cudaError_t e = launch_resize_norm(blob.view(c.d_misc.p), n_out, a.out_h, a.out_w, a.norm_mode, (float*)c.d_f32a.p,
-                                           nullptr, c.stream);
+                                           nullptr, blob.max_src_w, blob.n_area, blob.n_other, c.stream);
         if (e != cudaSuccess) { cudaStreamSynchronize(c.stream); return cuda_fail(e, "resize/normalise kernel"); }
         WICCA_CUDA(cudaEventRecord(c.ev[2], c.stream));
         // D2H through the slot's pinned buffer (the destination batch is usually pageable NumPy memory)

@@ -619,7 +619,7 @@ int wicca_plan_resize_norm(wicca_plan* p, int depth_index, int out_h, int out_w,
         }
     }
     cudaError_t e = launch_resize_norm(ep->blob.view(ep->d_tables.p), p->n, out_h, out_w, norm_mode, d_dst, d_dst_u8,
-                                       (cudaStream_t)stream_v);
+                                       ep->blob.max_src_w, ep->blob.n_area, ep->blob.n_other, (cudaStream_t)stream_v);
     if (e != cudaSuccess) return cuda_fail(e, "resize/normalise kernel");
     return 0;
 }

@@ -20,7 +20,7 @@ extern "C" int wicca_icon_resize_norm_f32(const uint8_t* const* icons, const int
     size_t src_bytes = 0;
     for (int i = 0; i < n; ++i) {
         if (!icons[i] || hs[i] <= 0 || ws[i] <= 0) return fail(WICCA_EINVAL, "icon %d is empty", i);
-        src_bytes += (size_t)align_up((int64_t)hs[i] * ws[i] * 3, 256);
+        src_bytes += (size_t)(align_up((int64_t)ws[i] * 3, 128) * hs[i]);
     }
     CtxLease L;
     int rc = acquire_ctx(device, &L.c);
@@ -30,8 +30,9 @@ extern "C" int wicca_icon_resize_norm_f32(const uint8_t* const* icons, const int
     std::vector<ResizeSrc> srcs(n);
     size_t off = 0;
     for (int i = 0; i < n; ++i) {
-        srcs[i] = {(const uint8_t*)c.d_src.p + off, hs[i], ws[i], (int64_t)ws[i] * 3};
-        off += (size_t)align_up((int64_t)hs[i] * ws[i] * 3, 256);
+        const int64_t pitch = align_up((int64_t)ws[i] * 3, 128);      // 16-byte aligned rows for the row-streaming kernel
+        srcs[i] = {(const uint8_t*)c.d_src.p + off, hs[i], ws[i], pitch};
+        off += (size_t)(pitch * hs[i]);
     }
     const ResizeTableBlob blob = build_resize_tables(srcs, out_h, out_w);
     WICCA_CUDA(c.h_desc.reserve(blob.bytes.size()));
@@ -45,10 +46,12 @@ extern "C" int wicca_icon_resize_norm_f32(const uint8_t* const* icons, const int
     WICCA_CUDA(cudaEventRecord(c.ev[0], c.stream));
     WICCA_CUDA(cudaMemcpyAsync(c.d_desc.p, c.h_desc.p, blob.bytes.size(), cudaMemcpyHostToDevice, c.stream));
     for (int i = 0; i < n; ++i)
-        WICCA_CUDA(cudaMemcpyAsync((void*)srcs[i].d_ptr, icons[i], (size_t)hs[i] * ws[i] * 3, cudaMemcpyHostToDevice, c.stream));
+        WICCA_CUDA(cudaMemcpy2DAsync((void*)srcs[i].d_ptr, (size_t)srcs[i].pitch, icons[i], (size_t)ws[i] * 3, (size_t)ws[i] * 3,
+                                     (size_t)hs[i], cudaMemcpyHostToDevice, c.stream));
     WICCA_CUDA(cudaEventRecord(c.ev[1], c.stream));
     cudaError_t e = launch_resize_norm(blob.view(c.d_desc.p), n, out_h, out_w, norm_mode, (float*)c.d_f32a.p,
-                                       dst_u8 ? (uint8_t*)c.d_misc.p : nullptr, c.stream);
+                                       dst_u8 ? (uint8_t*)c.d_misc.p : nullptr, blob.max_src_w, blob.n_area, blob.n_other,
+                                       c.stream);
     if (e != cudaSuccess) return cuda_fail(e, "resize/normalise kernel");
     WICCA_CUDA(cudaEventRecord(c.ev[2], c.stream));
     WICCA_CUDA(cudaMemcpyAsync(dst, c.d_f32a.p, out_elems * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
@@ -87,7 +90,8 @@ extern "C" int wicca_resize_norm_dev(const uint8_t* const* d_srcs, const int* hs
     WICCA_CUDA(cudaMallocAsync(&d_tables, blob.bytes.size(), stream));          // stream-ordered scratch
     // pageable source: staged by the runtime before the call returns, so `blob` may go out of scope
     cudaError_t e = cudaMemcpyAsync(d_tables, blob.bytes.data(), blob.bytes.size(), cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess) e = launch_resize_norm(blob.view(d_tables), n, out_h, out_w, norm_mode, d_dst, d_dst_u8, stream);
+    if (e == cudaSuccess) e = launch_resize_norm(blob.view(d_tables), n, out_h, out_w, norm_mode, d_dst, d_dst_u8,
+                                                      blob.max_src_w, blob.n_area, blob.n_other, stream);
     cudaError_t e2 = cudaFreeAsync(d_tables, stream);
     if (e != cudaSuccess) return cuda_fail(e, "resize/normalise kernel");
     if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFreeAsync");

@@ -45,6 +45,6 @@ struct ResizeTables {
     const LinTap* lin;
 };
 cudaError_t launch_resize_norm(const ResizeTables& t, int n, int out_h, int out_w, int norm_mode, float* d_out,
-                               uint8_t* d_out_u8, cudaStream_t stream);
+                               uint8_t* d_out_u8, int max_src_w, int n_area, int n_other, cudaStream_t stream);
 
 }  // namespace wicca

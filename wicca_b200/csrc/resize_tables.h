@@ -17,6 +17,7 @@ struct ResizeSrc { const uint8_t* d_ptr; int h, w; int64_t pitch; };
 struct ResizeTableBlob {
     std::vector<uint8_t> bytes;          // [jobs][area][lin], 256-byte aligned sections
     size_t o_jobs = 0, o_area = 0, o_ln = 0;
+    int max_src_w = 0, n_area = 0, n_other = 0;      // launch hints: widest source, images per regime class
     ResizeTables view(const void* device_base) const {
         const uint8_t* b = (const uint8_t*)device_base;
         ResizeTables t;
@@ -98,6 +99,10 @@ inline ResizeTableBlob build_resize_tables(const std::vector<ResizeSrc>& srcs, i
         }
     }
     ResizeTableBlob b;
+    for (const ResizeJob& jj : jobs) {
+        if (jj.sw > b.max_src_w) b.max_src_w = jj.sw;
+        if (jj.regime == 2) ++b.n_area; else ++b.n_other;
+    }
     b.o_jobs = 0;
     b.o_area = (size_t)align_up((int64_t)(b.o_jobs + jobs.size() * sizeof(ResizeJob)), 256);
     b.o_ln = (size_t)align_up((int64_t)(b.o_area + area.size() * sizeof(AreaDesc)), 256);
