@@ -26,6 +26,9 @@ __device__ __forceinline__ float norm_value(float v, int c, int mode) {
     }
 }
 
+// uint8 -> float without the quarter-rate I2F: 0x4B000000 | v is the float 2^23 + v, exactly.
+__device__ __forceinline__ float u8_to_float(uint32_t v) { return __fsub_rn(__uint_as_float(0x4B000000u | v), 8388608.0f); }
+
 __device__ __forceinline__ uint8_t sat_rint_u8(float x) {
     const float r = rintf(x);                       // round half to even, like cvRound
     return (uint8_t)fminf(fmaxf(r, 0.0f), 255.0f);
@@ -77,10 +80,11 @@ __global__ void resize_norm_kernel(ResizeTables t, int n, int out_h, int out_w, 
             auto hrow = [&](int sy) -> float {
                 const uint8_t* p = s + (int64_t)sy * srow;
                 float h = 0.0f;
-                if (ax.w_left != 0.0f) h = __fmul_rn((float)p[(int64_t)ax.s_left * 3], ax.w_left);
+                if (ax.w_left != 0.0f) h = __fmul_rn(u8_to_float(p[(int64_t)ax.s_left * 3]), ax.w_left);
                 const uint8_t* q = p + (int64_t)ax.s_first * 3;
-                for (int kx = 0; kx < ax.n_full; ++kx) h = __fadd_rn(h, __fmul_rn((float)q[kx * 3], ax.w_full));
-                if (ax.w_right != 0.0f) h = __fadd_rn(h, __fmul_rn((float)p[(int64_t)ax.s_right * 3], ax.w_right));
+#pragma unroll 4
+                for (int kx = 0; kx < ax.n_full; ++kx) h = __fadd_rn(h, __fmul_rn(u8_to_float(q[kx * 3]), ax.w_full));
+                if (ax.w_right != 0.0f) h = __fadd_rn(h, __fmul_rn(u8_to_float(p[(int64_t)ax.s_right * 3]), ax.w_right));
                 return h;
             };
             // sum = beta * buf for the first y tap, sum += beta * buf for the others
@@ -171,10 +175,12 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
             if (threadIdx.x + m * kRowsThreads < n_elems) {
                 const uint8_t* p = s + ch[m];
                 float h = 0.0f;
-                if (ax[m].w_left != 0.0f) h = __fmul_rn((float)p[ax[m].s_left * 3], ax[m].w_left);
+                if (ax[m].w_left != 0.0f) h = __fmul_rn(u8_to_float(p[ax[m].s_left * 3]), ax[m].w_left);
                 const uint8_t* q = p + ax[m].s_first * 3;
-                for (int kx = 0; kx < ax[m].n_full; ++kx) h = __fadd_rn(h, __fmul_rn((float)q[kx * 3], ax[m].w_full));
-                if (ax[m].w_right != 0.0f) h = __fadd_rn(h, __fmul_rn((float)p[ax[m].s_right * 3], ax[m].w_right));
+                const float wf = ax[m].w_full;
+#pragma unroll 4
+                for (int kx = 0; kx < ax[m].n_full; ++kx) h = __fadd_rn(h, __fmul_rn(u8_to_float(q[kx * 3]), wf));
+                if (ax[m].w_right != 0.0f) h = __fadd_rn(h, __fmul_rn(u8_to_float(p[ax[m].s_right * 3]), ax[m].w_right));
                 const float bh = __fmul_rn(beta, h);
                 acc[m] = (k == 0) ? bh : __fadd_rn(acc[m], bh);
             }
