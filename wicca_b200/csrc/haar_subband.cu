@@ -160,6 +160,10 @@ forward_tile_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int W
                     TileGeom g) {
     __shared__ float s_a[32 * 32 * C];
     __shared__ float s_b[16 * 16 * C];
+    // level-1 rows are handed from "one thread = one block, all channels" to "one lane = one float of
+    // the row" through this per-warp buffer, so that every store instruction covers 128 contiguous bytes
+    __shared__ float s_st[kTileThreads / 32][4][32 * C];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
     const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
     const int y0 = ty * kTile, x0 = tx * kTile;
@@ -203,7 +207,33 @@ forward_tile_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int W
             float vll[C], vhl[C], vlh[C], vhh[C];
             analyse<C>(a, b, cc, d, vll, vhl, vlh, vhh);
             const int gy = ty * n + by, gx = tx * n + bx;
-            if (gy < hl_ && gx < wl_) {
+            if (l == 1) {
+                // the warp owns block row `by` (bx == lane): stage, then store lane-contiguous rows
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    s_st[warp][0][lane * C + c] = vhl[c]; s_st[warp][1][lane * C + c] = vlh[c];
+                    s_st[warp][2][lane * C + c] = vhh[c]; s_st[warp][3][lane * C + c] = vll[c];
+                }
+                __syncwarp();
+                if (gy < hl_) {
+                    const int gx0 = tx * n;
+                    int valid = (wl_ - gx0) * C;                 // floats of this row segment inside the sub-band
+                    if (valid > 32 * C) valid = 32 * C;
+                    float* r_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(wl_ + gx0) * C;
+                    float* r_lh = g.plane + (int64_t)(gy + hl_) * g.pl_stride + (int64_t)gx0 * C;
+                    float* r_hh = r_lh + (int64_t)wl_ * C;
+                    float* r_ll = g.ll + (int64_t)gy * g.ll_stride + (int64_t)gx0 * C;
+#pragma unroll
+                    for (int k = 0; k < C; ++k) {
+                        const int jj = lane + 32 * k;
+                        if (jj < valid) {
+                            r_hl[jj] = s_st[warp][0][jj]; r_lh[jj] = s_st[warp][1][jj]; r_hh[jj] = s_st[warp][2][jj];
+                            if (last) r_ll[jj] = s_st[warp][3][jj];
+                        }
+                    }
+                }
+                __syncwarp();
+            } else if (gy < hl_ && gx < wl_) {
                 float* q_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(wl_ + gx) * C;
                 float* q_lh = g.plane + (int64_t)(gy + hl_) * g.pl_stride + (int64_t)gx * C;
                 float* q_hh = q_lh + (int64_t)wl_ * C;
@@ -231,6 +261,8 @@ __global__ void __launch_bounds__(kTileThreads)
 inverse_tile_kernel(TileGeom g, float* __restrict__ out, int64_t out_stride) {
     __shared__ float s_a[32 * 32 * C];
     __shared__ float s_b[16 * 16 * C];
+    __shared__ float s_st[kTileThreads / 32][2][64 * C];    // per-warp staging of two output rows (see forward kernel)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
     const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
     const float* in_f = nullptr;
@@ -263,11 +295,27 @@ inverse_tile_kernel(TileGeom g, float* __restrict__ out, int64_t out_stride) {
                 a[c] = __fadd_rn(s0, d0); b[c] = __fadd_rn(s1, d1); cc[c] = __fsub_rn(s0, d0); d[c] = __fsub_rn(s1, d1);
             }
             if (l == 1) {
-                if (inside) {       // 2 rows x 2 pixels x C consecutive floats per thread, consecutive threads adjacent
-                    float* q = out + (int64_t)(2 * gy) * out_stride + (int64_t)(2 * gx) * C;
+                // the warp owns block row `by` (bx == lane): two output rows of 64*C floats, staged and then
+                // stored with lane-contiguous addresses (128 contiguous bytes per store instruction)
 #pragma unroll
-                    for (int c = 0; c < C; ++c) { q[c] = a[c]; q[C + c] = b[c]; q[out_stride + c] = cc[c]; q[out_stride + C + c] = d[c]; }
+                for (int c = 0; c < C; ++c) {
+                    s_st[warp][0][lane * 2 * C + c] = a[c]; s_st[warp][0][lane * 2 * C + C + c] = b[c];
+                    s_st[warp][1][lane * 2 * C + c] = cc[c]; s_st[warp][1][lane * 2 * C + C + c] = d[c];
                 }
+                __syncwarp();
+                if (gy < hl_) {
+                    const int gx0 = tx * n;
+                    int valid = (wl_ - gx0) * 2 * C;
+                    if (valid > 64 * C) valid = 64 * C;
+                    float* r0 = out + (int64_t)(2 * gy) * out_stride + (int64_t)(2 * gx0) * C;
+                    float* r1 = r0 + out_stride;
+#pragma unroll
+                    for (int k = 0; k < 2 * C; ++k) {
+                        const int jj = lane + 32 * k;
+                        if (jj < valid) { r0[jj] = s_st[warp][0][jj]; r1[jj] = s_st[warp][1][jj]; }
+                    }
+                }
+                __syncwarp();
             } else {
                 const int out_row = 2 * n * C;
                 float* q = out_f + (2 * by) * out_row + (2 * bx) * C;
