@@ -48,7 +48,8 @@ def test_inverse_matches_oracle_on_arbitrary_coefficients(coder):
 
 
 def test_config3_large_round_trip(coder):
-    """BASELINE.json configs[2] (scaled to fit the test budget: 8192x8192x3; bench.py runs 16384^2)."""
+    """Host-buffer entry points on a large image (8192x8192x3; the 16384^2 case of BASELINE.json configs[2]
+    runs device-resident in test_config3_device_resident_16384 below)."""
     img = gen_input("noise", 3, 8192, 8192, 3)
     for depth in (1, 6):
         co = coder.forward(img, depth)
@@ -57,3 +58,35 @@ def test_config3_large_round_trip(coder):
         assert np.max(np.abs(rec - img.astype(np.float32))) == 0.0
         # linearity / energy: LL mean equals image mean (Haar LL is a block average)
         assert abs(float(co[0].mean(dtype=np.float64)) - float(img.mean(dtype=np.float64))) < 1e-6
+
+
+def test_config3_device_resident_16384():
+    """BASELINE.json configs[2]: forward DWT + inverse IDWT round trip, all sub-bands kept, on a
+    16384 x 16384 x 3 image, reconstruction error check (device-resident entry points)."""
+    import ctypes as C
+    import torch
+    from wicca_b200 import _capi
+    from wicca_b200.plan import pitch_bytes
+    lib = _capi.load()
+    S = 16384
+    pitch = pitch_bytes(S, 3)
+    g = torch.Generator(device="cuda:0"); g.manual_seed(7)
+    img = torch.randint(0, 256, (S, pitch), dtype=torch.uint8, device="cuda:0", generator=g)
+    coeffs = torch.empty((S, S, 3), dtype=torch.float32, device="cuda:0")
+    work = torch.empty((S * S * 3 * 5 // 16 + 64,), dtype=torch.float32, device="cuda:0")
+    rec = torch.empty((S, S, 3), dtype=torch.float32, device="cuda:0")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ref = img[:, : S * 3].reshape(S, S, 3)
+    for depth in (1, 3, 6):
+        _capi.check(lib.wicca_haar_forward_dev(img.data_ptr(), S, S, 3, pitch, depth, 1, 0.0, coeffs.data_ptr(),
+                                               work.data_ptr(), 0, st), "forward_dev")
+        _capi.check(lib.wicca_haar_inverse_dev(coeffs.data_ptr(), S, S, 3, depth, rec.data_ptr(), work.data_ptr(), 0, st),
+                    "inverse_dev")
+        torch.cuda.synchronize()
+        assert float((rec - ref.float()).abs().max().item()) == 0.0, depth
+        # LL of the plane, truncated, is the reference's icon (spot check against the oracle on a corner crop)
+        n = S >> depth
+        ll = coeffs[: 64, : 64].cpu().numpy()
+        crop = ref[: 64 << depth, : 64 << depth].cpu().numpy()
+        assert np.array_equal(ll.astype(np.uint8), ho.haar_icon_blocksum(crop, depth)), depth
+        assert n * (1 << depth) == S
