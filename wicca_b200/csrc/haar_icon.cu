@@ -91,9 +91,7 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-// ------------------------------------------------------------------------------------------
-// The one-pass kernel
-// ------------------------------------------------------------------------------------------
+
 // Work item of a CTA's k-th turn.  run_len consecutive turns take horizontally adjacent items, so
 // the narrow output rows of neighbouring items reach L2 together and merge into full lines.
 __device__ __forceinline__ int item_index(int k, int run_len) {
