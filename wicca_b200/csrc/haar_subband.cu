@@ -11,6 +11,7 @@
 // because consecutive threads own consecutive (x, c) elements of an output row.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "haar_math.cuh"
 #include "kernels.h"
@@ -328,10 +329,238 @@ inverse_tile_kernel(TileGeom g, float* __restrict__ out, int64_t out_stride) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Forward, depth >= 2: the same 64 x 64 tile, but each lane owns a whole 4 x 4-pixel patch (one
+// level-2 block): levels 1 and 2 are computed in registers, levels 3 and 4 with warp shuffles, and
+// only the sixteen LL_4 values of the tile cross warps (one barrier instead of one per level).
+// Warp w covers level-2 blocks rows 4*(w>>1)..+3, columns 8*(w&1)..+7 (lane = 8*ly + lx).
+// ------------------------------------------------------------------------------------------
+// Store R x (UNIT*UPR) staged floats as rows of a sub-band: store instruction k writes the 32 consecutive
+// staged floats 32k..32k+31, i.e. 32/UNIT whole UNIT-float pieces, each inside one row.
+template <int R, int UNIT, int UPR, int PITCH, bool kCheck>
+__device__ __forceinline__ void store_staged_impl(const float* stage, int lane, float* base, int stride, int rows_valid,
+                                                  int seg_valid) {
+    constexpr int K = R * UNIT * UPR / 32;               // store instructions
+    constexpr int PER = 32 / UNIT;                       // pieces per instruction
+    const int piece = lane / UNIT, lo = lane % UNIT;
+    float* lbase = base + lo;
+    const float* lstage = stage + lo;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        // piece 0 of the instruction is at a compile-time position; the others are written as lane-dependent
+        // deltas that repeat across k, so the compiler keeps them in a few registers
+        const int r0 = (k * PER) / UPR, j0 = ((k * PER) % UPR) * UNIT;
+        int so = r0 * PITCH + j0, go = r0 * stride + j0, r = r0, j = j0;
+#pragma unroll
+        for (int q = 1; q < PER; ++q) {
+            const int rq = (k * PER + q) / UPR, jq = ((k * PER + q) % UPR) * UNIT;
+            const int sel = (piece == q) ? 1 : 0;
+            so += sel * ((rq - r0) * PITCH + (jq - j0));
+            go += sel * ((rq - r0) * stride + (jq - j0));
+            if (kCheck) { r += sel * (rq - r0); j += sel * (jq - j0); }
+        }
+        if (!kCheck || (r < rows_valid && j + lo < seg_valid)) lbase[go] = lstage[so];
+    }
+}
+template <int C, int R, int UNIT, int UPR, int PITCH>
+__device__ __forceinline__ void store_staged(const float* stage, int lane, float* base, int stride, bool full,
+                                             int rows_valid, int seg_valid) {
+    if (full) store_staged_impl<R, UNIT, UPR, PITCH, false>(stage, lane, base, stride, rows_valid, seg_valid);
+    else store_staged_impl<R, UNIT, UPR, PITCH, true>(stage, lane, base, stride, rows_valid, seg_valid);
+}
+
+template <int C>
+__global__ void __launch_bounds__(kTileThreads, C <= 3 ? 4 : 3)
+forward_patch_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int W, int border_type, int border_const,
+                     TileGeom g) {
+    constexpr int kPitch1 = 16 * C + 8;                        // staged level-1 row (+8: float2 writes hit every bank once)
+    __shared__ __align__(16) float s_st[kTileThreads / 32][8 * kPitch1];   // per-warp staging of one sub-band of one level
+    __shared__ float s_ll2[16][16][C], s_ll3[8][8][C];
+    __shared__ int s_arrived;                                  // warps that have published their LL_2 values
+    if (threadIdx.x == 0) s_arrived = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wy = warp >> 1, wx = warp & 1, ly = lane >> 3, lx = lane & 7;
+    const int tile = blockIdx.x;
+    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+    const int b2y = 4 * wy + ly, b2x = 8 * wx + lx;                       // level-2 block inside the tile
+    const int py = ty * kTile + 4 * b2y, px = tx * kTile + 4 * b2x;       // top-left pixel of the lane's patch
+    const bool interior = (ty * kTile + kTile <= H) && (tx * kTile + kTile <= W);
+    const bool full = (ty * kTile + kTile <= g.Hp) && (tx * kTile + kTile <= g.Wp);   // no clipped sub-band rows
+    const bool wide = ((uintptr_t)src % 4 == 0) && (pitch % 4 == 0);
+    const float fc = (float)border_const;
+    float* stage = s_st[warp];
+    const int stride = (int)g.pl_stride;
+
+    // ---- the 4 x 4 patch as floats
+    float pix[4][4][C];
+    if (interior && wide) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (int64_t)(py + r) * pitch + (int64_t)px * C);
+            uint32_t wds[C];
+#pragma unroll
+            for (int k = 0; k < C; ++k) wds[k] = p[k];
+#pragma unroll
+            for (int b = 0; b < 4 * C; ++b) pix[r][b / C][b % C] = (float)((wds[b >> 2] >> (8 * (b & 3))) & 0xFFu);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int ym = border_index(py + r, H, border_type);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int xm = border_index(px + q, W, border_type);
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    pix[r][q][c] = (ym < 0 || xm < 0) ? fc : (float)src[(int64_t)ym * pitch + (int64_t)xm * C + c];
+            }
+        }
+    }
+    // ---- level 1: four 2 x 2 blocks per lane
+    float ll1[2][2][C], hl1[2][2][C], lh1[2][2][C], hh1[2][2][C];
+#pragma unroll
+    for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < 2; ++ix)
+            analyse<C>(pix[2 * iy][2 * ix], pix[2 * iy][2 * ix + 1], pix[2 * iy + 1][2 * ix], pix[2 * iy + 1][2 * ix + 1],
+                       ll1[iy][ix], hl1[iy][ix], lh1[iy][ix], hh1[iy][ix]);
+    {
+        const int h1 = g.Hp >> 1, w1 = g.Wp >> 1;
+        const int gy0 = ty * 32 + 8 * wy, gx0 = tx * 32 + 16 * wx;       // first level-1 block row / column of the warp
+        const int rows_valid = h1 - gy0, seg_valid = (w1 - gx0) * C;
+        float* base_hl = g.plane + (int64_t)gy0 * g.pl_stride + (int64_t)(w1 + gx0) * C;
+        float* base_lh = g.plane + (int64_t)(gy0 + h1) * g.pl_stride + (int64_t)gx0 * C;
+        float* base_hh = base_lh + (int64_t)w1 * C;
+        auto put = [&](const float (&v)[2][2][C]) {
+#pragma unroll
+            for (int iy = 0; iy < 2; ++iy) {
+                float2* q = reinterpret_cast<float2*>(stage + (2 * ly + iy) * kPitch1 + 2 * lx * C);
+#pragma unroll
+                for (int e = 0; e < C; ++e)
+                    q[e] = make_float2(v[iy][(2 * e) / C][(2 * e) % C], v[iy][(2 * e + 1) / C][(2 * e + 1) % C]);
+            }
+            __syncwarp();
+        };
+        put(hl1); store_staged<C, 8, 16, C, kPitch1>(stage, lane, base_hl, stride, full, rows_valid, seg_valid); __syncwarp();
+        put(lh1); store_staged<C, 8, 16, C, kPitch1>(stage, lane, base_lh, stride, full, rows_valid, seg_valid); __syncwarp();
+        put(hh1); store_staged<C, 8, 16, C, kPitch1>(stage, lane, base_hh, stride, full, rows_valid, seg_valid); __syncwarp();
+        if (g.levels == 1) {
+            put(ll1);
+            store_staged<C, 8, 16, C, kPitch1>(stage, lane, g.ll + (int64_t)gy0 * g.ll_stride + (int64_t)gx0 * C,
+                                               (int)g.ll_stride, full, rows_valid, seg_valid);
+            return;
+        }
+    }
+    // ---- level 2: one block per lane, straight from the level-1 LLs in registers
+    float ll2[C], hl2[C], lh2[C], hh2[C];
+    analyse<C>(ll1[0][0], ll1[0][1], ll1[1][0], ll1[1][1], ll2, hl2, lh2, hh2);
+    {
+        const int h2 = g.Hp >> 2, w2 = g.Wp >> 2;
+        const int gy0 = ty * 16 + 4 * wy, gx0 = tx * 16 + 8 * wx;
+        const int rows_valid = h2 - gy0, seg_valid = (w2 - gx0) * C;
+        constexpr int seg = 8 * C;                               // 4 rows of 8C floats = C store instructions
+        float* base_hl = g.plane + (int64_t)gy0 * g.pl_stride + (int64_t)(w2 + gx0) * C;
+        float* base_lh = g.plane + (int64_t)(gy0 + h2) * g.pl_stride + (int64_t)gx0 * C;
+        float* base_hh = base_lh + (int64_t)w2 * C;
+        auto put = [&](const float (&v)[C]) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) stage[ly * seg + lx * C + c] = v[c];
+            __syncwarp();
+        };
+        put(hl2); store_staged<C, 4, 8, C, seg>(stage, lane, base_hl, stride, full, rows_valid, seg_valid); __syncwarp();
+        put(lh2); store_staged<C, 4, 8, C, seg>(stage, lane, base_lh, stride, full, rows_valid, seg_valid); __syncwarp();
+        put(hh2); store_staged<C, 4, 8, C, seg>(stage, lane, base_hh, stride, full, rows_valid, seg_valid); __syncwarp();
+        if (g.levels == 2) {
+            put(ll2);
+            store_staged<C, 4, 8, C, seg>(stage, lane, g.ll + (int64_t)gy0 * g.ll_stride + (int64_t)gx0 * C, (int)g.ll_stride,
+                                          full, rows_valid, seg_valid);
+            return;
+        }
+    }
+    // ---- levels 3..6 need LL_2 of other warps: every warp publishes its 4 x 8 LL_2 values, and whichever warp
+    //      publishes last finishes the tile alone (nobody waits at a barrier)
+#pragma unroll
+    for (int c = 0; c < C; ++c) s_ll2[b2y][b2x][c] = ll2[c];
+    __syncwarp();
+    int is_last = 0;
+    if (lane == 0) { __threadfence_block(); is_last = (atomicAdd(&s_arrived, 1) == kTileThreads / 32 - 1); }
+    is_last = __shfl_sync(0xFFFFFFFFu, is_last, 0);
+    if (!is_last) return;
+    __threadfence_block();
+    auto write_details = [&](int level, int gy, int gx, const float (&hl)[C], const float (&lh)[C], const float (&hh)[C],
+                             const float (&ll)[C]) {
+        const int hL = g.Hp >> level, wL = g.Wp >> level;
+        if (gy >= hL || gx >= wL) return;
+        float* q_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(wL + gx) * C;
+        float* q_lh = g.plane + (int64_t)(gy + hL) * g.pl_stride + (int64_t)gx * C;
+        float* q_hh = q_lh + (int64_t)wL * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { q_hl[c] = hl[c]; q_lh[c] = lh[c]; q_hh[c] = hh[c]; }
+        if (g.levels == level) {
+            float* q_ll = g.ll + (int64_t)gy * g.ll_stride + (int64_t)gx * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) q_ll[c] = ll[c];
+        }
+    };
+    // level 3: 8 x 8 blocks, two per lane
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int by = (lane >> 3) + 4 * i, bx = lane & 7;
+        float ll[C], hl[C], lh[C], hh[C];
+        analyse<C>(s_ll2[2 * by][2 * bx], s_ll2[2 * by][2 * bx + 1], s_ll2[2 * by + 1][2 * bx], s_ll2[2 * by + 1][2 * bx + 1], ll,
+                   hl, lh, hh);
+        write_details(3, ty * 8 + by, tx * 8 + bx, hl, lh, hh, ll);
+#pragma unroll
+        for (int c = 0; c < C; ++c) s_ll3[by][bx][c] = ll[c];
+    }
+    if (g.levels == 3) return;
+    __syncwarp();
+    // level 4: 4 x 4 blocks on lanes 0..15 (lane = 4 * by + bx; the upper half-warp mirrors it and stores nothing)
+    float ll4[C];
+    {
+        const int by = (lane >> 2) & 3, bx = lane & 3;
+        float hl[C], lh[C], hh[C];
+        analyse<C>(s_ll3[2 * by][2 * bx], s_ll3[2 * by][2 * bx + 1], s_ll3[2 * by + 1][2 * bx], s_ll3[2 * by + 1][2 * bx + 1], ll4,
+                   hl, lh, hh);
+        if (lane < 16) write_details(4, ty * 4 + by, tx * 4 + bx, hl, lh, hh, ll4);
+    }
+    if (g.levels == 4) return;
+    // level 5: lane groups {m, m+1, m+4, m+5}
+    float ll5[C];
+    {
+        const int base = lane & 10;
+        float a[C], b[C], cc[C], d[C], hl[C], lh[C], hh[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            a[c] = __shfl_sync(0xFFFFFFFFu, ll4[c], base); b[c] = __shfl_sync(0xFFFFFFFFu, ll4[c], base + 1);
+            cc[c] = __shfl_sync(0xFFFFFFFFu, ll4[c], base + 4); d[c] = __shfl_sync(0xFFFFFFFFu, ll4[c], base + 5);
+        }
+        analyse<C>(a, b, cc, d, ll5, hl, lh, hh);
+        if (lane == base) write_details(5, ty * 2 + (lane >> 3), tx * 2 + ((lane >> 1) & 1), hl, lh, hh, ll5);
+    }
+    if (g.levels == 5) return;
+    // level 6: the four level-5 owners are lanes 0, 2, 8, 10
+    {
+        float a[C], b[C], cc[C], d[C], ll6[C], hl[C], lh[C], hh[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            a[c] = __shfl_sync(0xFFFFFFFFu, ll5[c], 0); b[c] = __shfl_sync(0xFFFFFFFFu, ll5[c], 2);
+            cc[c] = __shfl_sync(0xFFFFFFFFu, ll5[c], 8); d[c] = __shfl_sync(0xFFFFFFFFu, ll5[c], 10);
+        }
+        analyse<C>(a, b, cc, d, ll6, hl, lh, hh);
+        if (lane == 0) write_details(6, ty, tx, hl, lh, hh, ll6);
+    }
+}
+
 template <int C>
 static cudaError_t launch_forward_tiles(const uint8_t* d_src, int64_t pitch, int H, int W, int border_type,
                                         int border_const, const TileGeom& g, cudaStream_t stream) {
-    forward_tile_kernel<C><<<g.tiles_x * g.tiles_y, kTileThreads, 0, stream>>>(d_src, pitch, H, W, border_type, border_const, g);
+    // depth 1: one warp per full tile row (384-byte row segments); deeper: one 4 x 4 patch per lane, one barrier
+    if (getenv("WICCA_FORWARD_TILE"))
+        forward_tile_kernel<C><<<g.tiles_x * g.tiles_y, kTileThreads, 0, stream>>>(d_src, pitch, H, W, border_type, border_const, g);
+    else
+        forward_patch_kernel<C><<<g.tiles_x * g.tiles_y, kTileThreads, 0, stream>>>(d_src, pitch, H, W, border_type, border_const, g);
     return cudaGetLastError();
 }
 template <int C>
