@@ -7,11 +7,10 @@
 // of the reference's LL.  Coefficients are stored Mallat-style in one fp32 HWC plane of the
 // padded size: HL_l right of LL_l, LH_l below, HH_l diagonal.
 //
-// Every thread produces one coefficient quadruple; float4-free scalar stores are coalesced
-// because consecutive threads own consecutive (x, c) elements of an output row.
+// Two sets of kernels: per-level ones (any channel count, any depth; one thread per coefficient
+// quadruple) and the fused patch kernels below for C <= 4, which do the first four levels in one pass.
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include "haar_math.cuh"
 #include "kernels.h"
@@ -97,22 +96,21 @@ __global__ void inverse_level_f32_kernel(const float* __restrict__ ll, int64_t l
 }
 
 // ------------------------------------------------------------------------------------------
-// Fused tile kernels: all levels 1..min(depth, 6) of one 64 x 64-pixel tile in one pass.
-// Forward: the uint8 tile is read once (3 B/px), every coefficient is written once (12 B/px);
-// the shrinking LL pyramid stays in shared memory.  Inverse: every coefficient is read once,
-// the image is written once.  One thread owns one 2 x 2 block with all its channels, and
-// consecutive threads own consecutive blocks of a row, so a warp reads/writes runs of whole
-// sectors; the channel count is a template parameter and every index is a shift.
+// Fused kernels: levels 1..min(depth, 4) of one 64 x 64-pixel tile in one pass (the per-level
+// kernels above finish depths > 4 on a plane that is 256 times smaller).  Forward: the uint8 tile is
+// read once (C B/px), every coefficient is written once (4C B/px).  Inverse: every coefficient is
+// read once, the image is written once.  The channel count is a template parameter.
 // ------------------------------------------------------------------------------------------
 constexpr int kTile = 64;
 constexpr int kTileThreads = 256;
+constexpr int kFusedLevels = 4;
 
 struct TileGeom {
     int Hp, Wp;                 // padded extents (multiples of 2^depth)
-    int levels;                 // levels done inside the tile: min(depth, 6)
+    int levels;                 // levels done inside the tile: min(depth, kFusedLevels)
     int tiles_x, tiles_y;
     float* plane; int64_t pl_stride;      // Mallat plane
-    float* ll; int64_t ll_stride;         // where LL_levels lives (the plane itself when depth <= 6)
+    float* ll; int64_t ll_stride;         // where LL_levels lives (the plane itself when depth <= kFusedLevels)
 };
 
 template <int C>
@@ -130,243 +128,40 @@ __device__ __forceinline__ void analyse(const float (&a)[C], const float (&b)[C]
     }
 }
 
-// 2*C consecutive bytes (two horizontally adjacent pixels) -> floats, with the widest loads the
-// alignment allows (p is 4-byte aligned when `wide`).
-template <int C>
-__device__ __forceinline__ void load_pixel_pair(const uint8_t* p, bool wide, float (&a)[C], float (&b)[C]) {
-    uint8_t v[2 * C];
-    if (wide && (2 * C) % 4 == 0) {
-#pragma unroll
-        for (int k = 0; k < 2 * C / 4; ++k) {
-            const uint32_t w = reinterpret_cast<const uint32_t*>(p)[k];
-            v[4 * k] = (uint8_t)w; v[4 * k + 1] = (uint8_t)(w >> 8); v[4 * k + 2] = (uint8_t)(w >> 16); v[4 * k + 3] = (uint8_t)(w >> 24);
-        }
-    } else if (wide) {                       // 2*C is even: 16-bit loads (p is even because x is even)
-#pragma unroll
-        for (int k = 0; k < C; ++k) {
-            const uint16_t w = reinterpret_cast<const uint16_t*>(p)[k];
-            v[2 * k] = (uint8_t)w; v[2 * k + 1] = (uint8_t)(w >> 8);
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 2 * C; ++k) v[k] = p[k];
-    }
-#pragma unroll
-    for (int c = 0; c < C; ++c) { a[c] = (float)v[c]; b[c] = (float)v[C + c]; }
-}
-
-template <int C>
-__global__ void __launch_bounds__(kTileThreads)
-forward_tile_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int W, int border_type, int border_const,
-                    TileGeom g) {
-    __shared__ float s_a[32 * 32 * C];
-    __shared__ float s_b[16 * 16 * C];
-    // level-1 rows are handed from "one thread = one block, all channels" to "one lane = one float of
-    // the row" through this per-warp buffer, so that every store instruction covers 128 contiguous bytes
-    __shared__ float s_st[kTileThreads / 32][4][32 * C];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
-    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
-    const int y0 = ty * kTile, x0 = tx * kTile;
-    const bool interior = (y0 + kTile <= H) && (x0 + kTile <= W);
-    const float fc = (float)border_const;
-    const bool wide = ((uintptr_t)src % 4 == 0) && (pitch % 4 == 0);      // x0*C and 2*bx*C are multiples of 2*C
-    const float* in_f = nullptr;
-#pragma unroll
-    for (int l = 1; l <= 6; ++l) {
-        if (l > g.levels) break;
-        const int sh = 6 - l;                           // log2(blocks per tile side)
-        const int n = 1 << sh;
-        const int hl_ = g.Hp >> l, wl_ = g.Wp >> l;     // sub-band extents
-        float* out_f = (l & 1) ? s_a : s_b;
-        const bool last = (l == g.levels);
-        for (int blk = threadIdx.x; blk < n * n; blk += kTileThreads) {
-            const int by = blk >> sh, bx = blk & (n - 1);
-            float a[C], b[C], cc[C], d[C];
-            if (l == 1) {
-                if (interior) {
-                    const uint8_t* p = src + (int64_t)(y0 + 2 * by) * pitch + (int64_t)(x0 + 2 * bx) * C;
-                    load_pixel_pair<C>(p, wide, a, b);
-                    load_pixel_pair<C>(p + pitch, wide, cc, d);
-                } else {
-                    const int ya = border_index(y0 + 2 * by, H, border_type), yb = border_index(y0 + 2 * by + 1, H, border_type);
-                    const int xa = border_index(x0 + 2 * bx, W, border_type), xb = border_index(x0 + 2 * bx + 1, W, border_type);
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        a[c] = (ya < 0 || xa < 0) ? fc : (float)src[(int64_t)ya * pitch + (int64_t)xa * C + c];
-                        b[c] = (ya < 0 || xb < 0) ? fc : (float)src[(int64_t)ya * pitch + (int64_t)xb * C + c];
-                        cc[c] = (yb < 0 || xa < 0) ? fc : (float)src[(int64_t)yb * pitch + (int64_t)xa * C + c];
-                        d[c] = (yb < 0 || xb < 0) ? fc : (float)src[(int64_t)yb * pitch + (int64_t)xb * C + c];
-                    }
-                }
-            } else {
-                const int in_row = 2 * n * C;
-                const float* p = in_f + (2 * by) * in_row + (2 * bx) * C;
-#pragma unroll
-                for (int c = 0; c < C; ++c) { a[c] = p[c]; b[c] = p[C + c]; cc[c] = p[in_row + c]; d[c] = p[in_row + C + c]; }
-            }
-            float vll[C], vhl[C], vlh[C], vhh[C];
-            analyse<C>(a, b, cc, d, vll, vhl, vlh, vhh);
-            const int gy = ty * n + by, gx = tx * n + bx;
-            if (l == 1) {
-                // the warp owns block row `by` (bx == lane): stage, then store lane-contiguous rows
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    s_st[warp][0][lane * C + c] = vhl[c]; s_st[warp][1][lane * C + c] = vlh[c];
-                    s_st[warp][2][lane * C + c] = vhh[c]; s_st[warp][3][lane * C + c] = vll[c];
-                }
-                __syncwarp();
-                if (gy < hl_) {
-                    const int gx0 = tx * n;
-                    int valid = (wl_ - gx0) * C;                 // floats of this row segment inside the sub-band
-                    if (valid > 32 * C) valid = 32 * C;
-                    float* r_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(wl_ + gx0) * C;
-                    float* r_lh = g.plane + (int64_t)(gy + hl_) * g.pl_stride + (int64_t)gx0 * C;
-                    float* r_hh = r_lh + (int64_t)wl_ * C;
-                    float* r_ll = g.ll + (int64_t)gy * g.ll_stride + (int64_t)gx0 * C;
-#pragma unroll
-                    for (int k = 0; k < C; ++k) {
-                        const int jj = lane + 32 * k;
-                        if (jj < valid) {
-                            r_hl[jj] = s_st[warp][0][jj]; r_lh[jj] = s_st[warp][1][jj]; r_hh[jj] = s_st[warp][2][jj];
-                            if (last) r_ll[jj] = s_st[warp][3][jj];
-                        }
-                    }
-                }
-                __syncwarp();
-            } else if (gy < hl_ && gx < wl_) {
-                float* q_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(wl_ + gx) * C;
-                float* q_lh = g.plane + (int64_t)(gy + hl_) * g.pl_stride + (int64_t)gx * C;
-                float* q_hh = q_lh + (int64_t)wl_ * C;
-#pragma unroll
-                for (int c = 0; c < C; ++c) { q_hl[c] = vhl[c]; q_lh[c] = vlh[c]; q_hh[c] = vhh[c]; }
-                if (last) {
-                    float* q_ll = g.ll + (int64_t)gy * g.ll_stride + (int64_t)gx * C;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) q_ll[c] = vll[c];
-                }
-            }
-            if (!last) {
-                float* q = out_f + (by * n + bx) * C;
-#pragma unroll
-                for (int c = 0; c < C; ++c) q[c] = vll[c];
-            }
-        }
-        __syncthreads();
-        in_f = out_f;
-    }
-}
-
-template <int C>
-__global__ void __launch_bounds__(kTileThreads)
-inverse_tile_kernel(TileGeom g, float* __restrict__ out, int64_t out_stride) {
-    __shared__ float s_a[32 * 32 * C];
-    __shared__ float s_b[16 * 16 * C];
-    __shared__ float s_st[kTileThreads / 32][2][64 * C];    // per-warp staging of two output rows (see forward kernel)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
-    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
-    const float* in_f = nullptr;
-    for (int l = g.levels; l >= 1; --l) {
-        const int sh = 6 - l;
-        const int n = 1 << sh;                          // LL_l tile is n x n
-        const int hl_ = g.Hp >> l, wl_ = g.Wp >> l;
-        float* out_f = ((l - 1) & 1) ? s_a : s_b;
-        for (int blk = threadIdx.x; blk < n * n; blk += kTileThreads) {
-            const int by = blk >> sh, bx = blk & (n - 1);
-            const int gy = ty * n + by, gx = tx * n + bx;
-            const bool inside = gy < hl_ && gx < wl_;
-            float vll[C], vhl[C], vlh[C], vhh[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) vll[c] = vhl[c] = vlh[c] = vhh[c] = 0.f;
-            if (inside) {
-                const float* q_ll = (l == g.levels) ? g.ll + (int64_t)gy * g.ll_stride + (int64_t)gx * C
-                                                    : in_f + (by * n + bx) * C;
-                const float* q_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(wl_ + gx) * C;
-                const float* q_lh = g.plane + (int64_t)(gy + hl_) * g.pl_stride + (int64_t)gx * C;
-                const float* q_hh = q_lh + (int64_t)wl_ * C;
-#pragma unroll
-                for (int c = 0; c < C; ++c) { vll[c] = q_ll[c]; vhl[c] = q_hl[c]; vlh[c] = q_lh[c]; vhh[c] = q_hh[c]; }
-            }
-            float a[C], b[C], cc[C], d[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float s0 = __fadd_rn(vll[c], vhl[c]), s1 = __fsub_rn(vll[c], vhl[c]);
-                const float d0 = __fadd_rn(vlh[c], vhh[c]), d1 = __fsub_rn(vlh[c], vhh[c]);
-                a[c] = __fadd_rn(s0, d0); b[c] = __fadd_rn(s1, d1); cc[c] = __fsub_rn(s0, d0); d[c] = __fsub_rn(s1, d1);
-            }
-            if (l == 1) {
-                // the warp owns block row `by` (bx == lane): two output rows of 64*C floats, staged and then
-                // stored with lane-contiguous addresses (128 contiguous bytes per store instruction)
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    s_st[warp][0][lane * 2 * C + c] = a[c]; s_st[warp][0][lane * 2 * C + C + c] = b[c];
-                    s_st[warp][1][lane * 2 * C + c] = cc[c]; s_st[warp][1][lane * 2 * C + C + c] = d[c];
-                }
-                __syncwarp();
-                if (gy < hl_) {
-                    const int gx0 = tx * n;
-                    int valid = (wl_ - gx0) * 2 * C;
-                    if (valid > 64 * C) valid = 64 * C;
-                    float* r0 = out + (int64_t)(2 * gy) * out_stride + (int64_t)(2 * gx0) * C;
-                    float* r1 = r0 + out_stride;
-#pragma unroll
-                    for (int k = 0; k < 2 * C; ++k) {
-                        const int jj = lane + 32 * k;
-                        if (jj < valid) { r0[jj] = s_st[warp][0][jj]; r1[jj] = s_st[warp][1][jj]; }
-                    }
-                }
-                __syncwarp();
-            } else {
-                const int out_row = 2 * n * C;
-                float* q = out_f + (2 * by) * out_row + (2 * bx) * C;
-#pragma unroll
-                for (int c = 0; c < C; ++c) { q[c] = a[c]; q[C + c] = b[c]; q[out_row + c] = cc[c]; q[out_row + C + c] = d[c]; }
-            }
-        }
-        __syncthreads();
-        in_f = out_f;
-    }
-}
-
 // ------------------------------------------------------------------------------------------
-// Forward, depth >= 2: the same 64 x 64 tile, but each lane owns a whole 4 x 4-pixel patch (one
-// level-2 block): levels 1 and 2 are computed in registers, levels 3 and 4 with warp shuffles, and
-// only the sixteen LL_4 values of the tile cross warps (one barrier instead of one per level).
-// Warp w covers level-2 blocks rows 4*(w>>1)..+3, columns 8*(w&1)..+7 (lane = 8*ly + lx).
+// Forward: a CTA covers a 64 x 64-pixel tile, a warp a 16-row x 32-pixel region of it, and a lane
+// one 4 x 4-pixel patch (one level-2 block; lane = 8*ly + lx inside the warp's 4 x 8 level-2 blocks).
+// Levels 1 and 2 are computed in registers, levels 3 and 4 with warp shuffles: nothing crosses a warp,
+// so there is no barrier and no shared-memory pyramid.  Sub-band rows leave through a per-warp stage
+// so that every store instruction writes 128 contiguous bytes of one row.
 // ------------------------------------------------------------------------------------------
-// Store R x (UNIT*UPR) staged floats as rows of a sub-band: store instruction k writes the 32 consecutive
-// staged floats 32k..32k+31, i.e. 32/UNIT whole UNIT-float pieces, each inside one row.
-template <int R, int UNIT, int UPR, int PITCH, bool kCheck>
-__device__ __forceinline__ void store_staged_impl(const float* stage, int lane, float* base, int stride, int rows_valid,
-                                                  int seg_valid) {
-    constexpr int K = R * UNIT * UPR / 32;               // store instructions
-    constexpr int PER = 32 / UNIT;                       // pieces per instruction
-    const int piece = lane / UNIT, lo = lane % UNIT;
-    float* lbase = base + lo;
-    const float* lstage = stage + lo;
+// Store ROWS staged rows of SEG floats (row pitch PITCH in the stage) to rows of a sub-band.  One store
+// instruction covers 32 consecutive floats of one row (or 32/SEG whole rows when SEG is 8 or 16); the row pointer
+// is bumped by the stride, every other offset is an immediate.
+template <int SEG, int ROWS, int PITCH, bool kCheck>
+__device__ __forceinline__ void store_rows_impl(const float* stage, int lane, float* base, int64_t stride, int rows_valid,
+                                                int seg_valid) {
+    constexpr int RPI = (SEG == 8 || SEG == 16) ? 32 / SEG : 1;       // rows per store instruction
+    constexpr int IPR = (SEG + 31) / 32;                               // store instructions per row (RPI == 1)
+    const int sub = RPI > 1 ? lane / SEG : 0, j = RPI > 1 ? lane % SEG : lane;
+    float* p = base + (int64_t)sub * stride + j;
+    const float* q = stage + sub * PITCH + j;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        // piece 0 of the instruction is at a compile-time position; the others are written as lane-dependent
-        // deltas that repeat across k, so the compiler keeps them in a few registers
-        const int r0 = (k * PER) / UPR, j0 = ((k * PER) % UPR) * UNIT;
-        int so = r0 * PITCH + j0, go = r0 * stride + j0, r = r0, j = j0;
+    for (int r = 0; r < ROWS; r += RPI) {
 #pragma unroll
-        for (int q = 1; q < PER; ++q) {
-            const int rq = (k * PER + q) / UPR, jq = ((k * PER + q) % UPR) * UNIT;
-            const int sel = (piece == q) ? 1 : 0;
-            so += sel * ((rq - r0) * PITCH + (jq - j0));
-            go += sel * ((rq - r0) * stride + (jq - j0));
-            if (kCheck) { r += sel * (rq - r0); j += sel * (jq - j0); }
+        for (int i = 0; i < IPR; ++i) {
+            bool ok = (SEG % 32 == 0 || RPI > 1) ? true : (j + 32 * i < SEG);
+            if (kCheck) ok = ok && (r + sub < rows_valid) && (j + 32 * i < seg_valid);
+            if (ok) p[32 * i] = q[r * PITCH + 32 * i];
         }
-        if (!kCheck || (r < rows_valid && j + lo < seg_valid)) lbase[go] = lstage[so];
+        p += RPI * stride;
     }
 }
-template <int C, int R, int UNIT, int UPR, int PITCH>
-__device__ __forceinline__ void store_staged(const float* stage, int lane, float* base, int stride, bool full,
-                                             int rows_valid, int seg_valid) {
-    if (full) store_staged_impl<R, UNIT, UPR, PITCH, false>(stage, lane, base, stride, rows_valid, seg_valid);
-    else store_staged_impl<R, UNIT, UPR, PITCH, true>(stage, lane, base, stride, rows_valid, seg_valid);
+template <int SEG, int ROWS, int PITCH>
+__device__ __forceinline__ void store_rows(const float* stage, int lane, float* base, int64_t stride, bool full,
+                                           int rows_valid, int seg_valid) {
+    if (full) store_rows_impl<SEG, ROWS, PITCH, false>(stage, lane, base, stride, rows_valid, seg_valid);
+    else store_rows_impl<SEG, ROWS, PITCH, true>(stage, lane, base, stride, rows_valid, seg_valid);
 }
 
 template <int C>
@@ -375,14 +170,9 @@ forward_patch_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int 
                      TileGeom g) {
     constexpr int kPitch1 = 16 * C + 8;                        // staged level-1 row (+8: float2 writes hit every bank once)
     __shared__ __align__(16) float s_st[kTileThreads / 32][8 * kPitch1];   // per-warp staging of one sub-band of one level
-    __shared__ float s_ll2[16][16][C], s_ll3[8][8][C];
-    __shared__ int s_arrived;                                  // warps that have published their LL_2 values
-    if (threadIdx.x == 0) s_arrived = 0;
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wy = warp >> 1, wx = warp & 1, ly = lane >> 3, lx = lane & 7;
-    const int tile = blockIdx.x;
-    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+    const int ty = blockIdx.y, tx = blockIdx.x;
     const int b2y = 4 * wy + ly, b2x = 8 * wx + lx;                       // level-2 block inside the tile
     const int py = ty * kTile + 4 * b2y, px = tx * kTile + 4 * b2x;       // top-left pixel of the lane's patch
     const bool interior = (ty * kTile + kTile <= H) && (tx * kTile + kTile <= W);
@@ -390,7 +180,7 @@ forward_patch_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int 
     const bool wide = ((uintptr_t)src % 4 == 0) && (pitch % 4 == 0);
     const float fc = (float)border_const;
     float* stage = s_st[warp];
-    const int stride = (int)g.pl_stride;
+    const int64_t stride = g.pl_stride;
 
     // ---- the 4 x 4 patch as floats
     float pix[4][4][C];
@@ -442,13 +232,13 @@ forward_patch_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int 
             }
             __syncwarp();
         };
-        put(hl1); store_staged<C, 8, 16, C, kPitch1>(stage, lane, base_hl, stride, full, rows_valid, seg_valid); __syncwarp();
-        put(lh1); store_staged<C, 8, 16, C, kPitch1>(stage, lane, base_lh, stride, full, rows_valid, seg_valid); __syncwarp();
-        put(hh1); store_staged<C, 8, 16, C, kPitch1>(stage, lane, base_hh, stride, full, rows_valid, seg_valid); __syncwarp();
+        put(hl1); store_rows<16 * C, 8, kPitch1>(stage, lane, base_hl, stride, full, rows_valid, seg_valid); __syncwarp();
+        put(lh1); store_rows<16 * C, 8, kPitch1>(stage, lane, base_lh, stride, full, rows_valid, seg_valid); __syncwarp();
+        put(hh1); store_rows<16 * C, 8, kPitch1>(stage, lane, base_hh, stride, full, rows_valid, seg_valid); __syncwarp();
         if (g.levels == 1) {
             put(ll1);
-            store_staged<C, 8, 16, C, kPitch1>(stage, lane, g.ll + (int64_t)gy0 * g.ll_stride + (int64_t)gx0 * C,
-                                               (int)g.ll_stride, full, rows_valid, seg_valid);
+            store_rows<16 * C, 8, kPitch1>(stage, lane, g.ll + (int64_t)gy0 * g.ll_stride + (int64_t)gx0 * C,
+                                               g.ll_stride, full, rows_valid, seg_valid);
             return;
         }
     }
@@ -468,26 +258,16 @@ forward_patch_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int 
             for (int c = 0; c < C; ++c) stage[ly * seg + lx * C + c] = v[c];
             __syncwarp();
         };
-        put(hl2); store_staged<C, 4, 8, C, seg>(stage, lane, base_hl, stride, full, rows_valid, seg_valid); __syncwarp();
-        put(lh2); store_staged<C, 4, 8, C, seg>(stage, lane, base_lh, stride, full, rows_valid, seg_valid); __syncwarp();
-        put(hh2); store_staged<C, 4, 8, C, seg>(stage, lane, base_hh, stride, full, rows_valid, seg_valid); __syncwarp();
+        put(hl2); store_rows<seg, 4, seg>(stage, lane, base_hl, stride, full, rows_valid, seg_valid); __syncwarp();
+        put(lh2); store_rows<seg, 4, seg>(stage, lane, base_lh, stride, full, rows_valid, seg_valid); __syncwarp();
+        put(hh2); store_rows<seg, 4, seg>(stage, lane, base_hh, stride, full, rows_valid, seg_valid); __syncwarp();
         if (g.levels == 2) {
             put(ll2);
-            store_staged<C, 4, 8, C, seg>(stage, lane, g.ll + (int64_t)gy0 * g.ll_stride + (int64_t)gx0 * C, (int)g.ll_stride,
+            store_rows<seg, 4, seg>(stage, lane, g.ll + (int64_t)gy0 * g.ll_stride + (int64_t)gx0 * C, g.ll_stride,
                                           full, rows_valid, seg_valid);
             return;
         }
     }
-    // ---- levels 3..6 need LL_2 of other warps: every warp publishes its 4 x 8 LL_2 values, and whichever warp
-    //      publishes last finishes the tile alone (nobody waits at a barrier)
-#pragma unroll
-    for (int c = 0; c < C; ++c) s_ll2[b2y][b2x][c] = ll2[c];
-    __syncwarp();
-    int is_last = 0;
-    if (lane == 0) { __threadfence_block(); is_last = (atomicAdd(&s_arrived, 1) == kTileThreads / 32 - 1); }
-    is_last = __shfl_sync(0xFFFFFFFFu, is_last, 0);
-    if (!is_last) return;
-    __threadfence_block();
     auto write_details = [&](int level, int gy, int gx, const float (&hl)[C], const float (&lh)[C], const float (&hh)[C],
                              const float (&ll)[C]) {
         const int hL = g.Hp >> level, wL = g.Wp >> level;
@@ -503,69 +283,188 @@ forward_patch_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int 
             for (int c = 0; c < C; ++c) q_ll[c] = ll[c];
         }
     };
-    // level 3: 8 x 8 blocks, two per lane
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int by = (lane >> 3) + 4 * i, bx = lane & 7;
-        float ll[C], hl[C], lh[C], hh[C];
-        analyse<C>(s_ll2[2 * by][2 * bx], s_ll2[2 * by][2 * bx + 1], s_ll2[2 * by + 1][2 * bx], s_ll2[2 * by + 1][2 * bx + 1], ll,
-                   hl, lh, hh);
-        write_details(3, ty * 8 + by, tx * 8 + bx, hl, lh, hh, ll);
-#pragma unroll
-        for (int c = 0; c < C; ++c) s_ll3[by][bx][c] = ll[c];
-    }
-    if (g.levels == 3) return;
-    __syncwarp();
-    // level 4: 4 x 4 blocks on lanes 0..15 (lane = 4 * by + bx; the upper half-warp mirrors it and stores nothing)
-    float ll4[C];
+    // ---- level 3 inside the warp: 2 x 2 lane groups (lx ^ 1, ly ^ 1); the group's first lane owns the block
+    float ll3[C];
     {
-        const int by = (lane >> 2) & 3, bx = lane & 3;
-        float hl[C], lh[C], hh[C];
-        analyse<C>(s_ll3[2 * by][2 * bx], s_ll3[2 * by][2 * bx + 1], s_ll3[2 * by + 1][2 * bx], s_ll3[2 * by + 1][2 * bx + 1], ll4,
-                   hl, lh, hh);
-        if (lane < 16) write_details(4, ty * 4 + by, tx * 4 + bx, hl, lh, hh, ll4);
-    }
-    if (g.levels == 4) return;
-    // level 5: lane groups {m, m+1, m+4, m+5}
-    float ll5[C];
-    {
-        const int base = lane & 10;
+        const int base = lane & ~9;
         float a[C], b[C], cc[C], d[C], hl[C], lh[C], hh[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            a[c] = __shfl_sync(0xFFFFFFFFu, ll4[c], base); b[c] = __shfl_sync(0xFFFFFFFFu, ll4[c], base + 1);
-            cc[c] = __shfl_sync(0xFFFFFFFFu, ll4[c], base + 4); d[c] = __shfl_sync(0xFFFFFFFFu, ll4[c], base + 5);
+            a[c] = __shfl_sync(0xFFFFFFFFu, ll2[c], base); b[c] = __shfl_sync(0xFFFFFFFFu, ll2[c], base + 1);
+            cc[c] = __shfl_sync(0xFFFFFFFFu, ll2[c], base + 8); d[c] = __shfl_sync(0xFFFFFFFFu, ll2[c], base + 9);
         }
-        analyse<C>(a, b, cc, d, ll5, hl, lh, hh);
-        if (lane == base) write_details(5, ty * 2 + (lane >> 3), tx * 2 + ((lane >> 1) & 1), hl, lh, hh, ll5);
+        analyse<C>(a, b, cc, d, ll3, hl, lh, hh);
+        const int by = 2 * wy + (ly >> 1), bx = 4 * wx + (lx >> 1);
+        if (lane == base) write_details(3, ty * 8 + by, tx * 8 + bx, hl, lh, hh, ll3);
     }
-    if (g.levels == 5) return;
-    // level 6: the four level-5 owners are lanes 0, 2, 8, 10
+    if (g.levels == 3) return;
+    // ---- level 4 inside the warp: lanes {m, m+2, m+16, m+18}, m = lane & 4 (the warp's 1 x 2 level-4 blocks)
     {
-        float a[C], b[C], cc[C], d[C], ll6[C], hl[C], lh[C], hh[C];
+        const int base = lane & 4;
+        float a[C], b[C], cc[C], d[C], ll4[C], hl[C], lh[C], hh[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            a[c] = __shfl_sync(0xFFFFFFFFu, ll5[c], 0); b[c] = __shfl_sync(0xFFFFFFFFu, ll5[c], 2);
-            cc[c] = __shfl_sync(0xFFFFFFFFu, ll5[c], 8); d[c] = __shfl_sync(0xFFFFFFFFu, ll5[c], 10);
+            a[c] = __shfl_sync(0xFFFFFFFFu, ll3[c], base); b[c] = __shfl_sync(0xFFFFFFFFu, ll3[c], base + 2);
+            cc[c] = __shfl_sync(0xFFFFFFFFu, ll3[c], base + 16); d[c] = __shfl_sync(0xFFFFFFFFu, ll3[c], base + 18);
         }
-        analyse<C>(a, b, cc, d, ll6, hl, lh, hh);
-        if (lane == 0) write_details(6, ty, tx, hl, lh, hh, ll6);
+        analyse<C>(a, b, cc, d, ll4, hl, lh, hh);
+        if (lane == base) write_details(4, ty * 4 + wy, tx * 4 + 2 * wx + (lane >> 2), hl, lh, hh, ll4);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Inverse, the mirror image: a lane owns one level-2 block = a 4 x 4 patch of the output.  It walks
+// down from the top fused level reading the detail coefficients of its own ancestors (lanes that share
+// an ancestor read the same address: one broadcast transaction) and keeps only its own quadrant, so no
+// level needs another lane's result: no shared-memory pyramid, no barrier, no shuffle.  Levels 2 and 1
+// are expanded in registers and the 4 x 4 x C patch leaves through the per-warp stage as whole rows.
+// ------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void load_run(const float* p, bool vec, bool inside, float (&v)[N]) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = 0.f;
+    if (!inside) return;
+    if (vec && N % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < N / 2; ++k) { const float2 t = reinterpret_cast<const float2*>(p)[k]; v[2 * k] = t.x; v[2 * k + 1] = t.y; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) v[k] = p[k];
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kTileThreads, C <= 3 ? 4 : 3)
+inverse_patch_kernel(TileGeom g, float* __restrict__ out, int64_t out_stride) {
+    constexpr int kSeg = 32 * C;                                  // floats of one output row of the warp's region
+    __shared__ __align__(16) float s_st[kTileThreads / 32][4 * kSeg];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wy = warp >> 1, wx = warp & 1, ly = lane >> 3, lx = lane & 7;
+    const int ty = blockIdx.y, tx = blockIdx.x;
+    const int gy2 = ty * 16 + 4 * wy + ly, gx2 = tx * 16 + 8 * wx + lx;      // the lane's level-2 block (global)
+    const int L = g.levels;
+    const int h1 = g.Hp >> 1, w1 = g.Wp >> 1;
+    const bool full = (ty * kTile + kTile <= g.Hp) && (tx * kTile + kTile <= g.Wp);
+    float* stage = s_st[warp];
+
+    // ---- LL of the lane's level-2 block (levels >= 2), walking down from the top fused level
+    float ll2[C];
+    const bool in2 = (2 * gy2 < h1) && (2 * gx2 < w1);            // L >= 2: extents are multiples of 4, all or nothing
+    if (L >= 2) {
+        {
+            const int sh = L - 2;
+            const float* q = g.ll + (int64_t)(gy2 >> sh) * g.ll_stride + (int64_t)(gx2 >> sh) * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) ll2[c] = in2 ? q[c] : 0.f;
+        }
+#pragma unroll
+        for (int T = 4; T >= 3; --T) {
+            if (T > L) continue;
+            const int sh = T - 2;
+            const int gy = gy2 >> sh, gx = gx2 >> sh, hT = g.Hp >> T, wT = g.Wp >> T;
+            const bool qy = (gy2 >> (sh - 1)) & 1, qx = (gx2 >> (sh - 1)) & 1;
+            const float* q_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(wT + gx) * C;
+            const float* q_lh = g.plane + (int64_t)(gy + hT) * g.pl_stride + (int64_t)gx * C;
+            const float* q_hh = q_lh + (int64_t)wT * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float vhl = in2 ? q_hl[c] : 0.f, vlh = in2 ? q_lh[c] : 0.f, vhh = in2 ? q_hh[c] : 0.f;
+                // a = (ll+hl)+(lh+hh)  b = (ll-hl)+(lh-hh)  c = (ll+hl)-(lh+hh)  d = (ll-hl)-(lh-hh): pick the quadrant
+                const float s = __fadd_rn(ll2[c], qx ? -vhl : vhl);
+                const float dd = __fadd_rn(vlh, qx ? -vhh : vhh);
+                ll2[c] = __fadd_rn(s, qy ? -dd : dd);
+            }
+        }
+    }
+    // ---- level 2 -> the four LL_1 values of the patch (or LL_1 itself when only one level is fused)
+    float ll1[2][2][C];
+    bool in1[2][2];
+#pragma unroll
+    for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < 2; ++ix) in1[iy][ix] = (2 * gy2 + iy < h1) && (2 * gx2 + ix < w1);
+    if (L >= 2) {
+        const int h2 = g.Hp >> 2, w2 = g.Wp >> 2;
+        const float* q_hl = g.plane + (int64_t)gy2 * g.pl_stride + (int64_t)(w2 + gx2) * C;
+        const float* q_lh = g.plane + (int64_t)(gy2 + h2) * g.pl_stride + (int64_t)gx2 * C;
+        const float* q_hh = q_lh + (int64_t)w2 * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float vhl = in2 ? q_hl[c] : 0.f, vlh = in2 ? q_lh[c] : 0.f, vhh = in2 ? q_hh[c] : 0.f;
+            const float s0 = __fadd_rn(ll2[c], vhl), s1 = __fsub_rn(ll2[c], vhl);
+            const float d0 = __fadd_rn(vlh, vhh), d1 = __fsub_rn(vlh, vhh);
+            ll1[0][0][c] = __fadd_rn(s0, d0); ll1[0][1][c] = __fadd_rn(s1, d1);
+            ll1[1][0][c] = __fsub_rn(s0, d0); ll1[1][1][c] = __fsub_rn(s1, d1);
+        }
+    } else {
+#pragma unroll
+        for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+            for (int ix = 0; ix < 2; ++ix) {
+                const float* q = g.ll + (int64_t)(2 * gy2 + iy) * g.ll_stride + (int64_t)(2 * gx2 + ix) * C;
+#pragma unroll
+                for (int c = 0; c < C; ++c) ll1[iy][ix][c] = in1[iy][ix] ? q[c] : 0.f;
+            }
+    }
+    // ---- level 1: two block rows; each output row of the patch goes through the stage as soon as it exists
+    const bool vec = ((w1 * C) % 2 == 0) && ((uintptr_t)g.plane % 8 == 0);
+    const int row0 = ty * kTile + 16 * wy;                        // first output row of the warp's region
+    const int rows_left = g.Hp - row0;                            // valid rows of the region (may exceed 16)
+    const int seg_valid = (g.Wp - (tx * kTile + 32 * wx)) * C;
+    float* obase = out + (int64_t)row0 * out_stride + (int64_t)(tx * kTile + 32 * wx) * C;
+#pragma unroll
+    for (int iy = 0; iy < 2; ++iy) {
+        const int gy1 = 2 * gy2 + iy;
+        float hl[2 * C], lh[2 * C], hh[2 * C];
+        const bool rin = in1[iy][0];
+        const float* q_hl = g.plane + (int64_t)gy1 * g.pl_stride + (int64_t)(w1 + 2 * gx2) * C;
+        const float* q_lh = g.plane + (int64_t)(gy1 + h1) * g.pl_stride + (int64_t)(2 * gx2) * C;
+        const float* q_hh = q_lh + (int64_t)w1 * C;
+        if (in1[iy][0] && in1[iy][1]) {
+            load_run<2 * C>(q_hl, vec, rin, hl); load_run<2 * C>(q_lh, vec, rin, lh); load_run<2 * C>(q_hh, vec, rin, hh);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 2 * C; ++k) {
+                const bool ok = in1[iy][k / C];
+                hl[k] = ok ? q_hl[k] : 0.f; lh[k] = ok ? q_lh[k] : 0.f; hh[k] = ok ? q_hh[k] : 0.f;
+            }
+        }
+        float top[4 * C], bot[4 * C];                             // the two pixel rows this block row expands to
+#pragma unroll
+        for (int ix = 0; ix < 2; ++ix)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float vll = ll1[iy][ix][c], vhl = hl[ix * C + c], vlh = lh[ix * C + c], vhh = hh[ix * C + c];
+                const float s0 = __fadd_rn(vll, vhl), s1 = __fsub_rn(vll, vhl);
+                const float d0 = __fadd_rn(vlh, vhh), d1 = __fsub_rn(vlh, vhh);
+                top[(2 * ix) * C + c] = __fadd_rn(s0, d0); top[(2 * ix + 1) * C + c] = __fadd_rn(s1, d1);
+                bot[(2 * ix) * C + c] = __fsub_rn(s0, d0); bot[(2 * ix + 1) * C + c] = __fsub_rn(s1, d1);
+            }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int r = 2 * iy + half;                          // patch row: region rows r, 4 + r, 8 + r, 12 + r
+            float4* q = reinterpret_cast<float4*>(stage + ly * kSeg + lx * 4 * C);
+#pragma unroll
+            for (int e = 0; e < C; ++e)
+                q[e] = half ? make_float4(bot[4 * e], bot[4 * e + 1], bot[4 * e + 2], bot[4 * e + 3])
+                            : make_float4(top[4 * e], top[4 * e + 1], top[4 * e + 2], top[4 * e + 3]);
+            __syncwarp();
+            store_rows<kSeg, 4, kSeg>(stage, lane, obase + (int64_t)r * out_stride, 4 * out_stride, full,
+                                      (rows_left - r + 3) >> 2, seg_valid);
+            __syncwarp();
+        }
     }
 }
 
 template <int C>
 static cudaError_t launch_forward_tiles(const uint8_t* d_src, int64_t pitch, int H, int W, int border_type,
                                         int border_const, const TileGeom& g, cudaStream_t stream) {
-    // depth 1: one warp per full tile row (384-byte row segments); deeper: one 4 x 4 patch per lane, one barrier
-    if (getenv("WICCA_FORWARD_TILE"))
-        forward_tile_kernel<C><<<g.tiles_x * g.tiles_y, kTileThreads, 0, stream>>>(d_src, pitch, H, W, border_type, border_const, g);
-    else
-        forward_patch_kernel<C><<<g.tiles_x * g.tiles_y, kTileThreads, 0, stream>>>(d_src, pitch, H, W, border_type, border_const, g);
+    forward_patch_kernel<C><<<dim3(g.tiles_x, g.tiles_y), kTileThreads, 0, stream>>>(d_src, pitch, H, W, border_type, border_const, g);
     return cudaGetLastError();
 }
 template <int C>
 static cudaError_t launch_inverse_tiles(const TileGeom& g, float* out, int64_t out_stride, cudaStream_t stream) {
-    inverse_tile_kernel<C><<<g.tiles_x * g.tiles_y, kTileThreads, 0, stream>>>(g, out, out_stride);
+    inverse_patch_kernel<C><<<dim3(g.tiles_x, g.tiles_y), kTileThreads, 0, stream>>>(g, out, out_stride);
     return cudaGetLastError();
 }
 
@@ -586,12 +485,12 @@ cudaError_t launch_forward(const uint8_t* d_src, int64_t pitch, int H, int W, in
     int64_t in_stride = 0;
     int first = 1;
     if (C <= 4) {
-        // levels 1..min(depth,6) in one pass per 64 x 64 tile
+        // levels 1..min(depth, kFusedLevels) in one pass per 64 x 64 tile
         TileGeom g;
-        g.Hp = Hp; g.Wp = Wp; g.levels = depth < 6 ? depth : 6;
+        g.Hp = Hp; g.Wp = Wp; g.levels = depth < kFusedLevels ? depth : kFusedLevels;
         g.tiles_x = (Wp + kTile - 1) / kTile; g.tiles_y = (Hp + kTile - 1) / kTile;
         g.plane = d_coeffs; g.pl_stride = pl_stride;
-        if (depth <= 6) { g.ll = d_coeffs; g.ll_stride = pl_stride; }
+        if (depth <= g.levels) { g.ll = d_coeffs; g.ll_stride = pl_stride; }
         else { g.ll = (g.levels & 1) ? workA : workB; g.ll_stride = (int64_t)(Wp >> g.levels) * C; }
         cudaError_t e;
         switch (C) {
@@ -628,8 +527,8 @@ cudaError_t launch_inverse(const float* d_coeffs, int Hp, int Wp, int C, int dep
     float* workB = d_work + ((int64_t)Hp / 2) * ((int64_t)Wp / 2) * C;
     const float* ll = d_coeffs;
     int64_t ll_stride = pl_stride;
-    const int fused_levels = (C <= 4) ? (depth < 6 ? depth : 6) : 0;
-    // levels depth .. fused_levels+1 one by one (only when depth > 6 or C > 4)
+    const int fused_levels = (C <= 4) ? (depth < kFusedLevels ? depth : kFusedLevels) : 0;
+    // levels depth .. fused_levels+1 one by one (only when depth > kFusedLevels or C > 4)
     for (int l = depth; l > fused_levels; --l) {
         const int h = Hp >> l, w = Wp >> l;
         float* out; int64_t out_stride;
