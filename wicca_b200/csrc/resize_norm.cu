@@ -109,33 +109,88 @@ __global__ void resize_norm_kernel(ResizeTables t, int n, int out_h, int out_w, 
 }
 
 // ------------------------------------------------------------------------------------------
-// General-area regime, row-streaming form: one CTA per (output row, image).  The few source
-// rows that feed the output row are streamed through a double-buffered shared-memory row with
-// 16-byte cp.async copies (every source byte is read from HBM/L2 exactly once, coalesced); each
-// thread owns up to kRowsMaxElems (dx, c) elements of the output row, keeps their closed-form x
-// taps in registers and accumulates the rows in OpenCV's order.
+// General-area regime, row-streaming form: one CTA per (output row, image), one thread per output
+// pixel.  The few source rows that feed the output row are streamed through a double-buffered
+// shared-memory row (one 1-D bulk copy per row, completion on an mbarrier; every source byte is
+// read from HBM/L2 exactly once).  A thread's x taps are a contiguous run of pixels of the row:
+// [left partial] + n_full whole pixels + [right partial].  The run is read as 32-bit words,
+// realigned with one funnel shift per word and consumed four taps (12 bytes) at a time, per channel
+// in OpenCV's order (three independent chains per thread).  The run always starts at pixel
+// s_first - 1 and is padded to whole groups with weight-0 taps: src * 0 = +0 and h + 0 = h exactly,
+// so a padded tap changes nothing, and only the first and the last group need per-tap weights
+// (kept in registers: they do not depend on the row).
+//
+// src * alpha costs two instructions per byte: PRMT builds the float 2^23 + src, and
+// fma(2^23 + src, alpha, -2^23 * alpha) rounds the exact product src * alpha once, i.e. it is
+// bit-identical to (float)src * alpha (2^23 * alpha is exact).
 // ------------------------------------------------------------------------------------------
-constexpr int kRowsThreads = 256;
-constexpr int kRowsMaxElems = 4;          // covers out_w * 3 <= 1024
+constexpr int kRowsMaxThreads = 512;      // one thread per output pixel: out_w <= 512
+constexpr int kRowPadFront = 16;          // bytes in front of a staged row (pixel -1 of a weight-0 left tap)
+constexpr int kRowPadBack = 32;           // bytes behind it (weight-0 taps of the last group + word overread)
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+__device__ __forceinline__ uint32_t rs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rs_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rs_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rs_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rs_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rs_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(rs_smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void rs_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     rs_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(rs_smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(kRowsThreads)
+// (float)byte_k(word) * w, exactly: see the note above.  nw = -2^23 * w.
+template <int K>
+__device__ __forceinline__ float byte_times(uint32_t word, float w, float nw) {
+    return __fmaf_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440 | K)), w, nw);
+}
+
+// Four taps = 12 bytes = three realigned words; tap t has weight w[t].  Channel chains stay in tap order.
+__device__ __forceinline__ void area_group(const uint32_t*& wp, uint32_t& w0, uint32_t shift, const float (&w)[4],
+                                           const float (&nw)[4], float (&h)[3]) {
+    const uint32_t w1 = wp[1], w2 = wp[2], w3 = wp[3];
+    const uint32_t a0 = __funnelshift_r(w0, w1, shift), a1 = __funnelshift_r(w1, w2, shift), a2 = __funnelshift_r(w2, w3, shift);
+    h[0] = __fadd_rn(h[0], byte_times<0>(a0, w[0], nw[0])); h[1] = __fadd_rn(h[1], byte_times<1>(a0, w[0], nw[0]));
+    h[2] = __fadd_rn(h[2], byte_times<2>(a0, w[0], nw[0])); h[0] = __fadd_rn(h[0], byte_times<3>(a0, w[1], nw[1]));
+    h[1] = __fadd_rn(h[1], byte_times<0>(a1, w[1], nw[1])); h[2] = __fadd_rn(h[2], byte_times<1>(a1, w[1], nw[1]));
+    h[0] = __fadd_rn(h[0], byte_times<2>(a1, w[2], nw[2])); h[1] = __fadd_rn(h[1], byte_times<3>(a1, w[2], nw[2]));
+    h[2] = __fadd_rn(h[2], byte_times<0>(a2, w[2], nw[2])); h[0] = __fadd_rn(h[0], byte_times<1>(a2, w[3], nw[3]));
+    h[1] = __fadd_rn(h[1], byte_times<2>(a2, w[3], nw[3])); h[2] = __fadd_rn(h[2], byte_times<3>(a2, w[3], nw[3]));
+    w0 = w3;
+    wp += 3;
+}
+
+__global__ void __launch_bounds__(kRowsMaxThreads)
 resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, float* __restrict__ out,
                         uint8_t* __restrict__ out_u8, int buf_bytes) {
     extern __shared__ __align__(16) uint8_t s_rows[];          // two row buffers of buf_bytes each
+    __shared__ __align__(8) uint64_t s_full[2];
     const int img = blockIdx.y, dy = blockIdx.x;
     const ResizeJob j = t.jobs[img];
     if (j.regime != 2) return;
     const AreaDesc ay = t.area[j.yoff + dy];
     const int row_bytes = j.sw * 3;
-    const int n_elems = out_w * 3;
+    const int copy_bytes = (row_bytes + 15) & ~15;
+    // a row can be bulk-copied when it starts on a 16-byte boundary and its rounded-up length stays inside the pitch
+    const bool bulk = (((uintptr_t)j.src | (uintptr_t)j.pitch) & 15) == 0 && copy_bytes <= j.pitch;
+    if (threadIdx.x == 0) {
+        rs_mbar_init(&s_full[0], 1); rs_mbar_init(&s_full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     // the y taps of this output row, in OpenCV's order: [left partial] + full rows + [right partial]
     const int has_l = ay.w_left != 0.0f, has_r = ay.w_right != 0.0f;
     const int n_rows = has_l + ay.n_full + has_r;
@@ -143,57 +198,59 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
     auto row_weight = [&](int k) { return (has_l && k == 0) ? ay.w_left : (k - has_l < ay.n_full ? ay.w_full : ay.w_right); };
     auto fetch = [&](int k) {
         const uint8_t* g = j.src + (int64_t)row_index(k) * j.pitch;
-        uint8_t* s = s_rows + (k & 1) * buf_bytes;
-        if (((uintptr_t)g & 15) == 0) {
-            const int chunks = row_bytes >> 4;
-            for (int q = threadIdx.x; q < chunks; q += kRowsThreads) cp_async16(s + q * 16, g + q * 16);
-            for (int b = (chunks << 4) + threadIdx.x; b < row_bytes; b += kRowsThreads) s[b] = g[b];
+        uint8_t* s = s_rows + (k & 1) * buf_bytes + kRowPadFront;
+        if (bulk) {
+            if (threadIdx.x == 0) {
+                rs_mbar_expect_tx(&s_full[k & 1], (uint32_t)copy_bytes);
+                rs_bulk_load(s, g, (uint32_t)copy_bytes, &s_full[k & 1]);
+            }
         } else {
-            for (int b = threadIdx.x; b < row_bytes; b += kRowsThreads) s[b] = g[b];
+            for (int b = threadIdx.x; b < row_bytes; b += blockDim.x) s[b] = g[b];
         }
-        cp_async_commit();
     };
-    AreaDesc ax[kRowsMaxElems];
-    int ch[kRowsMaxElems];
-    float acc[kRowsMaxElems];
+    // ---- this thread's x taps (independent of the row)
+    const int dx = threadIdx.x;
+    const bool active = dx < out_w;
+    const AreaDesc ax = t.area[j.xoff + (active ? dx : 0)];
+    const int n_taps = ax.n_full + 2;                          // pixels s_first - 1 .. s_first + n_full
+    const int groups = (n_taps + 3) >> 2;
+    auto tap_weight = [&](int tp) { return tp == 0 ? ax.w_left : (tp <= ax.n_full ? ax.w_full : (tp == ax.n_full + 1 ? ax.w_right : 0.0f)); };
+    float wa[4], nwa[4], wz[4], nwz[4], wm[4], nwm[4];
 #pragma unroll
-    for (int m = 0; m < kRowsMaxElems; ++m) {
-        const int e = threadIdx.x + m * kRowsThreads;
-        const int dx = e < n_elems ? e / 3 : 0;
-        ch[m] = e - (e / 3) * 3;
-        ax[m] = t.area[j.xoff + dx];
-        acc[m] = 0.0f;
+    for (int q = 0; q < 4; ++q) {
+        wa[q] = tap_weight(q); nwa[q] = -8388608.0f * wa[q];
+        wz[q] = tap_weight(4 * (groups - 1) + q); nwz[q] = -8388608.0f * wz[q];
+        wm[q] = ax.w_full; nwm[q] = -8388608.0f * ax.w_full;
     }
-    if (n_rows > 0) fetch(0);
+    const int b_start = (ax.s_first - 1) * 3 + kRowPadFront;   // >= 13
+    const uint32_t shift = (uint32_t)(b_start & 3) * 8;
+    float acc[3] = {0.0f, 0.0f, 0.0f};
+    __syncthreads();                                           // mbarrier init visible
+    fetch(0);
     for (int k = 0; k < n_rows; ++k) {
-        if (k + 1 < n_rows) { fetch(k + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-        __syncthreads();
-        const uint8_t* s = s_rows + (k & 1) * buf_bytes;
-        const float beta = row_weight(k);
+        if (k + 1 < n_rows) fetch(k + 1);
+        if (bulk) rs_mbar_wait(&s_full[k & 1], (uint32_t)(k >> 1) & 1u);
+        else __syncthreads();
+        if (active) {
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_rows + (k & 1) * buf_bytes) + (b_start >> 2);
+            uint32_t w0 = wp[0];
+            float h[3] = {0.0f, 0.0f, 0.0f};
+            area_group(wp, w0, shift, wa, nwa, h);
+            for (int g = 1; g < groups - 1; ++g) area_group(wp, w0, shift, wm, nwm, h);
+            if (groups > 1) area_group(wp, w0, shift, wz, nwz, h);
+            const float beta = row_weight(k);
 #pragma unroll
-        for (int m = 0; m < kRowsMaxElems; ++m) {
-            if (threadIdx.x + m * kRowsThreads < n_elems) {
-                const uint8_t* p = s + ch[m];
-                float h = 0.0f;
-                if (ax[m].w_left != 0.0f) h = __fmul_rn(u8_to_float(p[ax[m].s_left * 3]), ax[m].w_left);
-                const uint8_t* q = p + ax[m].s_first * 3;
-                const float wf = ax[m].w_full;
-#pragma unroll 4
-                for (int kx = 0; kx < ax[m].n_full; ++kx) h = __fadd_rn(h, __fmul_rn(u8_to_float(q[kx * 3]), wf));
-                if (ax[m].w_right != 0.0f) h = __fadd_rn(h, __fmul_rn(u8_to_float(p[ax[m].s_right * 3]), ax[m].w_right));
-                const float bh = __fmul_rn(beta, h);
-                acc[m] = (k == 0) ? bh : __fadd_rn(acc[m], bh);
+            for (int c = 0; c < 3; ++c) {
+                const float bh = __fmul_rn(beta, h[c]);
+                acc[c] = (k == 0) ? bh : __fadd_rn(acc[c], bh);
             }
         }
         __syncthreads();          // the buffer is refilled two iterations later
     }
+    if (active) {
+        const int64_t i = (((int64_t)img * out_h + dy) * out_w + dx) * 3;
 #pragma unroll
-    for (int m = 0; m < kRowsMaxElems; ++m) {
-        const int e = threadIdx.x + m * kRowsThreads;
-        if (e < n_elems) {
-            const int64_t i = ((int64_t)img * out_h + dy) * n_elems + e;
-            emit_value(sat_rint_u8(acc[m]), ch[m], i, norm_mode, out, out_u8);
-        }
+        for (int c = 0; c < 3; ++c) emit_value(sat_rint_u8(acc[c]), c, i + c, norm_mode, out, out_u8);
     }
 }
 
@@ -203,20 +260,20 @@ cudaError_t launch_resize_norm(const ResizeTables& t, int n, int out_h, int out_
                                uint8_t* d_out_u8, int max_src_w, int n_area, int n_other, cudaStream_t stream) {
     const int64_t total = (int64_t)n * out_h * out_w * 3;
     if (total <= 0) return cudaSuccess;
-    const int buf_bytes = (max_src_w * 3 + 31) / 16 * 16;
+    const int buf_bytes = kRowPadFront + (max_src_w * 3 + 15) / 16 * 16 + kRowPadBack;
     const size_t smem = (size_t)2 * buf_bytes;
-    const bool rows_ok = n_area > 0 && out_w * 3 <= kRowsThreads * kRowsMaxElems && smem <= 200 * 1024 && n <= 65535;
+    const bool rows_ok = n_area > 0 && out_w <= kRowsMaxThreads && smem <= 200 * 1024 && n <= 65535;
     if (rows_ok) {
         static thread_local int configured_dev = -1;
-        static thread_local size_t configured_smem = 0;
         int dev = 0;
         cudaGetDevice(&dev);
-        if (configured_dev != dev || configured_smem < smem) {
+        if (configured_dev != dev) {
             cudaError_t e = cudaFuncSetAttribute(resize_area_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e != cudaSuccess) return e;
-            configured_dev = dev; configured_smem = 200 * 1024;
+            configured_dev = dev;
         }
-        resize_area_rows_kernel<<<dim3(out_h, n), kRowsThreads, smem, stream>>>(t, out_h, out_w, norm_mode, d_out, d_out_u8, buf_bytes);
+        const int threads = (out_w + 31) / 32 * 32;
+        resize_area_rows_kernel<<<dim3(out_h, n), threads, smem, stream>>>(t, out_h, out_w, norm_mode, d_out, d_out_u8, buf_bytes);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_other == 0) return cudaSuccess;

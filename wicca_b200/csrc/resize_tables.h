@@ -5,6 +5,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <map>
+#include <utility>
 #include <vector>
 
 #include "host_common.h"
@@ -71,6 +73,25 @@ inline ResizeTableBlob build_resize_tables(const std::vector<ResizeSrc>& srcs, i
     std::vector<ResizeJob> jobs(srcs.size());
     std::vector<AreaDesc> area;
     std::vector<LinTap> lin;
+    // a tap table depends only on (source length, target length): images of equal size share theirs, which
+    // keeps the blob of a uniform batch small enough to be staged inline by the H2D copy
+    std::map<std::pair<int, int>, int> area_at, lin_at;
+    auto area_for = [&](int ssize, int dsize, double scale) {
+        auto it = area_at.find({ssize, dsize});
+        if (it != area_at.end()) return it->second;
+        const int off = (int)area.size();
+        area_tab(ssize, dsize, scale, area);
+        area_at[{ssize, dsize}] = off;
+        return off;
+    };
+    auto lin_for = [&](int ssize, int dsize, double inv, double scale) {
+        auto it = lin_at.find({ssize, dsize});
+        if (it != lin_at.end()) return it->second;
+        const int off = (int)lin.size();
+        linear_tab(ssize, dsize, inv, scale, lin);
+        lin_at[{ssize, dsize}] = off;
+        return off;
+    };
     for (size_t i = 0; i < srcs.size(); ++i) {
         ResizeJob& j = jobs[i];
         memset(&j, 0, sizeof j);
@@ -85,17 +106,13 @@ inline ResizeTableBlob build_resize_tables(const std::vector<ResizeSrc>& srcs, i
                 j.regime = 1; j.isx = isx; j.isy = isy;
             } else {
                 j.regime = 2;
-                j.xoff = (int)area.size();
-                area_tab(j.sw, out_w, sx, area);
-                j.yoff = (int)area.size();
-                area_tab(j.sh, out_h, sy, area);
+                j.xoff = area_for(j.sw, out_w, sx);
+                j.yoff = area_for(j.sh, out_h, sy);
             }
         } else {
             j.regime = 3;
-            j.xoff = (int)lin.size();
-            linear_tab(j.sw, out_w, inv_x, sx, lin);
-            j.yoff = (int)lin.size();
-            linear_tab(j.sh, out_h, inv_y, sy, lin);
+            j.xoff = lin_for(j.sw, out_w, inv_x, sx);
+            j.yoff = lin_for(j.sh, out_h, inv_y, sy);
         }
     }
     ResizeTableBlob b;
