@@ -194,6 +194,23 @@ WICCA_API int wicca_batch_classifier_inputs_f32(const uint8_t* const* srcs, cons
                                                 float* dst_icons, float* dst_images,
                                                 const int* devices, int n_devices, wicca_timing* t);
 
+/* One upload, every (depth, target) batch - row N3 of the hot-path table: the reference re-runs
+ * _get_img_batch once per (classifier, depth) pair (loops at classifying_tools.py:546-551 and :339-346), i.e.
+ * it reloads, re-transforms and re-resizes every image for every classifier input size and preprocessing
+ * family.  Here image i is uploaded once, all `depths` are produced by one pass of the fused icon kernel, and
+ * for every target t (out_h, out_w, norm_mode):
+ *   dst_icons[t * n_depths + k][i] = preprocess_t(cv2.resize(get_small_copy(image_i, depths[k]), target_t, INTER_AREA))
+ *   dst_images[t][i]               = preprocess_t(cv2.resize(image_i, target_t, INTER_AREA))      (dst_images may be NULL)
+ * Every destination is a host float32 (n_images, out_h_t, out_w_t, 3) batch.  depths must be >= 1. */
+typedef struct wicca_target { int out_h, out_w, norm_mode; } wicca_target;
+WICCA_API int wicca_batch_classifier_inputs_multi_f32(const uint8_t* const* srcs, const int* Hs, const int* Ws,
+                                                      const int64_t* strides, int n_images,
+                                                      const int* depths, int n_depths,
+                                                      int border_type, double border_const,
+                                                      const wicca_target* targets, int n_targets,
+                                                      float* const* dst_icons, float* const* dst_images,
+                                                      const int* devices, int n_devices, wicca_timing* t);
+
 /* Device-resident variant for sources that already live in HBM - icons, or the full-size source images of
  * the reference's other branch, cv2.resize(image, shape, interpolation) (classifying_tools.py:315).
  * d_srcs[i]: device uint8 (hs[i], ws[i], 3), rows pitches[i] bytes apart.  Enqueues on `stream`. */

@@ -112,3 +112,43 @@ def test_classifier_batches_one_call(coder, depth, shape, mode):
     assert np.array_equal(batch_images, exp_images)
     only_icons = coder.classifier_batches(imgs, depth, shape, mode, with_source=False)
     assert only_icons[0] is None and np.array_equal(only_icons[1], exp_icons)
+
+
+def test_classifier_batches_multi_one_upload(coder):
+    """Row N3: every (target, depth) batch of the reference's classifier x depth loops from one upload per
+    image, bit-identical to the oracle and to the one-target call."""
+    from oracle import haar_oracle as ho
+    rng = np.random.default_rng(11)
+    imgs = [gen_input("noise", 900 + i, 1300 + int(rng.integers(-150, 150)), 1900 + int(rng.integers(-250, 250)), 3)
+            for i in range(4)]
+    depths = [2, 3, 4, 5, 6]
+    targets = [((224, 224), "tf"), ((224, 224), "caffe"), ((299, 299), "tf"), ((240, 240), "identity"), ((331, 331), "torch")]
+    out = coder.classifier_batches_multi(imgs, depths, targets)
+    assert len(out) == len(targets)
+    icons = {d: [ho.haar_icon_blocksum(im, d) for im in imgs] for d in depths}
+    for (shape, mode), (batch_images, by_depth) in zip(targets, out):
+        ow, oh = shape
+        exp_images = ro.preprocess_input(np.stack([ro.resize_area(im, ow, oh) for im in imgs]), mode)
+        assert batch_images.shape == (4, oh, ow, 3) and np.array_equal(batch_images, exp_images)
+        assert sorted(by_depth) == depths
+        for d in depths:
+            exp = ro.preprocess_input(np.stack([ro.resize_area(ic, ow, oh) for ic in icons[d]]), mode)
+            assert np.array_equal(by_depth[d], exp), (shape, mode, d)
+    one_images, one_icons = coder.classifier_batches(imgs, 3, (299, 299), "tf")
+    assert np.array_equal(one_images, out[2][0]) and np.array_equal(one_icons, out[2][1][3])
+    no_src = coder.classifier_batches_multi(imgs, [2], [((224, 224), "tf")], with_source=False)
+    assert no_src[0][0] is None and np.array_equal(no_src[0][1][2], out[0][1][2])
+
+
+def test_classifier_batches_multi_rejects_bad_arguments(coder):
+    img = gen_input("noise", 1, 64, 64, 3)
+    with pytest.raises(ValueError):
+        coder.classifier_batches_multi([img], [], [((224, 224), "tf")])
+    with pytest.raises(ValueError):
+        coder.classifier_batches_multi([img], [2, 2], [((224, 224), "tf")])
+    with pytest.raises(ValueError):
+        coder.classifier_batches_multi([img], [2], [((224, 224), "keras")])
+    with pytest.raises(ValueError):
+        coder.classifier_batches_multi([img], [0], [((224, 224), "tf")])
+    with pytest.raises(ValueError):
+        coder.classifier_batches_multi([img], [2], [])

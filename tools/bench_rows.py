@@ -157,6 +157,23 @@ def row_batch():
         mp = sum(a.shape[0] * a.shape[1] for a in images[:30]) / 1e6
         emit(row="A3+A5+A6+N1 one call", config=f"30 pinned host images -> depth-{depth} icons + source -> two ({target},{target},3) tf batches",
              s=dt, MP_per_s=mp / dt, batches_of_30_per_s=1 / dt, stage_ms_sum=coder.last_timing)
+    # row N3: the reference's classifier x depth loops (9 distinct classifier inputs of the demo x depths 2-6 = 45
+    # _get_img_batch calls per batch) from ONE upload per image
+    targets = [((224, 224), "tf"), ((224, 224), "caffe"), ((224, 224), "torch"), ((224, 224), "identity"),
+               ((240, 240), "identity"), ((260, 260), "identity"), ((299, 299), "tf"), ((331, 331), "tf"), ((300, 300), "identity")]
+    coder.classifier_batches_multi(images[:4], depths, targets)
+    t0 = time.perf_counter()
+    res = coder.classifier_batches_multi(images[:30], depths, targets)
+    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    one = coder.classifier_batches(images[:30], 3, (299, 299), "tf")
+    dt_one = time.perf_counter() - t0
+    assert np.array_equal(one[1], res[6][1][3]) and np.array_equal(one[0], res[6][0])
+    mp = sum(a.shape[0] * a.shape[1] for a in images[:30]) / 1e6
+    emit(row="N3 one upload, all classifier inputs", config=f"30 pinned host images -> {len(targets)} targets x depths 2-6 = "
+         f"{len(targets) * len(depths)} icon batches + {len(targets)} source batches (fp32)", s=dt, MP_per_s=mp / dt,
+         one_target_one_depth_call_s=dt_one, same_work_by_single_calls_s=dt_one * len(targets) * len(depths),
+         stage_ms_sum=coder.last_timing)
     for p in ptrs:
         lib.wicca_host_free(p)
 

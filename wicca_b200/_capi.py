@@ -27,6 +27,11 @@ class Timing(C.Structure):
         return {k: float(getattr(self, k)) for k, _ in self._fields_}
 
 
+class Target(C.Structure):
+    """``wicca_target``: one classifier input, (out_h, out_w) and the ``preprocess_input`` family (0..3)."""
+    _fields_ = [("out_h", C.c_int), ("out_w", C.c_int), ("norm_mode", C.c_int)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/wicca_b200.h
 SIGNATURES = {
     "wicca_version": (C.c_char_p, []),
@@ -65,6 +70,10 @@ SIGNATURES = {
     "wicca_batch_classifier_inputs_f32": (C.c_int, [C.POINTER(C.c_void_p), c_intp, c_intp, c_i64p, C.c_int, C.c_int, C.c_int,
                                                     C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, c_intp,
                                                     C.c_int, C.POINTER(Timing)]),
+    "wicca_batch_classifier_inputs_multi_f32": (C.c_int, [C.POINTER(C.c_void_p), c_intp, c_intp, c_i64p, C.c_int, c_intp, C.c_int,
+                                                          C.c_int, C.c_double, C.POINTER(Target), C.c_int,
+                                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_intp, C.c_int,
+                                                          C.POINTER(Timing)]),
     "wicca_resize_norm_dev": (C.c_int, [C.POINTER(C.c_void_p), c_intp, c_intp, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "wicca_icon_resize_norm_f32": (C.c_int, [C.POINTER(C.c_void_p), c_intp, c_intp, C.c_int, C.c_int, C.c_int, C.c_int,

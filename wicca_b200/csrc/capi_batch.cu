@@ -146,8 +146,9 @@ namespace {
 
 struct ClsArgs {
     const uint8_t* const* srcs; const int* Hs; const int* Ws; const int64_t* strides; int n_images;
-    int depth, border_type, bconst, out_h, out_w, norm_mode;
-    float* dst_icons; float* dst_images;
+    const int* depths; int n_depths; int border_type, bconst;
+    const wicca_target* targets; int n_targets;
+    float* const* dst_icons; float* const* dst_images;
 };
 
 int cls_worker(const ClsArgs& a, int device, int first, int step, WorkerResult& res) {
@@ -161,13 +162,19 @@ int cls_worker(const ClsArgs& a, int device, int first, int step, WorkerResult& 
     size_t max_src = 0;
     for (int i = first; i < a.n_images; i += step)
         max_src = std::max(max_src, (size_t)wicca_pitch_bytes(a.Ws[i], 3) * a.Hs[i] + 256);
-    const size_t slot_elems = (size_t)a.out_h * a.out_w * 3;
-    const int n_out = a.dst_images ? 2 : 1;
+    // per image and target: n_depths icon slots followed by the source-image slot
+    const int n_out = a.n_depths + (a.dst_images ? 1 : 0);
+    std::vector<size_t> slot_elems(a.n_targets), out_off(a.n_targets + 1, 0);
+    for (int t = 0; t < a.n_targets; ++t) {
+        slot_elems[t] = (size_t)a.targets[t].out_h * a.targets[t].out_w * 3;
+        out_off[t + 1] = out_off[t] + slot_elems[t] * n_out;
+    }
+    const size_t out_bytes = out_off[a.n_targets] * sizeof(float);
     for (int s = 0; s < 2; ++s) {
         Ctx& c = *slot[s].c;
         WICCA_CUDA(c.d_src.reserve(max_src));
-        WICCA_CUDA(c.d_f32a.reserve(slot_elems * sizeof(float) * n_out));
-        WICCA_CUDA(c.h_out.reserve(slot_elems * sizeof(float) * n_out));
+        WICCA_CUDA(c.d_f32a.reserve(out_bytes));
+        WICCA_CUDA(c.h_out.reserve(out_bytes));
     }
     int j = 0;
     for (int i = first; i < a.n_images; i += step, ++j) {
@@ -186,26 +193,39 @@ int cls_worker(const ClsArgs& a, int device, int first, int step, WorkerResult& 
         if (rc) { cudaStreamSynchronize(c.stream); c.pending.clear(); return rc; }
         WICCA_CUDA(cudaEventRecord(c.ev[1], c.stream));
         std::vector<IconOut> outs;
-        rc = enqueue_icons_resident(c, H, W, 3, pitch, &a.depth, 1, a.border_type, a.bconst, outs);
+        rc = enqueue_icons_resident(c, H, W, 3, pitch, a.depths, a.n_depths, a.border_type, a.bconst, outs);
         if (rc) { cudaStreamSynchronize(c.stream); c.pending.clear(); return rc; }
-        // tap tables for [icon] (+ [source image]); each resize launch handles one image into its slot
+        // tap tables per target for [icons..., source image]; one resize launch per target fills its slots
         std::vector<ResizeSrc> rs;
-        rs.push_back({outs[0].d_ptr, outs[0].h, outs[0].w, outs[0].pitch});
+        for (int k = 0; k < a.n_depths; ++k) rs.push_back({outs[k].d_ptr, outs[k].h, outs[k].w, outs[k].pitch});
         if (a.dst_images) rs.push_back({(const uint8_t*)c.d_src.p, H, W, pitch});
-        const ResizeTableBlob blob = build_resize_tables(rs, a.out_h, a.out_w);
-        WICCA_CUDA(c.h_bounce.reserve(blob.bytes.size()));
-        WICCA_CUDA(c.d_misc.reserve(blob.bytes.size()));
-        memcpy(c.h_bounce.p, blob.bytes.data(), blob.bytes.size());
-        WICCA_CUDA(cudaMemcpyAsync(c.d_misc.p, c.h_bounce.p, blob.bytes.size(), cudaMemcpyHostToDevice, c.stream));
-        cudaError_t e = launch_resize_norm(blob.view(c.d_misc.p), n_out, a.out_h, a.out_w, a.norm_mode, (float*)c.d_f32a.p,
-                                           nullptr, blob.max_src_w, blob.n_area, blob.n_other, c.stream);
-        if (e != cudaSuccess) { cudaStreamSynchronize(c.stream); return cuda_fail(e, "resize/normalise kernel"); }
+        std::vector<ResizeTableBlob> blobs;
+        std::vector<size_t> blob_off(a.n_targets + 1, 0);
+        for (int t = 0; t < a.n_targets; ++t) {
+            blobs.push_back(build_resize_tables(rs, a.targets[t].out_h, a.targets[t].out_w));
+            blob_off[t + 1] = (size_t)align_up((int64_t)(blob_off[t] + blobs[t].bytes.size()), 256);
+        }
+        WICCA_CUDA(c.h_bounce.reserve(blob_off[a.n_targets]));
+        WICCA_CUDA(c.d_misc.reserve(blob_off[a.n_targets]));
+        for (int t = 0; t < a.n_targets; ++t) memcpy((uint8_t*)c.h_bounce.p + blob_off[t], blobs[t].bytes.data(), blobs[t].bytes.size());
+        WICCA_CUDA(cudaMemcpyAsync(c.d_misc.p, c.h_bounce.p, blob_off[a.n_targets], cudaMemcpyHostToDevice, c.stream));
+        for (int t = 0; t < a.n_targets; ++t) {
+            cudaError_t e = launch_resize_norm(blobs[t].view((uint8_t*)c.d_misc.p + blob_off[t]), n_out, a.targets[t].out_h,
+                                               a.targets[t].out_w, a.targets[t].norm_mode, (float*)c.d_f32a.p + out_off[t],
+                                               nullptr, blobs[t].max_src_w, blobs[t].n_area, blobs[t].n_other, c.stream);
+            if (e != cudaSuccess) { cudaStreamSynchronize(c.stream); return cuda_fail(e, "resize/normalise kernel"); }
+        }
         WICCA_CUDA(cudaEventRecord(c.ev[2], c.stream));
-        // D2H through the slot's pinned buffer (the destination batch is usually pageable NumPy memory)
-        WICCA_CUDA(cudaMemcpyAsync(c.h_out.p, c.d_f32a.p, slot_elems * sizeof(float) * n_out, cudaMemcpyDeviceToHost, c.stream));
-        c.pending.push_back({a.dst_icons + (size_t)i * slot_elems, c.h_out.p, slot_elems * sizeof(float)});
-        if (a.dst_images)
-            c.pending.push_back({a.dst_images + (size_t)i * slot_elems, (const float*)c.h_out.p + slot_elems, slot_elems * sizeof(float)});
+        // D2H through the slot's pinned buffer (the destination batches are usually pageable NumPy memory)
+        WICCA_CUDA(cudaMemcpyAsync(c.h_out.p, c.d_f32a.p, out_bytes, cudaMemcpyDeviceToHost, c.stream));
+        for (int t = 0; t < a.n_targets; ++t) {
+            const float* h = (const float*)c.h_out.p + out_off[t];
+            const size_t bytes = slot_elems[t] * sizeof(float);
+            for (int k = 0; k < a.n_depths; ++k)
+                c.pending.push_back({a.dst_icons[(size_t)t * a.n_depths + k] + (size_t)i * slot_elems[t], h + (size_t)k * slot_elems[t], bytes});
+            if (a.dst_images)
+                c.pending.push_back({a.dst_images[t] + (size_t)i * slot_elems[t], h + (size_t)a.n_depths * slot_elems[t], bytes});
+        }
         WICCA_CUDA(cudaEventRecord(c.ev[3], c.stream));
         busy[j & 1] = true;
     }
@@ -220,20 +240,29 @@ int cls_worker(const ClsArgs& a, int device, int first, int step, WorkerResult& 
 
 }  // namespace
 
-extern "C" int wicca_batch_classifier_inputs_f32(const uint8_t* const* srcs, const int* Hs, const int* Ws,
-                                                 const int64_t* strides, int n_images, int depth, int border_type,
-                                                 double border_const, int out_h, int out_w, int norm_mode,
-                                                 float* dst_icons, float* dst_images, const int* devices, int n_devices,
-                                                 wicca_timing* t) {
+extern "C" int wicca_batch_classifier_inputs_multi_f32(const uint8_t* const* srcs, const int* Hs, const int* Ws,
+                                                       const int64_t* strides, int n_images, const int* depths,
+                                                       int n_depths, int border_type, double border_const,
+                                                       const wicca_target* targets, int n_targets,
+                                                       float* const* dst_icons, float* const* dst_images,
+                                                       const int* devices, int n_devices, wicca_timing* t) {
     if (t) memset(t, 0, sizeof(*t));
     if (n_images < 0) return fail(WICCA_EINVAL, "negative image count");
     if (n_images == 0) return 0;
-    if (!srcs || !Hs || !Ws || !dst_icons) return fail(WICCA_EINVAL, "null array");
-    if (depth < 1) return fail(WICCA_EDEPTH, "transform depth must be >= 1");
-    if (out_h <= 0 || out_w <= 0 || norm_mode < 0 || norm_mode > 3) return fail(WICCA_EINVAL, "bad target size / mode");
+    if (!srcs || !Hs || !Ws || !depths || !targets || !dst_icons) return fail(WICCA_EINVAL, "null array");
+    if (n_depths <= 0 || n_targets <= 0) return fail(WICCA_EINVAL, "need at least one depth and one target");
+    for (int k = 0; k < n_depths; ++k)
+        if (depths[k] < 1) return fail(WICCA_EDEPTH, "transform depth must be >= 1");
+    for (int q = 0; q < n_targets; ++q) {
+        if (targets[q].out_h <= 0 || targets[q].out_w <= 0 || targets[q].norm_mode < 0 || targets[q].norm_mode > 3)
+            return fail(WICCA_EINVAL, "bad target size / mode (target %d)", q);
+        for (int k = 0; k < n_depths; ++k)
+            if (!dst_icons[(size_t)q * n_depths + k]) return fail(WICCA_EINVAL, "dst_icons[%d][%d] is NULL", q, k);
+        if (dst_images && !dst_images[q]) return fail(WICCA_EINVAL, "dst_images[%d] is NULL", q);
+    }
     if (n_devices <= 0) return fail(WICCA_EDEVICE, "need at least one device");
     for (int i = 0; i < n_images; ++i) {
-        int rc = validate_icon_args(srcs[i], Hs[i], Ws[i], 3, &depth, 1, border_type);
+        int rc = validate_icon_args(srcs[i], Hs[i], Ws[i], 3, depths, n_depths, border_type);
         if (rc) return rc;
         if (strides && strides[i] && strides[i] < (int64_t)Ws[i] * 3) return fail(WICCA_EINVAL, "strides[%d] < W*3", i);
     }
@@ -243,7 +272,7 @@ extern "C" int wicca_batch_classifier_inputs_f32(const uint8_t* const* srcs, con
         int rc = check_device(devs[k]);
         if (rc) return rc;
     }
-    ClsArgs a{srcs, Hs, Ws, strides, n_images, depth, border_type, saturate_u8(border_const), out_h, out_w, norm_mode,
+    ClsArgs a{srcs, Hs, Ws, strides, n_images, depths, n_depths, border_type, saturate_u8(border_const), targets, n_targets,
               dst_icons, dst_images};
     const int nw = n_devices < n_images ? n_devices : n_images;
     std::vector<WorkerResult> results(nw);
@@ -261,4 +290,17 @@ extern "C" int wicca_batch_classifier_inputs_f32(const uint8_t* const* srcs, con
     }
     if (t) *t = sum;
     return 0;
+}
+
+extern "C" int wicca_batch_classifier_inputs_f32(const uint8_t* const* srcs, const int* Hs, const int* Ws,
+                                                 const int64_t* strides, int n_images, int depth, int border_type,
+                                                 double border_const, int out_h, int out_w, int norm_mode,
+                                                 float* dst_icons, float* dst_images, const int* devices, int n_devices,
+                                                 wicca_timing* t) {
+    if (n_images > 0 && !dst_icons) return fail(WICCA_EINVAL, "null array");
+    const wicca_target target = {out_h, out_w, norm_mode};
+    float* icons[1] = {dst_icons};
+    float* images[1] = {dst_images};
+    return wicca_batch_classifier_inputs_multi_f32(srcs, Hs, Ws, strides, n_images, &depth, 1, border_type, border_const, &target,
+                                                   1, icons, dst_images ? images : nullptr, devices, n_devices, t);
 }

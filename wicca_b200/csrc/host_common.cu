@@ -82,8 +82,40 @@ cudaError_t Ctx::init(int dev) {
     return cudaSuccess;
 }
 
+// Threads for large host-side copies (staged uploads, result hand-over): half the cores, at most 8.
+int host_copy_threads() {
+    unsigned hw = std::thread::hardware_concurrency();
+    int n = (int)(hw / 2);
+    if (n > 8) n = 8;
+    if (n < 1) n = 1;
+    if (const char* e = getenv("WICCA_UPLOAD_THREADS")) n = atoi(e) > 0 ? atoi(e) : n;
+    return n;
+}
+
 void Ctx::flush_pending() {
-    for (const Pending& q : pending) memcpy(q.dst, q.src, q.bytes);
+    size_t total = 0;
+    for (const Pending& q : pending) total += q.bytes;
+    int n_threads = host_copy_threads();
+    if (total < ((size_t)8 << 20) || n_threads < 2) {
+        for (const Pending& q : pending) memcpy(q.dst, q.src, q.bytes);
+    } else {
+        // large results (classifier batches: tens of MB per image, into freshly allocated pageable arrays):
+        // 2 MB pieces handed round-robin to a few threads - copy bandwidth and first-touch faults both scale
+        struct Piece { uint8_t* dst; const uint8_t* src; size_t bytes; };
+        std::vector<Piece> pieces;
+        const size_t piece = (size_t)2 << 20;
+        for (const Pending& q : pending)
+            for (size_t o = 0; o < q.bytes; o += piece)
+                pieces.push_back({(uint8_t*)q.dst + o, (const uint8_t*)q.src + o, std::min(piece, q.bytes - o)});
+        if (n_threads > (int)pieces.size()) n_threads = (int)pieces.size();
+        auto work = [&](int t) {
+            for (size_t k = (size_t)t; k < pieces.size(); k += (size_t)n_threads) memcpy(pieces[k].dst, pieces[k].src, pieces[k].bytes);
+        };
+        std::vector<std::thread> threads;
+        for (int t = 1; t < n_threads; ++t) threads.emplace_back(work, t);
+        work(0);
+        for (auto& th : threads) th.join();
+    }
     pending.clear();
 }
 
@@ -275,11 +307,7 @@ int upload_image_async(Ctx& c, const uint8_t* src, int H, int64_t row_bytes, int
     int rows_per_band = (int)(((size_t)4 << 20) / (size_t)row_bytes);
     if (rows_per_band < 1) rows_per_band = 1;
     const int n_bands = (H + rows_per_band - 1) / rows_per_band;
-    unsigned hw = std::thread::hardware_concurrency();
-    int n_threads = (int)(hw / 2);                     // staging is a plain memcpy: bandwidth scales with cores
-    if (n_threads > 8) n_threads = 8;
-    if (n_threads < 1) n_threads = 1;
-    if (const char* e = getenv("WICCA_UPLOAD_THREADS")) n_threads = atoi(e) > 0 ? atoi(e) : n_threads;
+    int n_threads = host_copy_threads();               // staging is a plain memcpy: bandwidth scales with cores
     if (n_threads > n_bands) n_threads = n_bands;
     std::vector<cudaError_t> errs(n_threads, cudaSuccess);
     auto work = [&](int t) {

@@ -88,6 +88,7 @@ int encode_image_tmap(CUtensorMap* tm, const void* d_src, int H, int64_t pitch);
 int encode_icon_tmap(CUtensorMap* tm, const void* d_icon, int h, int64_t w_bytes, int64_t pitch, int box_w, int box_h);
 
 bool is_pinned_host(const void* p);
+int host_copy_threads();          // threads for large host-side copies (WICCA_UPLOAD_THREADS overrides)
 
 // NUMA locality: CPUs attached to the same socket / PCIe root as `device` (from sysfs; empty when unknown).
 // ScopedAffinity binds the calling thread to them for its lifetime, so that page-locked memory

@@ -183,10 +183,18 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
     const ResizeJob j = t.jobs[img];
     if (j.regime != 2) return;
     const AreaDesc ay = t.area[j.yoff + dy];
+    // this CTA's segment of the output row (blockIdx.z) and the source bytes that feed it
+    const int x0 = blockIdx.z * blockDim.x;
+    if (x0 >= out_w) return;
+    const int x_last = min(x0 + (int)blockDim.x, out_w) - 1;
+    const AreaDesc a_first = t.area[j.xoff + x0], a_last = t.area[j.xoff + x_last];
     const int row_bytes = j.sw * 3;
-    const int copy_bytes = (row_bytes + 15) & ~15;
-    // a row can be bulk-copied when it starts on a 16-byte boundary and its rounded-up length stays inside the pitch
-    const bool bulk = (((uintptr_t)j.src | (uintptr_t)j.pitch) & 15) == 0 && copy_bytes <= j.pitch;
+    const int lo = max(0, (a_first.s_first - 1) * 3) & ~15;                            // first byte fetched
+    const int hi = min(row_bytes, (a_last.s_first + a_last.n_full + 1) * 3);           // one past the last byte needed
+    const int seg_bytes = hi - lo;
+    const int copy_bytes = (seg_bytes + 15) & ~15;
+    // a segment can be bulk-copied when it starts on a 16-byte boundary and its rounded-up length stays inside the pitch
+    const bool bulk = (((uintptr_t)j.src | (uintptr_t)j.pitch) & 15) == 0 && lo + copy_bytes <= j.pitch;
     if (threadIdx.x == 0) {
         rs_mbar_init(&s_full[0], 1); rs_mbar_init(&s_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -197,7 +205,7 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
     auto row_index = [&](int k) { return (has_l && k == 0) ? ay.s_left : (k - has_l < ay.n_full ? ay.s_first + (k - has_l) : ay.s_right); };
     auto row_weight = [&](int k) { return (has_l && k == 0) ? ay.w_left : (k - has_l < ay.n_full ? ay.w_full : ay.w_right); };
     auto fetch = [&](int k) {
-        const uint8_t* g = j.src + (int64_t)row_index(k) * j.pitch;
+        const uint8_t* g = j.src + (int64_t)row_index(k) * j.pitch + lo;
         uint8_t* s = s_rows + (k & 1) * buf_bytes + kRowPadFront;
         if (bulk) {
             if (threadIdx.x == 0) {
@@ -205,11 +213,11 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
                 rs_bulk_load(s, g, (uint32_t)copy_bytes, &s_full[k & 1]);
             }
         } else {
-            for (int b = threadIdx.x; b < row_bytes; b += blockDim.x) s[b] = g[b];
+            for (int b = threadIdx.x; b < seg_bytes; b += blockDim.x) s[b] = g[b];
         }
     };
     // ---- this thread's x taps (independent of the row)
-    const int dx = threadIdx.x;
+    const int dx = x0 + threadIdx.x;
     const bool active = dx < out_w;
     const AreaDesc ax = t.area[j.xoff + (active ? dx : 0)];
     const int n_taps = ax.n_full + 2;                          // pixels s_first - 1 .. s_first + n_full
@@ -222,7 +230,7 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
         wz[q] = tap_weight(4 * (groups - 1) + q); nwz[q] = -8388608.0f * wz[q];
         wm[q] = ax.w_full; nwm[q] = -8388608.0f * ax.w_full;
     }
-    const int b_start = (ax.s_first - 1) * 3 + kRowPadFront;   // >= 13
+    const int b_start = (ax.s_first - 1) * 3 - lo + kRowPadFront;   // >= 13
     const uint32_t shift = (uint32_t)(b_start & 3) * 8;
     float acc[3] = {0.0f, 0.0f, 0.0f};
     __syncthreads();                                           // mbarrier init visible
@@ -260,9 +268,16 @@ cudaError_t launch_resize_norm(const ResizeTables& t, int n, int out_h, int out_
                                uint8_t* d_out_u8, int max_src_w, int n_area, int n_other, cudaStream_t stream) {
     const int64_t total = (int64_t)n * out_h * out_w * 3;
     if (total <= 0) return cudaSuccess;
-    const int buf_bytes = kRowPadFront + (max_src_w * 3 + 15) / 16 * 16 + kRowPadBack;
+    // one CTA per (output row, image, row segment); a segment is as wide as possible while the grid still fills
+    // the GPU a few times over (a lone 53 MP image would otherwise run on 224 CTAs, each streaming 0.7 MB)
+    int seg_w = (out_w + 31) / 32 * 32;
+    while (seg_w > 32 && (int64_t)out_h * (n_area > 0 ? n_area : 1) * ((out_w + seg_w - 1) / seg_w) < 148 * 8) seg_w = (seg_w / 2 + 31) / 32 * 32;
+    const int segs = (out_w + seg_w - 1) / seg_w;
+    // source span of one segment: seg_w target pixels x scale, + the early pixel, the padded last group, alignment slack
+    const int64_t span_px = segs == 1 ? (int64_t)max_src_w + 8 : ((int64_t)seg_w * max_src_w + out_w - 1) / out_w + 10;
+    const int buf_bytes = kRowPadFront + (int)((span_px * 3 + 16 + 15) / 16 * 16) + kRowPadBack;
     const size_t smem = (size_t)2 * buf_bytes;
-    const bool rows_ok = n_area > 0 && out_w <= kRowsMaxThreads && smem <= 200 * 1024 && n <= 65535;
+    const bool rows_ok = n_area > 0 && out_w <= kRowsMaxThreads && smem <= 200 * 1024 && n <= 65535 && segs <= 65535;
     if (rows_ok) {
         static thread_local int configured_dev = -1;
         int dev = 0;
@@ -272,8 +287,7 @@ cudaError_t launch_resize_norm(const ResizeTables& t, int n, int out_h, int out_
             if (e != cudaSuccess) return e;
             configured_dev = dev;
         }
-        const int threads = (out_w + 31) / 32 * 32;
-        resize_area_rows_kernel<<<dim3(out_h, n), threads, smem, stream>>>(t, out_h, out_w, norm_mode, d_out, d_out_u8, buf_bytes);
+        resize_area_rows_kernel<<<dim3(out_h, n, segs), seg_w, smem, stream>>>(t, out_h, out_w, norm_mode, d_out, d_out_u8, buf_bytes);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_other == 0) return cudaSuccess;

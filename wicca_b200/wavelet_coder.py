@@ -325,6 +325,67 @@ class HaarCoder(WaveletCoder):
         self._tls.timing = t.as_dict()
         return srcs_out, icons
 
+    def classifier_batches_multi(self, images: Sequence[np.ndarray], transform_depths: Sequence[int],
+                                 targets: Sequence[tuple], border_type: int = BORDER_REPLICATE,
+                                 border_constant: int = 0, with_source: bool = True,
+                                 devices: Sequence[int] | None = None):
+        """Every batch the reference's ``for classifier: for depth:`` loops build from one set of images
+        (``classifying_tools.py:546-551`` around ``:339-346``), from ONE upload per image.
+
+        ``targets`` is a sequence of ``((w, h), mode)`` pairs, one per distinct classifier input
+        (e.g. ``((224, 224), "tf")``, ``((224, 224), "caffe")``, ``((331, 331), "tf")``).  Returns a list
+        with one ``(batch_images, {depth: batch_icons})`` entry per target, each array float32
+        ``(B, h, w, 3)`` and equal to what ``classifier_batches(images, depth, (w, h), mode)`` returns;
+        ``batch_images`` is ``None`` when ``with_source`` is false."""
+        depths = [_as_depth(d) for d in transform_depths]
+        if not depths or any(d < 1 for d in depths):
+            raise ValueError("transform_depths must be a non-empty sequence of depths >= 1")
+        if len(set(depths)) != len(depths):
+            raise ValueError("transform_depths must not repeat")
+        tlist = []
+        for shape, mode in targets:
+            if mode not in NORM_MODES:
+                raise ValueError(f"unknown preprocess mode {mode!r}; expected one of {sorted(NORM_MODES)}")
+            ow, oh = int(shape[0]), int(shape[1])
+            if ow <= 0 or oh <= 0:
+                raise ValueError("target shape must be positive")
+            tlist.append((oh, ow, NORM_MODES[mode]))
+        if not tlist:
+            raise ValueError("need at least one target")
+        views = []
+        for img in images:
+            validate_image(img)
+            _check_layout(img, tuple(depths), border_type)
+            if img.ndim != 3 or img.shape[2] != 3:
+                raise ValueError("classifier batches need (H, W, 3) images")
+            views.append(_row_major_view(img))
+        n, nd, nt = len(views), len(depths), len(tlist)
+        out = []
+        for oh, ow, _ in tlist:
+            src = np.empty((n, oh, ow, 3), dtype=np.float32) if with_source else None
+            out.append((src, {d: np.empty((n, oh, ow, 3), dtype=np.float32) for d in depths}))
+        if n == 0:
+            return out
+        lib = _capi.load()
+        if devices is None:
+            devices = list(range(max(1, lib.wicca_device_count())))
+        srcs = (C.c_void_p * n)(*[v.ctypes.data for v, _ in views])
+        hs = (C.c_int * n)(*[v.shape[0] for v, _ in views])
+        ws = (C.c_int * n)(*[v.shape[1] for v, _ in views])
+        strides = (C.c_int64 * n)(*[s for _, s in views])
+        c_depths = (C.c_int * nd)(*depths)
+        c_targets = (_capi.Target * nt)(*[_capi.Target(*t) for t in tlist])
+        dst_icons = (C.c_void_p * (nt * nd))(*[out[t][1][d].ctypes.data for t in range(nt) for d in depths])
+        dst_images = (C.c_void_p * nt)(*[out[t][0].ctypes.data for t in range(nt)]) if with_source else None
+        dev = (C.c_int * len(devices))(*[int(x) for x in devices])
+        t = _capi.Timing()
+        rc = lib.wicca_batch_classifier_inputs_multi_f32(srcs, hs, ws, strides, n, c_depths, nd, int(border_type),
+                                                         float(border_constant), c_targets, nt, dst_icons, dst_images, dev,
+                                                         len(devices), C.byref(t))
+        _capi.check(rc, "wicca_batch_classifier_inputs_multi_f32")
+        self._tls.timing = t.as_dict()
+        return out
+
     @property
     def last_timing(self) -> dict | None:
         """Device-side stage times (ms) of this thread's last call."""
