@@ -50,6 +50,7 @@ extern "C" {
 #define WICCA_EALIGN      (-6)  /* device pointer / pitch alignment not met (device-pointer entry points) */
 #define WICCA_ENOMEM      (-7)  /* host allocation failed                                    */
 #define WICCA_ESTATE      (-8)  /* plan / handle used incorrectly                            */
+#define WICCA_EUNSUPPORTED (-9) /* a valid file outside the decoded subset (see wicca_jpeg_probe) */
 
 /* OpenCV border codes accepted by cv2.copyMakeBorder (data_loader.py:116); bit 16 (BORDER_ISOLATED) is ignored */
 #define WICCA_BORDER_CONSTANT    0
@@ -217,6 +218,43 @@ WICCA_API int wicca_batch_classifier_inputs_multi_f32(const uint8_t* const* srcs
 WICCA_API int wicca_resize_norm_dev(const uint8_t* const* d_srcs, const int* hs, const int* ws, const int64_t* pitches,
                                     int n, int out_h, int out_w, int norm_mode, float* d_dst, uint8_t* d_dst_u8,
                                     int device, void* stream);
+
+/* ---- JPEG ingest (row N2 of the hot-path table) -------------------------
+ * Replaces `cv2.imread(file_path)` + `cv2.cvtColor(image, cv2.COLOR_BGR2RGB)` in load_image
+ * (wicca/data_loader.py:53-58) for baseline JPEG files.  The entropy-coded scan is Huffman-decoded on the host
+ * (serial by construction); dequantisation, the inverse DCT, chroma upsampling and YCbCr->RGB run on the GPU with
+ * libjpeg-turbo's default arithmetic (islow IDCT, fancy upsampling), so the result is bit-identical to cv2's.
+ * Decoded subset: SOF0/SOF1 Huffman frames, 8-bit, 1 (grey, returned as 3 equal channels like IMREAD_COLOR) or
+ * 3 (YCbCr) components in one interleaved scan, integral sampling ratios, restart intervals, EXIF orientation 1.
+ * Everything else returns WICCA_EUNSUPPORTED with the reason in wicca_last_error() - nothing is ever decoded
+ * approximately and there is no CPU fallback: route such files through cv2.imread as before. */
+WICCA_API int wicca_jpeg_probe(const uint8_t* data, size_t len, int* H, int* W, int* n_components,
+                               int* h_max, int* v_max);
+/* Host-only helpers (no GPU): number of int16 coefficients of the dense coefficient array (negative = error code),
+ * and the Huffman decoder itself - per component, blocks in raster order, 64 quantised coefficients each in
+ * natural order; blocks_w/blocks_h [n_components], qt [n_components * 64] (natural order) are optional outputs. */
+WICCA_API int64_t wicca_jpeg_coeff_count(const uint8_t* data, size_t len);
+WICCA_API int wicca_jpeg_decode_coeffs(const uint8_t* data, size_t len, int16_t* dst, int64_t dst_count,
+                                       int* blocks_w, int* blocks_h, uint16_t* qt);
+/* JPEG bytes -> host RGB image (H, W, 3), rows dst_stride bytes apart (0 = tight).  host_decode_ms (nullable):
+ * wall time of the Huffman stage; t: device stages. */
+WICCA_API int wicca_jpeg_decode_u8(const uint8_t* data, size_t len, uint8_t* dst, int64_t dst_stride, int device,
+                                   wicca_timing* t, float* host_decode_ms);
+/* JPEG bytes -> device RGB image, rows d_pitch bytes apart (use wicca_pitch_bytes for the fused icon path).
+ * Work is enqueued on `stream` and the call returns after it has completed (its staging buffers are pooled). */
+WICCA_API int wicca_jpeg_decode_dev(const uint8_t* data, size_t len, uint8_t* d_dst, int64_t d_pitch, int device,
+                                    void* stream);
+/* JPEG bytes -> icons: load_image + get_small_copy for every depth (>= 1) without the RGB image ever existing on
+ * the host.  dsts[k]: host (icon_dim(H, d_k), icon_dim(W, d_k), 3) uint8, tight. */
+WICCA_API int wicca_jpeg_icons_multi_u8(const uint8_t* data, size_t len, const int* depths, int n_depths,
+                                        int border_type, double border_const, uint8_t* const* dsts, int device,
+                                        wicca_timing* t, float* host_decode_ms);
+/* The same for n files: dsts[i * n_depths + k]; file i runs on devices[i % n_devices]; n_threads host threads
+ * (0 = one per core, at most 32) each take the next file - Huffman decoding is the bottleneck and scales with cores. */
+WICCA_API int wicca_batch_icons_from_jpeg(const uint8_t* const* datas, const size_t* lens, int n_images,
+                                          const int* depths, int n_depths, int border_type, double border_const,
+                                          uint8_t* const* dsts, const int* devices, int n_devices, int n_threads,
+                                          float* host_decode_ms);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,106 @@
+"""GPU parity tests of the JPEG ingest path (row N2): the library's load_image / decode_jpeg against
+cv2.imdecode + BGR2RGB run live (what the reference's load_image does, data_loader.py:53-58), bit for bit."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+
+from tests.test_oracle_jpeg import SAMPLING, encode, photo_like, reference_rgb  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("sampling", list(SAMPLING))
+def test_decode_matches_cv2(sampling):
+    from wicca_b200 import decode_jpeg
+    rng = np.random.default_rng(21)
+    for (h, w) in [(1, 1), (2, 3), (8, 8), (17, 33), (37, 53), (70, 31), (255, 257), (600, 401)]:
+        for q, restart in ((35, 0), (90, 7), (100, 0)):
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if q == 35 else photo_like(rng, h, w)
+            data = encode(img, q, sampling, restart, optimize=(q == 100))
+            got = decode_jpeg(data)
+            assert got.dtype == np.uint8 and np.array_equal(got, reference_rgb(data)), (h, w, q, sampling, restart)
+
+
+def test_decode_grey_and_flat_images():
+    from wicca_b200 import decode_jpeg
+    rng = np.random.default_rng(22)
+    grey = photo_like(rng, 123, 77)[:, :, 0]
+    data = encode(grey, 80)
+    assert np.array_equal(decode_jpeg(data), reference_rgb(data))
+    for value in (0, 255, 128):
+        flat = np.full((64, 48, 3), value, np.uint8)
+        data = encode(flat, 90)
+        assert np.array_equal(decode_jpeg(data), reference_rgb(data))
+
+
+def test_large_photo_and_oracle_agree():
+    """A 12 MP 4:2:0 file: library == cv2; and on a crop-sized file library == oracle restatement too."""
+    from oracle import jpeg_oracle as jo
+    from wicca_b200 import decode_jpeg
+    rng = np.random.default_rng(23)
+    big = photo_like(rng, 3000, 4000)
+    data = encode(big, 92, "420")
+    timing = {}
+    got = decode_jpeg(data, timing=timing)
+    assert np.array_equal(got, reference_rgb(data))
+    assert timing["host_decode_ms"] > 0 and timing["kernel_ms"] > 0
+    small = encode(photo_like(rng, 90, 150), 75, "422", 4)
+    assert np.array_equal(decode_jpeg(small), jo.decode_rgb(small))
+
+
+def test_load_image_and_icons_from_files(tmp_path):
+    from oracle import haar_oracle as ho
+    from wicca_b200 import HaarCoder, icons_from_jpeg, icons_from_jpeg_files, load_image
+    rng = np.random.default_rng(24)
+    paths, refs = [], []
+    for i, (h, w, s) in enumerate([(700, 900, "420"), (513, 1025, "422"), (640, 480, "444"), (333, 777, "420"), (1200, 800, "420")]):
+        data = encode(photo_like(rng, h, w), 88, s, restart=(i % 2) * 11)
+        p = tmp_path / f"img{i}.jpg"
+        p.write_bytes(data)
+        paths.append(str(p))
+        refs.append(reference_rgb(data))
+    img = load_image(paths[0])
+    assert np.array_equal(img, refs[0])
+    assert np.array_equal(img, cv2.cvtColor(cv2.imread(paths[0]), cv2.COLOR_BGR2RGB))
+    depths = [1, 2, 3, 5]
+    one = icons_from_jpeg(open(paths[1], "rb").read(), depths)
+    for d, icon in zip(depths, one):
+        assert np.array_equal(icon, ho.haar_icon_blocksum(refs[1], d))
+        assert np.array_equal(icon, HaarCoder().get_small_copy(refs[1], d))
+    per_file = icons_from_jpeg_files(paths, depths, threads=3)
+    assert len(per_file) == len(paths)
+    for ref, icons in zip(refs, per_file):
+        for d, icon in zip(depths, icons):
+            assert np.array_equal(icon, ho.haar_icon_blocksum(ref, d))
+    with pytest.raises(ValueError):
+        load_image("")
+
+
+def test_decode_to_device_buffer():
+    torch = pytest.importorskip("torch")
+    from wicca_b200 import _capi, jpeg_info
+    from wicca_b200.plan import pitch_bytes
+    rng = np.random.default_rng(25)
+    data = encode(photo_like(rng, 301, 523), 90, "420")
+    info = jpeg_info(data)
+    pitch = pitch_bytes(info["width"], 3)
+    buf = torch.full((info["height"] + 1, pitch), 0xAB, dtype=torch.uint8, device="cuda:0")
+    rc = _capi.load().wicca_jpeg_decode_dev(data, len(data), buf.data_ptr(), pitch, 0,
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _capi.check(rc, "wicca_jpeg_decode_dev")
+    host = buf.cpu().numpy()
+    assert np.array_equal(host[:info["height"], :info["width"] * 3].reshape(info["height"], info["width"], 3), reference_rgb(data))
+    assert (host[info["height"]] == 0xAB).all()                                  # the guard row is untouched
+    assert (host[:info["height"], (info["width"] * 3 + 3) // 4 * 4:] == 0xAB).all()  # and so is the row padding
+
+
+def test_unsupported_files_fail_loudly():
+    from wicca_b200 import UnsupportedImageError, decode_jpeg
+    rng = np.random.default_rng(26)
+    with pytest.raises(UnsupportedImageError):
+        decode_jpeg(encode(photo_like(rng, 32, 32), progressive=True))
+    with pytest.raises(ValueError):
+        decode_jpeg(encode(photo_like(rng, 64, 64))[:300])                      # scan cut short after the header

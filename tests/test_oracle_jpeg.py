@@ -1,0 +1,121 @@
+"""CPU tests of the JPEG ingest path (row N2): the oracle restatement of libjpeg-turbo's decoder is pinned on
+cv2.imdecode (the reference's own dependency, run live), and the library's host-side Huffman decoder is
+checked against the oracle.  No GPU needed."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+
+from oracle import jpeg_oracle as jo  # noqa: E402
+from wicca_b200 import _capi  # noqa: E402
+
+SAMPLING = {"444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+            "420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, "440": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440,
+            "411": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411}
+
+
+def photo_like(rng, h, w):
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([128 + 100 * np.sin(xx / 17.0 + c) + 60 * np.cos(yy / 11.0 - c) for c in range(3)], -1)
+    return np.clip(base + rng.normal(0, 12, (h, w, 3)), 0, 255).astype(np.uint8)
+
+
+def encode(img, quality=90, sampling="420", restart=0, optimize=False, progressive=False):
+    params = [cv2.IMWRITE_JPEG_QUALITY, quality]
+    if img.ndim == 3:
+        params += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, SAMPLING[sampling]]
+    if restart:
+        params += [cv2.IMWRITE_JPEG_RST_INTERVAL, restart]
+    if optimize:
+        params += [cv2.IMWRITE_JPEG_OPTIMIZE, 1]
+    if progressive:
+        params += [cv2.IMWRITE_JPEG_PROGRESSIVE, 1]
+    ok, enc = cv2.imencode(".jpg", img, params)
+    assert ok
+    return bytes(enc)
+
+
+def reference_rgb(data):
+    """What the reference's load_image returns (data_loader.py:53-58)."""
+    return cv2.cvtColor(cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+
+
+CASES = [(h, w, q, s, r) for (h, w) in [(8, 8), (1, 1), (2, 3), (17, 33), (37, 53), (70, 31)] for q in (35, 90, 100)
+         for s in SAMPLING for r in (0, 3)]
+
+
+@pytest.mark.parametrize("sampling", list(SAMPLING))
+def test_oracle_matches_cv2(sampling):
+    rng = np.random.default_rng(5)
+    for (h, w, q, s, r) in CASES:
+        if s != sampling:
+            continue
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if q == 35 else photo_like(rng, h, w)
+        data = encode(img, q, s, r, optimize=(q == 100))
+        assert np.array_equal(jo.decode_rgb(data), reference_rgb(data)), (h, w, q, s, r)
+
+
+def test_oracle_grey_and_rejects_progressive():
+    rng = np.random.default_rng(6)
+    grey = photo_like(rng, 40, 23)[:, :, 0]
+    data = encode(grey, 85)
+    assert np.array_equal(jo.decode_rgb(data), reference_rgb(data))
+    with pytest.raises(jo.Unsupported):
+        jo.decode_rgb(encode(photo_like(rng, 16, 16), progressive=True))
+
+
+def host_coefficients(data):
+    lib = _capi.load()
+    n = lib.wicca_jpeg_coeff_count(data, len(data))
+    assert n > 0, _capi.last_error()
+    dst = np.empty(n, np.int16)
+    bw, bh = (C.c_int * 3)(), (C.c_int * 3)()
+    qt = np.empty(192, np.uint16)
+    _capi.check(lib.wicca_jpeg_decode_coeffs(data, len(data), dst.ctypes.data, n, bw, bh, qt.ctypes.data), "decode_coeffs")
+    return dst, list(bw), list(bh), qt
+
+
+@pytest.mark.parametrize("sampling", list(SAMPLING))
+def test_host_huffman_decoder_matches_oracle(sampling):
+    """The product's host stage (parser + Huffman decoder) against the oracle's, coefficient by coefficient."""
+    rng = np.random.default_rng(7)
+    for (h, w, q, s, r) in CASES + [(130, 97, 90, sampling, 5)]:
+        if s != sampling:
+            continue
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if q == 35 else photo_like(rng, h, w)
+        data = encode(img, q, s, r, optimize=(q == 100))
+        dst, bw, bh, qt = host_coefficients(data)
+        exp = jo.decode_coefficients(data)
+        off = 0
+        for k, cf in enumerate(exp["coefs"]):
+            assert (bh[k], bw[k]) == cf.shape[:2]
+            assert np.array_equal(dst[off:off + cf.size].reshape(cf.shape), cf), (h, w, q, s, r, k)
+            assert np.array_equal(qt[64 * k:64 * k + 64], exp["qt"][k])
+            off += cf.size
+        assert off == dst.size
+
+
+def test_probe_and_unsupported_flavours():
+    from wicca_b200 import UnsupportedImageError, jpeg_info
+    rng = np.random.default_rng(8)
+    img = photo_like(rng, 33, 47)
+    info = jpeg_info(encode(img, 90, "420"))
+    assert info == {"height": 33, "width": 47, "components": 3, "h_max": 2, "v_max": 2}
+    assert jpeg_info(encode(img[:, :, 0], 90))["components"] == 1
+    with pytest.raises(UnsupportedImageError):
+        jpeg_info(encode(img, progressive=True))
+    ok, png = cv2.imencode(".png", img)
+    with pytest.raises(UnsupportedImageError):
+        jpeg_info(bytes(png))
+    with pytest.raises(ValueError):
+        jpeg_info(encode(img)[:40])                     # truncated header
+    # EXIF orientation 6 (cv2.imread would rotate): spliced in front of the first DQT segment
+    data = encode(img)
+    exif = b"Exif\x00\x00MM\x00\x2a\x00\x00\x00\x08\x00\x01\x01\x12\x00\x03\x00\x00\x00\x01\x00\x06\x00\x00\x00\x00\x00\x00"
+    seg = b"\xff\xe1" + (len(exif) + 2).to_bytes(2, "big") + exif
+    rotated = data[:2] + seg + data[2:]
+    assert reference_rgb(rotated).shape == (47, 33, 3)  # cv2 really rotates this file
+    with pytest.raises(UnsupportedImageError):
+        jpeg_info(rotated)

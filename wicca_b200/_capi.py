@@ -74,6 +74,17 @@ SIGNATURES = {
                                                           C.c_int, C.c_double, C.POINTER(Target), C.c_int,
                                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_intp, C.c_int,
                                                           C.POINTER(Timing)]),
+    "wicca_jpeg_probe": (C.c_int, [C.c_void_p, C.c_size_t, c_intp, c_intp, c_intp, c_intp, c_intp]),
+    "wicca_jpeg_coeff_count": (C.c_int64, [C.c_void_p, C.c_size_t]),
+    "wicca_jpeg_decode_coeffs": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, c_intp, c_intp, C.c_void_p]),
+    "wicca_jpeg_decode_u8": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.c_int, C.POINTER(Timing),
+                                       C.POINTER(C.c_float)]),
+    "wicca_jpeg_decode_dev": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "wicca_jpeg_icons_multi_u8": (C.c_int, [C.c_void_p, C.c_size_t, c_intp, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_void_p),
+                                            C.c_int, C.POINTER(Timing), C.POINTER(C.c_float)]),
+    "wicca_batch_icons_from_jpeg": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, c_intp, C.c_int, C.c_int,
+                                              C.c_double, C.POINTER(C.c_void_p), c_intp, C.c_int, C.c_int,
+                                              C.POINTER(C.c_float)]),
     "wicca_resize_norm_dev": (C.c_int, [C.POINTER(C.c_void_p), c_intp, c_intp, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "wicca_icon_resize_norm_f32": (C.c_int, [C.POINTER(C.c_void_p), c_intp, c_intp, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -81,7 +92,7 @@ SIGNATURES = {
 }
 
 # error codes of include/wicca_b200.h
-EINVAL, ECHANNELS, EBORDER, EDEPTH, EDEVICE, EALIGN, ENOMEM, ESTATE = -1, -2, -3, -4, -5, -6, -7, -8
+EINVAL, ECHANNELS, EBORDER, EDEPTH, EDEVICE, EALIGN, ENOMEM, ESTATE, EUNSUPPORTED = -1, -2, -3, -4, -5, -6, -7, -8, -9
 
 _lib = None
 _lock = threading.Lock()
@@ -139,9 +150,14 @@ def check(rc: int, what: str = "") -> None:
         raise RuntimeError(f"{what}: {msg}" if what else msg)
     if rc == EBORDER:
         raise border_error_type()(msg)
-    if rc in (EDEPTH,):
-        raise ValueError(msg)
+    if rc == EUNSUPPORTED:
+        raise UnsupportedImageError(msg)
     raise ValueError(msg)
+
+
+class UnsupportedImageError(ValueError):
+    """A valid image file outside the subset the GPU ingest path decodes (progressive JPEG, PNG, EXIF-rotated ...).
+    Nothing is decoded approximately and there is no CPU fallback: read such a file with ``cv2.imread``."""
 
 
 def border_error_type():

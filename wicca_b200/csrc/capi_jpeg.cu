@@ -1,0 +1,288 @@
+// capi_jpeg.cu - C entry points of the JPEG ingest path (row N2).  Replaces `cv2.imread(path)` +
+// `cv2.cvtColor(image, cv2.COLOR_BGR2RGB)` (wicca/data_loader.py:53-58) for baseline JPEG files: Huffman
+// decoding on the host, everything else on the GPU, the RGB image lands directly in the pitched device
+// buffer the icon kernel reads.
+#include <string.h>
+
+#include <atomic>
+#include <chrono>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "host_common.h"
+#include "jpeg_host.h"
+#include "kernels.h"
+
+using namespace wicca;
+
+namespace {
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int parse_or_fail(const uint8_t* data, size_t len, JpegFrame& f) {
+    std::string why;
+    const int rc = jpeg_parse(data, len, f, why);
+    if (rc) return fail(rc, "%s", why.c_str());
+    return 0;
+}
+
+int upsample_mode(const JpegFrame& f, const JpegComponent& q) {
+    const int hf = f.hmax / q.h, vf = f.vmax / q.v;
+    if (hf == 1 && vf == 1) return 0;
+    if (hf == 2 && vf == 1) return q.dw > 2 ? 1 : 4;       // jdsample.c: fancy only when downsampled_width > 2
+    if (hf == 2 && vf == 2) return q.dw > 2 ? 2 : 4;
+    if (hf == 1 && vf == 2) return 3;
+    return 4;
+}
+
+// Decode `data` into d_dst (RGB, rows d_pitch bytes apart) on `stream`, staging through c's buffers.
+// The coefficients are Huffman-decoded into c.h_in (page-locked) before anything is enqueued.
+int jpeg_enqueue(Ctx& c, const uint8_t* data, size_t len, const JpegFrame& f, uint8_t* d_dst, int64_t d_pitch,
+                 cudaStream_t stream, float* host_ms) {
+    const size_t coef_bytes = (size_t)f.total_coefs * sizeof(int16_t);
+    WICCA_CUDA(c.h_in.reserve(coef_bytes));
+    const double t0 = now_ms();
+    std::string why;
+    int rc = jpeg_decode_coefficients(data, len, f, (int16_t*)c.h_in.p, why);
+    if (rc) return fail(rc, "%s", why.c_str());
+    if (host_ms) *host_ms += (float)(now_ms() - t0);
+    size_t plane_bytes = 0;
+    JpegImageDesc d;
+    memset(&d, 0, sizeof d);
+    d.ncomp = f.ncomp; d.width = f.width; d.height = f.height; d.dst = d_dst; d.dst_pitch = d_pitch;
+    size_t plane_off[3];
+    for (int k = 0; k < f.ncomp; ++k) {
+        const JpegComponent& q = f.comp[k];
+        plane_off[k] = plane_bytes;
+        plane_bytes += (size_t)q.blocks_w * 8 * q.blocks_h * 8;
+    }
+    WICCA_CUDA(c.d_f32a.reserve(coef_bytes));
+    WICCA_CUDA(c.d_f32b.reserve(plane_bytes + 256));
+    for (int k = 0; k < f.ncomp; ++k) {
+        const JpegComponent& q = f.comp[k];
+        JpegPlaneDesc& p = d.comp[k];
+        p.coefs = (const int16_t*)c.d_f32a.p + q.coef_offset;
+        p.plane = (uint8_t*)c.d_f32b.p + plane_off[k];
+        p.blocks_w = q.blocks_w; p.blocks_h = q.blocks_h; p.plane_pitch = q.blocks_w * 8;
+        p.dw = q.dw; p.dh = q.dh; p.hf = f.hmax / q.h; p.vf = f.vmax / q.v;
+        p.mode = upsample_mode(f, q);
+        memcpy(p.qt, f.qt[q.tq], sizeof p.qt);
+    }
+    WICCA_CUDA(cudaMemcpyAsync(c.d_f32a.p, c.h_in.p, coef_bytes, cudaMemcpyHostToDevice, stream));
+    cudaError_t e = launch_jpeg_decode(d, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "JPEG decode kernels");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wicca_jpeg_probe(const uint8_t* data, size_t len, int* H, int* W, int* n_components, int* h_max, int* v_max) {
+    JpegFrame f;
+    int rc = parse_or_fail(data, len, f);
+    if (rc) return rc;
+    if (H) *H = f.height;
+    if (W) *W = f.width;
+    if (n_components) *n_components = f.ncomp;
+    if (h_max) *h_max = f.hmax;
+    if (v_max) *v_max = f.vmax;
+    return 0;
+}
+
+int64_t wicca_jpeg_coeff_count(const uint8_t* data, size_t len) {
+    JpegFrame f;
+    int rc = parse_or_fail(data, len, f);
+    return rc ? (int64_t)rc : f.total_coefs;
+}
+
+int wicca_jpeg_decode_coeffs(const uint8_t* data, size_t len, int16_t* dst, int64_t dst_count, int* blocks_w, int* blocks_h,
+                             uint16_t* qt) {
+    JpegFrame f;
+    int rc = parse_or_fail(data, len, f);
+    if (rc) return rc;
+    if (!dst || dst_count < f.total_coefs) return fail(WICCA_EINVAL, "coefficient buffer too small (%lld needed)", (long long)f.total_coefs);
+    for (int k = 0; k < f.ncomp; ++k) {
+        if (blocks_w) blocks_w[k] = f.comp[k].blocks_w;
+        if (blocks_h) blocks_h[k] = f.comp[k].blocks_h;
+        if (qt) memcpy(qt + 64 * k, f.qt[f.comp[k].tq], 64 * sizeof(uint16_t));
+    }
+    std::string why;
+    rc = jpeg_decode_coefficients(data, len, f, dst, why);
+    if (rc) return fail(rc, "%s", why.c_str());
+    return 0;
+}
+
+int wicca_jpeg_decode_u8(const uint8_t* data, size_t len, uint8_t* dst, int64_t dst_stride, int device, wicca_timing* t,
+                         float* host_decode_ms) {
+    if (t) memset(t, 0, sizeof(*t));
+    if (host_decode_ms) *host_decode_ms = 0;
+    JpegFrame f;
+    int rc = parse_or_fail(data, len, f);
+    if (rc) return rc;
+    const int64_t rowb = (int64_t)f.width * 3;
+    if (!dst) return fail(WICCA_EINVAL, "dst is NULL");
+    if (dst_stride == 0) dst_stride = rowb;
+    if (dst_stride < rowb) return fail(WICCA_EINVAL, "dst_stride < W*3");
+    rc = check_device(device);
+    if (rc) return rc;
+    CtxLease lease;
+    rc = acquire_ctx(device, &lease.c);
+    if (rc) return rc;
+    Ctx& c = *lease.c;
+    const int64_t pitch = wicca_pitch_bytes(f.width, 3);
+    WICCA_CUDA(c.d_src.reserve((size_t)pitch * f.height + 256));
+    float host_ms = 0;
+    // the host part runs first, so the events bracket only the device work
+    WICCA_CUDA(c.h_in.reserve((size_t)f.total_coefs * sizeof(int16_t)));
+    WICCA_CUDA(cudaEventRecord(c.ev[0], c.stream));
+    rc = jpeg_enqueue(c, data, len, f, (uint8_t*)c.d_src.p, pitch, c.stream, &host_ms);
+    if (rc) { cudaStreamSynchronize(c.stream); return rc; }
+    WICCA_CUDA(cudaEventRecord(c.ev[2], c.stream));
+    uint8_t* target = dst;
+    int64_t target_stride = dst_stride;
+    const bool direct = is_pinned_host(dst);
+    if (!direct) {
+        WICCA_CUDA(c.h_bounce.reserve((size_t)rowb * f.height));
+        target = (uint8_t*)c.h_bounce.p;
+        target_stride = rowb;
+    }
+    WICCA_CUDA(cudaMemcpy2DAsync(target, (size_t)target_stride, c.d_src.p, (size_t)pitch, (size_t)rowb, (size_t)f.height,
+                                 cudaMemcpyDeviceToHost, c.stream));
+    WICCA_CUDA(cudaEventRecord(c.ev[3], c.stream));
+    WICCA_CUDA(cudaStreamSynchronize(c.stream));
+    if (!direct) {
+        if (dst_stride == rowb) {
+            c.pending.push_back({dst, target, (size_t)rowb * f.height});
+            c.flush_pending();
+        } else {
+            for (int y = 0; y < f.height; ++y) memcpy(dst + (size_t)y * dst_stride, target + (size_t)y * rowb, (size_t)rowb);
+        }
+    }
+    if (t) {
+        cudaEventElapsedTime(&t->kernel_ms, c.ev[0], c.ev[2]);      // coefficient upload + both kernels
+        cudaEventElapsedTime(&t->d2h_ms, c.ev[2], c.ev[3]);
+        cudaEventElapsedTime(&t->total_ms, c.ev[0], c.ev[3]);
+    }
+    if (host_decode_ms) *host_decode_ms = host_ms;
+    return 0;
+}
+
+int wicca_jpeg_decode_dev(const uint8_t* data, size_t len, uint8_t* d_dst, int64_t d_pitch, int device, void* stream_v) {
+    JpegFrame f;
+    int rc = parse_or_fail(data, len, f);
+    if (rc) return rc;
+    if (!d_dst) return fail(WICCA_EINVAL, "d_dst is NULL");
+    if (d_pitch < (int64_t)f.width * 3) return fail(WICCA_EINVAL, "d_pitch < W*3");
+    rc = check_device(device);
+    if (rc) return rc;
+    CtxLease lease;
+    rc = acquire_ctx(device, &lease.c);
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    rc = jpeg_enqueue(*lease.c, data, len, f, d_dst, d_pitch, stream, nullptr);
+    // the staging buffers belong to the leased context: they may be reused as soon as this returns
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+    return 0;
+}
+
+int wicca_jpeg_icons_multi_u8(const uint8_t* data, size_t len, const int* depths, int n_depths, int border_type,
+                              double border_const, uint8_t* const* dsts, int device, wicca_timing* t, float* host_decode_ms) {
+    if (t) memset(t, 0, sizeof(*t));
+    if (host_decode_ms) *host_decode_ms = 0;
+    JpegFrame f;
+    int rc = parse_or_fail(data, len, f);
+    if (rc) return rc;
+    if (!dsts) return fail(WICCA_EINVAL, "dsts is NULL");
+    uint8_t probe = 0;                                     // validate_icon_args only checks the pointer for NULL
+    rc = validate_icon_args(&probe, f.height, f.width, 3, depths, n_depths, border_type);
+    if (rc) return rc;
+    for (int k = 0; k < n_depths; ++k) {
+        if (!dsts[k]) return fail(WICCA_EINVAL, "dsts[%d] is NULL", k);
+        if (depths[k] <= 0) return fail(WICCA_EDEPTH, "depths must be >= 1 here (depth 0 is the decoded image: use wicca_jpeg_decode_u8)");
+    }
+    rc = check_device(device);
+    if (rc) return rc;
+    CtxLease lease;
+    rc = acquire_ctx(device, &lease.c);
+    if (rc) return rc;
+    Ctx& c = *lease.c;
+    const int64_t pitch = wicca_pitch_bytes(f.width, 3);
+    WICCA_CUDA(c.d_src.reserve((size_t)pitch * f.height + 256));
+    WICCA_CUDA(c.h_in.reserve((size_t)f.total_coefs * sizeof(int16_t)));
+    float host_ms = 0;
+    WICCA_CUDA(cudaEventRecord(c.ev[0], c.stream));
+    rc = jpeg_enqueue(c, data, len, f, (uint8_t*)c.d_src.p, pitch, c.stream, &host_ms);
+    if (rc) { cudaStreamSynchronize(c.stream); return rc; }
+    WICCA_CUDA(cudaEventRecord(c.ev[1], c.stream));
+    rc = icons_from_resident(c, f.height, f.width, 3, pitch, depths, n_depths, border_type, saturate_u8(border_const), dsts);
+    if (rc) { cudaStreamSynchronize(c.stream); c.pending.clear(); return rc; }
+    WICCA_CUDA(cudaStreamSynchronize(c.stream));
+    c.flush_pending();
+    if (t) {
+        cudaEventElapsedTime(&t->h2d_ms, c.ev[0], c.ev[1]);        // coefficient upload + decode kernels
+        cudaEventElapsedTime(&t->kernel_ms, c.ev[1], c.ev[2]);
+        cudaEventElapsedTime(&t->d2h_ms, c.ev[2], c.ev[3]);
+        cudaEventElapsedTime(&t->total_ms, c.ev[0], c.ev[3]);
+    }
+    if (host_decode_ms) *host_decode_ms = host_ms;
+    return 0;
+}
+
+int wicca_batch_icons_from_jpeg(const uint8_t* const* datas, const size_t* lens, int n_images, const int* depths, int n_depths,
+                                int border_type, double border_const, uint8_t* const* dsts, const int* devices, int n_devices,
+                                int n_threads, float* host_decode_ms) {
+    if (host_decode_ms) *host_decode_ms = 0;
+    if (n_images < 0) return fail(WICCA_EINVAL, "negative image count");
+    if (n_images == 0) return 0;
+    if (!datas || !lens || !dsts || !depths) return fail(WICCA_EINVAL, "null array");
+    if (n_devices <= 0) return fail(WICCA_EDEVICE, "need at least one device");
+    std::vector<int> devs(n_devices);
+    for (int k = 0; k < n_devices; ++k) {
+        devs[k] = devices ? devices[k] : k;
+        int rc = check_device(devs[k]);
+        if (rc) return rc;
+    }
+    if (n_threads <= 0) {
+        n_threads = (int)std::thread::hardware_concurrency();
+        if (n_threads > 32) n_threads = 32;
+        if (n_threads < 1) n_threads = 1;
+    }
+    if (n_threads > n_images) n_threads = n_images;
+    // Huffman decoding is serial per file and ~50x slower than everything the GPU does with the result, so the
+    // unit of parallelism is the file: each worker thread takes the next file, decodes it on its own context
+    // (own stream and buffers) on device i % n_devices, and the device work of different files overlaps.
+    std::atomic<int> next(0);
+    std::vector<int> rcs(n_threads, 0);
+    std::vector<std::string> msgs(n_threads);
+    std::vector<float> host_ms(n_threads, 0.f);
+    auto work = [&](int tix) {
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= n_images) return;
+            float hm = 0;
+            int rc = wicca_jpeg_icons_multi_u8(datas[i], lens[i], depths, n_depths, border_type, border_const,
+                                               dsts + (size_t)i * n_depths, devs[i % n_devices], nullptr, &hm);
+            host_ms[tix] += hm;
+            if (rc) { rcs[tix] = rc; msgs[tix] = "image " + std::to_string(i) + ": " + last_error_ref(); next.store(n_images); return; }
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int k = 1; k < n_threads; ++k) threads.emplace_back(work, k);
+    work(0);
+    for (auto& th : threads) th.join();
+    float sum = 0;
+    for (int k = 0; k < n_threads; ++k) {
+        if (rcs[k]) { last_error_ref() = msgs[k]; return rcs[k]; }
+        sum += host_ms[k];
+    }
+    if (host_decode_ms) *host_decode_ms = sum;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,299 @@
+// jpeg_host.cu - JPEG marker parser and Huffman decoder (host code; see jpeg_host.h).
+// Subset: baseline / extended-sequential Huffman frames (SOF0, SOF1), 8-bit samples, one grey component or
+// three YCbCr components in a single interleaved scan, integral sampling ratios, restart intervals.
+// Anything else cv2.imread can read (progressive, arithmetic, CMYK, EXIF-rotated ...) is reported as
+// WICCA_EUNSUPPORTED so that the caller can route that file elsewhere - never decoded approximately.
+#include "jpeg_host.h"
+
+#include <string.h>
+
+#include "host_common.h"
+
+namespace wicca {
+
+namespace {
+
+const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                             41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                             30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+inline int be16(const uint8_t* p) { return (p[0] << 8) | p[1]; }
+
+// EXIF orientation (tag 0x0112) of an APP1 segment, 1 when absent or unreadable.
+int exif_orientation(const uint8_t* seg, size_t n) {
+    if (n < 14 || memcmp(seg, "Exif\0\0", 6) != 0) return 1;
+    const uint8_t* t = seg + 6;
+    const size_t tn = n - 6;
+    const bool le = t[0] == 'I' && t[1] == 'I';
+    if (!le && !(t[0] == 'M' && t[1] == 'M')) return 1;
+    auto u16 = [&](size_t o) -> uint32_t { return le ? (uint32_t)(t[o] | (t[o + 1] << 8)) : (uint32_t)((t[o] << 8) | t[o + 1]); };
+    auto u32 = [&](size_t o) -> uint32_t {
+        return le ? (uint32_t)t[o] | ((uint32_t)t[o + 1] << 8) | ((uint32_t)t[o + 2] << 16) | ((uint32_t)t[o + 3] << 24)
+                  : ((uint32_t)t[o] << 24) | ((uint32_t)t[o + 1] << 16) | ((uint32_t)t[o + 2] << 8) | (uint32_t)t[o + 3];
+    };
+    const size_t ifd = u32(4);
+    if (ifd + 2 > tn) return 1;
+    const uint32_t entries = u16(ifd);
+    for (uint32_t e = 0; e < entries; ++e) {
+        const size_t o = ifd + 2 + 12 * (size_t)e;
+        if (o + 12 > tn) break;
+        if (u16(o) == 0x0112) return (int)u16(o + 8);
+    }
+    return 1;
+}
+
+int build_huff(const uint8_t* counts, const uint8_t* symbols, int n_symbols, JpegHuff& h) {
+    memset(&h, 0, sizeof h);
+    memcpy(h.symbols, symbols, (size_t)n_symbols);
+    int code = 0, k = 0;
+    for (int len = 1; len <= 16; ++len) {
+        h.valoffset[len] = k - code;
+        if (counts[len - 1]) {
+            for (int i = 0; i < counts[len - 1]; ++i, ++k, ++code) {
+                if (len <= 9) {
+                    const int first = code << (9 - len), span = 1 << (9 - len);
+                    for (int j = 0; j < span; ++j) h.look[first + j] = (uint16_t)((len << 8) | symbols[k]);
+                }
+            }
+            h.maxcode[len] = code - 1;
+            if (code > (1 << len)) return -1;                 // over-subscribed table
+        } else {
+            h.maxcode[len] = -1;
+        }
+        code <<= 1;
+    }
+    h.maxcode[17] = 0x7FFFFFFF;
+    h.present = true;
+    return 0;
+}
+
+// MSB-first bit reader: the next bit of the stream is bit 63 of `acc`; `bits` of them are valid.
+struct BitReader {
+    const uint8_t* p;
+    const uint8_t* end;
+    uint64_t acc = 0;
+    int bits = 0;
+
+    // After refill() at least 57 bits are valid (zeros are fed in front of a marker / past the end).
+    inline void refill() {
+        if (p + 8 <= end) {
+            uint64_t x;
+            memcpy(&x, p, 8);
+            const uint64_t inv = ~x;                                     // a 0xFF byte of x is a zero byte of inv
+            if (!((inv - 0x0101010101010101ull) & ~inv & 0x8080808080808080ull)) {
+                const int take = (64 - bits) >> 3;                       // whole bytes that fit
+                acc |= (__builtin_bswap64(x) >> bits) & ~((1ull << (64 - bits - 8 * take)) - 1ull);
+                p += take;
+                bits += 8 * take;
+                return;
+            }
+        }
+        while (bits <= 56) {
+            uint64_t b = 0;
+            if (p < end) {
+                b = *p;
+                if (b == 0xFF) {
+                    if (p + 1 < end && p[1] == 0) p += 2;                // stuffed zero
+                    else b = 0;                                          // a marker: feed zeros, stay in front of it
+                } else {
+                    ++p;
+                }
+            }
+            acc |= b << (56 - bits);
+            bits += 8;
+        }
+    }
+    inline uint32_t peek(int k) const { return (uint32_t)(acc >> (64 - k)); }
+    inline void skip(int k) { acc <<= k; bits -= k; }
+    inline int receive_extend(int s) {                                   // T.81 F.2.2.1 EXTEND, branch-free; s in 1..15
+        const int v = (int)peek(s);
+        skip(s);
+        return v + (((v - (1 << (s - 1))) >> 31) & ((-1 << s) + 1));
+    }
+    inline int decode(const JpegHuff& h) {
+        const uint32_t e = h.look[peek(9)];
+        if (e) { skip((int)(e >> 8)); return (int)(e & 255); }
+        int len = 10;
+        int32_t code = (int32_t)peek(10);
+        while (code > h.maxcode[len]) { ++len; if (len > 16) return -1; code = (int32_t)peek(len); }
+        skip(len);
+        return h.symbols[(code + h.valoffset[len]) & 255];
+    }
+};
+
+}  // namespace
+
+int jpeg_parse(const uint8_t* data, size_t len, JpegFrame& f, std::string& why) {
+    f = JpegFrame();
+    if (!data || len < 4 || data[0] != 0xFF || data[1] != 0xD8) { why = "not a JPEG stream (no SOI marker)"; return WICCA_EUNSUPPORTED; }
+    bool have_frame = false, jfif = false, adobe = false;
+    int adobe_transform = -1;
+    size_t i = 2;
+    for (;;) {
+        if (i + 4 > len) { why = "truncated JPEG header"; return WICCA_EINVAL; }
+        if (data[i] != 0xFF) { why = "JPEG marker expected"; return WICCA_EINVAL; }
+        while (i + 1 < len && data[i + 1] == 0xFF) ++i;
+        const int m = data[i + 1];
+        i += 2;
+        if (m == 0xD9) { why = "JPEG ends before any scan"; return WICCA_EINVAL; }
+        if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;                  // stand-alone markers
+        if (i + 2 > len) { why = "truncated JPEG header"; return WICCA_EINVAL; }
+        const size_t seglen = (size_t)be16(data + i);
+        if (seglen < 2 || i + seglen > len) { why = "bad JPEG segment length"; return WICCA_EINVAL; }
+        const uint8_t* seg = data + i + 2;
+        const size_t n = seglen - 2;
+        i += seglen;
+        switch (m) {
+            case 0xDB: {
+                size_t k = 0;
+                while (k < n) {
+                    const int pq = seg[k] >> 4, tq = seg[k] & 15;
+                    ++k;
+                    if (tq > 3 || k + (pq ? 128 : 64) > n) { why = "bad quantisation table"; return WICCA_EINVAL; }
+                    for (int j = 0; j < 64; ++j) f.qt[tq][kZigzag[j]] = (uint16_t)(pq ? be16(seg + k + 2 * j) : seg[k + j]);
+                    k += pq ? 128 : 64;
+                    f.qt_present[tq] = true;
+                }
+                break;
+            }
+            case 0xC4: {
+                size_t k = 0;
+                while (k < n) {
+                    if (k + 17 > n) { why = "bad Huffman table"; return WICCA_EINVAL; }
+                    const int tc = seg[k] >> 4, th = seg[k] & 15;
+                    int total = 0;
+                    for (int j = 0; j < 16; ++j) total += seg[k + 1 + j];
+                    if (tc > 1 || th > 3 || total > 256 || k + 17 + (size_t)total > n) { why = "bad Huffman table"; return WICCA_EINVAL; }
+                    if (build_huff(seg + k + 1, seg + k + 17, total, tc ? f.ac[th] : f.dc[th])) { why = "bad Huffman table"; return WICCA_EINVAL; }
+                    k += 17 + (size_t)total;
+                }
+                break;
+            }
+            case 0xC0: case 0xC1: {
+                if (n < 6) { why = "bad frame header"; return WICCA_EINVAL; }
+                if (seg[0] != 8) { why = "only 8-bit JPEG samples are supported"; return WICCA_EUNSUPPORTED; }
+                f.height = be16(seg + 1); f.width = be16(seg + 3); f.ncomp = seg[5];
+                if (f.height <= 0 || f.width <= 0) { why = "JPEG with zero size (DNL marker) is not supported"; return WICCA_EUNSUPPORTED; }
+                if (f.ncomp != 1 && f.ncomp != 3) { why = "only 1- and 3-component JPEGs are supported"; return WICCA_EUNSUPPORTED; }
+                if (n < 6 + 3 * (size_t)f.ncomp) { why = "bad frame header"; return WICCA_EINVAL; }
+                for (int c = 0; c < f.ncomp; ++c) {
+                    JpegComponent& q = f.comp[c];
+                    q.id = seg[6 + 3 * c]; q.h = seg[7 + 3 * c] >> 4; q.v = seg[7 + 3 * c] & 15; q.tq = seg[8 + 3 * c];
+                    if (q.h < 1 || q.h > 4 || q.v < 1 || q.v > 4 || q.tq > 3) { why = "bad component description"; return WICCA_EINVAL; }
+                }
+                have_frame = true;
+                break;
+            }
+            case 0xC2: case 0xC3: case 0xC5: case 0xC6: case 0xC7: case 0xC9: case 0xCA: case 0xCB: case 0xCD: case 0xCE: case 0xCF:
+                why = "only baseline / extended-sequential Huffman JPEGs are supported (this one is progressive, lossless or arithmetic)";
+                return WICCA_EUNSUPPORTED;
+            case 0xDD:
+                if (n < 2) { why = "bad restart interval"; return WICCA_EINVAL; }
+                f.restart_interval = be16(seg);
+                break;
+            case 0xE0:
+                if (n >= 5 && memcmp(seg, "JFIF\0", 5) == 0) jfif = true;
+                break;
+            case 0xE1:
+                if (exif_orientation(seg, n) > 1) { why = "EXIF orientation other than 1 (cv2.imread would rotate the image)"; return WICCA_EUNSUPPORTED; }
+                break;
+            case 0xEE:
+                if (n >= 12 && memcmp(seg, "Adobe", 5) == 0) { adobe = true; adobe_transform = seg[11]; }
+                break;
+            case 0xDA: {
+                if (!have_frame) { why = "scan before frame header"; return WICCA_EINVAL; }
+                if (n < 1 || seg[0] != f.ncomp || n < 1 + 2 * (size_t)f.ncomp + 3) { why = "only a single interleaved scan is supported"; return WICCA_EUNSUPPORTED; }
+                for (int s = 0; s < f.ncomp; ++s) {
+                    const int cid = seg[1 + 2 * s], tabs = seg[2 + 2 * s];
+                    if (cid != f.comp[s].id) { why = "scan components out of frame order"; return WICCA_EUNSUPPORTED; }
+                    f.comp[s].td = tabs >> 4; f.comp[s].ta = tabs & 15;
+                    if (f.comp[s].td > 3 || f.comp[s].ta > 3 || !f.dc[f.comp[s].td].present || !f.ac[f.comp[s].ta].present) { why = "scan refers to a missing Huffman table"; return WICCA_EINVAL; }
+                    if (!f.qt_present[f.comp[s].tq]) { why = "frame refers to a missing quantisation table"; return WICCA_EINVAL; }
+                }
+                const uint8_t* tail = seg + 1 + 2 * f.ncomp;
+                if (tail[0] != 0 || tail[1] != 63 || tail[2] != 0) { why = "spectral selection / successive approximation in a sequential scan"; return WICCA_EUNSUPPORTED; }
+                // colour space as libjpeg guesses it: JFIF => YCbCr; Adobe transform 0 => RGB; ids 'R','G','B' => RGB
+                if (f.ncomp == 3) {
+                    const bool rgb_ids = f.comp[0].id == 'R' && f.comp[1].id == 'G' && f.comp[2].id == 'B';
+                    if ((adobe && adobe_transform == 0) || (!jfif && !adobe && rgb_ids)) { why = "RGB-coded JPEG (no YCbCr transform)"; return WICCA_EUNSUPPORTED; }
+                }
+                if (f.ncomp == 1) f.comp[0].h = f.comp[0].v = 1;          // a lone component is never interleaved
+                f.hmax = f.vmax = 1;
+                for (int c = 0; c < f.ncomp; ++c) { if (f.comp[c].h > f.hmax) f.hmax = f.comp[c].h; if (f.comp[c].v > f.vmax) f.vmax = f.comp[c].v; }
+                f.mcux = (f.width + 8 * f.hmax - 1) / (8 * f.hmax);
+                f.mcuy = (f.height + 8 * f.vmax - 1) / (8 * f.vmax);
+                int blocks_in_mcu = 0;
+                f.total_coefs = 0;
+                for (int c = 0; c < f.ncomp; ++c) {
+                    JpegComponent& q = f.comp[c];
+                    if (f.hmax % q.h || f.vmax % q.v) { why = "fractional chroma sampling ratio"; return WICCA_EUNSUPPORTED; }
+                    q.blocks_w = f.mcux * q.h; q.blocks_h = f.mcuy * q.v;
+                    q.dw = (f.width * q.h + f.hmax - 1) / f.hmax; q.dh = (f.height * q.v + f.vmax - 1) / f.vmax;
+                    q.coef_offset = f.total_coefs;
+                    f.total_coefs += (int64_t)q.blocks_w * q.blocks_h * 64;
+                    blocks_in_mcu += q.h * q.v;
+                }
+                if (blocks_in_mcu > 10) { why = "more than 10 blocks per MCU"; return WICCA_EINVAL; }
+                f.scan_offset = i;
+                return 0;
+            }
+            default:
+                break;                                                    // APPn, COM, ... skipped
+        }
+    }
+}
+
+int jpeg_decode_coefficients(const uint8_t* data, size_t len, const JpegFrame& f, int16_t* dst, std::string& why) {
+    BitReader br;
+    br.p = data + f.scan_offset;
+    br.end = data + len;
+    int pred[3] = {0, 0, 0};
+    int64_t count = 0;
+    for (int my = 0; my < f.mcuy; ++my) {
+        for (int mx = 0; mx < f.mcux; ++mx, ++count) {
+            if (f.restart_interval && count && count % f.restart_interval == 0) {
+                // byte-align, step over the RSTn marker, reset the predictors
+                const uint8_t* q = br.p;
+                while (q + 1 < br.end && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) ++q;
+                if (q + 1 >= br.end) { why = "restart marker missing"; return WICCA_EINVAL; }
+                br.p = q + 2; br.acc = 0; br.bits = 0;
+                pred[0] = pred[1] = pred[2] = 0;
+            }
+            for (int c = 0; c < f.ncomp; ++c) {
+                const JpegComponent& q = f.comp[c];
+                const JpegHuff& hd = f.dc[q.td];
+                const JpegHuff& ha = f.ac[q.ta];
+                for (int by = 0; by < q.v; ++by) {
+                    for (int bx = 0; bx < q.h; ++bx) {
+                        int16_t* blk = dst + q.coef_offset + ((int64_t)(my * q.v + by) * q.blocks_w + (mx * q.h + bx)) * 64;
+                        memset(blk, 0, 64 * sizeof(int16_t));
+                        if (br.bits < 32) br.refill();
+                        int s = br.decode(hd);
+                        if (s < 0 || s > 15) { why = "corrupt JPEG data (DC code)"; return WICCA_EINVAL; }
+                        if (s) pred[c] += br.receive_extend(s);
+                        blk[0] = (int16_t)pred[c];
+                        for (int k = 1; k < 64;) {
+                            if (br.bits < 32) br.refill();
+                            const int rs = br.decode(ha);
+                            if (rs < 0) { why = "corrupt JPEG data (AC code)"; return WICCA_EINVAL; }
+                            const int r = rs >> 4;
+                            s = rs & 15;
+                            if (s) {
+                                k += r;
+                                if (k > 63) { why = "corrupt JPEG data (run past the block)"; return WICCA_EINVAL; }
+                                blk[kZigzag[k]] = (int16_t)br.receive_extend(s);
+                                ++k;
+                            } else {
+                                if (r != 15) break;                        // end of block
+                                k += 16;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+}  // namespace wicca

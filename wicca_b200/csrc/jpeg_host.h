@@ -1,0 +1,49 @@
+// jpeg_host.h - host half of the JPEG ingest path (row N2: cv2.imread + BGR2RGB, wicca/data_loader.py:53-58).
+// The entropy-coded segment is decoded on the CPU into dense quantised coefficients (the serial part of a
+// JPEG); dequantisation, the inverse DCT, chroma upsampling and the colour transform run on the GPU
+// (jpeg_kernels.cu), bit-exact with libjpeg-turbo's defaults, which is what cv2.imread uses.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace wicca {
+
+struct JpegComponent {
+    int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0;
+    int blocks_w = 0, blocks_h = 0;        // whole MCUs
+    int dw = 0, dh = 0;                    // real ("downsampled") samples
+    int64_t coef_offset = 0;               // first coefficient of the component in the dense array (int16 units)
+};
+
+struct JpegHuff {
+    // 9-bit lookahead: (length << 8) | symbol for codes of <= 9 bits, 0 otherwise; then the canonical tables
+    uint16_t look[512];
+    int32_t maxcode[18];                   // largest code of each length (-1: none), [17] = sentinel
+    int32_t valoffset[17];
+    uint8_t symbols[256];
+    bool present = false;
+};
+
+struct JpegFrame {
+    int width = 0, height = 0, ncomp = 0;
+    int hmax = 1, vmax = 1, mcux = 0, mcuy = 0;
+    int restart_interval = 0;
+    JpegComponent comp[3];
+    uint16_t qt[4][64];                    // natural (row-major) order
+    bool qt_present[4] = {false, false, false, false};
+    JpegHuff dc[4], ac[4];
+    size_t scan_offset = 0;                // first entropy-coded byte
+    int64_t total_coefs = 0;               // int16 count of the dense coefficient array
+};
+
+// 0 on success; a negative WICCA_* code otherwise, with the reason in `why`.  WICCA_EUNSUPPORTED marks valid
+// JPEGs outside the subset (progressive, arithmetic coding, 12-bit, CMYK, several scans, rotated by EXIF ...).
+int jpeg_parse(const uint8_t* data, size_t len, JpegFrame& f, std::string& why);
+
+// Huffman-decode the scan into dst[total_coefs]: per component, blocks in raster order, 64 coefficients each
+// in natural order, not dequantised.  Every element of dst is written (no pre-zeroing needed).
+int jpeg_decode_coefficients(const uint8_t* data, size_t len, const JpegFrame& f, int16_t* dst, std::string& why);
+
+}  // namespace wicca

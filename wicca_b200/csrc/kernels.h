@@ -47,4 +47,21 @@ struct ResizeTables {
 cudaError_t launch_resize_norm(const ResizeTables& t, int n, int out_h, int out_w, int norm_mode, float* d_out,
                                uint8_t* d_out_u8, int max_src_w, int n_area, int n_other, cudaStream_t stream);
 
+// ---- JPEG ingest (jpeg_kernels.cu): dense quantised coefficients -> pitched RGB image, libjpeg-turbo arithmetic
+struct JpegPlaneDesc {
+    const int16_t* coefs;     // (blocks_h, blocks_w, 64) natural order, quantised
+    uint8_t* plane;           // (blocks_h * 8, plane_pitch) samples
+    int blocks_w, blocks_h, plane_pitch;
+    int dw, dh;               // real samples of the component
+    int hf, vf;               // expansion factors to the image grid
+    int mode;                 // 0 none, 1 h2v1 fancy, 2 h2v2 fancy, 3 h1v2 fancy, 4 box
+    uint16_t qt[64];          // natural order
+};
+struct JpegImageDesc {
+    JpegPlaneDesc comp[3];
+    int ncomp, width, height;
+    uint8_t* dst; int64_t dst_pitch;     // RGB, HWC
+};
+cudaError_t launch_jpeg_decode(const JpegImageDesc& d, cudaStream_t stream);
+
 }  // namespace wicca
