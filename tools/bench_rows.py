@@ -178,6 +178,60 @@ def row_batch():
         lib.wicca_host_free(p)
 
 
+def row_jpeg():
+    """Row N2: load_image (cv2.imread + BGR2RGB, data_loader.py:53-58) from a 53 MP baseline JPEG."""
+    import cv2
+    from concurrent.futures import ThreadPoolExecutor
+    from wicca_b200 import decode_jpeg, icons_from_jpeg
+    rng = np.random.default_rng(3)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    img = np.stack([128 + 90 * np.sin(xx / (37.0 + 9 * c) + c) + 70 * np.cos(yy / (23.0 + 5 * c) - c) for c in range(3)], -1)
+    img = np.clip(img + rng.normal(0, 6, img.shape).astype(np.float32), 0, 255).astype(np.uint8)
+    del yy, xx
+    for quality, sampling, tag in ((90, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, "4:2:0"), (95, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, "4:4:4")):
+        ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, quality, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sampling])
+        data = bytes(enc)
+        ref_t = []
+        for _ in range(3):
+            t0 = time.perf_counter(); ref = cv2.cvtColor(cv2.imdecode(enc, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB); ref_t.append(time.perf_counter() - t0)
+        decode_jpeg(data)
+        ours_t, tm = [], {}
+        for _ in range(3):
+            t0 = time.perf_counter(); got = decode_jpeg(data, timing=tm); ours_t.append(time.perf_counter() - t0)
+        assert np.array_equal(got, ref)
+        icon_t = []
+        for _ in range(3):
+            t0 = time.perf_counter(); icons = icons_from_jpeg(data, [1, 2, 3, 4, 5, 6], timing=tm); icon_t.append(time.perf_counter() - t0)
+        from oracle import haar_oracle as ho
+        assert np.array_equal(icons[2], ho.haar_icon_blocksum(ref, 3))
+        emit(row="N2 JPEG ingest, one file", config=f"({H},{W},3) baseline JPEG q{quality} {tag}, {len(data) / 1e6:.1f} MB",
+             cv2_imdecode_bgr2rgb_s=min(ref_t), decode_to_host_rgb_s=min(ours_t), jpeg_to_icons_depths_1_6_s=min(icon_t),
+             host_huffman_ms=tm["host_decode_ms"], coef_upload_ms=tm["h2d_ms"], decode_and_icon_kernels_ms=tm["kernel_ms"], icons_d2h_ms=tm["d2h_ms"], MP_per_s_to_icons=H * W / 1e6 / min(icon_t),
+             MP_per_s_cv2=H * W / 1e6 / min(ref_t))
+        # many files, all host cores: the reference's loader in a thread pool (cv2 releases the GIL) against the batch entry
+        n, cores = 32, len(os.sched_getaffinity(0))
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as ex:
+            list(ex.map(lambda _: cv2.cvtColor(cv2.imdecode(enc, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB).shape, range(n)))
+        dt_ref = time.perf_counter() - t0
+        depths = [2, 3, 4, 5, 6]
+        outs = [[np.empty((lib.wicca_icon_dim(H, d), lib.wicca_icon_dim(W, d), 3), np.uint8) for d in depths] for _ in range(n)]
+        datas = (C.c_void_p * n)(*[C.cast(C.c_char_p(data), C.c_void_p).value] * n)
+        lens = (C.c_size_t * n)(*[len(data)] * n)
+        dsts = (C.c_void_p * (n * len(depths)))(*[o.ctypes.data for per in outs for o in per])
+        ndev = lib.wicca_device_count()
+        hm = C.c_float()
+        for rep in range(2):
+            t0 = time.perf_counter()
+            _capi.check(lib.wicca_batch_icons_from_jpeg(datas, lens, n, (C.c_int * len(depths))(*depths), len(depths), 1, 0.0, dsts,
+                                                        (C.c_int * ndev)(*range(ndev)), ndev, 0, C.byref(hm)), "batch_icons_from_jpeg")
+            dt = time.perf_counter() - t0
+        assert np.array_equal(outs[7][1], ho.haar_icon_blocksum(ref, 3))
+        emit(row="N2 JPEG ingest, 32 files", config=f"32 x ({H},{W},3) JPEG q{quality} {tag} -> icons depths 2-6, {cores} host threads, {ndev} GPU(s)",
+             s=dt, MP_per_s=n * H * W / 1e6 / dt, files_per_s=n / dt, host_huffman_ms_sum=hm.value,
+             cv2_thread_pool_decode_only_s=dt_ref, cv2_MP_per_s=n * H * W / 1e6 / dt_ref)
+
+
 def row_oneshot():
     """The call the reference's callers make: one get_small_copy on a host array (pageable vs pinned)."""
     coder = HaarCoder()
@@ -214,13 +268,15 @@ def cpu_side():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["icons", "subbands", "batch", "oneshot", "cpu"]
+    which = sys.argv[1:] or ["icons", "subbands", "batch", "jpeg", "oneshot", "cpu"]
     if "icons" in which:
         row_icons()
     if "subbands" in which:
         row_subbands()
     if "batch" in which:
         row_batch()
+    if "jpeg" in which:
+        row_jpeg()
     if "oneshot" in which:
         row_oneshot()
     if "cpu" in which:

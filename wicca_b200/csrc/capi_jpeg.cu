@@ -38,17 +38,20 @@ int upsample_mode(const JpegFrame& f, const JpegComponent& q) {
     return 4;
 }
 
-// Decode `data` into d_dst (RGB, rows d_pitch bytes apart) on `stream`, staging through c's buffers.
-// The coefficients are Huffman-decoded into c.h_in (page-locked) before anything is enqueued.
-int jpeg_enqueue(Ctx& c, const uint8_t* data, size_t len, const JpegFrame& f, uint8_t* d_dst, int64_t d_pitch,
-                 cudaStream_t stream, float* host_ms) {
-    const size_t coef_bytes = (size_t)f.total_coefs * sizeof(int16_t);
-    WICCA_CUDA(c.h_in.reserve(coef_bytes));
+// Host stage: Huffman-decode the scan into c.h_in (page-locked), before anything is enqueued.
+int jpeg_host_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFrame& f, float* host_ms) {
+    WICCA_CUDA(c.h_in.reserve((size_t)f.total_coefs * sizeof(int16_t)));
     const double t0 = now_ms();
     std::string why;
     int rc = jpeg_decode_coefficients(data, len, f, (int16_t*)c.h_in.p, why);
     if (rc) return fail(rc, "%s", why.c_str());
     if (host_ms) *host_ms += (float)(now_ms() - t0);
+    return 0;
+}
+
+// Device stage: coefficients in c.h_in -> d_dst (RGB, rows d_pitch bytes apart) on `stream`, through c's scratch.
+int jpeg_device_stage(Ctx& c, const JpegFrame& f, uint8_t* d_dst, int64_t d_pitch, cudaStream_t stream) {
+    const size_t coef_bytes = (size_t)f.total_coefs * sizeof(int16_t);
     size_t plane_bytes = 0;
     JpegImageDesc d;
     memset(&d, 0, sizeof d);
@@ -72,6 +75,7 @@ int jpeg_enqueue(Ctx& c, const uint8_t* data, size_t len, const JpegFrame& f, ui
         memcpy(p.qt, f.qt[q.tq], sizeof p.qt);
     }
     WICCA_CUDA(cudaMemcpyAsync(c.d_f32a.p, c.h_in.p, coef_bytes, cudaMemcpyHostToDevice, stream));
+    WICCA_CUDA(cudaEventRecord(c.ev[4], stream));                 // coefficients resident
     cudaError_t e = launch_jpeg_decode(d, stream);
     if (e != cudaSuccess) return cuda_fail(e, "JPEG decode kernels");
     return 0;
@@ -136,10 +140,10 @@ int wicca_jpeg_decode_u8(const uint8_t* data, size_t len, uint8_t* dst, int64_t 
     const int64_t pitch = wicca_pitch_bytes(f.width, 3);
     WICCA_CUDA(c.d_src.reserve((size_t)pitch * f.height + 256));
     float host_ms = 0;
-    // the host part runs first, so the events bracket only the device work
-    WICCA_CUDA(c.h_in.reserve((size_t)f.total_coefs * sizeof(int16_t)));
+    rc = jpeg_host_stage(c, data, len, f, &host_ms);       // the host part runs first: the events bracket device work only
+    if (rc) return rc;
     WICCA_CUDA(cudaEventRecord(c.ev[0], c.stream));
-    rc = jpeg_enqueue(c, data, len, f, (uint8_t*)c.d_src.p, pitch, c.stream, &host_ms);
+    rc = jpeg_device_stage(c, f, (uint8_t*)c.d_src.p, pitch, c.stream);
     if (rc) { cudaStreamSynchronize(c.stream); return rc; }
     WICCA_CUDA(cudaEventRecord(c.ev[2], c.stream));
     uint8_t* target = dst;
@@ -163,7 +167,8 @@ int wicca_jpeg_decode_u8(const uint8_t* data, size_t len, uint8_t* dst, int64_t 
         }
     }
     if (t) {
-        cudaEventElapsedTime(&t->kernel_ms, c.ev[0], c.ev[2]);      // coefficient upload + both kernels
+        cudaEventElapsedTime(&t->h2d_ms, c.ev[0], c.ev[4]);         // coefficient upload
+        cudaEventElapsedTime(&t->kernel_ms, c.ev[4], c.ev[2]);      // IDCT + upsampling/colour kernels
         cudaEventElapsedTime(&t->d2h_ms, c.ev[2], c.ev[3]);
         cudaEventElapsedTime(&t->total_ms, c.ev[0], c.ev[3]);
     }
@@ -183,7 +188,9 @@ int wicca_jpeg_decode_dev(const uint8_t* data, size_t len, uint8_t* d_dst, int64
     rc = acquire_ctx(device, &lease.c);
     if (rc) return rc;
     cudaStream_t stream = (cudaStream_t)stream_v;
-    rc = jpeg_enqueue(*lease.c, data, len, f, d_dst, d_pitch, stream, nullptr);
+    rc = jpeg_host_stage(*lease.c, data, len, f, nullptr);
+    if (rc) return rc;
+    rc = jpeg_device_stage(*lease.c, f, d_dst, d_pitch, stream);
     // the staging buffers belong to the leased context: they may be reused as soon as this returns
     cudaError_t e = cudaStreamSynchronize(stream);
     if (rc) return rc;
@@ -214,10 +221,11 @@ int wicca_jpeg_icons_multi_u8(const uint8_t* data, size_t len, const int* depths
     Ctx& c = *lease.c;
     const int64_t pitch = wicca_pitch_bytes(f.width, 3);
     WICCA_CUDA(c.d_src.reserve((size_t)pitch * f.height + 256));
-    WICCA_CUDA(c.h_in.reserve((size_t)f.total_coefs * sizeof(int16_t)));
     float host_ms = 0;
+    rc = jpeg_host_stage(c, data, len, f, &host_ms);
+    if (rc) return rc;
     WICCA_CUDA(cudaEventRecord(c.ev[0], c.stream));
-    rc = jpeg_enqueue(c, data, len, f, (uint8_t*)c.d_src.p, pitch, c.stream, &host_ms);
+    rc = jpeg_device_stage(c, f, (uint8_t*)c.d_src.p, pitch, c.stream);
     if (rc) { cudaStreamSynchronize(c.stream); return rc; }
     WICCA_CUDA(cudaEventRecord(c.ev[1], c.stream));
     rc = icons_from_resident(c, f.height, f.width, 3, pitch, depths, n_depths, border_type, saturate_u8(border_const), dsts);
@@ -225,8 +233,8 @@ int wicca_jpeg_icons_multi_u8(const uint8_t* data, size_t len, const int* depths
     WICCA_CUDA(cudaStreamSynchronize(c.stream));
     c.flush_pending();
     if (t) {
-        cudaEventElapsedTime(&t->h2d_ms, c.ev[0], c.ev[1]);        // coefficient upload + decode kernels
-        cudaEventElapsedTime(&t->kernel_ms, c.ev[1], c.ev[2]);
+        cudaEventElapsedTime(&t->h2d_ms, c.ev[0], c.ev[4]);        // coefficient upload
+        cudaEventElapsedTime(&t->kernel_ms, c.ev[4], c.ev[2]);     // decode kernels + icon kernel
         cudaEventElapsedTime(&t->d2h_ms, c.ev[2], c.ev[3]);
         cudaEventElapsedTime(&t->total_ms, c.ev[0], c.ev[3]);
     }

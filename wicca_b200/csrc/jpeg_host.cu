@@ -50,8 +50,8 @@ int build_huff(const uint8_t* counts, const uint8_t* symbols, int n_symbols, Jpe
         h.valoffset[len] = k - code;
         if (counts[len - 1]) {
             for (int i = 0; i < counts[len - 1]; ++i, ++k, ++code) {
-                if (len <= 9) {
-                    const int first = code << (9 - len), span = 1 << (9 - len);
+                if (len <= 10) {
+                    const int first = code << (10 - len), span = 1 << (10 - len);
                     for (int j = 0; j < span; ++j) h.look[first + j] = (uint16_t)((len << 8) | symbols[k]);
                 }
             }
@@ -63,6 +63,15 @@ int build_huff(const uint8_t* counts, const uint8_t* symbols, int n_symbols, Jpe
         code <<= 1;
     }
     h.maxcode[17] = 0x7FFFFFFF;
+    for (int i = 0; i < 1024; ++i) {
+        const int e = h.look[i];
+        if (!e) continue;
+        const int len = e >> 8, run = (e >> 4) & 15, mag = e & 15;
+        if (!mag || len + mag > 10) continue;
+        int v = ((i << len) & 1023) >> (10 - mag);
+        if (v < (1 << (mag - 1))) v += (-1 << mag) + 1;
+        if (v >= -128 && v <= 127) h.fast_ac[i] = (int16_t)(v * 256 + run * 16 + len + mag);
+    }
     h.present = true;
     return 0;
 }
@@ -111,10 +120,10 @@ struct BitReader {
         return v + (((v - (1 << (s - 1))) >> 31) & ((-1 << s) + 1));
     }
     inline int decode(const JpegHuff& h) {
-        const uint32_t e = h.look[peek(9)];
+        const uint32_t e = h.look[peek(10)];
         if (e) { skip((int)(e >> 8)); return (int)(e & 255); }
-        int len = 10;
-        int32_t code = (int32_t)peek(10);
+        int len = 11;
+        int32_t code = (int32_t)peek(11);
         while (code > h.maxcode[len]) { ++len; if (len > 16) return -1; code = (int32_t)peek(len); }
         skip(len);
         return h.symbols[(code + h.valoffset[len]) & 255];
@@ -274,6 +283,15 @@ int jpeg_decode_coefficients(const uint8_t* data, size_t len, const JpegFrame& f
                         blk[0] = (int16_t)pred[c];
                         for (int k = 1; k < 64;) {
                             if (br.bits < 32) br.refill();
+                            const int fast = ha.fast_ac[br.peek(10)];
+                            if (fast) {                                     // code + value in one lookup
+                                k += (fast >> 4) & 15;
+                                if (k > 63) { why = "corrupt JPEG data (run past the block)"; return WICCA_EINVAL; }
+                                br.skip(fast & 15);
+                                blk[kZigzag[k]] = (int16_t)(fast >> 8);
+                                ++k;
+                                continue;
+                            }
                             const int rs = br.decode(ha);
                             if (rs < 0) { why = "corrupt JPEG data (AC code)"; return WICCA_EINVAL; }
                             const int r = rs >> 4;

@@ -18,8 +18,11 @@ struct JpegComponent {
 };
 
 struct JpegHuff {
-    // 9-bit lookahead: (length << 8) | symbol for codes of <= 9 bits, 0 otherwise; then the canonical tables
-    uint16_t look[512];
+    // 10-bit lookahead: (length << 8) | symbol for codes of <= 10 bits, 0 otherwise; then the canonical tables
+    uint16_t look[1024];
+    // AC tables only: when a code and the value bits that follow it fit in the 10 lookahead bits and the value
+    // fits in 8 bits, (value << 8) | (run << 4) | (bits consumed); 0 otherwise
+    int16_t fast_ac[1024];
     int32_t maxcode[18];                   // largest code of each length (-1: none), [17] = sentinel
     int32_t valoffset[17];
     uint8_t symbols[256];
