@@ -236,6 +236,11 @@ WICCA_API int wicca_jpeg_probe(const uint8_t* data, size_t len, int* H, int* W, 
 WICCA_API int64_t wicca_jpeg_coeff_count(const uint8_t* data, size_t len);
 WICCA_API int wicca_jpeg_decode_coeffs(const uint8_t* data, size_t len, int16_t* dst, int64_t dst_count,
                                        int* blocks_w, int* blocks_h, uint16_t* qt);
+/* The same coefficients from the GPU Huffman decoder (files without restart markers; the default first stage of
+ * every entry point below - WICCA_JPEG_HUFFMAN=host selects the host decoder).  passes (nullable): re-synchronisation
+ * passes it took.  For tests and measurements. */
+WICCA_API int wicca_jpeg_decode_coeffs_gpu(const uint8_t* data, size_t len, int16_t* dst, int64_t dst_count, int device,
+                                           int* passes);
 /* JPEG bytes -> host RGB image (H, W, 3), rows dst_stride bytes apart (0 = tight).  host_decode_ms (nullable):
  * wall time of the Huffman stage; t: device stages. */
 WICCA_API int wicca_jpeg_decode_u8(const uint8_t* data, size_t len, uint8_t* dst, int64_t dst_stride, int device,

@@ -104,3 +104,30 @@ def test_unsupported_files_fail_loudly():
         decode_jpeg(encode(photo_like(rng, 32, 32), progressive=True))
     with pytest.raises(ValueError):
         decode_jpeg(encode(photo_like(rng, 64, 64))[:300])                      # scan cut short after the header
+
+
+@pytest.mark.parametrize("sampling", list(SAMPLING))
+def test_gpu_huffman_decoder_matches_host_decoder(sampling):
+    """The self-synchronising GPU Huffman decoder against the host decoder, coefficient by coefficient."""
+    from tests.test_oracle_jpeg import host_coefficients
+    from wicca_b200 import _capi
+    lib = _capi.load()
+    rng = np.random.default_rng(31)
+    for (h, w, q) in [(8, 8, 90), (40, 56, 35), (257, 511, 75), (600, 800, 92), (1500, 2100, 85), (333, 1001, 100)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if q == 35 else photo_like(rng, h, w)
+        data = encode(img, q, sampling, optimize=(q == 100))
+        exp, _, _, _ = host_coefficients(data)
+        got = np.empty_like(exp)
+        passes = C.c_int()
+        _capi.check(lib.wicca_jpeg_decode_coeffs_gpu(data, len(data), got.ctypes.data, got.size, 0, C.byref(passes)), "coeffs_gpu")
+        assert np.array_equal(got, exp), (h, w, q, sampling, passes.value)
+
+
+def test_both_huffman_stages_give_the_same_image(monkeypatch):
+    from wicca_b200 import decode_jpeg
+    rng = np.random.default_rng(32)
+    data = encode(photo_like(rng, 1111, 1777), 90, "420")
+    a = decode_jpeg(data)
+    monkeypatch.setenv("WICCA_JPEG_HUFFMAN", "host")
+    b = decode_jpeg(data)
+    assert np.array_equal(a, b) and np.array_equal(a, reference_rgb(data))

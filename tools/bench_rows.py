@@ -206,7 +206,7 @@ def row_jpeg():
         assert np.array_equal(icons[2], ho.haar_icon_blocksum(ref, 3))
         emit(row="N2 JPEG ingest, one file", config=f"({H},{W},3) baseline JPEG q{quality} {tag}, {len(data) / 1e6:.1f} MB",
              cv2_imdecode_bgr2rgb_s=min(ref_t), decode_to_host_rgb_s=min(ours_t), jpeg_to_icons_depths_1_6_s=min(icon_t),
-             host_huffman_ms=tm["host_decode_ms"], coef_upload_ms=tm["h2d_ms"], decode_and_icon_kernels_ms=tm["kernel_ms"], icons_d2h_ms=tm["d2h_ms"], MP_per_s_to_icons=H * W / 1e6 / min(icon_t),
+             host_stage_ms=tm["host_decode_ms"], scan_upload_ms=tm["h2d_ms"], huffman_idct_colour_icon_kernels_ms=tm["kernel_ms"], icons_d2h_ms=tm["d2h_ms"], MP_per_s_to_icons=H * W / 1e6 / min(icon_t),
              MP_per_s_cv2=H * W / 1e6 / min(ref_t))
         # many files, all host cores: the reference's loader in a thread pool (cv2 releases the GIL) against the batch entry
         n, cores = 32, len(os.sched_getaffinity(0))
@@ -228,7 +228,7 @@ def row_jpeg():
             dt = time.perf_counter() - t0
         assert np.array_equal(outs[7][1], ho.haar_icon_blocksum(ref, 3))
         emit(row="N2 JPEG ingest, 32 files", config=f"32 x ({H},{W},3) JPEG q{quality} {tag} -> icons depths 2-6, {cores} host threads, {ndev} GPU(s)",
-             s=dt, MP_per_s=n * H * W / 1e6 / dt, files_per_s=n / dt, host_huffman_ms_sum=hm.value,
+             s=dt, MP_per_s=n * H * W / 1e6 / dt, files_per_s=n / dt, host_stage_ms_sum=hm.value,
              cv2_thread_pool_decode_only_s=dt_ref, cv2_MP_per_s=n * H * W / 1e6 / dt_ref)
 
 

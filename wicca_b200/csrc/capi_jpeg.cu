@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "host_common.h"
+#include "jpeg_gpu.h"
 #include "jpeg_host.h"
 #include "kernels.h"
 
@@ -49,8 +50,84 @@ int jpeg_host_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFrame& f,
     return 0;
 }
 
-// Device stage: coefficients in c.h_in -> d_dst (RGB, rows d_pitch bytes apart) on `stream`, through c's scratch.
-int jpeg_device_stage(Ctx& c, const JpegFrame& f, uint8_t* d_dst, int64_t d_pitch, cudaStream_t stream) {
+bool gpu_huffman_wanted(const JpegFrame& f) {
+    if (f.restart_interval) return false;                    // restart markers: the host decoder handles those
+    const char* e = getenv("WICCA_JPEG_HUFFMAN");
+    return !(e && e[0] == 'h');                              // WICCA_JPEG_HUFFMAN=host forces the CPU stage
+}
+
+// Huffman stage on the GPU: the host only strips the byte stuffing; coefficients end up in c.d_f32a.
+// Returns 1 when the fixed point was not reached within the pass budget (the caller falls back to the host stage).
+int jpeg_gpu_huffman_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFrame& f, cudaStream_t stream, float* host_ms,
+                           int* passes_out) {
+    const size_t cap = len - f.scan_offset + 32;
+    WICCA_CUDA(c.h_in.reserve(cap));
+    const double t0 = now_ms();
+    const size_t n_bytes = jpeg_unstuff_scan(data, len, f, (uint8_t*)c.h_in.p);
+    if (host_ms) *host_ms += (float)(now_ms() - t0);
+    if (n_bytes == 0 || n_bytes >= ((size_t)1 << 28)) return 1;
+    WICCA_CUDA(cudaEventRecord(c.ev[0], stream));                 // device work starts here
+    JpegGpuScan sc;
+    memset(&sc, 0, sizeof sc);
+    sc.total_bits = (uint32_t)(n_bytes * 8);
+    sc.n_sub = (sc.total_bits + kSubBits - 1) / kSubBits;
+    sc.mcux = f.mcux; sc.ncomp = f.ncomp; sc.total_coefs = f.total_coefs;
+    int slot = 0;
+    for (int k = 0; k < f.ncomp; ++k) {
+        const JpegComponent& q = f.comp[k];
+        sc.comp[k] = {q.coef_offset, (int64_t)q.blocks_w * q.blocks_h, q.h, q.v, q.blocks_w};
+        for (int by = 0; by < q.v; ++by)
+            for (int bx = 0; bx < q.h; ++bx, ++slot) sc.slot[slot] = {q.coef_offset, q.h, q.v, bx, by, q.blocks_w, q.td, q.ta};
+    }
+    sc.blocks_per_mcu = slot;
+    sc.total_blocks = (int64_t)f.mcux * f.mcuy * slot;
+    // host copy of the tables + the flag the fixed-point loop polls, in page-locked memory
+    // (h_bounce: the only later user of that buffer is a stream-ordered D2H copy, so the upload below cannot race)
+    WICCA_CUDA(c.h_bounce.reserve(sizeof(JpegGpuTables) + 64));
+    JpegGpuTables* ht = (JpegGpuTables*)c.h_bounce.p;
+    memset(ht, 0, sizeof *ht);
+    for (int id = 0; id < 4; ++id) {
+        const JpegHuff* src[2] = {&f.dc[id], &f.ac[id]};
+        for (int kind = 0; kind < 2; ++kind) {
+            if (!src[kind]->present) continue;
+            const int t = 4 * kind + id;
+            memcpy(ht->look[t], src[kind]->look, sizeof ht->look[t]);
+            memcpy(ht->maxcode[t], src[kind]->maxcode, sizeof ht->maxcode[t]);
+            memcpy(ht->valoffset[t], src[kind]->valoffset, sizeof ht->valoffset[t]);
+            memcpy(ht->symbols[t], src[kind]->symbols, sizeof ht->symbols[t]);
+        }
+    }
+    int* h_changed = (int*)((uint8_t*)c.h_bounce.p + sizeof(JpegGpuTables));
+    // device scratch: [scan words][tables][exit a][exit b][start used][count][base][changed][chunk sums]
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = (size_t)align_up((int64_t)(off + bytes), 256); return o; };
+    const size_t o_words = take(n_bytes + 16), o_tab = take(sizeof(JpegGpuTables));
+    const size_t o_ea = take((size_t)sc.n_sub * 8), o_eb = take((size_t)sc.n_sub * 8), o_su = take((size_t)sc.n_sub * 8);
+    const size_t o_cnt = take((size_t)sc.n_sub * 4), o_base = take((size_t)sc.n_sub * 4), o_chg = take(4);
+    const size_t o_sums = take(jpeg_gpu_chunk_sum_capacity(sc));
+    WICCA_CUDA(c.d_misc.reserve(off));
+    WICCA_CUDA(c.d_f32a.reserve((size_t)f.total_coefs * sizeof(int16_t)));
+    uint8_t* m = (uint8_t*)c.d_misc.p;
+    sc.words = (const uint32_t*)(m + o_words);
+    sc.tables = (const JpegGpuTables*)(m + o_tab);
+    sc.start_used = (uint64_t*)(m + o_su);
+    sc.count = (uint32_t*)(m + o_cnt);
+    sc.base = (uint32_t*)(m + o_base);
+    sc.changed = (int*)(m + o_chg);
+    sc.coefs = (int16_t*)c.d_f32a.p;
+    WICCA_CUDA(cudaMemcpyAsync(m + o_words, c.h_in.p, n_bytes + 16, cudaMemcpyHostToDevice, stream));
+    WICCA_CUDA(cudaMemcpyAsync(m + o_tab, ht, sizeof(JpegGpuTables), cudaMemcpyHostToDevice, stream));
+    WICCA_CUDA(cudaEventRecord(c.ev[4], stream));                 // scan resident
+    cudaError_t e = launch_jpeg_huffman(sc, (uint64_t*)(m + o_ea), (uint64_t*)(m + o_eb), (int64_t*)(m + o_sums), h_changed, 1024,
+                                        passes_out, stream);
+    if (e == cudaErrorNotReady) return 1;
+    if (e != cudaSuccess) return cuda_fail(e, "JPEG Huffman kernels");
+    return 0;
+}
+
+// Device stage: coefficients (in c.h_in, or already in c.d_f32a when `resident`) -> d_dst (RGB, rows d_pitch bytes
+// apart) on `stream`, through c's scratch.
+int jpeg_device_stage(Ctx& c, const JpegFrame& f, uint8_t* d_dst, int64_t d_pitch, cudaStream_t stream, bool resident = false) {
     const size_t coef_bytes = (size_t)f.total_coefs * sizeof(int16_t);
     size_t plane_bytes = 0;
     JpegImageDesc d;
@@ -74,11 +151,29 @@ int jpeg_device_stage(Ctx& c, const JpegFrame& f, uint8_t* d_dst, int64_t d_pitc
         p.mode = upsample_mode(f, q);
         memcpy(p.qt, f.qt[q.tq], sizeof p.qt);
     }
-    WICCA_CUDA(cudaMemcpyAsync(c.d_f32a.p, c.h_in.p, coef_bytes, cudaMemcpyHostToDevice, stream));
-    WICCA_CUDA(cudaEventRecord(c.ev[4], stream));                 // coefficients resident
+    if (!resident) {
+        WICCA_CUDA(cudaMemcpyAsync(c.d_f32a.p, c.h_in.p, coef_bytes, cudaMemcpyHostToDevice, stream));
+        WICCA_CUDA(cudaEventRecord(c.ev[4], stream));             // coefficients resident
+    }
     cudaError_t e = launch_jpeg_decode(d, stream);
     if (e != cudaSuccess) return cuda_fail(e, "JPEG decode kernels");
     return 0;
+}
+
+// Both stages: JPEG bytes -> RGB in d_dst.  ev[0] is recorded when the device work starts, ev[4] when its input
+// (scan bytes or coefficients) is resident.
+int jpeg_to_device(Ctx& c, const uint8_t* data, size_t len, const JpegFrame& f, uint8_t* d_dst, int64_t d_pitch,
+                   cudaStream_t stream, float* host_ms) {
+    if (gpu_huffman_wanted(f)) {
+        int rc = jpeg_gpu_huffman_stage(c, data, len, f, stream, host_ms, nullptr);
+        if (rc < 0 || rc > 1) return rc;
+        if (rc == 0) return jpeg_device_stage(c, f, d_dst, d_pitch, stream, true);
+        WICCA_CUDA(cudaStreamSynchronize(stream));            // no fixed point within the budget: host stage instead
+    }
+    int rc = jpeg_host_stage(c, data, len, f, host_ms);
+    if (rc) return rc;
+    WICCA_CUDA(cudaEventRecord(c.ev[0], stream));
+    return jpeg_device_stage(c, f, d_dst, d_pitch, stream);
 }
 
 }  // namespace
@@ -120,6 +215,26 @@ int wicca_jpeg_decode_coeffs(const uint8_t* data, size_t len, int16_t* dst, int6
     return 0;
 }
 
+int wicca_jpeg_decode_coeffs_gpu(const uint8_t* data, size_t len, int16_t* dst, int64_t dst_count, int device, int* passes) {
+    JpegFrame f;
+    int rc = parse_or_fail(data, len, f);
+    if (rc) return rc;
+    if (!dst || dst_count < f.total_coefs) return fail(WICCA_EINVAL, "coefficient buffer too small (%lld needed)", (long long)f.total_coefs);
+    if (f.restart_interval) return fail(WICCA_EUNSUPPORTED, "files with restart markers are Huffman-decoded on the host");
+    rc = check_device(device);
+    if (rc) return rc;
+    CtxLease lease;
+    rc = acquire_ctx(device, &lease.c);
+    if (rc) return rc;
+    Ctx& c = *lease.c;
+    rc = jpeg_gpu_huffman_stage(c, data, len, f, c.stream, nullptr, passes);
+    if (rc == 1) { cudaStreamSynchronize(c.stream); return fail(WICCA_ESTATE, "GPU Huffman decoder found no fixed point within its pass budget"); }
+    if (rc) { cudaStreamSynchronize(c.stream); return rc; }
+    WICCA_CUDA(cudaMemcpyAsync(dst, c.d_f32a.p, (size_t)f.total_coefs * sizeof(int16_t), cudaMemcpyDeviceToHost, c.stream));
+    WICCA_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
 int wicca_jpeg_decode_u8(const uint8_t* data, size_t len, uint8_t* dst, int64_t dst_stride, int device, wicca_timing* t,
                          float* host_decode_ms) {
     if (t) memset(t, 0, sizeof(*t));
@@ -140,10 +255,7 @@ int wicca_jpeg_decode_u8(const uint8_t* data, size_t len, uint8_t* dst, int64_t 
     const int64_t pitch = wicca_pitch_bytes(f.width, 3);
     WICCA_CUDA(c.d_src.reserve((size_t)pitch * f.height + 256));
     float host_ms = 0;
-    rc = jpeg_host_stage(c, data, len, f, &host_ms);       // the host part runs first: the events bracket device work only
-    if (rc) return rc;
-    WICCA_CUDA(cudaEventRecord(c.ev[0], c.stream));
-    rc = jpeg_device_stage(c, f, (uint8_t*)c.d_src.p, pitch, c.stream);
+    rc = jpeg_to_device(c, data, len, f, (uint8_t*)c.d_src.p, pitch, c.stream, &host_ms);
     if (rc) { cudaStreamSynchronize(c.stream); return rc; }
     WICCA_CUDA(cudaEventRecord(c.ev[2], c.stream));
     uint8_t* target = dst;
@@ -188,9 +300,7 @@ int wicca_jpeg_decode_dev(const uint8_t* data, size_t len, uint8_t* d_dst, int64
     rc = acquire_ctx(device, &lease.c);
     if (rc) return rc;
     cudaStream_t stream = (cudaStream_t)stream_v;
-    rc = jpeg_host_stage(*lease.c, data, len, f, nullptr);
-    if (rc) return rc;
-    rc = jpeg_device_stage(*lease.c, f, d_dst, d_pitch, stream);
+    rc = jpeg_to_device(*lease.c, data, len, f, d_dst, d_pitch, stream, nullptr);
     // the staging buffers belong to the leased context: they may be reused as soon as this returns
     cudaError_t e = cudaStreamSynchronize(stream);
     if (rc) return rc;
@@ -222,10 +332,7 @@ int wicca_jpeg_icons_multi_u8(const uint8_t* data, size_t len, const int* depths
     const int64_t pitch = wicca_pitch_bytes(f.width, 3);
     WICCA_CUDA(c.d_src.reserve((size_t)pitch * f.height + 256));
     float host_ms = 0;
-    rc = jpeg_host_stage(c, data, len, f, &host_ms);
-    if (rc) return rc;
-    WICCA_CUDA(cudaEventRecord(c.ev[0], c.stream));
-    rc = jpeg_device_stage(c, f, (uint8_t*)c.d_src.p, pitch, c.stream);
+    rc = jpeg_to_device(c, data, len, f, (uint8_t*)c.d_src.p, pitch, c.stream, &host_ms);
     if (rc) { cudaStreamSynchronize(c.stream); return rc; }
     WICCA_CUDA(cudaEventRecord(c.ev[1], c.stream));
     rc = icons_from_resident(c, f.height, f.width, 3, pitch, depths, n_depths, border_type, saturate_u8(border_const), dsts);

@@ -314,4 +314,22 @@ int jpeg_decode_coefficients(const uint8_t* data, size_t len, const JpegFrame& f
     return 0;
 }
 
+size_t jpeg_unstuff_scan(const uint8_t* data, size_t len, const JpegFrame& f, uint8_t* dst) {
+    const uint8_t* p = data + f.scan_offset;
+    const uint8_t* end = data + len;
+    uint8_t* o = dst;
+    while (p < end) {
+        const uint8_t* q = (const uint8_t*)memchr(p, 0xFF, (size_t)(end - p));
+        if (!q) q = end;
+        memcpy(o, p, (size_t)(q - p));
+        o += q - p;
+        p = q;
+        if (p >= end) break;
+        if (p + 1 < end && p[1] == 0) { *o++ = 0xFF; p += 2; continue; }     // stuffed zero
+        break;                                                                 // a marker (EOI): the scan ends here
+    }
+    memset(o, 0, 16);
+    return (size_t)(o - dst);
+}
+
 }  // namespace wicca

@@ -1,0 +1,318 @@
+// jpeg_huffman.cu - Huffman decoding of a JPEG scan on the GPU (row N2).  A Huffman bit stream has no
+// random-access points, but decoders that start at a wrong position re-synchronise with the true symbol sequence
+// after a few symbols.  The scan (byte stuffing already removed) is cut into sub-sequences of kSubBits bits:
+//
+//   1. every thread decodes its sub-sequence from a guessed state (bit = start, first block of an MCU, DC
+//      expected) and records where - and in which state - it leaves the sub-sequence;
+//   2. repeat: thread i restarts from the exit state of thread i-1 whenever that differs from the state it used
+//      before.  Sub-sequence 0 starts from the true state, so after pass j at least sub-sequences 0..j are right;
+//      in practice the wrong starts have already synchronised and a handful of passes reach the fixed point,
+//      which is the true decode by induction;
+//   3. blocks completed per sub-sequence -> exclusive scan = the block each sub-sequence starts in;
+//   4. decode once more from the true states, writing coefficients (DC as differences) into the dense array;
+//   5. prefix-sum the DC differences per component in decode order.
+//
+// The decoder state is (bit position, block slot inside the MCU, next coefficient index); the step function is
+// deterministic for any input, so garbage decoded from a wrong start is harmless.  Files with restart markers
+// use the host decoder instead (jpeg_host.cu).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "jpeg_gpu.h"
+
+namespace wicca {
+
+namespace {
+
+__device__ const uint8_t d_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+struct State { uint32_t pos; int slot, k; };
+
+__device__ __forceinline__ uint64_t pack(const State& s) { return ((uint64_t)s.pos << 16) | ((uint64_t)s.slot << 8) | (uint64_t)s.k; }
+__device__ __forceinline__ State unpack(uint64_t v) { State s; s.pos = (uint32_t)(v >> 16); s.slot = (int)((v >> 8) & 255); s.k = (int)(v & 255); return s; }
+
+// 32 bits of the stream starting at bit `pos` (MSB first).  The buffer is padded with zero words.
+__device__ __forceinline__ uint32_t window(const uint32_t* __restrict__ words, uint32_t pos) {
+    const uint32_t i = pos >> 5;
+    const uint32_t hi = __byte_perm(words[i], 0, 0x0123), lo = __byte_perm(words[i + 1], 0, 0x0123);
+    return __funnelshift_l(lo, hi, pos & 31);
+}
+
+struct SharedTables {
+    uint16_t look[8][1024];          // 0..3 DC, 4..7 AC: (length << 8) | symbol for codes of <= 10 bits
+    JpegGpuSlot slot[10];
+    uint8_t zigzag[64];
+};
+
+// One Huffman symbol from the 32-bit window: returns its code length and the symbol (a deterministic fallback
+// for bit patterns that are no code at all: 16 bits, symbol 0).
+__device__ __forceinline__ void symbol(const SharedTables& T, const JpegGpuTables* __restrict__ gp, int table, uint32_t win, int& len, int& sym) {
+    const uint32_t e = T.look[table][win >> 22];
+    if (e) { len = (int)(e >> 8); sym = (int)(e & 255); return; }
+    for (len = 11; len <= 16; ++len) {
+        const int code = (int)(win >> (32 - len));
+        if (code <= gp->maxcode[table][len]) { sym = gp->symbols[table][(code + gp->valoffset[table][len]) & 255]; return; }
+    }
+    len = 16; sym = 0;
+}
+
+__device__ __forceinline__ int extend(uint32_t win, int len, int s) {          // the s bits after the code, sign-extended (T.81 F.12)
+    const int v = (int)((win << len) >> (32 - s));
+    return v + (((v - (1 << (s - 1))) >> 31) & ((-1 << s) + 1));
+}
+
+// Decode every symbol that starts in [st.pos, limit).  kWrite: also store coefficients, starting in block
+// `block` (global decode order), never past block_end.  Returns the number of blocks completed.
+template <bool kWrite>
+__device__ __forceinline__ uint32_t decode_span(const JpegGpuScan& sc, const SharedTables& T, State& st, uint32_t limit,
+                                                int64_t block, int64_t block_end) {
+    uint32_t done = 0;
+    int16_t* blk = nullptr;
+    int mx = 0, my = 0;
+    auto block_ptr = [&](int slot) -> int16_t* {
+        const JpegGpuSlot& q = T.slot[slot];
+        return sc.coefs + q.coef_offset + ((int64_t)(my * q.v + q.by) * q.blocks_w + (mx * q.h + q.bx)) * 64;
+    };
+    if (kWrite) {
+        if (block >= block_end) return 0;
+        const int64_t mcu = block / sc.blocks_per_mcu;
+        my = (int)(mcu / sc.mcux); mx = (int)(mcu - (int64_t)my * sc.mcux);
+        blk = block_ptr(st.slot);
+    }
+    while (st.pos < limit) {
+        const uint32_t win = window(sc.words, st.pos);
+        int len, sym;
+        if (st.k == 0) {
+            symbol(T, sc.tables, T.slot[st.slot].dc_table, win, len, sym);
+            const int s = sym & 15;
+            if (kWrite && s) blk[0] = (int16_t)extend(win, len, s);
+            st.pos += (uint32_t)(len + s);
+            st.k = 1;
+            continue;
+        }
+        symbol(T, sc.tables, 4 + T.slot[st.slot].ac_table, win, len, sym);
+        const int r = sym >> 4, s = sym & 15;
+        if (s) {
+            st.k += r;
+            if (kWrite && st.k <= 63) blk[T.zigzag[st.k]] = (int16_t)extend(win, len, s);
+            st.k += 1;
+            st.pos += (uint32_t)(len + s);
+        } else {
+            st.k = (r == 15) ? st.k + 16 : 64;               // ZRL / end of block
+            st.pos += (uint32_t)len;
+        }
+        if (st.k >= 64) {
+            st.k = 0;
+            ++done;
+            if (++st.slot == sc.blocks_per_mcu) {
+                st.slot = 0;
+                if (kWrite && ++mx == sc.mcux) { mx = 0; ++my; }
+            }
+            if (kWrite) {
+                if (++block >= block_end) break;
+                blk = block_ptr(st.slot);
+            }
+        }
+    }
+    return done;
+}
+
+__device__ __forceinline__ void load_tables(SharedTables& T, const JpegGpuScan& sc) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(sc.tables->look);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(T.look);
+    for (int i = threadIdx.x; i < 8 * 1024 / 2; i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x < 10) T.slot[threadIdx.x] = sc.slot[threadIdx.x];
+    if (threadIdx.x < 64) T.zigzag[threadIdx.x] = d_zigzag[threadIdx.x];
+    __syncthreads();
+}
+
+// Pass 1 (first != 0) and the re-synchronisation passes.
+__global__ void __launch_bounds__(128)
+huff_sync_kernel(JpegGpuScan sc, const uint64_t* __restrict__ exit_in, uint64_t* __restrict__ exit_out, int first) {
+    __shared__ SharedTables T;
+    load_tables(T, sc);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sc.n_sub) return;
+    const uint32_t start = i * kSubBits;
+    const uint32_t limit = min(start + kSubBits, sc.total_bits);
+    State st;
+    if (first || i == 0) {
+        st.pos = start; st.slot = 0; st.k = 0;
+        if (!first) { exit_out[i] = exit_in[i]; return; }       // sub-sequence 0 never changes
+    } else {
+        const uint64_t s = exit_in[i - 1];
+        if (s == sc.start_used[i]) { exit_out[i] = exit_in[i]; return; }
+        st = unpack(s);
+        atomicAdd(sc.changed, 1);
+    }
+    sc.start_used[i] = pack(st);
+    sc.count[i] = decode_span<false>(sc, T, st, limit, 0, 0);
+    exit_out[i] = pack(st);
+}
+
+__global__ void __launch_bounds__(128)
+huff_write_kernel(JpegGpuScan sc) {
+    __shared__ SharedTables T;
+    load_tables(T, sc);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sc.n_sub) return;
+    const uint32_t limit = min(i * kSubBits + kSubBits, sc.total_bits);
+    State st = unpack(sc.start_used[i]);
+    decode_span<true>(sc, T, st, limit, (int64_t)sc.base[i], sc.total_blocks);
+}
+
+// ---- exclusive scan of uint32 (block counts), three small kernels -------------------------------------------
+constexpr int kScanThreads = 256, kScanItems = 4, kScanChunk = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int64_t block_exclusive_scan(int64_t v, int64_t* s_warp, int64_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int64_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int64_t w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int64_t y = __shfl_up_sync(0xFFFFFFFFu, w, o); if (lane >= o) w += y; }
+        if (lane < (int)(blockDim.x >> 5)) s_warp[lane] = w;
+    }
+    __syncthreads();
+    total = s_warp[(blockDim.x >> 5) - 1];
+    const int64_t before = warp ? s_warp[warp - 1] : 0;
+    __syncthreads();
+    return before + x - v;
+}
+
+// value(j): element j of the sequence being scanned.  kind 0: block counts; kind 1: DC differences of a component.
+__device__ __forceinline__ int64_t dc_address(const JpegGpuScan& sc, int comp, int64_t j) {
+    const JpegGpuComp& q = sc.comp[comp];
+    const int per = q.h * q.v;
+    const int64_t mcu = j / per;
+    const int w = (int)(j - mcu * per);
+    const int by = w / q.h, bx = w - by * q.h;
+    const int my = (int)(mcu / sc.mcux), mx = (int)(mcu - (int64_t)my * sc.mcux);
+    return q.coef_offset + ((int64_t)(my * q.v + by) * q.blocks_w + (mx * q.h + bx)) * 64;
+}
+
+template <int kKind>
+__device__ __forceinline__ int64_t scan_value(const JpegGpuScan& sc, int comp, int64_t j, int64_t n) {
+    if (j >= n) return 0;
+    if (kKind == 0) return (int64_t)sc.count[j];
+    return (int64_t)sc.coefs[dc_address(sc, comp, j)];
+}
+
+template <int kKind>
+__global__ void __launch_bounds__(kScanThreads)
+scan_chunk_sums_kernel(JpegGpuScan sc, int comp, int64_t n, int64_t* __restrict__ chunk_sums) {
+    __shared__ int64_t s_warp[32];
+    const int64_t j0 = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanItems;
+    int64_t v = 0;
+#pragma unroll
+    for (int q = 0; q < kScanItems; ++q) v += scan_value<kKind>(sc, comp, j0 + q, n);
+    int64_t total;
+    block_exclusive_scan(v, s_warp, total);
+    if (threadIdx.x == 0) chunk_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024)
+scan_of_sums_kernel(int64_t* __restrict__ chunk_sums, int n_chunks) {
+    __shared__ int64_t s_warp[32];
+    int64_t carry = 0;
+    for (int base = 0; base < n_chunks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int64_t v = i < n_chunks ? chunk_sums[i] : 0;
+        int64_t total;
+        const int64_t ex = block_exclusive_scan(v, s_warp, total);
+        if (i < n_chunks) chunk_sums[i] = carry + ex;
+        carry += total;
+    }
+}
+
+template <int kKind>
+__global__ void __launch_bounds__(kScanThreads)
+scan_apply_kernel(JpegGpuScan sc, int comp, int64_t n, const int64_t* __restrict__ chunk_sums) {
+    __shared__ int64_t s_warp[32];
+    const int64_t j0 = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanItems;
+    int64_t item[kScanItems], v = 0;
+#pragma unroll
+    for (int q = 0; q < kScanItems; ++q) { item[q] = scan_value<kKind>(sc, comp, j0 + q, n); v += item[q]; }
+    int64_t total;
+    int64_t run = chunk_sums[blockIdx.x] + block_exclusive_scan(v, s_warp, total);
+#pragma unroll
+    for (int q = 0; q < kScanItems; ++q) {
+        if (j0 + q < n) {
+            if (kKind == 0) sc.base[j0 + q] = (uint32_t)run;                                   // exclusive: blocks before
+            else sc.coefs[dc_address(sc, comp, j0 + q)] = (int16_t)(run + item[q]);            // inclusive: the DC value
+        }
+        run += item[q];
+    }
+}
+
+template <int kKind>
+cudaError_t run_scan(const JpegGpuScan& sc, int comp, int64_t n, int64_t* d_chunk_sums, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const int n_chunks = (int)((n + kScanChunk - 1) / kScanChunk);
+    scan_chunk_sums_kernel<kKind><<<n_chunks, kScanThreads, 0, stream>>>(sc, comp, n, d_chunk_sums);
+    scan_of_sums_kernel<<<1, 1024, 0, stream>>>(d_chunk_sums, n_chunks);
+    scan_apply_kernel<kKind><<<n_chunks, kScanThreads, 0, stream>>>(sc, comp, n, d_chunk_sums);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t jpeg_gpu_chunk_sum_capacity(const JpegGpuScan& sc) {
+    int64_t n = (int64_t)sc.n_sub;
+    for (int c = 0; c < sc.ncomp; ++c) n = n > sc.comp[c].n_blocks ? n : sc.comp[c].n_blocks;
+    return (size_t)((n + kScanChunk - 1) / kScanChunk + 1) * sizeof(int64_t);
+}
+
+// h_changed: page-locked int the fixed-point loop polls.  Returns cudaErrorNotReady when max_passes were not enough.
+cudaError_t launch_jpeg_huffman(const JpegGpuScan& sc, uint64_t* d_exit_a, uint64_t* d_exit_b, int64_t* d_chunk_sums,
+                                int* h_changed, int max_passes, int* passes_out, cudaStream_t stream) {
+    const int threads = 128;
+    const int grid = (int)((sc.n_sub + threads - 1) / threads);
+    cudaError_t e = cudaMemsetAsync(sc.coefs, 0, (size_t)sc.total_coefs * sizeof(int16_t), stream);
+    if (e != cudaSuccess) return e;
+    huff_sync_kernel<<<grid, threads, 0, stream>>>(sc, d_exit_b, d_exit_a, 1);
+    uint64_t* cur = d_exit_a;
+    uint64_t* nxt = d_exit_b;
+    int passes = 0;
+    bool converged = sc.n_sub <= 1;
+    while (!converged && passes < max_passes) {
+        // a few passes per round trip: the flag is cleared, the passes run, the flag comes back
+        e = cudaMemsetAsync(sc.changed, 0, sizeof(int), stream);
+        if (e != cudaSuccess) return e;
+        // typical files settle in under ten passes; files almost without end-of-block codes (quality 100) need a
+        // couple of hundred, so the bursts between two looks at the flag grow
+        const int burst = passes == 0 ? 2 : (passes < 8 ? 4 : (passes < 32 ? 8 : 32));
+        for (int b = 0; b < burst; ++b, ++passes) {
+            // only the last pass of a burst decides: an earlier change is fine as long as the last one finds none
+            if (b == burst - 1) { e = cudaMemsetAsync(sc.changed, 0, sizeof(int), stream); if (e != cudaSuccess) return e; }
+            huff_sync_kernel<<<grid, threads, 0, stream>>>(sc, cur, nxt, 0);
+            uint64_t* t = cur; cur = nxt; nxt = t;
+        }
+        e = cudaMemcpyAsync(h_changed, sc.changed, sizeof(int), cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return e;
+        converged = (*h_changed == 0);
+        if (getenv("WICCA_JPEG_DEBUG")) fprintf(stderr, "[jpeg huffman] n_sub %u pass %d: %d sub-sequences re-decoded in the last pass\n", sc.n_sub, passes, *h_changed);
+    }
+    if (passes_out) *passes_out = passes;
+    if (!converged) return cudaErrorNotReady;
+    e = run_scan<0>(sc, 0, (int64_t)sc.n_sub, d_chunk_sums, stream);
+    if (e != cudaSuccess) return e;
+    huff_write_kernel<<<grid, threads, 0, stream>>>(sc);
+    for (int c = 0; c < sc.ncomp; ++c) {
+        e = run_scan<1>(sc, c, sc.comp[c].n_blocks, d_chunk_sums, stream);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace wicca
