@@ -35,12 +35,28 @@ struct State { uint32_t pos; int slot, k; };
 __device__ __forceinline__ uint64_t pack(const State& s) { return ((uint64_t)s.pos << 16) | ((uint64_t)s.slot << 8) | (uint64_t)s.k; }
 __device__ __forceinline__ State unpack(uint64_t v) { State s; s.pos = (uint32_t)(v >> 16); s.slot = (int)((v >> 8) & 255); s.k = (int)(v & 255); return s; }
 
-// 32 bits of the stream starting at bit `pos` (MSB first).  The buffer is padded with zero words.
-__device__ __forceinline__ uint32_t window(const uint32_t* __restrict__ words, uint32_t pos) {
-    const uint32_t i = pos >> 5;
-    const uint32_t hi = __byte_perm(words[i], 0, 0x0123), lo = __byte_perm(words[i + 1], 0, 0x0123);
-    return __funnelshift_l(lo, hi, pos & 31);
-}
+// The stream from bit `pos` on, MSB first, in a 64-bit register: at least 32 valid bits after every advance().
+// The buffer behind `words` is padded with zero words.
+struct BitWindow {
+    const uint32_t* __restrict__ words;
+    uint64_t buf;
+    uint32_t next;                   // index of the next word to append
+    int avail;
+    __device__ __forceinline__ static uint32_t be(uint32_t w) { return __byte_perm(w, 0, 0x0123); }
+    __device__ __forceinline__ void start(const uint32_t* w, uint32_t pos) {
+        words = w;
+        const uint32_t i = pos >> 5, sh = pos & 31;
+        buf = (((uint64_t)be(w[i]) << 32) | (uint64_t)be(w[i + 1])) << sh;
+        avail = 64 - (int)sh;
+        next = i + 2;
+    }
+    __device__ __forceinline__ uint32_t top32() const { return (uint32_t)(buf >> 32); }
+    __device__ __forceinline__ void advance(int n) {
+        buf <<= n;
+        avail -= n;
+        if (avail < 32) { buf |= (uint64_t)be(words[next++]) << (32 - avail); avail += 32; }
+    }
+};
 
 struct SharedTables {
     uint16_t look[8][1024];          // 0..3 DC, 4..7 AC: (length << 8) | symbol for codes of <= 10 bits
@@ -83,14 +99,17 @@ __device__ __forceinline__ uint32_t decode_span(const JpegGpuScan& sc, const Sha
         my = (int)(mcu / sc.mcux); mx = (int)(mcu - (int64_t)my * sc.mcux);
         blk = block_ptr(st.slot);
     }
+    BitWindow bw;
+    bw.start(sc.words, st.pos);
     while (st.pos < limit) {
-        const uint32_t win = window(sc.words, st.pos);
+        const uint32_t win = bw.top32();
         int len, sym;
         if (st.k == 0) {
             symbol(T, sc.tables, T.slot[st.slot].dc_table, win, len, sym);
             const int s = sym & 15;
             if (kWrite && s) blk[0] = (int16_t)extend(win, len, s);
             st.pos += (uint32_t)(len + s);
+            bw.advance(len + s);
             st.k = 1;
             continue;
         }
@@ -101,9 +120,11 @@ __device__ __forceinline__ uint32_t decode_span(const JpegGpuScan& sc, const Sha
             if (kWrite && st.k <= 63) blk[T.zigzag[st.k]] = (int16_t)extend(win, len, s);
             st.k += 1;
             st.pos += (uint32_t)(len + s);
+            bw.advance(len + s);
         } else {
             st.k = (r == 15) ? st.k + 16 : 64;               // ZRL / end of block
             st.pos += (uint32_t)len;
+            bw.advance(len);
         }
         if (st.k >= 64) {
             st.k = 0;
@@ -130,25 +151,28 @@ __device__ __forceinline__ void load_tables(SharedTables& T, const JpegGpuScan& 
     __syncthreads();
 }
 
-// Pass 1 (first != 0) and the re-synchronisation passes.
+// Pass 1 (first != 0) and the re-synchronisation passes.  In a re-synchronisation pass most thread blocks have
+// nothing to do: they find that out before touching the tables.
 __global__ void __launch_bounds__(128)
 huff_sync_kernel(JpegGpuScan sc, const uint64_t* __restrict__ exit_in, uint64_t* __restrict__ exit_out, int first) {
     __shared__ SharedTables T;
-    load_tables(T, sc);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= sc.n_sub) return;
-    const uint32_t start = i * kSubBits;
-    const uint32_t limit = min(start + kSubBits, sc.total_bits);
+    const bool inside = i < sc.n_sub;
     State st;
-    if (first || i == 0) {
-        st.pos = start; st.slot = 0; st.k = 0;
-        if (!first) { exit_out[i] = exit_in[i]; return; }       // sub-sequence 0 never changes
-    } else {
-        const uint64_t s = exit_in[i - 1];
-        if (s == sc.start_used[i]) { exit_out[i] = exit_in[i]; return; }
-        st = unpack(s);
-        atomicAdd(sc.changed, 1);
+    st.pos = i * kSubBits; st.slot = 0; st.k = 0;
+    bool work = inside && first;
+    if (inside && !first) {
+        if (i > 0) {
+            const uint64_t s = exit_in[i - 1];
+            if (s != sc.start_used[i]) { st = unpack(s); work = true; }
+        }
+        if (!work) exit_out[i] = exit_in[i];                  // unchanged (sub-sequence 0 never changes)
     }
+    if (!__syncthreads_or(work)) return;
+    load_tables(T, sc);
+    if (!work) return;
+    if (!first) atomicAdd(sc.changed, 1);
+    const uint32_t limit = min(i * kSubBits + kSubBits, sc.total_bits);
     sc.start_used[i] = pack(st);
     sc.count[i] = decode_span<false>(sc, T, st, limit, 0, 0);
     exit_out[i] = pack(st);

@@ -134,36 +134,114 @@ constexpr int FIX_1_40200 = 91881, FIX_1_77200 = 116130, FIX_0_71414 = 46802, FI
 
 __device__ __forceinline__ int clamp255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 
-// One thread = four horizontally adjacent pixels = three 32-bit words of the RGB row.
+// Eight upsampled samples of one component for the image positions x0 .. x0+7 (x0 a multiple of 8) of row y.
+// The planes are whole blocks wide (a multiple of 8 samples), so aligned word loads never leave a row; columns
+// beyond the real samples only feed pixels beyond the image, which are not stored.
+__device__ __forceinline__ void upsampled8(const JpegPlaneDesc& p, int x0, int y, int (&out)[8]) {
+    const uint8_t* P = p.plane;
+    const int pitch = p.plane_pitch;
+    auto load4 = [&](const uint8_t* row, int c, int (&v)[4]) {       // row[c .. c+3], c a multiple of 4; zeros outside
+        uint32_t w = 0;
+        if (c >= 0 && c < pitch) w = *reinterpret_cast<const uint32_t*>(row + c);
+        v[0] = w & 255; v[1] = (w >> 8) & 255; v[2] = (w >> 16) & 255; v[3] = w >> 24;
+    };
+    if (p.mode == 0 || p.mode == 3) {
+        const uint8_t* r0 = P + (int64_t)(p.mode == 0 ? y : (y >> 1)) * pitch + x0;
+        int a[4], b[4];
+        load4(r0, 0, a); load4(r0, 4, b);
+        int near8[8] = {a[0], a[1], a[2], a[3], b[0], b[1], b[2], b[3]};
+        if (p.mode == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) out[i] = near8[i];
+            return;
+        }
+        const int cy = y >> 1;
+        const int fy = (y & 1) ? min(cy + 1, p.dh - 1) : max(cy - 1, 0);
+        const uint8_t* r1 = P + (int64_t)fy * pitch + x0;
+        load4(r1, 0, a); load4(r1, 4, b);
+        const int far8[8] = {a[0], a[1], a[2], a[3], b[0], b[1], b[2], b[3]};
+        const int bias = (y & 1) ? 2 : 1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] = (3 * near8[i] + far8[i] + bias) >> 2;
+        return;
+    }
+    if (p.mode == 1 || p.mode == 2) {
+        const int c0 = x0 >> 1;                                      // first chroma column, a multiple of 4
+        int v[6];                                                    // columns c0-1 .. c0+4 (row sums for h2v2)
+        int a[4], b[4], c[4];
+        if (p.mode == 1) {
+            const uint8_t* row = P + (int64_t)y * pitch;
+            load4(row, c0 - 4, a); load4(row, c0, b); load4(row, c0 + 4, c);
+            v[0] = a[3]; v[1] = b[0]; v[2] = b[1]; v[3] = b[2]; v[4] = b[3]; v[5] = c[0];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cx = c0 + i;
+                out[2 * i] = cx == 0 ? v[1 + i] : (3 * v[1 + i] + v[i] + 1) >> 2;
+                out[2 * i + 1] = cx == p.dw - 1 ? v[1 + i] : (3 * v[1 + i] + v[2 + i] + 2) >> 2;
+            }
+            return;
+        }
+        const int cy = y >> 1;
+        const int fy = (y & 1) ? min(cy + 1, p.dh - 1) : max(cy - 1, 0);
+        const uint8_t* r0 = P + (int64_t)cy * pitch;
+        const uint8_t* r1 = P + (int64_t)fy * pitch;
+        int d[4], e[4], f[4];
+        load4(r0, c0 - 4, a); load4(r0, c0, b); load4(r0, c0 + 4, c);
+        load4(r1, c0 - 4, d); load4(r1, c0, e); load4(r1, c0 + 4, f);
+        v[0] = 3 * a[3] + d[3];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[1 + i] = 3 * b[i] + e[i];
+        v[5] = 3 * c[0] + f[0];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int cx = c0 + i;
+            out[2 * i] = cx == 0 ? (v[1 + i] * 4 + 8) >> 4 : (3 * v[1 + i] + v[i] + 8) >> 4;
+            out[2 * i + 1] = cx == p.dw - 1 ? (v[1 + i] * 4 + 7) >> 4 : (3 * v[1 + i] + v[2 + i] + 7) >> 4;
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = upsampled(p, x0 + i, y);      // box replication
+}
+
+// One thread = eight horizontally adjacent pixels = 24 bytes of the RGB row.
 __global__ void __launch_bounds__(256)
 jpeg_color_kernel(JpegImageDesc d) {
-    const int quads = (d.width + 3) >> 2;
-    const int64_t total = (int64_t)quads * d.height;
+    const int groups = (d.width + 7) >> 3;
+    const int64_t total = (int64_t)groups * d.height;
+    const bool wide = (((uintptr_t)d.dst | (uintptr_t)d.dst_pitch) & 7) == 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int y = (int)(i / quads), x0 = (int)(i - (int64_t)y * quads) * 4;
-        uint8_t rgb[12];
+        const int y = (int)(i / groups), x0 = (int)(i - (int64_t)y * groups) * 8;
+        int yy[8], cb[8], cr[8];
+        upsampled8(d.comp[0], x0, y, yy);
+        uint32_t rgb[6] = {0, 0, 0, 0, 0, 0};
+        if (d.ncomp == 3) {
+            upsampled8(d.comp[1], x0, y, cb);
+            upsampled8(d.comp[2], x0, y, cr);
+        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int x = min(x0 + k, d.width - 1);
-            const int yy = upsampled(d.comp[0], x, y);
+        for (int k = 0; k < 8; ++k) {
+            int r, g, b;
             if (d.ncomp == 1) {
-                rgb[3 * k] = rgb[3 * k + 1] = rgb[3 * k + 2] = (uint8_t)yy;
+                r = g = b = yy[k];
             } else {
-                const int cb = upsampled(d.comp[1], x, y) - 128, cr = upsampled(d.comp[2], x, y) - 128;
-                rgb[3 * k] = (uint8_t)clamp255(yy + ((FIX_1_40200 * cr + 32768) >> 16));
-                rgb[3 * k + 1] = (uint8_t)clamp255(yy + ((-FIX_0_34414 * cb + 32768 - FIX_0_71414 * cr) >> 16));
-                rgb[3 * k + 2] = (uint8_t)clamp255(yy + ((FIX_1_77200 * cb + 32768) >> 16));
+                const int u = cb[k] - 128, v = cr[k] - 128;
+                r = clamp255(yy[k] + ((FIX_1_40200 * v + 32768) >> 16));
+                g = clamp255(yy[k] + ((-FIX_0_34414 * u + 32768 - FIX_0_71414 * v) >> 16));
+                b = clamp255(yy[k] + ((FIX_1_77200 * u + 32768) >> 16));
             }
+            const int o = 3 * k;
+            rgb[o >> 2] |= (uint32_t)r << (8 * (o & 3));
+            rgb[(o + 1) >> 2] |= (uint32_t)g << (8 * ((o + 1) & 3));
+            rgb[(o + 2) >> 2] |= (uint32_t)b << (8 * ((o + 2) & 3));
         }
         uint8_t* row = d.dst + (int64_t)y * d.dst_pitch + (int64_t)x0 * 3;
-        if (x0 + 4 <= d.width && (((uintptr_t)d.dst | (uintptr_t)d.dst_pitch) & 3) == 0) {
-            uint32_t* w = reinterpret_cast<uint32_t*>(row);
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-                w[k] = (uint32_t)rgb[4 * k] | ((uint32_t)rgb[4 * k + 1] << 8) | ((uint32_t)rgb[4 * k + 2] << 16) | ((uint32_t)rgb[4 * k + 3] << 24);
+        if (x0 + 8 <= d.width && wide) {
+            uint2* w = reinterpret_cast<uint2*>(row);
+            w[0] = make_uint2(rgb[0], rgb[1]); w[1] = make_uint2(rgb[2], rgb[3]); w[2] = make_uint2(rgb[4], rgb[5]);
         } else {
-            const int n = min(4, d.width - x0) * 3;
-            for (int k = 0; k < n; ++k) row[k] = rgb[k];
+            const int n = min(8, d.width - x0) * 3;
+            for (int k = 0; k < n; ++k) row[k] = (uint8_t)(rgb[k >> 2] >> (8 * (k & 3)));
         }
     }
 }
@@ -179,7 +257,7 @@ cudaError_t launch_jpeg_decode(const JpegImageDesc& d, cudaStream_t stream) {
     jpeg_idct_kernel<<<dim3((unsigned)gx, d.ncomp), 128, 0, stream>>>(d);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const int64_t total = (int64_t)((d.width + 3) >> 2) * d.height;
+    const int64_t total = (int64_t)((d.width + 7) >> 3) * d.height;
     int64_t g2 = (total + 255) / 256;
     if (g2 > 148 * 16) g2 = 148 * 16;
     if (g2 < 1) g2 = 1;
