@@ -7,7 +7,7 @@ import pytest
 
 cv2 = pytest.importorskip("cv2")
 
-from tests.test_oracle_jpeg import SAMPLING, encode, photo_like, reference_rgb  # noqa: E402
+from tests.test_oracle_jpeg import SAMPLING, encode, photo_like, reference_rgb, with_exif_orientation  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -131,3 +131,17 @@ def test_both_huffman_stages_give_the_same_image(monkeypatch):
     monkeypatch.setenv("WICCA_JPEG_HUFFMAN", "host")
     b = decode_jpeg(data)
     assert np.array_equal(a, b) and np.array_equal(a, reference_rgb(data))
+
+
+@pytest.mark.parametrize("orientation", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_exif_orientation_is_applied_like_cv2(orientation):
+    from oracle import haar_oracle as ho
+    from wicca_b200 import decode_jpeg, icons_from_jpeg
+    rng = np.random.default_rng(40 + orientation)
+    for (h, w, s) in [(37, 53, "420"), (301, 190, "422"), (64, 64, "444")]:
+        data = with_exif_orientation(encode(photo_like(rng, h, w), 90, s), orientation)
+        ref = reference_rgb(data)
+        assert ref.shape == ((w, h, 3) if orientation >= 5 else (h, w, 3))
+        assert np.array_equal(decode_jpeg(data), ref), (orientation, h, w, s)
+    icon = icons_from_jpeg(data, [2])[0]
+    assert np.array_equal(icon, ho.haar_icon_blocksum(ref, 2))

@@ -111,11 +111,16 @@ def test_probe_and_unsupported_flavours():
         jpeg_info(bytes(png))
     with pytest.raises(ValueError):
         jpeg_info(encode(img)[:40])                     # truncated header
-    # EXIF orientation 6 (cv2.imread would rotate): spliced in front of the first DQT segment
-    data = encode(img)
-    exif = b"Exif\x00\x00MM\x00\x2a\x00\x00\x00\x08\x00\x01\x01\x12\x00\x03\x00\x00\x00\x01\x00\x06\x00\x00\x00\x00\x00\x00"
+    # EXIF orientation 6: cv2 rotates the image, and the probe reports the rotated size
+    rotated = with_exif_orientation(encode(img), 6)
+    assert reference_rgb(rotated).shape == (47, 33, 3)
+    info = jpeg_info(rotated)
+    assert (info["height"], info["width"]) == (47, 33)
+
+
+def with_exif_orientation(data, orientation):
+    """Splice an Exif APP1 segment carrying tag 0x0112 = orientation right after SOI."""
+    exif = (b"Exif\x00\x00MM\x00\x2a\x00\x00\x00\x08\x00\x01\x01\x12\x00\x03\x00\x00\x00\x01"
+            + bytes([0, orientation]) + b"\x00\x00\x00\x00\x00\x00")
     seg = b"\xff\xe1" + (len(exif) + 2).to_bytes(2, "big") + exif
-    rotated = data[:2] + seg + data[2:]
-    assert reference_rgb(rotated).shape == (47, 33, 3)  # cv2 really rotates this file
-    with pytest.raises(UnsupportedImageError):
-        jpeg_info(rotated)
+    return data[:2] + seg + data[2:]

@@ -133,6 +133,11 @@ int jpeg_device_stage(Ctx& c, const JpegFrame& f, uint8_t* d_dst, int64_t d_pitc
     JpegImageDesc d;
     memset(&d, 0, sizeof d);
     d.ncomp = f.ncomp; d.width = f.width; d.height = f.height; d.dst = d_dst; d.dst_pitch = d_pitch;
+    if (f.orientation != 1) {                                    // decode upright into scratch, then flip / transpose
+        const int64_t tmp_pitch = wicca_pitch_bytes(f.width, 3);
+        WICCA_CUDA(c.d_tmp.reserve((size_t)tmp_pitch * f.height + 256));
+        d.dst = (uint8_t*)c.d_tmp.p; d.dst_pitch = tmp_pitch;
+    }
     size_t plane_off[3];
     for (int k = 0; k < f.ncomp; ++k) {
         const JpegComponent& q = f.comp[k];
@@ -156,6 +161,8 @@ int jpeg_device_stage(Ctx& c, const JpegFrame& f, uint8_t* d_dst, int64_t d_pitc
         WICCA_CUDA(cudaEventRecord(c.ev[4], stream));             // coefficients resident
     }
     cudaError_t e = launch_jpeg_decode(d, stream);
+    if (e == cudaSuccess && f.orientation != 1)
+        e = launch_jpeg_orient(d.dst, d.dst_pitch, f.height, f.width, f.orientation, d_dst, d_pitch, stream);
     if (e != cudaSuccess) return cuda_fail(e, "JPEG decode kernels");
     return 0;
 }
@@ -184,8 +191,10 @@ int wicca_jpeg_probe(const uint8_t* data, size_t len, int* H, int* W, int* n_com
     JpegFrame f;
     int rc = parse_or_fail(data, len, f);
     if (rc) return rc;
-    if (H) *H = f.height;
-    if (W) *W = f.width;
+    int oh, ow;
+    jpeg_output_size(f, &oh, &ow);
+    if (H) *H = oh;
+    if (W) *W = ow;
     if (n_components) *n_components = f.ncomp;
     if (h_max) *h_max = f.hmax;
     if (v_max) *v_max = f.vmax;
@@ -242,7 +251,9 @@ int wicca_jpeg_decode_u8(const uint8_t* data, size_t len, uint8_t* dst, int64_t 
     JpegFrame f;
     int rc = parse_or_fail(data, len, f);
     if (rc) return rc;
-    const int64_t rowb = (int64_t)f.width * 3;
+    int oh, ow;
+    jpeg_output_size(f, &oh, &ow);
+    const int64_t rowb = (int64_t)ow * 3;
     if (!dst) return fail(WICCA_EINVAL, "dst is NULL");
     if (dst_stride == 0) dst_stride = rowb;
     if (dst_stride < rowb) return fail(WICCA_EINVAL, "dst_stride < W*3");
@@ -252,8 +263,8 @@ int wicca_jpeg_decode_u8(const uint8_t* data, size_t len, uint8_t* dst, int64_t 
     rc = acquire_ctx(device, &lease.c);
     if (rc) return rc;
     Ctx& c = *lease.c;
-    const int64_t pitch = wicca_pitch_bytes(f.width, 3);
-    WICCA_CUDA(c.d_src.reserve((size_t)pitch * f.height + 256));
+    const int64_t pitch = wicca_pitch_bytes(ow, 3);
+    WICCA_CUDA(c.d_src.reserve((size_t)pitch * oh + 256));
     float host_ms = 0;
     rc = jpeg_to_device(c, data, len, f, (uint8_t*)c.d_src.p, pitch, c.stream, &host_ms);
     if (rc) { cudaStreamSynchronize(c.stream); return rc; }
@@ -262,20 +273,20 @@ int wicca_jpeg_decode_u8(const uint8_t* data, size_t len, uint8_t* dst, int64_t 
     int64_t target_stride = dst_stride;
     const bool direct = is_pinned_host(dst);
     if (!direct) {
-        WICCA_CUDA(c.h_bounce.reserve((size_t)rowb * f.height));
+        WICCA_CUDA(c.h_bounce.reserve((size_t)rowb * oh));
         target = (uint8_t*)c.h_bounce.p;
         target_stride = rowb;
     }
-    WICCA_CUDA(cudaMemcpy2DAsync(target, (size_t)target_stride, c.d_src.p, (size_t)pitch, (size_t)rowb, (size_t)f.height,
+    WICCA_CUDA(cudaMemcpy2DAsync(target, (size_t)target_stride, c.d_src.p, (size_t)pitch, (size_t)rowb, (size_t)oh,
                                  cudaMemcpyDeviceToHost, c.stream));
     WICCA_CUDA(cudaEventRecord(c.ev[3], c.stream));
     WICCA_CUDA(cudaStreamSynchronize(c.stream));
     if (!direct) {
         if (dst_stride == rowb) {
-            c.pending.push_back({dst, target, (size_t)rowb * f.height});
+            c.pending.push_back({dst, target, (size_t)rowb * oh});
             c.flush_pending();
         } else {
-            for (int y = 0; y < f.height; ++y) memcpy(dst + (size_t)y * dst_stride, target + (size_t)y * rowb, (size_t)rowb);
+            for (int y = 0; y < oh; ++y) memcpy(dst + (size_t)y * dst_stride, target + (size_t)y * rowb, (size_t)rowb);
         }
     }
     if (t) {
@@ -293,7 +304,9 @@ int wicca_jpeg_decode_dev(const uint8_t* data, size_t len, uint8_t* d_dst, int64
     int rc = parse_or_fail(data, len, f);
     if (rc) return rc;
     if (!d_dst) return fail(WICCA_EINVAL, "d_dst is NULL");
-    if (d_pitch < (int64_t)f.width * 3) return fail(WICCA_EINVAL, "d_pitch < W*3");
+    int oh, ow;
+    jpeg_output_size(f, &oh, &ow);
+    if (d_pitch < (int64_t)ow * 3) return fail(WICCA_EINVAL, "d_pitch < W*3");
     rc = check_device(device);
     if (rc) return rc;
     CtxLease lease;
@@ -317,7 +330,9 @@ int wicca_jpeg_icons_multi_u8(const uint8_t* data, size_t len, const int* depths
     if (rc) return rc;
     if (!dsts) return fail(WICCA_EINVAL, "dsts is NULL");
     uint8_t probe = 0;                                     // validate_icon_args only checks the pointer for NULL
-    rc = validate_icon_args(&probe, f.height, f.width, 3, depths, n_depths, border_type);
+    int oh, ow;
+    jpeg_output_size(f, &oh, &ow);
+    rc = validate_icon_args(&probe, oh, ow, 3, depths, n_depths, border_type);
     if (rc) return rc;
     for (int k = 0; k < n_depths; ++k) {
         if (!dsts[k]) return fail(WICCA_EINVAL, "dsts[%d] is NULL", k);
@@ -329,13 +344,13 @@ int wicca_jpeg_icons_multi_u8(const uint8_t* data, size_t len, const int* depths
     rc = acquire_ctx(device, &lease.c);
     if (rc) return rc;
     Ctx& c = *lease.c;
-    const int64_t pitch = wicca_pitch_bytes(f.width, 3);
-    WICCA_CUDA(c.d_src.reserve((size_t)pitch * f.height + 256));
+    const int64_t pitch = wicca_pitch_bytes(ow, 3);
+    WICCA_CUDA(c.d_src.reserve((size_t)pitch * oh + 256));
     float host_ms = 0;
     rc = jpeg_to_device(c, data, len, f, (uint8_t*)c.d_src.p, pitch, c.stream, &host_ms);
     if (rc) { cudaStreamSynchronize(c.stream); return rc; }
     WICCA_CUDA(cudaEventRecord(c.ev[1], c.stream));
-    rc = icons_from_resident(c, f.height, f.width, 3, pitch, depths, n_depths, border_type, saturate_u8(border_const), dsts);
+    rc = icons_from_resident(c, oh, ow, 3, pitch, depths, n_depths, border_type, saturate_u8(border_const), dsts);
     if (rc) { cudaStreamSynchronize(c.stream); c.pending.clear(); return rc; }
     WICCA_CUDA(cudaStreamSynchronize(c.stream));
     c.flush_pending();

@@ -1,7 +1,7 @@
 // jpeg_host.cu - JPEG marker parser and Huffman decoder (host code; see jpeg_host.h).
 // Subset: baseline / extended-sequential Huffman frames (SOF0, SOF1), 8-bit samples, one grey component or
 // three YCbCr components in a single interleaved scan, integral sampling ratios, restart intervals.
-// Anything else cv2.imread can read (progressive, arithmetic, CMYK, EXIF-rotated ...) is reported as
+// Anything else cv2.imread can read (progressive, arithmetic, CMYK ...) is reported as
 // WICCA_EUNSUPPORTED so that the caller can route that file elsewhere - never decoded approximately.
 #include "jpeg_host.h"
 
@@ -204,7 +204,10 @@ int jpeg_parse(const uint8_t* data, size_t len, JpegFrame& f, std::string& why) 
                 if (n >= 5 && memcmp(seg, "JFIF\0", 5) == 0) jfif = true;
                 break;
             case 0xE1:
-                if (exif_orientation(seg, n) > 1) { why = "EXIF orientation other than 1 (cv2.imread would rotate the image)"; return WICCA_EUNSUPPORTED; }
+                if (f.orientation == 1) {                                  // the first Exif segment decides, as in OpenCV
+                    const int o = exif_orientation(seg, n);
+                    if (o >= 2 && o <= 8) f.orientation = o;
+                }
                 break;
             case 0xEE:
                 if (n >= 12 && memcmp(seg, "Adobe", 5) == 0) { adobe = true; adobe_transform = seg[11]; }

@@ -33,6 +33,7 @@ struct JpegFrame {
     int width = 0, height = 0, ncomp = 0;
     int hmax = 1, vmax = 1, mcux = 0, mcuy = 0;
     int restart_interval = 0;
+    int orientation = 1;                   // EXIF tag 0x0112 (1..8); cv2.imread applies it, so does this path
     JpegComponent comp[3];
     uint16_t qt[4][64];                    // natural (row-major) order
     bool qt_present[4] = {false, false, false, false};
@@ -41,8 +42,15 @@ struct JpegFrame {
     int64_t total_coefs = 0;               // int16 count of the dense coefficient array
 };
 
+// Size of the image the caller receives: the frame size, transposed for EXIF orientations 5..8.
+inline void jpeg_output_size(const JpegFrame& f, int* H, int* W) {
+    const bool swap = f.orientation >= 5;
+    *H = swap ? f.width : f.height;
+    *W = swap ? f.height : f.width;
+}
+
 // 0 on success; a negative WICCA_* code otherwise, with the reason in `why`.  WICCA_EUNSUPPORTED marks valid
-// JPEGs outside the subset (progressive, arithmetic coding, 12-bit, CMYK, several scans, rotated by EXIF ...).
+// JPEGs outside the subset (progressive, arithmetic coding, 12-bit, CMYK, several scans ...).
 int jpeg_parse(const uint8_t* data, size_t len, JpegFrame& f, std::string& why);
 
 // Huffman-decode the scan into dst[total_coefs]: per component, blocks in raster order, 64 coefficients each

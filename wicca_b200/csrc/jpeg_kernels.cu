@@ -246,7 +246,57 @@ jpeg_color_kernel(JpegImageDesc d) {
     }
 }
 
+// OpenCV's ApplyExifOrientation: 2 flip x, 3 flip both, 4 flip y, 5 transpose, 6 transpose + flip x, 7 transpose +
+// flip both, 8 transpose + flip y.  One thread = four output pixels of a row (three words).
+__global__ void __launch_bounds__(256)
+jpeg_orient_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, int H, int W, int orientation, uint8_t* __restrict__ dst,
+                   int64_t dst_pitch) {
+    const int Ho = orientation >= 5 ? W : H, Wo = orientation >= 5 ? H : W;
+    const int quads = (Wo + 3) >> 2;
+    const int64_t total = (int64_t)quads * Ho;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int oy = (int)(i / quads), ox0 = (int)(i - (int64_t)oy * quads) * 4;
+        uint8_t px[12];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ox = min(ox0 + k, Wo - 1);
+            int sy, sx;
+            switch (orientation) {
+                case 2: sy = oy; sx = W - 1 - ox; break;
+                case 3: sy = H - 1 - oy; sx = W - 1 - ox; break;
+                case 4: sy = H - 1 - oy; sx = ox; break;
+                case 5: sy = ox; sx = oy; break;
+                case 6: sy = H - 1 - ox; sx = oy; break;
+                case 7: sy = H - 1 - ox; sx = W - 1 - oy; break;
+                default: sy = ox; sx = W - 1 - oy; break;       // 8
+            }
+            const uint8_t* p = src + (int64_t)sy * src_pitch + (int64_t)sx * 3;
+            px[3 * k] = p[0]; px[3 * k + 1] = p[1]; px[3 * k + 2] = p[2];
+        }
+        uint8_t* row = dst + (int64_t)oy * dst_pitch + (int64_t)ox0 * 3;
+        if (ox0 + 4 <= Wo && (((uintptr_t)dst | (uintptr_t)dst_pitch) & 3) == 0) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(row);
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                w[k] = (uint32_t)px[4 * k] | ((uint32_t)px[4 * k + 1] << 8) | ((uint32_t)px[4 * k + 2] << 16) | ((uint32_t)px[4 * k + 3] << 24);
+        } else {
+            const int n = min(4, Wo - ox0) * 3;
+            for (int k = 0; k < n; ++k) row[k] = px[k];
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_jpeg_orient(const uint8_t* d_src, int64_t src_pitch, int H, int W, int orientation, uint8_t* d_dst,
+                               int64_t dst_pitch, cudaStream_t stream) {
+    const int Ho = orientation >= 5 ? W : H, Wo = orientation >= 5 ? H : W;
+    int64_t g = ((int64_t)((Wo + 3) >> 2) * Ho + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    jpeg_orient_kernel<<<(unsigned)g, 256, 0, stream>>>(d_src, src_pitch, H, W, orientation, d_dst, dst_pitch);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_jpeg_decode(const JpegImageDesc& d, cudaStream_t stream) {
     int64_t max_blocks = 0;

@@ -63,5 +63,9 @@ struct JpegImageDesc {
     uint8_t* dst; int64_t dst_pitch;     // RGB, HWC
 };
 cudaError_t launch_jpeg_decode(const JpegImageDesc& d, cudaStream_t stream);
+// EXIF orientation 2..8 as cv2.imread applies it (flip / transpose + flip): src (H, W, 3) -> dst, which is (W, H, 3)
+// for orientations >= 5.
+cudaError_t launch_jpeg_orient(const uint8_t* d_src, int64_t src_pitch, int H, int W, int orientation, uint8_t* d_dst,
+                               int64_t dst_pitch, cudaStream_t stream);
 
 }  // namespace wicca
