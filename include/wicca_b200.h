@@ -255,6 +255,15 @@ WICCA_API int wicca_jpeg_decode_dev(const uint8_t* data, size_t len, uint8_t* d_
 WICCA_API int wicca_jpeg_icons_multi_u8(const uint8_t* data, size_t len, const int* depths, int n_depths,
                                         int border_type, double border_const, uint8_t* const* dsts, int device,
                                         wicca_timing* t, float* host_decode_ms);
+/* Files -> every classifier-ready batch: wicca_batch_classifier_inputs_multi_f32 with load_image folded in, i.e. the
+ * whole of ClassifierProcessor._get_img_batch (classifying_tools.py:312-323, which starts from file paths) plus
+ * preprocess_input for every classifier input and depth, with nothing but the JPEG bytes crossing PCIe. */
+WICCA_API int wicca_batch_classifier_inputs_multi_from_jpeg(const uint8_t* const* datas, const size_t* lens, int n_images,
+                                                            const int* depths, int n_depths,
+                                                            int border_type, double border_const,
+                                                            const wicca_target* targets, int n_targets,
+                                                            float* const* dst_icons, float* const* dst_images,
+                                                            const int* devices, int n_devices, wicca_timing* t);
 /* The same for n files: dsts[i * n_depths + k]; file i runs on devices[i % n_devices]; n_threads host threads
  * (0 = one per core, at most 32) each take the next file - Huffman decoding is the bottleneck and scales with cores. */
 WICCA_API int wicca_batch_icons_from_jpeg(const uint8_t* const* datas, const size_t* lens, int n_images,

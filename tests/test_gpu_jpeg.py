@@ -145,3 +145,30 @@ def test_exif_orientation_is_applied_like_cv2(orientation):
         assert np.array_equal(decode_jpeg(data), ref), (orientation, h, w, s)
     icon = icons_from_jpeg(data, [2])[0]
     assert np.array_equal(icon, ho.haar_icon_blocksum(ref, 2))
+
+
+def test_classifier_batches_from_files(tmp_path):
+    """File paths -> every (target, depth) batch, equal to the same call on the cv2-decoded images and to the oracle."""
+    from oracle import haar_oracle as ho
+    from oracle import resize_oracle as ro
+    from wicca_b200 import HaarCoder
+    rng = np.random.default_rng(50)
+    paths, refs = [], []
+    for i, (h, w, s, o) in enumerate([(900, 1300, "420", 1), (1111, 801, "422", 6), (640, 960, "444", 1), (1001, 1500, "420", 3),
+                                      (777, 1234, "420", 1)]):
+        data = with_exif_orientation(encode(photo_like(rng, h, w), 90, s), o) if o != 1 else encode(photo_like(rng, h, w), 90, s)
+        p = tmp_path / f"c{i}.jpg"
+        p.write_bytes(data)
+        paths.append(str(p))
+        refs.append(reference_rgb(data))
+    coder = HaarCoder()
+    depths = [2, 4]
+    targets = [((224, 224), "tf"), ((299, 299), "caffe")]
+    got = coder.classifier_batches_multi_from_files(paths, depths, targets)
+    exp = coder.classifier_batches_multi(refs, depths, targets)
+    for (gi, gd), (ei, ed) in zip(got, exp):
+        assert np.array_equal(gi, ei)
+        for d in depths:
+            assert np.array_equal(gd[d], ed[d])
+    icon = ho.haar_icon_blocksum(refs[1], 2)
+    assert np.array_equal(got[0][1][2][1], ro.preprocess_input(ro.resize_area(icon, 224, 224)[None], "tf")[0])

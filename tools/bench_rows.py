@@ -227,6 +227,29 @@ def row_jpeg():
                                                         (C.c_int * ndev)(*range(ndev)), ndev, 0, C.byref(hm)), "batch_icons_from_jpeg")
             dt = time.perf_counter() - t0
         assert np.array_equal(outs[7][1], ho.haar_icon_blocksum(ref, 3))
+        if quality == 90:
+            # the whole of _get_img_batch for every classifier input and depth, from file bytes (N2 + N3)
+            import tempfile
+            tdir = tempfile.mkdtemp()
+            paths = []
+            for k in range(30):
+                pth = os.path.join(tdir, f"f{k}.jpg")
+                with open(pth, "wb") as fh:
+                    fh.write(data)
+                paths.append(pth)
+            targets = [((224, 224), "tf"), ((224, 224), "caffe"), ((224, 224), "torch"), ((224, 224), "identity"),
+                       ((240, 240), "identity"), ((260, 260), "identity"), ((299, 299), "tf"), ((331, 331), "tf"), ((300, 300), "identity")]
+            coder = HaarCoder()
+            coder.classifier_batches_multi_from_files(paths[:4], depths, targets)
+            t0 = time.perf_counter()
+            res = coder.classifier_batches_multi_from_files(paths, depths, targets)
+            dt_all = time.perf_counter() - t0
+            emit(row="N2+N3 files to all classifier inputs", config=f"30 JPEG files (53 MP each) -> {len(targets)} targets x depths 2-6 = "
+                 f"{len(targets) * len(depths)} icon batches + {len(targets)} source batches (fp32)", s=dt_all,
+                 MP_per_s=30 * H * W / 1e6 / dt_all, stage_ms_sum=coder.last_timing)
+            for pth in paths:
+                os.remove(pth)
+            os.rmdir(tdir)
         emit(row="N2 JPEG ingest, 32 files", config=f"32 x ({H},{W},3) JPEG q{quality} {tag} -> icons depths 2-6, {cores} host threads, {ndev} GPU(s)",
              s=dt, MP_per_s=n * H * W / 1e6 / dt, files_per_s=n / dt, host_stage_ms_sum=hm.value,
              cv2_thread_pool_decode_only_s=dt_ref, cv2_MP_per_s=n * H * W / 1e6 / dt_ref)

@@ -86,6 +86,10 @@ SIGNATURES = {
     "wicca_batch_icons_from_jpeg": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, c_intp, C.c_int, C.c_int,
                                               C.c_double, C.POINTER(C.c_void_p), c_intp, C.c_int, C.c_int,
                                               C.POINTER(C.c_float)]),
+    "wicca_batch_classifier_inputs_multi_from_jpeg": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, c_intp, C.c_int,
+                                                                C.c_int, C.c_double, C.POINTER(Target), C.c_int,
+                                                                C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_intp, C.c_int,
+                                                                C.POINTER(Timing)]),
     "wicca_resize_norm_dev": (C.c_int, [C.POINTER(C.c_void_p), c_intp, c_intp, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "wicca_icon_resize_norm_f32": (C.c_int, [C.POINTER(C.c_void_p), c_intp, c_intp, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -146,6 +146,7 @@ namespace {
 
 struct ClsArgs {
     const uint8_t* const* srcs; const int* Hs; const int* Ws; const int64_t* strides; int n_images;
+    const size_t* jpeg_lens;                  // not NULL: srcs[i] are JPEG files of jpeg_lens[i] bytes, decoded on the GPU
     const int* depths; int n_depths; int border_type, bconst;
     const wicca_target* targets; int n_targets;
     float* const* dst_icons; float* const* dst_images;
@@ -184,12 +185,18 @@ int cls_worker(const ClsArgs& a, int device, int first, int step, WorkerResult& 
             c.flush_pending();
             add_times(res, c);
         }
-        const int H = a.Hs[i], W = a.Ws[i];
-        const int64_t rowb = (int64_t)W * 3;
-        const int64_t stride = (a.strides && a.strides[i]) ? a.strides[i] : rowb;
-        const int64_t pitch = wicca_pitch_bytes(W, 3);
-        WICCA_CUDA(cudaEventRecord(c.ev[0], c.stream));
-        int rc = upload_image_async(c, a.srcs[i], H, rowb, stride, pitch);
+        int H = a.Hs[i], W = a.Ws[i];
+        int64_t pitch = wicca_pitch_bytes(W, 3);
+        int rc;
+        if (a.jpeg_lens) {
+            float host_ms = 0;
+            rc = jpeg_file_to_resident(c, a.srcs[i], a.jpeg_lens[i], &H, &W, &pitch, &host_ms);
+        } else {
+            const int64_t rowb = (int64_t)W * 3;
+            const int64_t stride = (a.strides && a.strides[i]) ? a.strides[i] : rowb;
+            WICCA_CUDA(cudaEventRecord(c.ev[0], c.stream));
+            rc = upload_image_async(c, a.srcs[i], H, rowb, stride, pitch);
+        }
         if (rc) { cudaStreamSynchronize(c.stream); c.pending.clear(); return rc; }
         WICCA_CUDA(cudaEventRecord(c.ev[1], c.stream));
         std::vector<IconOut> outs;
@@ -240,16 +247,16 @@ int cls_worker(const ClsArgs& a, int device, int first, int step, WorkerResult& 
 
 }  // namespace
 
-extern "C" int wicca_batch_classifier_inputs_multi_f32(const uint8_t* const* srcs, const int* Hs, const int* Ws,
-                                                       const int64_t* strides, int n_images, const int* depths,
-                                                       int n_depths, int border_type, double border_const,
-                                                       const wicca_target* targets, int n_targets,
-                                                       float* const* dst_icons, float* const* dst_images,
-                                                       const int* devices, int n_devices, wicca_timing* t) {
+namespace {
+
+int run_classifier_batches(const uint8_t* const* srcs, const size_t* jpeg_lens, const int* Hs, const int* Ws, const int64_t* strides,
+                           int n_images, const int* depths, int n_depths, int border_type, double border_const,
+                           const wicca_target* targets, int n_targets, float* const* dst_icons, float* const* dst_images,
+                           const int* devices, int n_devices, int workers_per_device, wicca_timing* t) {
     if (t) memset(t, 0, sizeof(*t));
     if (n_images < 0) return fail(WICCA_EINVAL, "negative image count");
     if (n_images == 0) return 0;
-    if (!srcs || !Hs || !Ws || !depths || !targets || !dst_icons) return fail(WICCA_EINVAL, "null array");
+    if (!srcs || !depths || !targets || !dst_icons) return fail(WICCA_EINVAL, "null array");
     if (n_depths <= 0 || n_targets <= 0) return fail(WICCA_EINVAL, "need at least one depth and one target");
     for (int k = 0; k < n_depths; ++k)
         if (depths[k] < 1) return fail(WICCA_EDEPTH, "transform depth must be >= 1");
@@ -264,17 +271,18 @@ extern "C" int wicca_batch_classifier_inputs_multi_f32(const uint8_t* const* src
     for (int i = 0; i < n_images; ++i) {
         int rc = validate_icon_args(srcs[i], Hs[i], Ws[i], 3, depths, n_depths, border_type);
         if (rc) return rc;
-        if (strides && strides[i] && strides[i] < (int64_t)Ws[i] * 3) return fail(WICCA_EINVAL, "strides[%d] < W*3", i);
+        if (!jpeg_lens && strides && strides[i] && strides[i] < (int64_t)Ws[i] * 3) return fail(WICCA_EINVAL, "strides[%d] < W*3", i);
     }
-    std::vector<int> devs(n_devices);
+    std::vector<int> devs;
     for (int k = 0; k < n_devices; ++k) {
-        devs[k] = devices ? devices[k] : k;
-        int rc = check_device(devs[k]);
+        const int d = devices ? devices[k] : k;
+        int rc = check_device(d);
         if (rc) return rc;
+        for (int w = 0; w < workers_per_device; ++w) devs.push_back(d);
     }
-    ClsArgs a{srcs, Hs, Ws, strides, n_images, depths, n_depths, border_type, saturate_u8(border_const), targets, n_targets,
-              dst_icons, dst_images};
-    const int nw = n_devices < n_images ? n_devices : n_images;
+    ClsArgs a{srcs, Hs, Ws, strides, n_images, jpeg_lens, depths, n_depths, border_type, saturate_u8(border_const), targets,
+              n_targets, dst_icons, dst_images};
+    const int nw = (int)devs.size() < n_images ? (int)devs.size() : n_images;
     std::vector<WorkerResult> results(nw);
     std::vector<std::thread> threads;
     for (int k = 0; k < nw; ++k)
@@ -290,6 +298,36 @@ extern "C" int wicca_batch_classifier_inputs_multi_f32(const uint8_t* const* src
     }
     if (t) *t = sum;
     return 0;
+}
+
+}  // namespace
+
+extern "C" int wicca_batch_classifier_inputs_multi_f32(const uint8_t* const* srcs, const int* Hs, const int* Ws,
+                                                       const int64_t* strides, int n_images, const int* depths,
+                                                       int n_depths, int border_type, double border_const,
+                                                       const wicca_target* targets, int n_targets,
+                                                       float* const* dst_icons, float* const* dst_images,
+                                                       const int* devices, int n_devices, wicca_timing* t) {
+    if (n_images > 0 && (!Hs || !Ws)) return fail(WICCA_EINVAL, "null array");
+    return run_classifier_batches(srcs, nullptr, Hs, Ws, strides, n_images, depths, n_depths, border_type, border_const, targets,
+                                  n_targets, dst_icons, dst_images, devices, n_devices, 1, t);
+}
+
+extern "C" int wicca_batch_classifier_inputs_multi_from_jpeg(const uint8_t* const* datas, const size_t* lens, int n_images,
+                                                             const int* depths, int n_depths, int border_type,
+                                                             double border_const, const wicca_target* targets, int n_targets,
+                                                             float* const* dst_icons, float* const* dst_images,
+                                                             const int* devices, int n_devices, wicca_timing* t) {
+    if (n_images > 0 && (!datas || !lens)) return fail(WICCA_EINVAL, "null array");
+    std::vector<int> Hs(n_images > 0 ? n_images : 0), Ws(Hs.size());
+    for (int i = 0; i < n_images; ++i) {
+        if (!datas[i]) return fail(WICCA_EINVAL, "datas[%d] is NULL", i);
+        int rc = jpeg_output_dims(datas[i], lens[i], &Hs[i], &Ws[i]);
+        if (rc) return rc;
+    }
+    // the host stage per file (marker parsing, byte unstuffing) is a few ms: four workers per GPU keep it fed
+    return run_classifier_batches(datas, lens, Hs.data(), Ws.data(), nullptr, n_images, depths, n_depths, border_type, border_const,
+                                  targets, n_targets, dst_icons, dst_images, devices, n_devices, 4, t);
 }
 
 extern "C" int wicca_batch_classifier_inputs_f32(const uint8_t* const* srcs, const int* Hs, const int* Ws,

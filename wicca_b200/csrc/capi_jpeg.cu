@@ -82,9 +82,9 @@ int jpeg_gpu_huffman_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFr
     sc.blocks_per_mcu = slot;
     sc.total_blocks = (int64_t)f.mcux * f.mcuy * slot;
     // host copy of the tables + the flag the fixed-point loop polls, in page-locked memory
-    // (h_bounce: the only later user of that buffer is a stream-ordered D2H copy, so the upload below cannot race)
-    WICCA_CUDA(c.h_bounce.reserve(sizeof(JpegGpuTables) + 64));
-    JpegGpuTables* ht = (JpegGpuTables*)c.h_bounce.p;
+    // (a buffer of its own: nothing else may write to it while the upload below is in flight)
+    WICCA_CUDA(c.h_jpeg.reserve(sizeof(JpegGpuTables) + 64));
+    JpegGpuTables* ht = (JpegGpuTables*)c.h_jpeg.p;
     memset(ht, 0, sizeof *ht);
     for (int id = 0; id < 4; ++id) {
         const JpegHuff* src[2] = {&f.dc[id], &f.ac[id]};
@@ -97,7 +97,7 @@ int jpeg_gpu_huffman_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFr
             memcpy(ht->symbols[t], src[kind]->symbols, sizeof ht->symbols[t]);
         }
     }
-    int* h_changed = (int*)((uint8_t*)c.h_bounce.p + sizeof(JpegGpuTables));
+    int* h_changed = (int*)((uint8_t*)c.h_jpeg.p + sizeof(JpegGpuTables));
     // device scratch: [scan words][tables][exit a][exit b][start used][count][base][changed][chunk sums]
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off = (size_t)align_up((int64_t)(off + bytes), 256); return o; };
@@ -184,6 +184,28 @@ int jpeg_to_device(Ctx& c, const uint8_t* data, size_t len, const JpegFrame& f, 
 }
 
 }  // namespace
+
+namespace wicca {
+
+int jpeg_output_dims(const uint8_t* data, size_t len, int* H, int* W) {
+    JpegFrame f;
+    int rc = parse_or_fail(data, len, f);
+    if (rc) return rc;
+    jpeg_output_size(f, H, W);
+    return 0;
+}
+
+int jpeg_file_to_resident(Ctx& c, const uint8_t* data, size_t len, int* H, int* W, int64_t* pitch, float* host_ms) {
+    JpegFrame f;
+    int rc = parse_or_fail(data, len, f);
+    if (rc) return rc;
+    jpeg_output_size(f, H, W);
+    *pitch = wicca_pitch_bytes(*W, 3);
+    WICCA_CUDA(c.d_src.reserve((size_t)*pitch * *H + 256));
+    return jpeg_to_device(c, data, len, f, (uint8_t*)c.d_src.p, *pitch, c.stream, host_ms);
+}
+
+}  // namespace wicca
 
 extern "C" {
 

@@ -53,7 +53,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};                // start, h2d done, kernels done, d2h done, spare x2
     DevBuf d_src, d_icons, d_desc, d_strip, d_f32a, d_f32b, d_misc, d_tmp;
-    PinBuf h_desc, h_bounce, h_in, h_out;
+    PinBuf h_desc, h_bounce, h_in, h_out, h_jpeg;
     // Results bound for pageable host memory are DMA'd into h_bounce (so the copy is truly
     // asynchronous) and moved to their destination after the stream has been synchronised.
     struct Pending { void* dst; const void* src; size_t bytes; };
@@ -107,6 +107,11 @@ struct ScopedAffinity {
 int upload_image_async(Ctx& c, const uint8_t* src, int H, int64_t row_bytes, int64_t stride, int64_t pitch);
 
 int icon_variant_from_env();
+
+// JPEG bytes -> c.d_src (RGB, oriented, rows *pitch bytes apart) on c.stream; ev[0] marks the start of the device
+// work.  capi_jpeg.cu.
+int jpeg_file_to_resident(Ctx& c, const uint8_t* data, size_t len, int* H, int* W, int64_t* pitch, float* host_ms);
+int jpeg_output_dims(const uint8_t* data, size_t len, int* H, int* W);
 
 struct IconOut {          // one requested depth of one image
     int depth = 0;

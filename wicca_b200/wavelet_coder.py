@@ -386,6 +386,59 @@ class HaarCoder(WaveletCoder):
         self._tls.timing = t.as_dict()
         return out
 
+    def classifier_batches_multi_from_files(self, file_paths: Sequence[str], transform_depths: Sequence[int],
+                                            targets: Sequence[tuple], border_type: int = BORDER_REPLICATE,
+                                            border_constant: int = 0, with_source: bool = True,
+                                            devices: Sequence[int] | None = None):
+        """``classifier_batches_multi`` starting where ``ClassifierProcessor._get_img_batch`` starts: from file
+        paths (``classifying_tools.py:312-314``).  Baseline JPEG files are decoded on the GPU
+        (``wicca_b200.data_loader``), so only the file bytes cross PCIe; other formats raise
+        ``UnsupportedImageError``.  Same return value as ``classifier_batches_multi``."""
+        depths = [_as_depth(d) for d in transform_depths]
+        if not depths or any(d < 1 for d in depths):
+            raise ValueError("transform_depths must be a non-empty sequence of depths >= 1")
+        if len(set(depths)) != len(depths):
+            raise ValueError("transform_depths must not repeat")
+        tlist = []
+        for shape, mode in targets:
+            if mode not in NORM_MODES:
+                raise ValueError(f"unknown preprocess mode {mode!r}; expected one of {sorted(NORM_MODES)}")
+            ow, oh = int(shape[0]), int(shape[1])
+            if ow <= 0 or oh <= 0:
+                raise ValueError("target shape must be positive")
+            tlist.append((oh, ow, NORM_MODES[mode]))
+        if not tlist:
+            raise ValueError("need at least one target")
+        blobs = []
+        for path in file_paths:
+            if not path:
+                raise ValueError("File path cannot be empty")
+            with open(path, "rb") as fh:
+                blobs.append(fh.read())
+        n, nd, nt = len(blobs), len(depths), len(tlist)
+        out = []
+        for oh, ow, _ in tlist:
+            src = np.empty((n, oh, ow, 3), dtype=np.float32) if with_source else None
+            out.append((src, {d: np.empty((n, oh, ow, 3), dtype=np.float32) for d in depths}))
+        if n == 0:
+            return out
+        lib = _capi.load()
+        if devices is None:
+            devices = list(range(max(1, lib.wicca_device_count())))
+        datas = (C.c_void_p * n)(*[C.cast(C.c_char_p(b), C.c_void_p).value for b in blobs])
+        lens = (C.c_size_t * n)(*[len(b) for b in blobs])
+        c_targets = (_capi.Target * nt)(*[_capi.Target(*t) for t in tlist])
+        dst_icons = (C.c_void_p * (nt * nd))(*[out[t][1][d].ctypes.data for t in range(nt) for d in depths])
+        dst_images = (C.c_void_p * nt)(*[out[t][0].ctypes.data for t in range(nt)]) if with_source else None
+        dev = (C.c_int * len(devices))(*[int(x) for x in devices])
+        t = _capi.Timing()
+        rc = lib.wicca_batch_classifier_inputs_multi_from_jpeg(datas, lens, n, (C.c_int * nd)(*depths), nd, int(border_type),
+                                                               float(border_constant), c_targets, nt, dst_icons, dst_images,
+                                                               dev, len(devices), C.byref(t))
+        _capi.check(rc, "wicca_batch_classifier_inputs_multi_from_jpeg")
+        self._tls.timing = t.as_dict()
+        return out
+
     @property
     def last_timing(self) -> dict | None:
         """Device-side stage times (ms) of this thread's last call."""
