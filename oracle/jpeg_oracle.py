@@ -14,9 +14,11 @@ decompressor at its defaults, so the published algorithm restated here is:
     otherwise (jdsample.c); rows above / below the image are copies of the first / last real row (jdmainct.c);
   * YCbCr -> RGB with the 16-bit fixed-point tables of jdcolor.c.
 
-Pinning: ``tests/test_oracle_jpeg.py`` checks this restatement against ``cv2.imdecode`` (run live, it is
-installed on the build container and on the GPU box) bit for bit over sizes, qualities, chroma samplings,
-restart intervals and grayscale files.  The Huffman decoder is a plain Python loop: small images only.
+Pinning: ``tests/test_oracle_jpeg.py`` checks this restatement (i) against ``tests/golden/jpeg_golden.npz`` -
+JPEG files and what the reference's own ``load_image`` returned for them, written by
+``tests/golden/make_golden.py jpeg`` in the build container - and (ii) against ``cv2.imdecode`` run live, bit
+for bit over sizes, qualities, chroma samplings, restart intervals, EXIF orientations and grayscale files.
+The Huffman decoder is a plain Python loop: small images only.
 """
 from __future__ import annotations
 
@@ -334,3 +336,48 @@ def decode_rgb(data: bytes) -> np.ndarray:
     if len(planes) == 1:
         return np.repeat(planes[0][:, :, None], 3, axis=2)
     return ycc_to_rgb(*planes)
+
+
+def exif_orientation(data: bytes) -> int:
+    """EXIF tag 0x0112 of the first Exif APP1 segment (1 when absent), as OpenCV's ExifReader finds it."""
+    i = 2
+    while i + 4 <= len(data) and data[i] == 0xFF:
+        m = data[i + 1]
+        if m == 0xDA or m == 0xD9:
+            break
+        n = (data[i + 2] << 8) | data[i + 3]
+        seg = data[i + 4:i + 2 + n]
+        i += 2 + n
+        if m == 0xE1 and seg[:6] == b"Exif\x00\x00":
+            t = seg[6:]
+            order = "little" if t[:2] == b"II" else "big"
+            ifd = int.from_bytes(t[4:8], order)
+            for e in range(int.from_bytes(t[ifd:ifd + 2], order)):
+                o = ifd + 2 + 12 * e
+                if int.from_bytes(t[o:o + 2], order) == 0x0112:
+                    v = int.from_bytes(t[o + 8:o + 10], order)
+                    return v if 1 <= v <= 8 else 1
+            return 1
+    return 1
+
+
+def decode_rgb_oriented(data: bytes) -> np.ndarray:
+    """``decode_rgb`` followed by OpenCV's ApplyExifOrientation - what ``cv2.imread`` / ``imdecode`` return."""
+    img = decode_rgb(data)
+    o = exif_orientation(data)
+    if o == 2:
+        return img[:, ::-1]
+    if o == 3:
+        return img[::-1, ::-1]
+    if o == 4:
+        return img[::-1]
+    t = img.transpose(1, 0, 2)
+    if o == 5:
+        return t
+    if o == 6:
+        return t[:, ::-1]
+    if o == 7:
+        return t[::-1, ::-1]
+    if o == 8:
+        return t[::-1]
+    return img

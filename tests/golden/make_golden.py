@@ -83,7 +83,67 @@ RESIZE_CASES = [
 ]
 
 
+# (seed, h, w, quality, sampling, restart interval, grey, EXIF orientation)
+JPEG_CASES = [
+    (1, 17, 33, 90, "420", 0, 0, 1), (2, 37, 53, 75, "420", 3, 0, 1), (3, 70, 31, 95, "422", 0, 0, 1),
+    (4, 96, 128, 85, "444", 0, 0, 1), (5, 64, 48, 35, "420", 0, 0, 1), (6, 33, 100, 100, "440", 0, 0, 1),
+    (7, 50, 75, 90, "411", 5, 0, 1), (8, 40, 23, 85, "420", 0, 1, 1), (9, 61, 45, 90, "420", 0, 0, 6),
+    (10, 45, 61, 80, "422", 0, 0, 3), (11, 1, 1, 90, "420", 0, 0, 1), (12, 2, 3, 90, "420", 0, 0, 1),
+    (13, 128, 160, 92, "420", 0, 0, 8), (14, 99, 77, 60, "444", 7, 0, 5),
+]
+
+
+def jpeg_case_bytes(cv2, case) -> bytes:
+    """The JPEG file of a case (encoded with OpenCV, EXIF orientation spliced in as an APP1 segment)."""
+    seed, h, w, q, sampling, restart, grey, orientation = case
+    rng = np.random.default_rng(2000 + seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.stack([128 + 100 * np.sin(xx / 17.0 + c) + 60 * np.cos(yy / 11.0 - c) for c in range(3)], -1)
+    img = np.clip(img + rng.normal(0, 12, (h, w, 3)), 0, 255).astype(np.uint8)
+    if q == 35:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    params = [cv2.IMWRITE_JPEG_QUALITY, q]
+    if grey:
+        img = img[:, :, 0]
+    else:
+        params += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, getattr(cv2, f"IMWRITE_JPEG_SAMPLING_FACTOR_{sampling}")]
+    if restart:
+        params += [cv2.IMWRITE_JPEG_RST_INTERVAL, restart]
+    ok, enc = cv2.imencode(".jpg", img, params)
+    assert ok
+    data = bytes(enc)
+    if orientation != 1:
+        exif = (b"Exif\x00\x00MM\x00\x2a\x00\x00\x00\x08\x00\x01\x01\x12\x00\x03\x00\x00\x00\x01"
+                + bytes([0, orientation]) + b"\x00\x00\x00\x00\x00\x00")
+        data = data[:2] + b"\xff\xe1" + (len(exif) + 2).to_bytes(2, "big") + exif + data[2:]
+    return data
+
+
+def make_jpeg() -> int:
+    """JPEG files + what the reference's own load_image (wicca/data_loader.py:27-63) returns for them."""
+    import tempfile
+    sys.path.insert(0, "/root/reference")
+    import cv2
+    from wicca.data_loader import load_image
+    out = {"cases": np.array([json.dumps(JPEG_CASES)])}
+    with tempfile.TemporaryDirectory() as tmp:
+        for i, case in enumerate(JPEG_CASES):
+            data = jpeg_case_bytes(cv2, case)
+            path = os.path.join(tmp, f"case{i}.jpg")
+            with open(path, "wb") as fh:
+                fh.write(data)
+            rgb = load_image(path)
+            assert rgb is not None and rgb.dtype == np.uint8 and rgb.ndim == 3
+            out[f"file_{i}"] = np.frombuffer(data, dtype=np.uint8)
+            out[f"rgb_{i}"] = rgb
+    np.savez_compressed(os.path.join(HERE, "jpeg_golden.npz"), **out)
+    print(f"wrote {len(JPEG_CASES)} JPEG cases; cv2 {cv2.__version__} ({[l.strip() for l in cv2.getBuildInformation().splitlines() if 'JPEG:' in l][0]})")
+    return 0
+
+
 def main() -> int:
+    if len(sys.argv) > 1 and sys.argv[1] == "jpeg":
+        return make_jpeg()
     sys.path.insert(0, "/root/reference")
     import cv2
     from wicca.wavelet_coder import HaarCoder

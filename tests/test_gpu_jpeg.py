@@ -172,3 +172,11 @@ def test_classifier_batches_from_files(tmp_path):
             assert np.array_equal(gd[d], ed[d])
     icon = ho.haar_icon_blocksum(refs[1], 2)
     assert np.array_equal(got[0][1][2][1], ro.preprocess_input(ro.resize_area(icon, 224, 224)[None], "tf")[0])
+
+
+def test_decode_matches_reference_goldens():
+    """Committed fixtures from the reference's own load_image (no OpenCV needed at test time)."""
+    from tests.test_oracle_jpeg import jpeg_golden
+    from wicca_b200 import decode_jpeg
+    for case, data, rgb in jpeg_golden():
+        assert np.array_equal(decode_jpeg(data), rgb), case

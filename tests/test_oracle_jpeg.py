@@ -42,6 +42,21 @@ def reference_rgb(data):
     return cv2.cvtColor(cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
 
 
+def jpeg_golden():
+    """Committed fixtures: JPEG files and what the reference's own load_image returned for them
+    (tests/golden/make_golden.py jpeg, run where /root/reference and its OpenCV are importable)."""
+    import json
+    from pathlib import Path
+    z = np.load(Path(__file__).parent / "golden" / "jpeg_golden.npz")
+    cases = json.loads(str(z["cases"][0]))
+    return [(tuple(c), bytes(z[f"file_{i}"]), z[f"rgb_{i}"]) for i, c in enumerate(cases)]
+
+
+def test_oracle_matches_reference_goldens():
+    for case, data, rgb in jpeg_golden():
+        assert np.array_equal(jo.decode_rgb_oriented(data), rgb), case
+
+
 CASES = [(h, w, q, s, r) for (h, w) in [(8, 8), (1, 1), (2, 3), (17, 33), (37, 53), (70, 31)] for q in (35, 90, 100)
          for s in SAMPLING for r in (0, 3)]
 
