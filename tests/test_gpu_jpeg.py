@@ -180,3 +180,25 @@ def test_decode_matches_reference_goldens():
     from wicca_b200 import decode_jpeg
     for case, data, rgb in jpeg_golden():
         assert np.array_equal(decode_jpeg(data), rgb), case
+
+
+def test_gpu_decoder_survives_corrupt_scans():
+    """Corrupt entropy-coded data must not take the device down: every call returns, and a clean file still
+    decodes bit-exactly afterwards (an out-of-bounds access in a kernel would poison the CUDA context)."""
+    from wicca_b200 import decode_jpeg
+    rng = np.random.default_rng(98)
+    for sampling in ("420", "444"):
+        good = encode(photo_like(rng, 333, 517), 85, sampling)
+        scan_start = good.index(b"\xff\xda") + 14
+        for it in range(60):
+            d = bytearray(good)
+            for _ in range(1 + int(rng.integers(0, 8))):
+                d[int(rng.integers(scan_start, len(d) - 2))] = int(rng.integers(0, 256))
+            if it % 5 == 0:
+                d = d[:int(rng.integers(scan_start + 10, len(d)))]
+            try:
+                out = decode_jpeg(bytes(d))
+                assert out.shape == (333, 517, 3)
+            except ValueError:
+                pass
+        assert np.array_equal(decode_jpeg(good), reference_rgb(good))

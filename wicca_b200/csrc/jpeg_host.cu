@@ -69,7 +69,7 @@ int build_huff(const uint8_t* counts, const uint8_t* symbols, int n_symbols, Jpe
         const int len = e >> 8, run = (e >> 4) & 15, mag = e & 15;
         if (!mag || len + mag > 10) continue;
         int v = ((i << len) & 1023) >> (10 - mag);
-        if (v < (1 << (mag - 1))) v += (-1 << mag) + 1;
+        if (v < (1 << (mag - 1))) v += 1 - (1 << mag);
         if (v >= -128 && v <= 127) h.fast_ac[i] = (int16_t)(v * 256 + run * 16 + len + mag);
     }
     h.present = true;
@@ -117,7 +117,7 @@ struct BitReader {
     inline int receive_extend(int s) {                                   // T.81 F.2.2.1 EXTEND, branch-free; s in 1..15
         const int v = (int)peek(s);
         skip(s);
-        return v + (((v - (1 << (s - 1))) >> 31) & ((-1 << s) + 1));
+        return v + (((v - (1 << (s - 1))) >> 31) & (1 - (1 << s)));
     }
     inline int decode(const JpegHuff& h) {
         const uint32_t e = h.look[peek(10)];
@@ -183,6 +183,7 @@ int jpeg_parse(const uint8_t* data, size_t len, JpegFrame& f, std::string& why) 
                 if (seg[0] != 8) { why = "only 8-bit JPEG samples are supported"; return WICCA_EUNSUPPORTED; }
                 f.height = be16(seg + 1); f.width = be16(seg + 3); f.ncomp = seg[5];
                 if (f.height <= 0 || f.width <= 0) { why = "JPEG with zero size (DNL marker) is not supported"; return WICCA_EUNSUPPORTED; }
+                if ((int64_t)f.height * f.width > ((int64_t)1 << 29)) { why = "JPEG larger than 512 megapixels"; return WICCA_EUNSUPPORTED; }
                 if (f.ncomp != 1 && f.ncomp != 3) { why = "only 1- and 3-component JPEGs are supported"; return WICCA_EUNSUPPORTED; }
                 if (n < 6 + 3 * (size_t)f.ncomp) { why = "bad frame header"; return WICCA_EINVAL; }
                 for (int c = 0; c < f.ncomp; ++c) {

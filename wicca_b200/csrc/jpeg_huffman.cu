@@ -78,7 +78,7 @@ __device__ __forceinline__ void symbol(const SharedTables& T, const JpegGpuTable
 
 __device__ __forceinline__ int extend(uint32_t win, int len, int s) {          // the s bits after the code, sign-extended (T.81 F.12)
     const int v = (int)((win << len) >> (32 - s));
-    return v + (((v - (1 << (s - 1))) >> 31) & ((-1 << s) + 1));
+    return v + (((v - (1 << (s - 1))) >> 31) & (1 - (1 << s)));
 }
 
 // Decode every symbol that starts in [st.pos, limit).  kWrite: also store coefficients, starting in block
