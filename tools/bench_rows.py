@@ -221,11 +221,13 @@ def row_jpeg():
         dsts = (C.c_void_p * (n * len(depths)))(*[o.ctypes.data for per in outs for o in per])
         ndev = lib.wicca_device_count()
         hm = C.c_float()
-        for rep in range(2):
+        dt = 1e9
+        for rep in range(4):                                 # the first pass allocates the per-thread contexts
             t0 = time.perf_counter()
             _capi.check(lib.wicca_batch_icons_from_jpeg(datas, lens, n, (C.c_int * len(depths))(*depths), len(depths), 1, 0.0, dsts,
                                                         (C.c_int * ndev)(*range(ndev)), ndev, 0, C.byref(hm)), "batch_icons_from_jpeg")
-            dt = time.perf_counter() - t0
+            if rep:
+                dt = min(dt, time.perf_counter() - t0)
         assert np.array_equal(outs[7][1], ho.haar_icon_blocksum(ref, 3))
         if quality == 90:
             # the whole of _get_img_batch for every classifier input and depth, from file bytes (N2 + N3)
