@@ -237,8 +237,8 @@ WICCA_API int wicca_jpeg_probe(const uint8_t* data, size_t len, int* H, int* W, 
 WICCA_API int64_t wicca_jpeg_coeff_count(const uint8_t* data, size_t len);
 WICCA_API int wicca_jpeg_decode_coeffs(const uint8_t* data, size_t len, int16_t* dst, int64_t dst_count,
                                        int* blocks_w, int* blocks_h, uint16_t* qt);
-/* The same coefficients from the GPU Huffman decoder (files without restart markers; the default first stage of
- * every entry point below - WICCA_JPEG_HUFFMAN=host selects the host decoder).  passes (nullable): re-synchronisation
+/* The same coefficients from the GPU Huffman decoder (the default first stage of every entry point below;
+ * WICCA_JPEG_HUFFMAN=host selects the host decoder).  passes (nullable): re-synchronisation
  * passes it took.  For tests and measurements. */
 WICCA_API int wicca_jpeg_decode_coeffs_gpu(const uint8_t* data, size_t len, int16_t* dst, int64_t dst_count, int device,
                                            int* passes);

@@ -113,14 +113,16 @@ def test_gpu_huffman_decoder_matches_host_decoder(sampling):
     from wicca_b200 import _capi
     lib = _capi.load()
     rng = np.random.default_rng(31)
-    for (h, w, q) in [(8, 8, 90), (40, 56, 35), (257, 511, 75), (600, 800, 92), (1500, 2100, 85), (333, 1001, 100)]:
+    for (h, w, q, restart) in [(8, 8, 90, 0), (40, 56, 35, 0), (257, 511, 75, 0), (600, 800, 92, 0), (1500, 2100, 85, 0),
+                               (333, 1001, 100, 0), (40, 56, 90, 1), (257, 511, 35, 3), (600, 800, 92, 50), (1500, 2100, 85, 132),
+                               (333, 1001, 100, 7), (64, 64, 90, 1000)]:
         img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if q == 35 else photo_like(rng, h, w)
-        data = encode(img, q, sampling, optimize=(q == 100))
+        data = encode(img, q, sampling, restart, optimize=(q == 100))
         exp, _, _, _ = host_coefficients(data)
         got = np.empty_like(exp)
         passes = C.c_int()
         _capi.check(lib.wicca_jpeg_decode_coeffs_gpu(data, len(data), got.ctypes.data, got.size, 0, C.byref(passes)), "coeffs_gpu")
-        assert np.array_equal(got, exp), (h, w, q, sampling, passes.value)
+        assert np.array_equal(got, exp), (h, w, q, sampling, restart, passes.value)
 
 
 def test_both_huffman_stages_give_the_same_image(monkeypatch):

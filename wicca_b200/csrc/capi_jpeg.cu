@@ -51,7 +51,6 @@ int jpeg_host_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFrame& f,
 }
 
 bool gpu_huffman_wanted(const JpegFrame& f) {
-    if (f.restart_interval) return false;                    // restart markers: the host decoder handles those
     const char* e = getenv("WICCA_JPEG_HUFFMAN");
     return !(e && e[0] == 'h');                              // WICCA_JPEG_HUFFMAN=host forces the CPU stage
 }
@@ -63,9 +62,17 @@ int jpeg_gpu_huffman_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFr
     const size_t cap = len - f.scan_offset + 32;
     WICCA_CUDA(c.h_in.reserve(cap));
     const double t0 = now_ms();
-    const size_t n_bytes = jpeg_unstuff_scan(data, len, f, (uint8_t*)c.h_in.p);
+    std::vector<uint32_t> starts;
+    const size_t n_bytes = jpeg_unstuff_scan(data, len, f, (uint8_t*)c.h_in.p, &starts);
     if (host_ms) *host_ms += (float)(now_ms() - t0);
     if (n_bytes == 0 || n_bytes >= ((size_t)1 << 28)) return 1;
+    if (f.restart_interval) {
+        // exactly one marker between consecutive intervals, or the file is damaged: the host decoder copes better
+        const int64_t mcus = (int64_t)f.mcux * f.mcuy;
+        if ((int64_t)starts.size() != (mcus + f.restart_interval - 1) / f.restart_interval - 1) return 1;
+    } else if (!starts.empty()) {
+        return 1;
+    }
     WICCA_CUDA(cudaEventRecord(c.ev[0], stream));                 // device work starts here
     JpegGpuScan sc;
     memset(&sc, 0, sizeof sc);
@@ -83,7 +90,7 @@ int jpeg_gpu_huffman_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFr
     sc.total_blocks = (int64_t)f.mcux * f.mcuy * slot;
     // host copy of the tables + the flag the fixed-point loop polls, in page-locked memory
     // (a buffer of its own: nothing else may write to it while the upload below is in flight)
-    WICCA_CUDA(c.h_jpeg.reserve(sizeof(JpegGpuTables) + 64));
+    WICCA_CUDA(c.h_jpeg.reserve(sizeof(JpegGpuTables) + 64 + (starts.size() + 1) * sizeof(uint32_t)));
     JpegGpuTables* ht = (JpegGpuTables*)c.h_jpeg.p;
     memset(ht, 0, sizeof *ht);
     for (int id = 0; id < 4; ++id) {
@@ -105,6 +112,10 @@ int jpeg_gpu_huffman_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFr
     const size_t o_ea = take((size_t)sc.n_sub * 8), o_eb = take((size_t)sc.n_sub * 8), o_su = take((size_t)sc.n_sub * 8);
     const size_t o_cnt = take((size_t)sc.n_sub * 4), o_base = take((size_t)sc.n_sub * 4), o_chg = take(4);
     const size_t o_sums = take(jpeg_gpu_chunk_sum_capacity(sc));
+    int64_t max_blocks = 0;
+    for (int k = 0; k < f.ncomp; ++k) max_blocks = std::max(max_blocks, sc.comp[k].n_blocks);
+    const size_t o_bounds = take((starts.size() + 1) * sizeof(uint32_t));
+    const size_t o_prefix = take(starts.empty() ? 4 : (size_t)max_blocks * sizeof(int32_t));
     WICCA_CUDA(c.d_misc.reserve(off));
     WICCA_CUDA(c.d_f32a.reserve((size_t)f.total_coefs * sizeof(int16_t)));
     uint8_t* m = (uint8_t*)c.d_misc.p;
@@ -115,6 +126,17 @@ int jpeg_gpu_huffman_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFr
     sc.base = (uint32_t*)(m + o_base);
     sc.changed = (int*)(m + o_chg);
     sc.coefs = (int16_t*)c.d_f32a.p;
+    sc.bounds = (const uint32_t*)(m + o_bounds);
+    sc.n_bounds = (uint32_t)starts.size();
+    sc.blocks_per_interval = (int64_t)f.restart_interval * sc.blocks_per_mcu;
+    sc.dc_prefix = (int32_t*)(m + o_prefix);
+    {
+        // interval boundaries as bit offsets + sentinel, staged behind the tables in the page-locked buffer
+        uint32_t* hb = (uint32_t*)((uint8_t*)c.h_jpeg.p + sizeof(JpegGpuTables) + 64);
+        for (size_t k = 0; k < starts.size(); ++k) hb[k] = starts[k] * 8u;
+        hb[starts.size()] = 0xFFFFFFFFu;
+        WICCA_CUDA(cudaMemcpyAsync(m + o_bounds, hb, (starts.size() + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    }
     WICCA_CUDA(cudaMemcpyAsync(m + o_words, c.h_in.p, n_bytes + 16, cudaMemcpyHostToDevice, stream));
     WICCA_CUDA(cudaMemcpyAsync(m + o_tab, ht, sizeof(JpegGpuTables), cudaMemcpyHostToDevice, stream));
     WICCA_CUDA(cudaEventRecord(c.ev[4], stream));                 // scan resident
@@ -251,7 +273,6 @@ int wicca_jpeg_decode_coeffs_gpu(const uint8_t* data, size_t len, int16_t* dst, 
     int rc = parse_or_fail(data, len, f);
     if (rc) return rc;
     if (!dst || dst_count < f.total_coefs) return fail(WICCA_EINVAL, "coefficient buffer too small (%lld needed)", (long long)f.total_coefs);
-    if (f.restart_interval) return fail(WICCA_EUNSUPPORTED, "files with restart markers are Huffman-decoded on the host");
     rc = check_device(device);
     if (rc) return rc;
     CtxLease lease;

@@ -36,6 +36,11 @@ struct JpegGpuScan {
     uint32_t* base;                           // [n_sub] blocks before the sub-sequence
     int* changed;
     const JpegGpuTables* tables;              // device copy
+    // restart intervals: bit offsets at which intervals 1, 2, ... start, ascending, closed by 0xFFFFFFFF
+    const uint32_t* bounds;
+    uint32_t n_bounds;                        // without the sentinel; 0 for files without restart markers
+    int64_t blocks_per_interval;              // restart_interval * blocks_per_mcu
+    int32_t* dc_prefix;                       // [max component blocks] running sums for the segmented DC scan
 };
 
 size_t jpeg_gpu_chunk_sum_capacity(const JpegGpuScan& sc);

@@ -318,7 +318,7 @@ int jpeg_decode_coefficients(const uint8_t* data, size_t len, const JpegFrame& f
     return 0;
 }
 
-size_t jpeg_unstuff_scan(const uint8_t* data, size_t len, const JpegFrame& f, uint8_t* dst) {
+size_t jpeg_unstuff_scan(const uint8_t* data, size_t len, const JpegFrame& f, uint8_t* dst, std::vector<uint32_t>* interval_starts) {
     const uint8_t* p = data + f.scan_offset;
     const uint8_t* end = data + len;
     uint8_t* o = dst;
@@ -330,7 +330,13 @@ size_t jpeg_unstuff_scan(const uint8_t* data, size_t len, const JpegFrame& f, ui
         p = q;
         if (p >= end) break;
         if (p + 1 < end && p[1] == 0) { *o++ = 0xFF; p += 2; continue; }     // stuffed zero
-        break;                                                                 // a marker (EOI): the scan ends here
+        if (p + 1 < end && p[1] >= 0xD0 && p[1] <= 0xD7) {                     // RSTn: the next interval starts here
+            if (interval_starts) interval_starts->push_back((uint32_t)(o - dst));
+            p += 2;
+            continue;
+        }
+        if (p + 1 < end && p[1] == 0xFF) { ++p; continue; }                    // fill byte in front of a marker
+        break;                                                                 // any other marker (EOI): the scan ends here
     }
     memset(o, 0, 16);
     return (size_t)(o - dst);

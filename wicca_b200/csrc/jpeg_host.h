@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 namespace wicca {
 
@@ -57,8 +58,10 @@ int jpeg_parse(const uint8_t* data, size_t len, JpegFrame& f, std::string& why);
 // in natural order, not dequantised.  Every element of dst is written (no pre-zeroing needed).
 int jpeg_decode_coefficients(const uint8_t* data, size_t len, const JpegFrame& f, int16_t* dst, std::string& why);
 
-// Copy the entropy-coded bytes of the scan to dst with the byte stuffing (0xFF 0x00 -> 0xFF) removed, stopping at
-// the first marker; dst needs len - scan_offset + 16 bytes and is zero padded by 16 bytes.  Returns the byte count.
-size_t jpeg_unstuff_scan(const uint8_t* data, size_t len, const JpegFrame& f, uint8_t* dst);
+// Copy the entropy-coded bytes of the scan to dst with the byte stuffing (0xFF 0x00 -> 0xFF) and the RSTn markers
+// removed, stopping at the first other marker; dst needs len - scan_offset + 16 bytes and is zero padded by 16
+// bytes.  interval_starts receives the byte offset (in dst) at which every restart interval but the first begins.
+// Returns the byte count.
+size_t jpeg_unstuff_scan(const uint8_t* data, size_t len, const JpegFrame& f, uint8_t* dst, std::vector<uint32_t>* interval_starts);
 
 }  // namespace wicca

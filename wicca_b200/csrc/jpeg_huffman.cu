@@ -13,8 +13,9 @@
 //   5. prefix-sum the DC differences per component in decode order.
 //
 // The decoder state is (bit position, block slot inside the MCU, next coefficient index); the step function is
-// deterministic for any input, so garbage decoded from a wrong start is harmless.  Files with restart markers
-// use the host decoder instead (jpeg_host.cu).
+// deterministic for any input, so garbage decoded from a wrong start is harmless.  Restart markers (removed by the
+// host together with the byte stuffing) become hard synchronisation points: every decoder continues from an interval
+// boundary in the state intervals start in, and the DC prefix sums restart there.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -101,7 +102,36 @@ __device__ __forceinline__ uint32_t decode_span(const JpegGpuScan& sc, const Sha
     }
     BitWindow bw;
     bw.start(sc.words, st.pos);
+    // restart intervals: the first boundary after the start position (binary search), 0xFFFFFFFF when there is none
+    uint32_t bi = 0, bound = 0xFFFFFFFFu;
+    if (sc.n_bounds) {
+        uint32_t lo = 0, hi = sc.n_bounds;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (sc.bounds[mid] <= st.pos) lo = mid + 1; else hi = mid; }
+        bi = lo; bound = sc.bounds[bi];
+    }
     while (st.pos < limit) {
+        if (sc.n_bounds) {
+            // A correct decoder reaches an interval boundary exactly, or stops in front of it at an MCU boundary with
+            // fewer than 8 one-bits of padding left.  Anything that runs across the boundary was never synchronised:
+            // both cases continue from the boundary in the state every interval starts in, which also makes the
+            // boundaries hard synchronisation points.
+            bool jump = st.pos >= bound;
+            const uint32_t gap = bound - st.pos;                       // 1..7 in the padding case
+            if (!jump && st.slot == 0 && st.k == 0 && gap < 8) jump = (bw.top32() >> (32 - gap)) == (1u << gap) - 1u;
+            if (jump) {
+                st.pos = bound; st.slot = 0; st.k = 0;
+                bw.start(sc.words, st.pos);
+                if (kWrite) {
+                    block = (int64_t)(bi + 1) * sc.blocks_per_interval;
+                    if (block >= block_end) break;
+                    const int64_t mcu = block / sc.blocks_per_mcu;
+                    my = (int)(mcu / sc.mcux); mx = (int)(mcu - (int64_t)my * sc.mcux);
+                    blk = block_ptr(0);
+                }
+                bound = sc.bounds[++bi];
+                continue;
+            }
+        }
         const uint32_t win = bw.top32();
         int len, sym;
         if (st.k == 0) {
@@ -227,7 +257,7 @@ template <int kKind>
 __device__ __forceinline__ int64_t scan_value(const JpegGpuScan& sc, int comp, int64_t j, int64_t n) {
     if (j >= n) return 0;
     if (kKind == 0) return (int64_t)sc.count[j];
-    return (int64_t)sc.coefs[dc_address(sc, comp, j)];
+    return (int64_t)sc.coefs[dc_address(sc, comp, j)];          // kinds 1 and 2: the DC difference of block j
 }
 
 template <int kKind>
@@ -271,10 +301,21 @@ scan_apply_kernel(JpegGpuScan sc, int comp, int64_t n, const int64_t* __restrict
     for (int q = 0; q < kScanItems; ++q) {
         if (j0 + q < n) {
             if (kKind == 0) sc.base[j0 + q] = (uint32_t)run;                                   // exclusive: blocks before
-            else sc.coefs[dc_address(sc, comp, j0 + q)] = (int16_t)(run + item[q]);            // inclusive: the DC value
+            else if (kKind == 1) sc.coefs[dc_address(sc, comp, j0 + q)] = (int16_t)(run + item[q]);   // inclusive: the DC value
+            else sc.dc_prefix[j0 + q] = (int32_t)(run + item[q]);                              // running sum over the whole scan
         }
         run += item[q];
     }
+}
+
+// Restart intervals reset the DC predictor: DC(j) = prefix(j) - prefix(last block of the previous interval).
+__global__ void __launch_bounds__(256)
+dc_segment_kernel(JpegGpuScan sc, int comp, int64_t n, int64_t seg_blocks) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int64_t start = (j / seg_blocks) * seg_blocks;
+    const int32_t before = start ? sc.dc_prefix[start - 1] : 0;
+    sc.coefs[dc_address(sc, comp, j)] = (int16_t)(sc.dc_prefix[j] - before);
 }
 
 template <int kKind>
@@ -333,7 +374,16 @@ cudaError_t launch_jpeg_huffman(const JpegGpuScan& sc, uint64_t* d_exit_a, uint6
     if (e != cudaSuccess) return e;
     huff_write_kernel<<<grid, threads, 0, stream>>>(sc);
     for (int c = 0; c < sc.ncomp; ++c) {
-        e = run_scan<1>(sc, c, sc.comp[c].n_blocks, d_chunk_sums, stream);
+        const int64_t n = sc.comp[c].n_blocks;
+        if (sc.n_bounds == 0) {
+            e = run_scan<1>(sc, c, n, d_chunk_sums, stream);
+        } else {
+            e = run_scan<2>(sc, c, n, d_chunk_sums, stream);
+            if (e != cudaSuccess) return e;
+            const int64_t seg_blocks = sc.blocks_per_interval / sc.blocks_per_mcu * sc.comp[c].h * sc.comp[c].v;
+            dc_segment_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sc, c, n, seg_blocks);
+            e = cudaGetLastError();
+        }
         if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
