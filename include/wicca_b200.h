@@ -224,8 +224,9 @@ WICCA_API int wicca_resize_norm_dev(const uint8_t* const* d_srcs, const int* hs,
  * (wicca/data_loader.py:53-58) for baseline JPEG files.  The entropy-coded scan is Huffman-decoded on the host
  * (serial by construction); dequantisation, the inverse DCT, chroma upsampling and YCbCr->RGB run on the GPU with
  * libjpeg-turbo's default arithmetic (islow IDCT, fancy upsampling), so the result is bit-identical to cv2's.
- * Decoded subset: SOF0/SOF1 Huffman frames, 8-bit, 1 (grey, returned as 3 equal channels like IMREAD_COLOR) or
- * 3 (YCbCr) components in one interleaved scan, integral sampling ratios, restart intervals; the EXIF orientation
+ * Decoded subset: SOF0/SOF1 (Huffman decoding on the GPU) and SOF2 progressive / multi-scan files (entropy decoding
+ * on the host, the rest on the GPU), 8-bit, 1 (grey, returned as 3 equal channels like IMREAD_COLOR) or
+ * 3 (YCbCr) components, integral sampling ratios, restart intervals; the EXIF orientation
  * is applied as cv2.imread applies it (H and W below are those of the oriented image).
  * Everything else returns WICCA_EUNSUPPORTED with the reason in wicca_last_error() - nothing is ever decoded
  * approximately and there is no CPU fallback: route such files through cv2.imread as before. */

@@ -207,6 +207,186 @@ def decode_coefficients(data: bytes) -> dict:
             "qt": [p["qt"][c["tq"]] for c in comps]}
 
 
+# ------------------------------------------------------------------ multi-scan files: progressive (jdphuff.c)
+def parse_all(data: bytes) -> dict:
+    """Every scan of the file with the tables in force when it starts (tables may be redefined between scans)."""
+    if data[:2] != b"\xff\xd8":
+        raise Unsupported("not a JPEG (no SOI)")
+    qt, ht = {}, {}
+    frame, restart, scans = None, 0, []
+    i = 2
+    while i + 4 <= len(data):
+        if data[i] != 0xFF:
+            raise Unsupported("marker expected")
+        while data[i + 1] == 0xFF:
+            i += 1
+        m = data[i + 1]
+        i += 2
+        if m == 0xD9:
+            break
+        seglen = (data[i] << 8) | data[i + 1]
+        seg = data[i + 2:i + seglen]
+        i += seglen
+        if m == 0xDB:
+            k = 0
+            while k < len(seg):
+                pq, tq = seg[k] >> 4, seg[k] & 15
+                k += 1
+                vals = [(seg[k + 2 * j] << 8) | seg[k + 2 * j + 1] for j in range(64)] if pq else list(seg[k:k + 64])
+                k += 128 if pq else 64
+                t = np.zeros(64, dtype=np.int64)
+                t[ZIGZAG] = vals
+                qt[tq] = t
+        elif m == 0xC4:
+            k = 0
+            while k < len(seg):
+                tc, th = seg[k] >> 4, seg[k] & 15
+                counts = list(seg[k + 1:k + 17])
+                n = sum(counts)
+                ht[(tc, th)] = _huff_lookup(counts, list(seg[k + 17:k + 17 + n]))
+                k += 17 + n
+        elif m in (0xC0, 0xC1, 0xC2):
+            if seg[0] != 8:
+                raise Unsupported("only 8-bit samples")
+            h, w, nc = (seg[1] << 8) | seg[2], (seg[3] << 8) | seg[4], seg[5]
+            comps = [{"id": seg[6 + 3 * c], "h": seg[7 + 3 * c] >> 4, "v": seg[7 + 3 * c] & 15, "tq": seg[8 + 3 * c]} for c in range(nc)]
+            frame = {"h": h, "w": w, "comps": comps, "progressive": m == 0xC2}
+        elif m in (0xC3, 0xC5, 0xC6, 0xC7, 0xC9, 0xCA, 0xCB, 0xCD, 0xCE, 0xCF):
+            raise Unsupported("lossless / differential / arithmetic frames")
+        elif m == 0xDD:
+            restart = (seg[0] << 8) | seg[1]
+        elif m == 0xDA:
+            ns = seg[0]
+            sel = []
+            for c in range(ns):
+                cid, tabs = seg[1 + 2 * c], seg[2 + 2 * c]
+                ci = [x["id"] for x in frame["comps"]].index(cid)
+                sel.append((ci, tabs >> 4, tabs & 15))
+            ss, se, ahal = seg[1 + 2 * ns], seg[2 + 2 * ns], seg[3 + 2 * ns]
+            j = i                                      # entropy-coded data runs to the next marker that is not RSTn
+            while not (data[j] == 0xFF and data[j + 1] != 0 and not 0xD0 <= data[j + 1] <= 0xD7):
+                j += 1
+            scans.append({"comps": sel, "ss": ss, "se": se, "ah": ahal >> 4, "al": ahal & 15, "data": data[i:j],
+                          "ht": dict(ht), "restart": restart})
+            i = j
+    return {"frame": frame, "qt": qt, "scans": scans}
+
+
+def decode_coefficients_multiscan(data: bytes) -> dict:
+    """Coefficients of a progressive (or multi-scan sequential) file: all scans accumulated, as libjpeg does before
+    it outputs anything when the whole file is available (no block smoothing then)."""
+    p = parse_all(data)
+    fr = p["frame"]
+    comps = fr["comps"]
+    if len(comps) == 1:
+        comps[0]["h"] = comps[0]["v"] = 1
+    hmax, vmax = max(c["h"] for c in comps), max(c["v"] for c in comps)
+    mcux, mcuy = -(-fr["w"] // (8 * hmax)), -(-fr["h"] // (8 * vmax))
+    coefs = [np.zeros((mcuy * c["v"], mcux * c["h"], 64), dtype=np.int32) for c in comps]
+    for sc in p["scans"]:
+        br = _Bits(sc["data"])
+        ss, se, ah, al = sc["ss"], sc["se"], sc["ah"], sc["al"]
+        sel = sc["comps"]
+        if len(sel) > 1:                               # interleaved: whole MCUs
+            units = [(my, mx) for my in range(mcuy) for mx in range(mcux)]
+            def blocks_of(u):
+                my, mx = u
+                return [(ci, td, ta, my * comps[ci]["v"] + by, mx * comps[ci]["h"] + bx)
+                        for (ci, td, ta) in sel for by in range(comps[ci]["v"]) for bx in range(comps[ci]["h"])]
+        else:                                          # one component: only the blocks that cover real samples
+            ci, td, ta = sel[0]
+            bw = -(-(-(-fr["w"] * comps[ci]["h"] // hmax)) // 8)
+            bh = -(-(-(-fr["h"] * comps[ci]["v"] // vmax)) // 8)
+            units = [(by, bx) for by in range(bh) for bx in range(bw)]
+            def blocks_of(u, ci=ci, td=td, ta=ta):
+                return [(ci, td, ta, u[0], u[1])]
+        pred = [0] * len(comps)
+        eobrun = 0
+        p1, m1 = 1 << al, -(1 << al)
+        for n, u in enumerate(units):
+            if sc["restart"] and n and n % sc["restart"] == 0:
+                br.restart()
+                pred = [0] * len(comps)
+                eobrun = 0
+            for (ci, td, ta, by, bx) in blocks_of(u):
+                blk = coefs[ci][by, bx]
+                if not fr["progressive"]:              # sequential scan of a multi-scan file
+                    s = _decode_symbol(br, sc["ht"][(0, td)])
+                    if s:
+                        pred[ci] += _extend(br.bits(s), s)
+                    blk[0] = pred[ci]
+                    k = 1
+                    while k < 64:
+                        rs = _decode_symbol(br, sc["ht"][(1, ta)])
+                        r, s = rs >> 4, rs & 15
+                        if s == 0:
+                            if r != 15:
+                                break
+                            k += 16
+                            continue
+                        k += r
+                        blk[ZIGZAG[k]] = _extend(br.bits(s), s)
+                        k += 1
+                elif ss == 0 and ah == 0:              # DC first
+                    s = _decode_symbol(br, sc["ht"][(0, td)])
+                    if s:
+                        pred[ci] += _extend(br.bits(s), s)
+                    blk[0] = pred[ci] << al
+                elif ss == 0:                          # DC refinement
+                    if br.bit():
+                        blk[0] |= p1
+                elif ah == 0:                          # AC first
+                    if eobrun > 0:
+                        eobrun -= 1
+                        continue
+                    k = ss
+                    while k <= se:
+                        rs = _decode_symbol(br, sc["ht"][(1, ta)])
+                        r, s = rs >> 4, rs & 15
+                        if s:
+                            k += r
+                            blk[ZIGZAG[k]] = _extend(br.bits(s), s) << al
+                        elif r == 15:
+                            k += 15
+                        else:
+                            eobrun = (1 << r) + (br.bits(r) if r else 0) - 1
+                            break
+                        k += 1
+                else:                                  # AC refinement
+                    k = ss
+                    if eobrun == 0:
+                        while k <= se:
+                            rs = _decode_symbol(br, sc["ht"][(1, ta)])
+                            r, s = rs >> 4, rs & 15
+                            if s:
+                                s = p1 if br.bit() else m1
+                            elif r != 15:
+                                eobrun = (1 << r) + (br.bits(r) if r else 0)
+                                break
+                            while k <= se:
+                                z = ZIGZAG[k]
+                                if blk[z] != 0:
+                                    if br.bit() and (blk[z] & p1) == 0:
+                                        blk[z] += p1 if blk[z] >= 0 else m1
+                                else:
+                                    r -= 1
+                                    if r < 0:
+                                        break
+                                k += 1
+                            if s:
+                                blk[ZIGZAG[k]] = s
+                            k += 1
+                    if eobrun > 0:
+                        while k <= se:
+                            z = ZIGZAG[k]
+                            if blk[z] != 0 and br.bit() and (blk[z] & p1) == 0:
+                                blk[z] += p1 if blk[z] >= 0 else m1
+                            k += 1
+                        eobrun -= 1
+    return {"w": fr["w"], "h": fr["h"], "comps": comps, "hmax": hmax, "vmax": vmax, "coefs": coefs,
+            "qt": [p["qt"][c["tq"]] for c in comps]}
+
+
 # ------------------------------------------------------------------ jidctint.c: jpeg_idct_islow
 _F = dict(f0_298=2446, f0_390=3196, f0_541=4433, f0_765=6270, f0_899=7373, f1_175=9633, f1_501=12299, f1_847=15137,
           f1_961=16069, f2_053=16819, f2_562=20995, f3_072=25172)
@@ -325,7 +505,10 @@ def ycc_to_rgb(y: np.ndarray, cb: np.ndarray, cr: np.ndarray) -> np.ndarray:
 
 def decode_rgb(data: bytes) -> np.ndarray:
     """What ``cv2.cvtColor(cv2.imdecode(data, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)`` returns (no EXIF rotation)."""
-    d = decode_coefficients(data)
+    try:
+        d = decode_coefficients(data)
+    except Unsupported:
+        d = decode_coefficients_multiscan(data)        # progressive / several scans
     planes = []
     for c, coefs, qt in zip(d["comps"], d["coefs"], d["qt"]):
         full = idct_islow(coefs, qt)

@@ -83,19 +83,22 @@ RESIZE_CASES = [
 ]
 
 
-# (seed, h, w, quality, sampling, restart interval, grey, EXIF orientation)
+# (seed, h, w, quality, sampling, restart interval, grey, EXIF orientation[, progressive])
 JPEG_CASES = [
     (1, 17, 33, 90, "420", 0, 0, 1), (2, 37, 53, 75, "420", 3, 0, 1), (3, 70, 31, 95, "422", 0, 0, 1),
     (4, 96, 128, 85, "444", 0, 0, 1), (5, 64, 48, 35, "420", 0, 0, 1), (6, 33, 100, 100, "440", 0, 0, 1),
     (7, 50, 75, 90, "411", 5, 0, 1), (8, 40, 23, 85, "420", 0, 1, 1), (9, 61, 45, 90, "420", 0, 0, 6),
     (10, 45, 61, 80, "422", 0, 0, 3), (11, 1, 1, 90, "420", 0, 0, 1), (12, 2, 3, 90, "420", 0, 0, 1),
     (13, 128, 160, 92, "420", 0, 0, 8), (14, 99, 77, 60, "444", 7, 0, 5),
+    (15, 70, 90, 90, "420", 0, 0, 1, 1), (16, 37, 53, 75, "444", 3, 0, 1, 1), (17, 64, 40, 95, "422", 0, 0, 6, 1),
+    (18, 40, 23, 85, "420", 0, 1, 1, 1), (19, 120, 88, 100, "420", 0, 0, 1, 1), (20, 33, 33, 35, "411", 2, 0, 1, 1),
 ]
 
 
 def jpeg_case_bytes(cv2, case) -> bytes:
     """The JPEG file of a case (encoded with OpenCV, EXIF orientation spliced in as an APP1 segment)."""
-    seed, h, w, q, sampling, restart, grey, orientation = case
+    seed, h, w, q, sampling, restart, grey, orientation = case[:8]
+    progressive = len(case) > 8 and case[8]
     rng = np.random.default_rng(2000 + seed)
     yy, xx = np.mgrid[0:h, 0:w]
     img = np.stack([128 + 100 * np.sin(xx / 17.0 + c) + 60 * np.cos(yy / 11.0 - c) for c in range(3)], -1)
@@ -109,6 +112,8 @@ def jpeg_case_bytes(cv2, case) -> bytes:
         params += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, getattr(cv2, f"IMWRITE_JPEG_SAMPLING_FACTOR_{sampling}")]
     if restart:
         params += [cv2.IMWRITE_JPEG_RST_INTERVAL, restart]
+    if progressive:
+        params += [cv2.IMWRITE_JPEG_PROGRESSIVE, 1]
     ok, enc = cv2.imencode(".jpg", img, params)
     assert ok
     data = bytes(enc)

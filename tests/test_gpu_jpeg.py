@@ -97,11 +97,22 @@ def test_decode_to_device_buffer():
     assert (host[:info["height"], (info["width"] * 3 + 3) // 4 * 4:] == 0xAB).all()  # and so is the row padding
 
 
+@pytest.mark.parametrize("sampling", ["444", "422", "420"])
+def test_progressive_files_match_cv2(sampling):
+    from wicca_b200 import decode_jpeg
+    rng = np.random.default_rng(27)
+    for (h, w, q, r) in [(8, 8, 90, 0), (37, 53, 35, 0), (255, 257, 90, 4), (600, 401, 100, 0), (1200, 900, 85, 0)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if q == 35 else photo_like(rng, h, w)
+        data = encode(img, q, sampling, r, progressive=True)
+        assert np.array_equal(decode_jpeg(data), reference_rgb(data)), (h, w, q, sampling, r)
+
+
 def test_unsupported_files_fail_loudly():
     from wicca_b200 import UnsupportedImageError, decode_jpeg
     rng = np.random.default_rng(26)
+    ok, png = cv2.imencode(".png", photo_like(rng, 32, 32))
     with pytest.raises(UnsupportedImageError):
-        decode_jpeg(encode(photo_like(rng, 32, 32), progressive=True))
+        decode_jpeg(bytes(png))
     with pytest.raises(ValueError):
         decode_jpeg(encode(photo_like(rng, 64, 64))[:300])                      # scan cut short after the header
 

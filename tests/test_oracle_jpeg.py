@@ -72,13 +72,37 @@ def test_oracle_matches_cv2(sampling):
         assert np.array_equal(jo.decode_rgb(data), reference_rgb(data)), (h, w, q, s, r)
 
 
-def test_oracle_grey_and_rejects_progressive():
+def test_oracle_grey():
     rng = np.random.default_rng(6)
     grey = photo_like(rng, 40, 23)[:, :, 0]
-    data = encode(grey, 85)
-    assert np.array_equal(jo.decode_rgb(data), reference_rgb(data))
-    with pytest.raises(jo.Unsupported):
-        jo.decode_rgb(encode(photo_like(rng, 16, 16), progressive=True))
+    for progressive in (False, True):
+        data = encode(grey, 85, progressive=progressive)
+        assert np.array_equal(jo.decode_rgb(data), reference_rgb(data))
+
+
+@pytest.mark.parametrize("sampling", ["444", "422", "420", "411"])
+def test_oracle_progressive_matches_cv2(sampling):
+    rng = np.random.default_rng(9)
+    for (h, w) in [(8, 8), (1, 1), (17, 33), (37, 53), (70, 31)]:
+        for q, r in ((35, 0), (90, 3), (100, 0)):
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if q == 35 else photo_like(rng, h, w)
+            data = encode(img, q, sampling, r, progressive=True)
+            assert np.array_equal(jo.decode_rgb(data), reference_rgb(data)), (h, w, q, sampling, r)
+
+
+@pytest.mark.parametrize("sampling", ["444", "420"])
+def test_host_progressive_decoder_matches_oracle(sampling):
+    rng = np.random.default_rng(10)
+    for (h, w, q, r) in [(8, 8, 90, 0), (37, 53, 35, 0), (70, 31, 90, 3), (130, 97, 100, 0), (96, 64, 75, 5)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if q == 35 else photo_like(rng, h, w)
+        data = encode(img, q, sampling, r, progressive=True)
+        dst, bw, bh, _ = host_coefficients(data)
+        exp = jo.decode_coefficients_multiscan(data)
+        off = 0
+        for k, cf in enumerate(exp["coefs"]):
+            assert (bh[k], bw[k]) == cf.shape[:2]
+            assert np.array_equal(dst[off:off + cf.size].reshape(cf.shape), cf), (h, w, q, sampling, r, k)
+            off += cf.size
 
 
 def host_coefficients(data):
@@ -119,8 +143,7 @@ def test_probe_and_unsupported_flavours():
     info = jpeg_info(encode(img, 90, "420"))
     assert info == {"height": 33, "width": 47, "components": 3, "h_max": 2, "v_max": 2}
     assert jpeg_info(encode(img[:, :, 0], 90))["components"] == 1
-    with pytest.raises(UnsupportedImageError):
-        jpeg_info(encode(img, progressive=True))
+    assert jpeg_info(encode(img, progressive=True))["height"] == 33      # progressive files are decoded too
     ok, png = cv2.imencode(".png", img)
     with pytest.raises(UnsupportedImageError):
         jpeg_info(bytes(png))

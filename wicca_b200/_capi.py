@@ -161,7 +161,7 @@ def check(rc: int, what: str = "") -> None:
 
 
 class UnsupportedImageError(ValueError):
-    """A valid image file outside the subset the GPU ingest path decodes (progressive JPEG, PNG, TIFF ...).
+    """A valid image file outside the subset the GPU ingest path decodes (PNG, TIFF, arithmetic-coded JPEG ...).
     Nothing is decoded approximately and there is no CPU fallback: read such a file with ``cv2.imread``."""
 
 

@@ -44,13 +44,15 @@ int jpeg_host_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFrame& f,
     WICCA_CUDA(c.h_in.reserve((size_t)f.total_coefs * sizeof(int16_t)));
     const double t0 = now_ms();
     std::string why;
-    int rc = jpeg_decode_coefficients(data, len, f, (int16_t*)c.h_in.p, why);
+    int rc = f.multiscan ? jpeg_decode_multiscan(data, len, f, (int16_t*)c.h_in.p, why)
+                         : jpeg_decode_coefficients(data, len, f, (int16_t*)c.h_in.p, why);
     if (rc) return fail(rc, "%s", why.c_str());
     if (host_ms) *host_ms += (float)(now_ms() - t0);
     return 0;
 }
 
 bool gpu_huffman_wanted(const JpegFrame& f) {
+    if (f.multiscan) return false;                           // progressive / several scans: host entropy decoder
     const char* e = getenv("WICCA_JPEG_HUFFMAN");
     return !(e && e[0] == 'h');                              // WICCA_JPEG_HUFFMAN=host forces the CPU stage
 }
@@ -263,7 +265,7 @@ int wicca_jpeg_decode_coeffs(const uint8_t* data, size_t len, int16_t* dst, int6
         if (qt) memcpy(qt + 64 * k, f.qt[f.comp[k].tq], 64 * sizeof(uint16_t));
     }
     std::string why;
-    rc = jpeg_decode_coefficients(data, len, f, dst, why);
+    rc = f.multiscan ? jpeg_decode_multiscan(data, len, f, dst, why) : jpeg_decode_coefficients(data, len, f, dst, why);
     if (rc) return fail(rc, "%s", why.c_str());
     return 0;
 }
@@ -273,6 +275,7 @@ int wicca_jpeg_decode_coeffs_gpu(const uint8_t* data, size_t len, int16_t* dst, 
     int rc = parse_or_fail(data, len, f);
     if (rc) return rc;
     if (!dst || dst_count < f.total_coefs) return fail(WICCA_EINVAL, "coefficient buffer too small (%lld needed)", (long long)f.total_coefs);
+    if (f.multiscan) return fail(WICCA_EUNSUPPORTED, "progressive / multi-scan files are entropy-decoded on the host");
     rc = check_device(device);
     if (rc) return rc;
     CtxLease lease;

@@ -50,13 +50,13 @@ int build_huff(const uint8_t* counts, const uint8_t* symbols, int n_symbols, Jpe
         h.valoffset[len] = k - code;
         if (counts[len - 1]) {
             for (int i = 0; i < counts[len - 1]; ++i, ++k, ++code) {
+                if (code >= (1 << len)) return -1;            // over-subscribed table
                 if (len <= 10) {
                     const int first = code << (10 - len), span = 1 << (10 - len);
                     for (int j = 0; j < span; ++j) h.look[first + j] = (uint16_t)((len << 8) | symbols[k]);
                 }
             }
             h.maxcode[len] = code - 1;
-            if (code > (1 << len)) return -1;                 // over-subscribed table
         } else {
             h.maxcode[len] = -1;
         }
@@ -139,12 +139,18 @@ int jpeg_parse(const uint8_t* data, size_t len, JpegFrame& f, std::string& why) 
     int adobe_transform = -1;
     size_t i = 2;
     for (;;) {
-        if (i + 4 > len) { why = "truncated JPEG header"; return WICCA_EINVAL; }
+        if (i + 4 > len) {
+            if (f.multiscan && i + 2 <= len) return 0;                     // the closing EOI (2 bytes) or a file cut short
+            why = "truncated JPEG header"; return WICCA_EINVAL;
+        }
         if (data[i] != 0xFF) { why = "JPEG marker expected"; return WICCA_EINVAL; }
         while (i + 1 < len && data[i + 1] == 0xFF) ++i;
         const int m = data[i + 1];
         i += 2;
-        if (m == 0xD9) { why = "JPEG ends before any scan"; return WICCA_EINVAL; }
+        if (m == 0xD9) {
+            if (f.multiscan) return 0;                                     // all scans collected
+            why = "JPEG ends before any scan"; return WICCA_EINVAL;
+        }
         if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;                  // stand-alone markers
         if (i + 2 > len) { why = "truncated JPEG header"; return WICCA_EINVAL; }
         const size_t seglen = (size_t)be16(data + i);
@@ -178,7 +184,9 @@ int jpeg_parse(const uint8_t* data, size_t len, JpegFrame& f, std::string& why) 
                 }
                 break;
             }
-            case 0xC0: case 0xC1: {
+            case 0xC0: case 0xC1: case 0xC2: {
+                if (have_frame) { why = "more than one frame header"; return WICCA_EINVAL; }
+                f.progressive = (m == 0xC2);
                 if (n < 6) { why = "bad frame header"; return WICCA_EINVAL; }
                 if (seg[0] != 8) { why = "only 8-bit JPEG samples are supported"; return WICCA_EUNSUPPORTED; }
                 f.height = be16(seg + 1); f.width = be16(seg + 3); f.ncomp = seg[5];
@@ -194,8 +202,8 @@ int jpeg_parse(const uint8_t* data, size_t len, JpegFrame& f, std::string& why) 
                 have_frame = true;
                 break;
             }
-            case 0xC2: case 0xC3: case 0xC5: case 0xC6: case 0xC7: case 0xC9: case 0xCA: case 0xCB: case 0xCD: case 0xCE: case 0xCF:
-                why = "only baseline / extended-sequential Huffman JPEGs are supported (this one is progressive, lossless or arithmetic)";
+            case 0xC3: case 0xC5: case 0xC6: case 0xC7: case 0xC9: case 0xCA: case 0xCB: case 0xCD: case 0xCE: case 0xCF:
+                why = "lossless, differential and arithmetic-coded JPEGs are not supported";
                 return WICCA_EUNSUPPORTED;
             case 0xDD:
                 if (n < 2) { why = "bad restart interval"; return WICCA_EINVAL; }
@@ -215,40 +223,84 @@ int jpeg_parse(const uint8_t* data, size_t len, JpegFrame& f, std::string& why) 
                 break;
             case 0xDA: {
                 if (!have_frame) { why = "scan before frame header"; return WICCA_EINVAL; }
-                if (n < 1 || seg[0] != f.ncomp || n < 1 + 2 * (size_t)f.ncomp + 3) { why = "only a single interleaved scan is supported"; return WICCA_EUNSUPPORTED; }
-                for (int s = 0; s < f.ncomp; ++s) {
-                    const int cid = seg[1 + 2 * s], tabs = seg[2 + 2 * s];
-                    if (cid != f.comp[s].id) { why = "scan components out of frame order"; return WICCA_EUNSUPPORTED; }
-                    f.comp[s].td = tabs >> 4; f.comp[s].ta = tabs & 15;
-                    if (f.comp[s].td > 3 || f.comp[s].ta > 3 || !f.dc[f.comp[s].td].present || !f.ac[f.comp[s].ta].present) { why = "scan refers to a missing Huffman table"; return WICCA_EINVAL; }
-                    if (!f.qt_present[f.comp[s].tq]) { why = "frame refers to a missing quantisation table"; return WICCA_EINVAL; }
+                if (n < 1) { why = "bad scan header"; return WICCA_EINVAL; }
+                const int ns = seg[0];
+                if (ns < 1 || ns > f.ncomp || n < 1 + 2 * (size_t)ns + 3) { why = "bad scan header"; return WICCA_EINVAL; }
+                if (f.scans.empty()) {
+                    // geometry and colour space, once
+                    if (f.ncomp == 3) {
+                        // as libjpeg guesses it: JFIF => YCbCr; Adobe transform 0 => RGB; ids 'R','G','B' => RGB
+                        const bool rgb_ids = f.comp[0].id == 'R' && f.comp[1].id == 'G' && f.comp[2].id == 'B';
+                        if ((adobe && adobe_transform == 0) || (!jfif && !adobe && rgb_ids)) { why = "RGB-coded JPEG (no YCbCr transform)"; return WICCA_EUNSUPPORTED; }
+                    }
+                    if (f.ncomp == 1) f.comp[0].h = f.comp[0].v = 1;      // a lone component is never interleaved
+                    f.hmax = f.vmax = 1;
+                    for (int c = 0; c < f.ncomp; ++c) { if (f.comp[c].h > f.hmax) f.hmax = f.comp[c].h; if (f.comp[c].v > f.vmax) f.vmax = f.comp[c].v; }
+                    f.mcux = (f.width + 8 * f.hmax - 1) / (8 * f.hmax);
+                    f.mcuy = (f.height + 8 * f.vmax - 1) / (8 * f.vmax);
+                    int blocks_in_mcu = 0;
+                    f.total_coefs = 0;
+                    for (int c = 0; c < f.ncomp; ++c) {
+                        JpegComponent& q = f.comp[c];
+                        if (f.hmax % q.h || f.vmax % q.v) { why = "fractional chroma sampling ratio"; return WICCA_EUNSUPPORTED; }
+                        if (!f.qt_present[q.tq]) { why = "frame refers to a missing quantisation table"; return WICCA_EINVAL; }
+                        q.blocks_w = f.mcux * q.h; q.blocks_h = f.mcuy * q.v;
+                        q.dw = (f.width * q.h + f.hmax - 1) / f.hmax; q.dh = (f.height * q.v + f.vmax - 1) / f.vmax;
+                        q.coef_offset = f.total_coefs;
+                        f.total_coefs += (int64_t)q.blocks_w * q.blocks_h * 64;
+                        blocks_in_mcu += q.h * q.v;
+                    }
+                    if (blocks_in_mcu > 10) { why = "more than 10 blocks per MCU"; return WICCA_EINVAL; }
                 }
-                const uint8_t* tail = seg + 1 + 2 * f.ncomp;
-                if (tail[0] != 0 || tail[1] != 63 || tail[2] != 0) { why = "spectral selection / successive approximation in a sequential scan"; return WICCA_EUNSUPPORTED; }
-                // colour space as libjpeg guesses it: JFIF => YCbCr; Adobe transform 0 => RGB; ids 'R','G','B' => RGB
-                if (f.ncomp == 3) {
-                    const bool rgb_ids = f.comp[0].id == 'R' && f.comp[1].id == 'G' && f.comp[2].id == 'B';
-                    if ((adobe && adobe_transform == 0) || (!jfif && !adobe && rgb_ids)) { why = "RGB-coded JPEG (no YCbCr transform)"; return WICCA_EUNSUPPORTED; }
+                JpegScan sc;
+                sc.ns = ns;
+                for (int k = 0; k < ns; ++k) {
+                    const int cid = seg[1 + 2 * k], tabs = seg[2 + 2 * k];
+                    int ci = -1;
+                    for (int c = 0; c < f.ncomp; ++c) if (f.comp[c].id == cid) ci = c;
+                    if (ci < 0 || (k && ci <= sc.comp[k - 1])) { why = "scan components unknown or out of frame order"; return WICCA_EINVAL; }
+                    sc.comp[k] = ci; sc.td[k] = tabs >> 4; sc.ta[k] = tabs & 15;
+                    if (sc.td[k] > 3 || sc.ta[k] > 3) { why = "bad Huffman table id"; return WICCA_EINVAL; }
                 }
-                if (f.ncomp == 1) f.comp[0].h = f.comp[0].v = 1;          // a lone component is never interleaved
-                f.hmax = f.vmax = 1;
-                for (int c = 0; c < f.ncomp; ++c) { if (f.comp[c].h > f.hmax) f.hmax = f.comp[c].h; if (f.comp[c].v > f.vmax) f.vmax = f.comp[c].v; }
-                f.mcux = (f.width + 8 * f.hmax - 1) / (8 * f.hmax);
-                f.mcuy = (f.height + 8 * f.vmax - 1) / (8 * f.vmax);
-                int blocks_in_mcu = 0;
-                f.total_coefs = 0;
-                for (int c = 0; c < f.ncomp; ++c) {
-                    JpegComponent& q = f.comp[c];
-                    if (f.hmax % q.h || f.vmax % q.v) { why = "fractional chroma sampling ratio"; return WICCA_EUNSUPPORTED; }
-                    q.blocks_w = f.mcux * q.h; q.blocks_h = f.mcuy * q.v;
-                    q.dw = (f.width * q.h + f.hmax - 1) / f.hmax; q.dh = (f.height * q.v + f.vmax - 1) / f.vmax;
-                    q.coef_offset = f.total_coefs;
-                    f.total_coefs += (int64_t)q.blocks_w * q.blocks_h * 64;
-                    blocks_in_mcu += q.h * q.v;
+                const uint8_t* tail = seg + 1 + 2 * ns;
+                sc.ss = tail[0]; sc.se = tail[1]; sc.ah = tail[2] >> 4; sc.al = tail[2] & 15;
+                sc.restart_interval = f.restart_interval;
+                if (f.progressive) {
+                    const bool dc_scan = sc.ss == 0;
+                    if (sc.ss > sc.se || sc.se > 63 || (dc_scan && sc.se != 0) || (!dc_scan && ns != 1) || sc.al > 13 || (sc.ah && sc.ah != sc.al + 1)) { why = "bad progressive scan parameters"; return WICCA_EINVAL; }
+                } else if (sc.ss != 0 || sc.se != 63 || sc.ah != 0 || sc.al != 0) {
+                    why = "spectral selection / successive approximation in a sequential scan"; return WICCA_EINVAL;
                 }
-                if (blocks_in_mcu > 10) { why = "more than 10 blocks per MCU"; return WICCA_EINVAL; }
-                f.scan_offset = i;
-                return 0;
+                for (int k = 0; k < ns; ++k) {
+                    const bool need_dc = !f.progressive || sc.ss == 0, need_ac = !f.progressive || sc.ss > 0;
+                    if ((need_dc && !(sc.ah && f.progressive) && !f.dc[sc.td[k]].present) || (need_ac && !f.ac[sc.ta[k]].present)) { why = "scan refers to a missing Huffman table"; return WICCA_EINVAL; }
+                }
+                if (!f.progressive && ns == f.ncomp && f.scans.empty()) {
+                    // the common case: one interleaved sequential scan (the fast paths decode it in place)
+                    for (int k = 0; k < ns; ++k) { f.comp[k].td = sc.td[k]; f.comp[k].ta = sc.ta[k]; }
+                    f.scan_offset = i;
+                    return 0;
+                }
+                // progressive / several scans: keep this scan with the tables in force, find where its data ends
+                f.multiscan = true;
+                for (int t = 0; t < 4; ++t) { sc.dc[t] = f.dc[t]; sc.ac[t] = f.ac[t]; }
+                sc.data_offset = i;
+                size_t j = i;
+                for (;;) {                                                // to the next marker that is not RSTn
+                    const uint8_t* q = (const uint8_t*)memchr(data + j, 0xFF, len - j);
+                    if (!q || (size_t)(q - data) + 1 >= len) { j = len; break; }
+                    j = (size_t)(q - data);
+                    const uint8_t nx = data[j + 1];
+                    if (nx == 0 || (nx >= 0xD0 && nx <= 0xD7)) { j += 2; continue; }   // stuffing / restart: scan data
+                    if (nx == 0xFF) { j += 1; continue; }                             // fill byte
+                    break;
+                }
+                sc.data_end = j < len ? j : len;
+                f.scans.push_back(sc);
+                if (f.scans.size() > 1000) { why = "too many scans"; return WICCA_EINVAL; }
+                i = sc.data_end;
+                if (i + 1 >= len) return 0;                               // no EOI: decode what is there
+                break;
             }
             default:
                 break;                                                    // APPn, COM, ... skipped
@@ -308,6 +360,141 @@ int jpeg_decode_coefficients(const uint8_t* data, size_t len, const JpegFrame& f
                             } else {
                                 if (r != 15) break;                        // end of block
                                 k += 16;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+int jpeg_decode_multiscan(const uint8_t* data, size_t len, const JpegFrame& f, int16_t* dst, std::string& why) {
+    (void)len;
+    memset(dst, 0, (size_t)f.total_coefs * sizeof(int16_t));
+    for (const JpegScan& sc : f.scans) {
+        BitReader br;
+        br.p = data + sc.data_offset;
+        br.end = data + sc.data_end;
+        const int p1 = 1 << sc.al, m1 = -(1 << sc.al);
+        int pred[3] = {0, 0, 0};
+        int eobrun = 0;
+        // units: whole MCUs for an interleaved scan, else the blocks of the component that cover real samples
+        const bool inter = sc.ns > 1;
+        const JpegComponent& q0 = f.comp[sc.comp[0]];
+        const int ux = inter ? f.mcux : (q0.dw + 7) / 8, uy = inter ? f.mcuy : (q0.dh + 7) / 8;
+        int64_t count = 0;
+        for (int y = 0; y < uy; ++y) {
+            for (int x = 0; x < ux; ++x, ++count) {
+                if (sc.restart_interval && count && count % sc.restart_interval == 0) {
+                    const uint8_t* q = br.p;
+                    while (q + 1 < br.end && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) ++q;
+                    if (q + 1 >= br.end) { why = "restart marker missing"; return WICCA_EINVAL; }
+                    br.p = q + 2; br.acc = 0; br.bits = 0;
+                    pred[0] = pred[1] = pred[2] = 0;
+                    eobrun = 0;
+                }
+                for (int k = 0; k < sc.ns; ++k) {
+                    const int ci = sc.comp[k];
+                    const JpegComponent& q = f.comp[ci];
+                    const JpegHuff& hd = sc.dc[sc.td[k]];
+                    const JpegHuff& ha = sc.ac[sc.ta[k]];
+                    const int nby = inter ? q.v : 1, nbx = inter ? q.h : 1;
+                    for (int by = 0; by < nby; ++by) {
+                        for (int bx = 0; bx < nbx; ++bx) {
+                            const int row = inter ? y * q.v + by : y, col = inter ? x * q.h + bx : x;
+                            int16_t* blk = dst + q.coef_offset + ((int64_t)row * q.blocks_w + col) * 64;
+                            if (!f.progressive) {
+                                if (br.bits < 32) br.refill();
+                                int s = br.decode(hd);
+                                if (s < 0 || s > 15) { why = "corrupt JPEG data (DC code)"; return WICCA_EINVAL; }
+                                if (s) pred[ci] += br.receive_extend(s);
+                                blk[0] = (int16_t)pred[ci];
+                                for (int z = 1; z < 64;) {
+                                    if (br.bits < 32) br.refill();
+                                    const int rs = br.decode(ha);
+                                    if (rs < 0) { why = "corrupt JPEG data (AC code)"; return WICCA_EINVAL; }
+                                    const int r = rs >> 4;
+                                    s = rs & 15;
+                                    if (s) {
+                                        z += r;
+                                        if (z > 63) { why = "corrupt JPEG data (run past the block)"; return WICCA_EINVAL; }
+                                        blk[kZigzag[z]] = (int16_t)br.receive_extend(s);
+                                        ++z;
+                                    } else {
+                                        if (r != 15) break;
+                                        z += 16;
+                                    }
+                                }
+                            } else if (sc.ss == 0 && sc.ah == 0) {                 // DC, first pass
+                                if (br.bits < 32) br.refill();
+                                const int s = br.decode(hd);
+                                if (s < 0 || s > 15) { why = "corrupt JPEG data (DC code)"; return WICCA_EINVAL; }
+                                if (s) pred[ci] += br.receive_extend(s);
+                                blk[0] = (int16_t)(pred[ci] * p1);
+                            } else if (sc.ss == 0) {                                // DC, refinement: one bit
+                                if (br.bits < 32) br.refill();
+                                if (br.peek(1)) blk[0] = (int16_t)(blk[0] | p1);
+                                br.skip(1);
+                            } else if (sc.ah == 0) {                                // AC band, first pass
+                                if (eobrun > 0) { --eobrun; continue; }
+                                for (int z = sc.ss; z <= sc.se; ++z) {
+                                    if (br.bits < 32) br.refill();
+                                    const int rs = br.decode(ha);
+                                    if (rs < 0) { why = "corrupt JPEG data (AC code)"; return WICCA_EINVAL; }
+                                    const int r = rs >> 4, s = rs & 15;
+                                    if (s) {
+                                        z += r;
+                                        if (z > 63) { why = "corrupt JPEG data (run past the block)"; return WICCA_EINVAL; }
+                                        blk[kZigzag[z]] = (int16_t)(br.receive_extend(s) * p1);
+                                    } else if (r == 15) {
+                                        z += 15;
+                                    } else {                                        // end of band for 2^r + extra blocks
+                                        eobrun = 1 << r;
+                                        if (r) { eobrun += (int)br.peek(r); br.skip(r); }
+                                        --eobrun;
+                                        break;
+                                    }
+                                }
+                            } else {                                                // AC band, refinement
+                                int z = sc.ss;
+                                auto refine = [&](int16_t& c) {                     // one correction bit for a nonzero coefficient
+                                    if (br.bits < 32) br.refill();
+                                    const uint32_t bit = br.peek(1);
+                                    br.skip(1);
+                                    if (bit && (c & p1) == 0) c = (int16_t)(c + (c >= 0 ? p1 : m1));
+                                };
+                                if (eobrun == 0) {
+                                    for (; z <= sc.se; ++z) {
+                                        if (br.bits < 32) br.refill();
+                                        const int rs = br.decode(ha);
+                                        if (rs < 0) { why = "corrupt JPEG data (AC code)"; return WICCA_EINVAL; }
+                                        int r = rs >> 4, s = rs & 15;
+                                        if (s) {
+                                            s = br.peek(1) ? p1 : m1;              // a new +-1 coefficient
+                                            br.skip(1);
+                                        } else if (r != 15) {
+                                            eobrun = 1 << r;
+                                            if (r) { eobrun += (int)br.peek(r); br.skip(r); }
+                                            break;
+                                        }
+                                        // skip r coefficients that are still zero, correcting the nonzero ones on the way
+                                        for (; z <= sc.se; ++z) {
+                                            int16_t& c = blk[kZigzag[z]];
+                                            if (c != 0) refine(c);
+                                            else if (--r < 0) break;
+                                        }
+                                        if (s && z <= 63) blk[kZigzag[z]] = (int16_t)s;
+                                    }
+                                }
+                                if (eobrun > 0) {
+                                    for (; z <= sc.se; ++z) {
+                                        int16_t& c = blk[kZigzag[z]];
+                                        if (c != 0) refine(c);
+                                    }
+                                    --eobrun;
+                                }
                             }
                         }
                     }

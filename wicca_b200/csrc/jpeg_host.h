@@ -30,6 +30,14 @@ struct JpegHuff {
     bool present = false;
 };
 
+struct JpegScan {                          // one scan of a progressive / multi-scan file
+    int ns = 0, comp[3] = {0, 0, 0}, td[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
+    int ss = 0, se = 63, ah = 0, al = 0;
+    int restart_interval = 0;
+    size_t data_offset = 0, data_end = 0;  // entropy-coded bytes
+    JpegHuff dc[4], ac[4];                 // the tables in force when the scan starts
+};
+
 struct JpegFrame {
     int width = 0, height = 0, ncomp = 0;
     int hmax = 1, vmax = 1, mcux = 0, mcuy = 0;
@@ -39,8 +47,11 @@ struct JpegFrame {
     uint16_t qt[4][64];                    // natural (row-major) order
     bool qt_present[4] = {false, false, false, false};
     JpegHuff dc[4], ac[4];
-    size_t scan_offset = 0;                // first entropy-coded byte
+    size_t scan_offset = 0;                // first entropy-coded byte (single-scan files)
     int64_t total_coefs = 0;               // int16 count of the dense coefficient array
+    bool progressive = false;              // SOF2
+    bool multiscan = false;                // progressive, or sequential with more than one scan: see `scans`
+    std::vector<JpegScan> scans;
 };
 
 // Size of the image the caller receives: the frame size, transposed for EXIF orientations 5..8.
@@ -53,6 +64,10 @@ inline void jpeg_output_size(const JpegFrame& f, int* H, int* W) {
 // 0 on success; a negative WICCA_* code otherwise, with the reason in `why`.  WICCA_EUNSUPPORTED marks valid
 // JPEGs outside the subset (progressive, arithmetic coding, 12-bit, CMYK, several scans ...).
 int jpeg_parse(const uint8_t* data, size_t len, JpegFrame& f, std::string& why);
+
+// All scans of a progressive / multi-scan file accumulated into dst[total_coefs] (same layout as below); this is
+// what libjpeg holds when the whole file has been read, before it outputs the first row.
+int jpeg_decode_multiscan(const uint8_t* data, size_t len, const JpegFrame& f, int16_t* dst, std::string& why);
 
 // Huffman-decode the scan into dst[total_coefs]: per component, blocks in raster order, 64 coefficients each
 // in natural order, not dequantised.  Every element of dst is written (no pre-zeroing needed).
