@@ -6,7 +6,7 @@
 
 namespace wicca {
 
-constexpr uint32_t kSubBits = 1024;          // bits per sub-sequence (one thread each)
+constexpr uint32_t kSubBits = 2048;          // bits per sub-sequence (one thread each); 1024 decodes one file 10 % faster, 2048 a batch 11 % faster
 
 struct JpegGpuTables {                        // 0..3 DC tables, 4..7 AC tables (by Huffman table id)
     uint16_t look[8][1024];
