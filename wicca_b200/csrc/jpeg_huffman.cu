@@ -102,6 +102,7 @@ __device__ __forceinline__ uint32_t decode_span(const JpegGpuScan& sc, const Sha
     }
     BitWindow bw;
     bw.start(sc.words, st.pos);
+    int dc_tab = T.slot[st.slot].dc_table, ac_tab = 4 + T.slot[st.slot].ac_table;
     // restart intervals: the first boundary after the start position (binary search), 0xFFFFFFFF when there is none
     uint32_t bi = 0, bound = 0xFFFFFFFFu;
     if (sc.n_bounds) {
@@ -120,6 +121,7 @@ __device__ __forceinline__ uint32_t decode_span(const JpegGpuScan& sc, const Sha
             if (!jump && st.slot == 0 && st.k == 0 && gap < 8) jump = (bw.top32() >> (32 - gap)) == (1u << gap) - 1u;
             if (jump) {
                 st.pos = bound; st.slot = 0; st.k = 0;
+                dc_tab = T.slot[0].dc_table; ac_tab = 4 + T.slot[0].ac_table;
                 bw.start(sc.words, st.pos);
                 if (kWrite) {
                     block = (int64_t)(bi + 1) * sc.blocks_per_interval;
@@ -132,30 +134,19 @@ __device__ __forceinline__ uint32_t decode_span(const JpegGpuScan& sc, const Sha
                 continue;
             }
         }
+        // one symbol per iteration, DC and AC through the same instructions: lanes of a warp sit in different
+        // blocks and at different coefficients, so every branch here would serialise them
         const uint32_t win = bw.top32();
+        const bool dc = st.k == 0;
         int len, sym;
-        if (st.k == 0) {
-            symbol(T, sc.tables, T.slot[st.slot].dc_table, win, len, sym);
-            const int s = sym & 15;
-            if (kWrite && s) blk[0] = (int16_t)extend(win, len, s);
-            st.pos += (uint32_t)(len + s);
-            bw.advance(len + s);
-            st.k = 1;
-            continue;
-        }
-        symbol(T, sc.tables, 4 + T.slot[st.slot].ac_table, win, len, sym);
-        const int r = sym >> 4, s = sym & 15;
-        if (s) {
-            st.k += r;
-            if (kWrite && st.k <= 63) blk[T.zigzag[st.k]] = (int16_t)extend(win, len, s);
-            st.k += 1;
-            st.pos += (uint32_t)(len + s);
-            bw.advance(len + s);
-        } else {
-            st.k = (r == 15) ? st.k + 16 : 64;               // ZRL / end of block
-            st.pos += (uint32_t)len;
-            bw.advance(len);
-        }
+        symbol(T, sc.tables, dc ? dc_tab : ac_tab, win, len, sym);
+        const int s = sym & 15;
+        const int r = dc ? 0 : (sym >> 4);
+        const int idx = st.k + r;                                  // the coefficient a value belongs to (0 for DC)
+        if (kWrite && s && idx <= 63) blk[T.zigzag[idx]] = (int16_t)extend(win, len, s);
+        st.pos += (uint32_t)(len + s);
+        bw.advance(len + s);
+        st.k = s ? idx + 1 : (dc ? 1 : (r == 15 ? st.k + 16 : 64));   // value / empty DC / ZRL / end of block
         if (st.k >= 64) {
             st.k = 0;
             ++done;
@@ -163,6 +154,7 @@ __device__ __forceinline__ uint32_t decode_span(const JpegGpuScan& sc, const Sha
                 st.slot = 0;
                 if (kWrite && ++mx == sc.mcux) { mx = 0; ++my; }
             }
+            dc_tab = T.slot[st.slot].dc_table; ac_tab = 4 + T.slot[st.slot].ac_table;
             if (kWrite) {
                 if (++block >= block_end) break;
                 blk = block_ptr(st.slot);
