@@ -104,6 +104,13 @@ int jpeg_gpu_huffman_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFr
             memcpy(ht->maxcode[t], src[kind]->maxcode, sizeof ht->maxcode[t]);
             memcpy(ht->valoffset[t], src[kind]->valoffset, sizeof ht->valoffset[t]);
             memcpy(ht->symbols[t], src[kind]->symbols, sizeof ht->symbols[t]);
+            // canonical codes are assigned in increasing order: every code of <= l bits, left-aligned to 16 bits,
+            // is below (largest code of the longest length <= l, + 1) << (16 - that length)
+            int32_t lim = 0;
+            for (int l = 1; l <= 16; ++l) {
+                if (src[kind]->maxcode[l] >= 0) lim = (src[kind]->maxcode[l] + 1) << (16 - l);
+                if (l >= 10) ht->limit[t][l - 10] = lim;
+            }
         }
     }
     int* h_changed = (int*)((uint8_t*)c.h_jpeg.p + sizeof(JpegGpuTables));

@@ -61,20 +61,28 @@ struct BitWindow {
 
 struct SharedTables {
     uint16_t look[8][1024];          // 0..3 DC, 4..7 AC: (length << 8) | symbol for codes of <= 10 bits
+    uint8_t symbols[8][256];
+    int32_t limit[8][8];             // [t][l - 10]: first 16-bit window value that is NOT a code of <= l bits (l = 10..16)
+    int32_t valoffset[8][17];
     JpegGpuSlot slot[10];
     uint8_t zigzag[64];
 };
 
-// One Huffman symbol from the 32-bit window: returns its code length and the symbol (a deterministic fallback
-// for bit patterns that are no code at all: 16 bits, symbol 0).
-__device__ __forceinline__ void symbol(const SharedTables& T, const JpegGpuTables* __restrict__ gp, int table, uint32_t win, int& len, int& sym) {
+// One Huffman symbol from the 32-bit window: its code length and the symbol.  Codes longer than the 10 lookahead
+// bits are rare, but with 32 lanes in different places one of them meets one every other iteration, so that path is
+// branch-free too: the length is 10 + the number of length classes the 16-bit window lies beyond.  Bit patterns that
+// are no code at all decode as (16 bits, symbol 0): deterministic, which is all the fixed point needs.
+__device__ __forceinline__ void symbol(const SharedTables& T, int table, uint32_t win, int& len, int& sym) {
     const uint32_t e = T.look[table][win >> 22];
     if (e) { len = (int)(e >> 8); sym = (int)(e & 255); return; }
-    for (len = 11; len <= 16; ++len) {
-        const int code = (int)(win >> (32 - len));
-        if (code <= gp->maxcode[table][len]) { sym = gp->symbols[table][(code + gp->valoffset[table][len]) & 255]; return; }
-    }
-    len = 16; sym = 0;
+    const int w16 = (int)(win >> 16);
+    len = 11;
+#pragma unroll
+    for (int l = 1; l <= 5; ++l) len += (w16 >= T.limit[table][l]) ? 1 : 0;        // limit[1..5]: lengths 11..15
+    const bool valid = w16 < T.limit[table][6];
+    const int code = w16 >> (16 - len);
+    sym = valid ? T.symbols[table][(code + T.valoffset[table][len]) & 255] : 0;
+    len = valid ? len : 16;
 }
 
 __device__ __forceinline__ int extend(uint32_t win, int len, int s) {          // the s bits after the code, sign-extended (T.81 F.12)
@@ -139,7 +147,7 @@ __device__ __forceinline__ uint32_t decode_span(const JpegGpuScan& sc, const Sha
         const uint32_t win = bw.top32();
         const bool dc = st.k == 0;
         int len, sym;
-        symbol(T, sc.tables, dc ? dc_tab : ac_tab, win, len, sym);
+        symbol(T, dc ? dc_tab : ac_tab, win, len, sym);
         const int s = sym & 15;
         const int r = dc ? 0 : (sym >> 4);
         const int idx = st.k + r;                                  // the coefficient a value belongs to (0 for DC)
@@ -168,6 +176,13 @@ __device__ __forceinline__ void load_tables(SharedTables& T, const JpegGpuScan& 
     const uint32_t* src = reinterpret_cast<const uint32_t*>(sc.tables->look);
     uint32_t* dst = reinterpret_cast<uint32_t*>(T.look);
     for (int i = threadIdx.x; i < 8 * 1024 / 2; i += blockDim.x) dst[i] = src[i];
+    {
+        const uint32_t* ssrc = reinterpret_cast<const uint32_t*>(sc.tables->symbols);
+        uint32_t* sdst = reinterpret_cast<uint32_t*>(T.symbols);
+        for (int i = threadIdx.x; i < 8 * 256 / 4; i += blockDim.x) sdst[i] = ssrc[i];
+        for (int i = threadIdx.x; i < 8 * 17; i += blockDim.x) T.valoffset[i / 17][i % 17] = sc.tables->valoffset[i / 17][i % 17];
+        for (int i = threadIdx.x; i < 8 * 8; i += blockDim.x) T.limit[i >> 3][i & 7] = sc.tables->limit[i >> 3][i & 7];
+    }
     if (threadIdx.x < 10) T.slot[threadIdx.x] = sc.slot[threadIdx.x];
     if (threadIdx.x < 64) T.zigzag[threadIdx.x] = d_zigzag[threadIdx.x];
     __syncthreads();
