@@ -229,9 +229,9 @@ int jpeg_parse(const uint8_t* data, size_t len, JpegFrame& f, std::string& why) 
                 if (f.scans.empty()) {
                     // geometry and colour space, once
                     if (f.ncomp == 3) {
-                        // as libjpeg guesses it: JFIF => YCbCr; Adobe transform 0 => RGB; ids 'R','G','B' => RGB
+                        // as libjpeg guesses it (jdapimin.c): JFIF => YCbCr; else Adobe transform 0 => RGB; else ids 'R','G','B' => RGB
                         const bool rgb_ids = f.comp[0].id == 'R' && f.comp[1].id == 'G' && f.comp[2].id == 'B';
-                        if ((adobe && adobe_transform == 0) || (!jfif && !adobe && rgb_ids)) { why = "RGB-coded JPEG (no YCbCr transform)"; return WICCA_EUNSUPPORTED; }
+                        if (!jfif && ((adobe && adobe_transform == 0) || (!adobe && rgb_ids))) { why = "RGB-coded JPEG (no YCbCr transform)"; return WICCA_EUNSUPPORTED; }
                     }
                     if (f.ncomp == 1) f.comp[0].h = f.comp[0].v = 1;      // a lone component is never interleaved
                     f.hmax = f.vmax = 1;
