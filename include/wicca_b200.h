@@ -219,6 +219,19 @@ WICCA_API int wicca_resize_norm_dev(const uint8_t* const* d_srcs, const int* hs,
                                     int n, int out_h, int out_w, int norm_mode, float* d_dst, uint8_t* d_dst_u8,
                                     int device, void* stream);
 
+/* ---- other orthogonal wavelets behind WaveletCoder (row N4) ---------------
+ * The reference implements only Haar; its README (README.md:25, :222) lists Daubechies / Coiflet coders as the
+ * roadmap for the same abstract interface (wicca/wavelet_coder.py:26-38).  This is that get_small_copy for any
+ * orthogonal low-pass filter: pad bottom/right to a multiple of 2^depth as get_padded_copy does, then `depth`
+ * levels of separable low-pass filtering with periodic wrap-around and decimation by 2, float32, clip and truncate
+ * to uint8.  taps: n_taps (even, 2..16) float32 coefficients that sum to 1 (dec_lo / sqrt 2); tap n of output
+ * sample k multiplies input sample 2k + n - (n_taps/2 - 1).  With taps {0.5, 0.5} the result equals
+ * wicca_haar_icon_u8.  There is no reference implementation to be at parity with for the longer filters: the
+ * definition is restated in oracle/fir_oracle.py. */
+WICCA_API int wicca_wavelet_icon_u8(const uint8_t* src, int H, int W, int C, int64_t src_row_stride, int depth,
+                                    int border_type, double border_const, const float* taps, int n_taps,
+                                    uint8_t* dst, int device, wicca_timing* t);
+
 /* ---- JPEG ingest (row N2 of the hot-path table) -------------------------
  * Replaces `cv2.imread(file_path)` + `cv2.cvtColor(image, cv2.COLOR_BGR2RGB)` in load_image
  * (wicca/data_loader.py:53-58) for baseline JPEG files.  The entropy-coded scan is Huffman-decoded on the host

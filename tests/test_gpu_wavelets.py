@@ -1,0 +1,61 @@
+"""GPU tests of row N4: the longer orthogonal wavelets behind the WaveletCoder interface.  The kernels must agree
+bit for bit with the CPU restatement (oracle/fir_oracle.py); with the Haar taps they must agree with HaarCoder,
+i.e. with the reference."""
+import numpy as np
+import pytest
+
+from oracle import fir_oracle as fo
+from oracle import haar_oracle as ho
+from tests.golden.make_golden import gen_input
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["db2", "db3", "db4", "coif1"])
+def test_matches_oracle(name):
+    from wicca_b200 import OrthogonalWaveletCoder
+    coder = OrthogonalWaveletCoder(name)
+    assert np.array_equal(coder.taps, fo.taps_f32(name))
+    for (h, w, c, d, bt, bc) in [(64, 64, 3, 1, 1, 0), (77, 131, 3, 2, 1, 0), (300, 201, 3, 3, 4, 0), (129, 67, 3, 4, 0, 37), (128, 64, 1, 3, 1, 0),
+                                 (500, 333, 3, 5, 2, 0), (40, 56, 4, 2, 3, 0), (1, 1, 3, 3, 1, 0), (257, 1024, 3, 6, 1, 0)]:
+        img = gen_input("noise", 31 * h + w, h, w, c)
+        got = coder.get_small_copy(img, d, bt, bc)
+        exp = fo.wavelet_icon(img, d, name, bt, bc)
+        assert got.shape == exp.shape and got.dtype == np.uint8
+        assert np.array_equal(got, exp), (name, h, w, c, d, bt, bc)
+
+
+def test_haar_taps_equal_haarcoder_and_the_reference_formula():
+    from wicca_b200 import DaubechiesCoder, HaarCoder
+    fir, haar = DaubechiesCoder(1), HaarCoder()
+    for (h, w, d, bt) in [(96, 128, 3, 1), (77, 131, 2, 4), (301, 200, 5, 2), (513, 255, 1, 0)]:
+        img = gen_input("noise", h + w, h, w, 3)
+        a = fir.get_small_copy(img, d, bt, 9)
+        assert np.array_equal(a, haar.get_small_copy(img, d, bt, 9))
+        assert np.array_equal(a, ho.haar_icon_fp32(img, d, bt, 9))
+
+
+def test_interface_and_errors():
+    from wicca_b200 import CoifletCoder, DaubechiesCoder, OrthogonalWaveletCoder, WaveletCoder
+    coder = CoifletCoder()
+    assert isinstance(coder, WaveletCoder)
+    img = gen_input("noise", 5, 50, 70, 3)
+    assert np.array_equal(coder.get_small_copy(img, 0), img)                  # depth 0 returns the image, like the reference
+    assert coder.get_small_copy(image=img, transform_depth=2).shape == (13, 18, 3)
+    grey = gen_input("noise", 6, 40, 40, 1)[:, :, 0]
+    with pytest.raises(IndexError):                                           # 2-D input fails in the reference's loop too
+        coder.get_small_copy(grey, 2)
+    with pytest.raises(ValueError):
+        coder.get_small_copy(img.astype(np.float32), 2)
+    with pytest.raises(ValueError):
+        coder.get_small_copy(None, 2)
+    with pytest.raises(TypeError):
+        coder.get_small_copy(img, (2,))
+    with pytest.raises(ValueError):
+        OrthogonalWaveletCoder("db9")
+    with pytest.raises(ValueError):
+        OrthogonalWaveletCoder([0.5, 0.25, 0.25])
+    with pytest.raises(ValueError):
+        DaubechiesCoder(7)
+    custom = OrthogonalWaveletCoder(fo.DEC_LO["db2"])
+    assert np.array_equal(custom.get_small_copy(img, 2), DaubechiesCoder(2).get_small_copy(img, 2))

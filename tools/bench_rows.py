@@ -257,6 +257,23 @@ def row_jpeg():
              cv2_thread_pool_decode_only_s=dt_ref, cv2_MP_per_s=n * H * W / 1e6 / dt_ref)
 
 
+def row_wavelets():
+    """Row N4: longer orthogonal filters behind the WaveletCoder interface (host image in, icon out)."""
+    from oracle import fir_oracle as fo
+    from wicca_b200 import OrthogonalWaveletCoder
+    img = np.random.default_rng(5).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    small = img[:1024, :1024]
+    for name in ("db2", "db4", "coif1"):
+        coder = OrthogonalWaveletCoder(name)
+        coder.get_small_copy(img, 3)
+        t0 = time.perf_counter(); icon = coder.get_small_copy(img, 3); dt = time.perf_counter() - t0
+        t0 = time.perf_counter(); exp = fo.wavelet_icon(small, 3, name); dt_cpu = time.perf_counter() - t0
+        assert np.array_equal(coder.get_small_copy(small, 3), exp)
+        emit(row="N4 orthogonal wavelet icon", config=f"get_small_copy(({H},{W},3) pageable ndarray, depth 3), {name} ({len(coder.taps)} taps)",
+             ms=dt * 1e3, MP_per_s=H * W / 1e6 / dt, stage_ms=coder.last_timing,
+             cpu_oracle_MP_per_s_1_core=small.shape[0] * small.shape[1] / 1e6 / dt_cpu)
+
+
 def row_oneshot():
     """The call the reference's callers make: one get_small_copy on a host array (pageable vs pinned)."""
     coder = HaarCoder()
@@ -293,7 +310,7 @@ def cpu_side():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["icons", "subbands", "batch", "jpeg", "oneshot", "cpu"]
+    which = sys.argv[1:] or ["icons", "subbands", "batch", "jpeg", "wavelets", "oneshot", "cpu"]
     if "icons" in which:
         row_icons()
     if "subbands" in which:
@@ -302,6 +319,8 @@ if __name__ == "__main__":
         row_batch()
     if "jpeg" in which:
         row_jpeg()
+    if "wavelets" in which:
+        row_wavelets()
     if "oneshot" in which:
         row_oneshot()
     if "cpu" in which:

@@ -74,6 +74,8 @@ SIGNATURES = {
                                                           C.c_int, C.c_double, C.POINTER(Target), C.c_int,
                                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_intp, C.c_int,
                                                           C.POINTER(Timing)]),
+    "wicca_wavelet_icon_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double,
+                                        C.POINTER(C.c_float), C.c_int, C.c_void_p, C.c_int, C.POINTER(Timing)]),
     "wicca_jpeg_probe": (C.c_int, [C.c_void_p, C.c_size_t, c_intp, c_intp, c_intp, c_intp, c_intp]),
     "wicca_jpeg_coeff_count": (C.c_int64, [C.c_void_p, C.c_size_t]),
     "wicca_jpeg_decode_coeffs": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, c_intp, c_intp, C.c_void_p]),

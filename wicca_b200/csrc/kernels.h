@@ -47,6 +47,12 @@ struct ResizeTables {
 cudaError_t launch_resize_norm(const ResizeTables& t, int n, int out_h, int out_w, int norm_mode, float* d_out,
                                uint8_t* d_out_u8, int max_src_w, int n_area, int n_other, cudaStream_t stream);
 
+// ---- other orthogonal wavelets (wavelet_fir.cu): LL pyramid with a longer low-pass filter, periodic per level
+struct FirTaps { float g[16]; int n, c; };     // taps (sum 1), their count (even, <= 16), centre offset n/2 - 1
+cudaError_t launch_wavelet_fir(const uint8_t* d_src, int64_t pitch, int H, int W, int C, int depth, int border_type,
+                               int border_const, const FirTaps& taps, uint8_t* d_icon, int64_t icon_pitch, float* d_rows,
+                               float* d_ll, cudaStream_t stream);
+
 // ---- JPEG ingest (jpeg_kernels.cu): dense quantised coefficients -> pitched RGB image, libjpeg-turbo arithmetic
 struct JpegPlaneDesc {
     const int16_t* coefs;     // (blocks_h, blocks_w, 64) natural order, quantised
