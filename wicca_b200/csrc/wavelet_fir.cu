@@ -28,19 +28,37 @@ fir_rows_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int W, in
         const int64_t r = i / C;
         const int j = (int)(r % w2), y = (int)(r / w2);
         const int ym = kFromU8 ? (y < H ? y : border_index(y, H, border_type)) : y;
+        const int x0 = 2 * j - taps.c;
         float acc = 0.0f;
-        for (int n = 0; n < taps.n; ++n) {
-            int x = (2 * j + n - taps.c) % w;           // deep levels can be narrower than the filter: a true modulo
-            x += x < 0 ? w : 0;
-            float v;
+        if (x0 >= 0 && x0 + taps.n <= (kFromU8 ? W : w) && ym >= 0) {
+            // interior: no wrap-around, no border rule - the taps walk over consecutive pixels
             if (kFromU8) {
-                const int xm = x < W ? x : border_index(x, W, border_type);
-                v = (ym < 0 || xm < 0) ? fc : (float)src[(int64_t)ym * pitch + (int64_t)xm * C + ch];
+                const uint8_t* p = src + (int64_t)ym * pitch + (int64_t)x0 * C + ch;
+                for (int n = 0; n < taps.n; ++n) {
+                    const float q = __fmul_rn((float)p[n * C], taps.g[n]);
+                    acc = n == 0 ? q : __fadd_rn(acc, q);
+                }
             } else {
-                v = in[((int64_t)y * w + x) * C + ch];
+                const float* p = in + ((int64_t)y * w + x0) * C + ch;
+                for (int n = 0; n < taps.n; ++n) {
+                    const float q = __fmul_rn(p[n * C], taps.g[n]);
+                    acc = n == 0 ? q : __fadd_rn(acc, q);
+                }
             }
-            const float p = __fmul_rn(v, taps.g[n]);
-            acc = n == 0 ? p : __fadd_rn(acc, p);
+        } else {
+            for (int n = 0; n < taps.n; ++n) {
+                int x = (x0 + n) % w;                   // deep levels can be narrower than the filter: a true modulo
+                x += x < 0 ? w : 0;
+                float v;
+                if (kFromU8) {
+                    const int xm = x < W ? x : border_index(x, W, border_type);
+                    v = (ym < 0 || xm < 0) ? fc : (float)src[(int64_t)ym * pitch + (int64_t)xm * C + ch];
+                } else {
+                    v = in[((int64_t)y * w + x) * C + ch];
+                }
+                const float q = __fmul_rn(v, taps.g[n]);
+                acc = n == 0 ? q : __fadd_rn(acc, q);
+            }
         }
         t[i] = acc;
     }
@@ -57,11 +75,20 @@ fir_cols_kernel(const float* __restrict__ t, int h, int w2, int C, FirTaps taps,
         const int64_t e = i % row;
         const int y2 = (int)(i / row);
         float acc = 0.0f;
-        for (int m = 0; m < taps.n; ++m) {
-            int y = (2 * y2 + m - taps.c) % h;
-            y += y < 0 ? h : 0;
-            const float p = __fmul_rn(t[(int64_t)y * row + e], taps.g[m]);
-            acc = m == 0 ? p : __fadd_rn(acc, p);
+        const int y0 = 2 * y2 - taps.c;
+        if (y0 >= 0 && y0 + taps.n <= h) {
+            const float* p = t + (int64_t)y0 * row + e;
+            for (int m = 0; m < taps.n; ++m) {
+                const float q = __fmul_rn(p[(int64_t)m * row], taps.g[m]);
+                acc = m == 0 ? q : __fadd_rn(acc, q);
+            }
+        } else {
+            for (int m = 0; m < taps.n; ++m) {
+                int y = (y0 + m) % h;
+                y += y < 0 ? h : 0;
+                const float q = __fmul_rn(t[(int64_t)y * row + e], taps.g[m]);
+                acc = m == 0 ? q : __fadd_rn(acc, q);
+            }
         }
         if (icon) icon[(int64_t)y2 * icon_pitch + e] = (uint8_t)fminf(fmaxf(acc, 0.0f), 255.0f);      // clip, then truncate
         else out[i] = acc;
