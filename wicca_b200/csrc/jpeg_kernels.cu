@@ -52,7 +52,7 @@ __device__ __forceinline__ uint32_t range_limit(int x) {
     return idx < 128 ? idx + 128 : (idx < 512 ? 255 : (idx < 896 ? 0 : idx - 896));
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 jpeg_idct_kernel(JpegImageDesc d) {
     __shared__ int s_qt[3][64];
     for (int i = threadIdx.x; i < 64 * d.ncomp; i += blockDim.x) s_qt[i >> 6][i & 63] = d.comp[i >> 6].qt[i & 63];
