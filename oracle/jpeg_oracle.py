@@ -7,6 +7,8 @@ is not in /root/reference: libjpeg-turbo, bundled in the pinned ``opencv-python=
 decompressor at its defaults, so the published algorithm restated here is:
 
   * Huffman decoding of a sequential DCT frame (ITU T.81 F.2.2), DC prediction per component, restart markers;
+    for progressive frames (SOF2) the DC / AC first and refinement scans of T.81 G.1.2 (jdphuff.c), all scans
+    accumulated before anything is output, as libjpeg does when the whole file is available;
   * dequantisation + the accurate integer IDCT ``jpeg_idct_islow`` (jidctint.c: CONST_BITS = 13,
     PASS1_BITS = 2, the Loeffler-Ligtenberg-Moschytz factorisation);
   * "fancy" triangle-filter upsampling for 2:1 horizontal (``h2v1_fancy_upsample``) and 2:1 x 2:1
