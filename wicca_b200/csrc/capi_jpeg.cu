@@ -101,7 +101,6 @@ int jpeg_gpu_huffman_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFr
             if (!src[kind]->present) continue;
             const int t = 4 * kind + id;
             memcpy(ht->look[t], src[kind]->look, sizeof ht->look[t]);
-            memcpy(ht->maxcode[t], src[kind]->maxcode, sizeof ht->maxcode[t]);
             memcpy(ht->valoffset[t], src[kind]->valoffset, sizeof ht->valoffset[t]);
             memcpy(ht->symbols[t], src[kind]->symbols, sizeof ht->symbols[t]);
             // canonical codes are assigned in increasing order: every code of <= l bits, left-aligned to 16 bits,

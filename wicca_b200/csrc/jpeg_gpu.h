@@ -10,7 +10,6 @@ constexpr uint32_t kSubBits = 2048;          // bits per sub-sequence (one threa
 
 struct JpegGpuTables {                        // 0..3 DC tables, 4..7 AC tables (by Huffman table id)
     uint16_t look[8][1024];
-    int32_t maxcode[8][18];
     int32_t limit[8][8];                      // [t][l - 10], l = 10..16: first 16-bit window value beyond the codes of <= l bits
     int32_t valoffset[8][17];
     uint8_t symbols[8][256];
