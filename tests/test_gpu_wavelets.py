@@ -59,3 +59,22 @@ def test_interface_and_errors():
         DaubechiesCoder(7)
     custom = OrthogonalWaveletCoder(fo.DEC_LO["db2"])
     assert np.array_equal(custom.get_small_copy(img, 2), DaubechiesCoder(2).get_small_copy(img, 2))
+
+
+def test_long_custom_filter_and_two_channels_take_the_general_kernels():
+    """10 taps (not instantiated in the tiled kernel) and C = 2 (neither): same definition, same oracle."""
+    from wicca_b200 import OrthogonalWaveletCoder
+    rng = np.random.default_rng(3)
+    taps10 = rng.normal(size=10)
+    taps10 = taps10 / taps10.sum() * np.sqrt(2.0)
+    fo.DEC_LO["_custom10"] = list(taps10)
+    try:
+        coder = OrthogonalWaveletCoder(taps10)
+        for (h, w, c, d) in [(96, 130, 3, 2), (64, 64, 2, 3), (33, 200, 4, 1)]:
+            img = gen_input("noise", h * 7 + w, h, w, c)
+            assert np.array_equal(coder.get_small_copy(img, d), fo.wavelet_icon(img, d, "_custom10")), (h, w, c, d)
+        db2 = OrthogonalWaveletCoder("db2")
+        img2 = gen_input("noise", 77, 100, 60, 2)
+        assert np.array_equal(db2.get_small_copy(img2, 2), fo.wavelet_icon(img2, 2, "db2"))
+    finally:
+        del fo.DEC_LO["_custom10"]

@@ -95,6 +95,145 @@ fir_cols_kernel(const float* __restrict__ t, int h, int w2, int C, FirTaps taps,
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Tiled level kernel (C <= 4): a CTA produces kTileH x kTileW low-pass samples.
+//   stage   the (2*kTileH + L - 2) x (2*kTileW + L - 2) input pixels the tile needs go to shared memory; the
+//           periodic wrap-around and (level 1) the border rule are resolved here, once per pixel;
+//   rows    each thread filters one staged row for four neighbouring outputs and all channels: the 2*4 + L - 2
+//           pixels it loads are shared by the four outputs, the sums run tap by tap as in the oracle;
+//   cols    each thread filters one output element down the column of row results.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kTileH = 16, kTileW = 64, kTileThreads = 256, kOutPerThread = 4;
+
+template <typename TIn, int C, int L>
+__global__ void __launch_bounds__(kTileThreads)
+fir_tile_kernel(const TIn* __restrict__ src, int64_t pitch_elems, int H, int W, int border_type, int border_const, int h, int w,
+                FirTaps taps, float* __restrict__ out, uint8_t* __restrict__ icon, int64_t icon_pitch) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ float s_g[16];
+    if (threadIdx.x < 16) s_g[threadIdx.x] = taps.g[threadIdx.x];
+    constexpr int rows = 2 * kTileH + L - 2, cols = 2 * kTileW + L - 2;
+    TIn* s_in = reinterpret_cast<TIn*>(s_raw);                                       // [rows][cols][C]
+    float* s_t = reinterpret_cast<float*>(s_raw + (((size_t)rows * cols * C * sizeof(TIn) + 15) & ~(size_t)15));   // [rows][kTileW][C]
+    const int h2 = h >> 1, w2 = w >> 1;
+    const int oy0 = blockIdx.y * kTileH, ox0 = blockIdx.x * kTileW;
+    constexpr bool kU8 = sizeof(TIn) == 1;
+    // ---- stage
+    const int y0 = 2 * oy0 - taps.c, x0 = 2 * ox0 - taps.c;
+    const bool interior = y0 >= 0 && x0 >= 0 && y0 + rows <= (kU8 ? min(h, H) : h) && x0 + cols <= (kU8 ? min(w, W) : w);
+    if (interior) {
+        // no wrap-around and no border rule anywhere in the window: whole rows are contiguous in the source
+        const int row_elems = cols * C;
+        for (int r = threadIdx.x >> 5; r < rows; r += kTileThreads / 32) {
+            const TIn* p = src + (int64_t)(y0 + r) * pitch_elems + (int64_t)x0 * C;
+            TIn* d = s_in + (size_t)r * row_elems;
+            for (int b = threadIdx.x & 31; b < row_elems; b += 32) d[b] = p[b];
+        }
+    } else {
+        for (int e = threadIdx.x; e < rows * cols; e += kTileThreads) {
+            const int r = e / cols, k = e - r * cols;
+            int y = (y0 + r) % h;
+            y += y < 0 ? h : 0;
+            int x = (x0 + k) % w;
+            x += x < 0 ? w : 0;
+            const int ym = kU8 ? (y < H ? y : border_index(y, H, border_type)) : y;
+            const int xm = kU8 ? (x < W ? x : border_index(x, W, border_type)) : x;
+            TIn* d = s_in + (size_t)e * C;
+            if (ym < 0 || xm < 0) {
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) d[ch] = (TIn)border_const;
+            } else {
+                const TIn* p = src + (int64_t)ym * pitch_elems + (int64_t)xm * C;
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) d[ch] = p[ch];
+            }
+        }
+    }
+    __syncthreads();
+    // ---- rows: (row r, outputs 4 jg .. 4 jg + 3, all channels) per work item
+    constexpr int groups = kTileW / kOutPerThread;
+    for (int e = threadIdx.x; e < rows * groups; e += kTileThreads) {
+        const int r = e / groups, jg = e - r * groups;
+        const TIn* p = s_in + ((size_t)r * cols + 2 * kOutPerThread * jg) * C;
+        // the 2*4 + L - 2 pixels the four outputs share, converted once
+        constexpr int kPix = 2 * kOutPerThread + L - 2;
+        float px[kPix][C];
+#pragma unroll
+        for (int k = 0; k < kPix; ++k)
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) px[k][ch] = (float)p[k * C + ch];
+        float acc[kOutPerThread][C];
+#pragma unroll
+        for (int n = 0; n < L; ++n) {
+            const float g = s_g[n];
+#pragma unroll
+            for (int o = 0; o < kOutPerThread; ++o)
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    const float v = __fmul_rn(px[2 * o + n][ch], g);
+                    acc[o][ch] = n == 0 ? v : __fadd_rn(acc[o][ch], v);
+                }
+        }
+        float* d = s_t + ((size_t)r * kTileW + kOutPerThread * jg) * C;
+#pragma unroll
+        for (int o = 0; o < kOutPerThread; ++o)
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) d[o * C + ch] = acc[o][ch];
+    }
+    __syncthreads();
+    // ---- columns
+    constexpr int seg = kTileW * C;
+    for (int e = threadIdx.x; e < kTileH * seg; e += kTileThreads) {
+        const int i = e / seg, q = e - i * seg;
+        const int oi = oy0 + i, oj = ox0 + q / C;
+        if (oi >= h2 || oj >= w2) continue;
+        const float* p = s_t + (size_t)(2 * i) * seg + q;
+        float acc = 0.0f;
+#pragma unroll
+        for (int m = 0; m < L; ++m) {
+            const float v = __fmul_rn(p[m * seg], s_g[m]);
+            acc = m == 0 ? v : __fadd_rn(acc, v);
+        }
+        const int64_t o = (int64_t)ox0 * C + q;
+        if (icon) icon[(int64_t)oi * icon_pitch + o] = (uint8_t)fminf(fmaxf(acc, 0.0f), 255.0f);      // clip, then truncate
+        else out[(int64_t)oi * w2 * C + o] = acc;
+    }
+}
+
+template <typename TIn, int C, int L>
+cudaError_t launch_tile_l(const TIn* src, int64_t pitch_elems, int H, int W, int border_type, int border_const, int h, int w,
+                          const FirTaps& taps, float* out, uint8_t* icon, int64_t icon_pitch, cudaStream_t stream) {
+    constexpr int rows = 2 * kTileH + L - 2, cols = 2 * kTileW + L - 2;
+    constexpr size_t smem = (((size_t)rows * cols * C * sizeof(TIn) + 15) & ~(size_t)15) + (size_t)rows * kTileW * C * sizeof(float);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && configured_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(fir_tile_kernel<TIn, C, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured_dev = dev;
+    }
+    const dim3 grid((w / 2 + kTileW - 1) / kTileW, (h / 2 + kTileH - 1) / kTileH);
+    fir_tile_kernel<TIn, C, L><<<grid, kTileThreads, smem, stream>>>(src, pitch_elems, H, W, border_type, border_const, h, w, taps,
+                                                                    out, icon, icon_pitch);
+    return cudaGetLastError();
+}
+
+// The filter length is a template parameter (the pixel window lives in registers): 2, 4, 6 and 8 taps are
+// instantiated - Haar, db2, db3 / coif1, db4; longer filters take the per-element kernels below.
+constexpr bool tiled_taps(int n) { return n == 2 || n == 4 || n == 6 || n == 8; }
+
+template <typename TIn, int C>
+cudaError_t launch_tile(const TIn* src, int64_t pitch_elems, int H, int W, int border_type, int border_const, int h, int w,
+                        const FirTaps& taps, float* out, uint8_t* icon, int64_t icon_pitch, cudaStream_t stream) {
+    switch (taps.n) {
+        case 2: return launch_tile_l<TIn, C, 2>(src, pitch_elems, H, W, border_type, border_const, h, w, taps, out, icon, icon_pitch, stream);
+        case 4: return launch_tile_l<TIn, C, 4>(src, pitch_elems, H, W, border_type, border_const, h, w, taps, out, icon, icon_pitch, stream);
+        case 6: return launch_tile_l<TIn, C, 6>(src, pitch_elems, H, W, border_type, border_const, h, w, taps, out, icon, icon_pitch, stream);
+        default: return launch_tile_l<TIn, C, 8>(src, pitch_elems, H, W, border_type, border_const, h, w, taps, out, icon, icon_pitch, stream);
+    }
+}
+
 int grid_for(int64_t n) {
     int64_t b = (n + 255) / 256;
     if (b > 148 * 16) b = 148 * 16;
@@ -109,6 +248,29 @@ cudaError_t launch_wavelet_fir(const uint8_t* d_src, int64_t pitch, int H, int W
                                float* d_ll, cudaStream_t stream) {
     const int ratio = 1 << depth;
     int h = (H + ratio - 1) / ratio * ratio, w = (W + ratio - 1) / ratio * ratio;
+    if ((C == 1 || C == 3 || C == 4) && tiled_taps(taps.n)) {
+        // tiled path: one launch per level; LL planes ping-pong between the two scratch buffers (level 1 -> d_rows)
+        const float* in = nullptr;
+        for (int level = 1; level <= depth; ++level) {
+            float* out = (level & 1) ? d_rows : d_ll;
+            uint8_t* icon = level == depth ? d_icon : nullptr;
+            cudaError_t e;
+            if (level == 1) {
+                e = C == 1 ? launch_tile<uint8_t, 1>(d_src, pitch, H, W, border_type, border_const, h, w, taps, out, icon, icon_pitch, stream)
+                  : C == 3 ? launch_tile<uint8_t, 3>(d_src, pitch, H, W, border_type, border_const, h, w, taps, out, icon, icon_pitch, stream)
+                           : launch_tile<uint8_t, 4>(d_src, pitch, H, W, border_type, border_const, h, w, taps, out, icon, icon_pitch, stream);
+            } else {
+                const int64_t pe = (int64_t)w * C;
+                e = C == 1 ? launch_tile<float, 1>(in, pe, h, w, 0, 0, h, w, taps, out, icon, icon_pitch, stream)
+                  : C == 3 ? launch_tile<float, 3>(in, pe, h, w, 0, 0, h, w, taps, out, icon, icon_pitch, stream)
+                           : launch_tile<float, 4>(in, pe, h, w, 0, 0, h, w, taps, out, icon, icon_pitch, stream);
+            }
+            if (e != cudaSuccess) return e;
+            in = out;
+            h /= 2; w /= 2;
+        }
+        return cudaSuccess;
+    }
     for (int level = 1; level <= depth; ++level) {
         const int64_t n_rows = (int64_t)h * (w / 2) * C;
         if (level == 1) fir_rows_kernel<true><<<grid_for(n_rows), 256, 0, stream>>>(d_src, pitch, H, W, border_type, border_const, nullptr, h, w, C, taps, d_rows);
