@@ -99,7 +99,7 @@ def row_subbands():
     coeffs = torch.empty((S, S, 3), dtype=torch.float32, device=dev)
     work = torch.empty((S * S * 3 * 5 // 16 + 64,), dtype=torch.float32, device=dev)
     rec = torch.empty((S, S, 3), dtype=torch.float32, device=dev)
-    for depth in (1, 3, 6):
+    for depth in [int(x) for x in os.environ.get("WICCA_ROWS_SUBBAND_DEPTHS", "1,3,6").split(",")]:
         def fwd():
             _capi.check(lib.wicca_haar_forward_dev(img.data_ptr(), S, S, 3, pitch, depth, 1, 0.0, coeffs.data_ptr(),
                                                    work.data_ptr(), 0, C.c_void_p(stream)), "forward_dev")

@@ -268,47 +268,52 @@ forward_patch_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int 
             return;
         }
     }
-    auto write_details = [&](int level, int gy, int gx, const float (&hl)[C], const float (&lh)[C], const float (&hh)[C],
-                             const float (&ll)[C]) {
-        const int hL = g.Hp >> level, wL = g.Wp >> level;
-        if (gy >= hL || gx >= wL) return;
-        float* q_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(wL + gx) * C;
-        float* q_lh = g.plane + (int64_t)(gy + hL) * g.pl_stride + (int64_t)gx * C;
-        float* q_hh = q_lh + (int64_t)wL * C;
-#pragma unroll
-        for (int c = 0; c < C; ++c) { q_hl[c] = hl[c]; q_lh[c] = lh[c]; q_hh[c] = hh[c]; }
-        if (g.levels == level) {
-            float* q_ll = g.ll + (int64_t)gy * g.ll_stride + (int64_t)gx * C;
-#pragma unroll
-            for (int c = 0; c < C; ++c) q_ll[c] = ll[c];
-        }
-    };
-    // ---- level 3 inside the warp: 2 x 2 lane groups (lx ^ 1, ly ^ 1); the group's first lane owns the block
-    float ll3[C];
+    // ---- levels 3 and 4: the level-2 LLs of the warp's 4 x 8 blocks go through the stage once, then a lane owns one
+    // (level-3 block, channel) element, in the order of the sub-band rows: lane = row * 4C + block * C + channel.  Its
+    // coefficients go straight from registers to 4C-float runs of two rows (no per-lane scalar stores: those cost 6 x
+    // the L2 write transactions, and no redundant arithmetic on all 32 lanes: the kernel is close to issue bound).
     {
-        const int base = lane & ~9;
-        float a[C], b[C], cc[C], d[C], hl[C], lh[C], hh[C];
+        constexpr int seg2 = 8 * C, seg = 4 * C;                  // floats of a level-2 / level-3 row of the warp
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            a[c] = __shfl_sync(0xFFFFFFFFu, ll2[c], base); b[c] = __shfl_sync(0xFFFFFFFFu, ll2[c], base + 1);
-            cc[c] = __shfl_sync(0xFFFFFFFFu, ll2[c], base + 8); d[c] = __shfl_sync(0xFFFFFFFFu, ll2[c], base + 9);
+        for (int c = 0; c < C; ++c) stage[ly * seg2 + lx * C + c] = ll2[c];
+        __syncwarp();
+        const int row = lane / seg, j = lane % seg;               // lanes >= 2 * seg idle (C < 4)
+        float ll3 = 0.f;
+        if (lane < 2 * seg) {
+            const float* p = stage + (2 * row) * seg2 + 2 * (j / C) * C + (j % C);
+            const float a = p[0], b = p[C], cc = p[seg2], d = p[seg2 + C];
+            const float rs0 = __fadd_rn(a, cc), rs1 = __fadd_rn(b, d), rd0 = __fsub_rn(a, cc), rd1 = __fsub_rn(b, d);
+            ll3 = __fmul_rn(__fadd_rn(rs0, rs1), 0.25f);
+            const int h3 = g.Hp >> 3, w3 = g.Wp >> 3;
+            const int gy = ty * 8 + 2 * wy + row, gx0 = tx * 8 + 4 * wx;
+            if (gy < h3 && gx0 + j / C < w3) {
+                float* q_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(w3 + gx0) * C + j;
+                float* q_lh = g.plane + (int64_t)(gy + h3) * g.pl_stride + (int64_t)gx0 * C + j;
+                q_hl[0] = __fmul_rn(__fsub_rn(rs0, rs1), 0.25f);
+                q_lh[0] = __fmul_rn(__fadd_rn(rd0, rd1), 0.25f);
+                q_lh[(int64_t)w3 * C] = __fmul_rn(__fsub_rn(rd0, rd1), 0.25f);
+                if (g.levels == 3) g.ll[(int64_t)gy * g.ll_stride + (int64_t)gx0 * C + j] = ll3;
+            }
         }
-        analyse<C>(a, b, cc, d, ll3, hl, lh, hh);
-        const int by = 2 * wy + (ly >> 1), bx = 4 * wx + (lx >> 1);
-        if (lane == base) write_details(3, ty * 8 + by, tx * 8 + bx, hl, lh, hh, ll3);
-    }
-    if (g.levels == 3) return;
-    // ---- level 4 inside the warp: lanes {m, m+2, m+16, m+18}, m = lane & 4 (the warp's 1 x 2 level-4 blocks)
-    {
-        const int base = lane & 4;
-        float a[C], b[C], cc[C], d[C], ll4[C], hl[C], lh[C], hh[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            a[c] = __shfl_sync(0xFFFFFFFFu, ll3[c], base); b[c] = __shfl_sync(0xFFFFFFFFu, ll3[c], base + 2);
-            cc[c] = __shfl_sync(0xFFFFFFFFu, ll3[c], base + 16); d[c] = __shfl_sync(0xFFFFFFFFu, ll3[c], base + 18);
+        if (g.levels == 3) return;
+        // ---- level 4: the warp's 1 x 2 blocks; lane = block * C + channel takes its four LL_3 from the lanes above
+        const int t = lane % (2 * C);
+        const int s0 = (t / C) * 2 * C + (t % C);                 // lane holding LL_3 of (row 0, block 2 * (t / C), channel)
+        const float a = __shfl_sync(0xFFFFFFFFu, ll3, s0), b = __shfl_sync(0xFFFFFFFFu, ll3, s0 + C);
+        const float cc = __shfl_sync(0xFFFFFFFFu, ll3, s0 + seg), d = __shfl_sync(0xFFFFFFFFu, ll3, s0 + seg + C);
+        if (lane < 2 * C) {
+            const float rs0 = __fadd_rn(a, cc), rs1 = __fadd_rn(b, d), rd0 = __fsub_rn(a, cc), rd1 = __fsub_rn(b, d);
+            const int h4 = g.Hp >> 4, w4 = g.Wp >> 4;
+            const int gy = ty * 4 + wy, gx0 = tx * 4 + 2 * wx;
+            if (gy < h4 && gx0 + lane / C < w4) {
+                float* q_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(w4 + gx0) * C + lane;
+                float* q_lh = g.plane + (int64_t)(gy + h4) * g.pl_stride + (int64_t)gx0 * C + lane;
+                q_hl[0] = __fmul_rn(__fsub_rn(rs0, rs1), 0.25f);
+                q_lh[0] = __fmul_rn(__fadd_rn(rd0, rd1), 0.25f);
+                q_lh[(int64_t)w4 * C] = __fmul_rn(__fsub_rn(rd0, rd1), 0.25f);
+                g.ll[(int64_t)gy * g.ll_stride + (int64_t)gx0 * C + lane] = __fmul_rn(__fadd_rn(rs0, rs1), 0.25f);   // levels == 4 here
+            }
         }
-        analyse<C>(a, b, cc, d, ll4, hl, lh, hh);
-        if (lane == base) write_details(4, ty * 4 + wy, tx * 4 + 2 * wx + (lane >> 2), hl, lh, hh, ll4);
     }
 }
 
