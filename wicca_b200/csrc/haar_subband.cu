@@ -338,11 +338,40 @@ __device__ __forceinline__ void load_run(const float* p, bool vec, bool inside, 
     }
 }
 
+// Shared memory of the inverse kernel, per warp: the level-1 details of its region (3 sub-bands x 8 rows x 16C floats;
+// +8 floats of row pitch so that the lanes' float2 reads - 2C floats per lane, rows 2 ly + iy - hit every bank once)
+// followed by the 4-row output stage.
+template <int C>
+struct InvSmem {
+    static constexpr int kDetPitch = 16 * C + 8;
+    static constexpr int kDetRows = 24;
+    static constexpr int kWarpFloats = kDetRows * kDetPitch + 4 * 32 * C;
+    static constexpr size_t kBytes = (size_t)(kTileThreads / 32) * kWarpFloats * sizeof(float);
+};
+
+// cp.async of the 24 detail row segments (HL, LH, HH x 8 rows, 64C bytes each) in chunks of CB bytes.
+template <int C, int CB>
+__device__ __forceinline__ void fetch_details(float* det, const float* b_hl, const float* b_lh, int64_t hh_off, int64_t stride,
+                                              int lane) {
+    constexpr int kChunksPerRow = 64 * C / CB, kPerLane = 24 * kChunksPerRow / 32, kF = CB / 4;
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+        const int q = lane + 32 * i, seg = q / kChunksPerRow, ch = q % kChunksPerRow;
+        const int sb = seg >> 3, r = seg & 7;
+        const float* src = (sb == 0 ? b_hl : b_lh) + (int64_t)r * stride + (sb == 2 ? hh_off : 0) + ch * kF;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(det + seg * InvSmem<C>::kDetPitch + ch * kF);
+        if (CB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        else if (CB == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+        else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+    }
+}
+
 template <int C>
 __global__ void __launch_bounds__(kTileThreads, C <= 3 ? 4 : 3)
 inverse_patch_kernel(TileGeom g, float* __restrict__ out, int64_t out_stride) {
     constexpr int kSeg = 32 * C;                                  // floats of one output row of the warp's region
-    __shared__ __align__(16) float s_st[kTileThreads / 32][4 * kSeg];
+    constexpr int kDetPitch = InvSmem<C>::kDetPitch, kDetRows = InvSmem<C>::kDetRows;
+    extern __shared__ __align__(16) float s_inv[];                // per warp: [level-1 details][output stage]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wy = warp >> 1, wx = warp & 1, ly = lane >> 3, lx = lane & 7;
     const int ty = blockIdx.y, tx = blockIdx.x;
@@ -350,36 +379,83 @@ inverse_patch_kernel(TileGeom g, float* __restrict__ out, int64_t out_stride) {
     const int L = g.levels;
     const int h1 = g.Hp >> 1, w1 = g.Wp >> 1;
     const bool full = (ty * kTile + kTile <= g.Hp) && (tx * kTile + kTile <= g.Wp);
-    float* stage = s_st[warp];
+    float* det = s_inv + warp * InvSmem<C>::kWarpFloats;          // 3 sub-bands x 8 rows x 16C floats (row pitch kDetPitch)
+    float* stage = det + kDetRows * kDetPitch;
 
-    // ---- LL of the lane's level-2 block (levels >= 2), walking down from the top fused level
-    float ll2[C];
+    // ---- the bulk of the tile's input - the level-1 details of the warp's 8 x 16 blocks - starts its way to shared
+    // memory now (cp.async: no registers, no stall), so that it is in flight while the LL of the patch is walked
+    // down from the top level; issued after that walk it would cost every warp a second, serial trip to HBM.
+    if (full) {
+        const int gy0 = ty * 32 + 8 * wy, gx0 = tx * 32 + 16 * wx;
+        const float* b_hl = g.plane + (int64_t)gy0 * g.pl_stride + (int64_t)(w1 + gx0) * C;
+        const float* b_lh = g.plane + (int64_t)(gy0 + h1) * g.pl_stride + (int64_t)gx0 * C;
+        const int al = (int)(((uintptr_t)g.plane | (uintptr_t)(g.pl_stride * 4) | (uintptr_t)((int64_t)w1 * C * 4)) & 15);
+        if (al == 0) fetch_details<C, 16>(det, b_hl, b_lh, (int64_t)w1 * C, g.pl_stride, lane);
+        else if ((al & 7) == 0) fetch_details<C, 8>(det, b_hl, b_lh, (int64_t)w1 * C, g.pl_stride, lane);
+        else fetch_details<C, 4>(det, b_hl, b_lh, (int64_t)w1 * C, g.pl_stride, lane);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
+    // ---- LL of the lane's level-2 block (levels >= 2).  Levels 4 and 3 are expanded by one lane per (block, channel)
+    // element - lane = row * 4C + block * C + channel, the order of the sub-band rows, so the detail loads are whole
+    // runs - and handed down through the stage; a lane then picks up the LL_2 of its own block.  Every global load of
+    // levels 4, 3 and 2 is issued here, before the first wait: they do not depend on each other, only the sums do.
+    constexpr int seg3 = 4 * C, seg2 = 8 * C;                     // floats of a level-3 / level-2 row of the warp
     const bool in2 = (2 * gy2 < h1) && (2 * gx2 < w1);            // L >= 2: extents are multiples of 4, all or nothing
+    // v = {LL, HL, LH, HH} of element e of the run at (gy, gx0) of level T (LL only when take_ll)
+    auto load_quad = [&](int T, int gy, int gx0, int e, bool take_ll, float (&v)[4]) {
+        const int hT = g.Hp >> T, wT = g.Wp >> T;
+        const float* q_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(wT + gx0) * C + e;
+        const float* q_lh = g.plane + (int64_t)(gy + hT) * g.pl_stride + (int64_t)gx0 * C + e;
+        v[0] = take_ll ? g.ll[(int64_t)gy * g.ll_stride + (int64_t)gx0 * C + e] : 0.f;
+        v[1] = q_hl[0]; v[2] = q_lh[0]; v[3] = q_lh[(int64_t)wT * C];
+    };
+    auto expand = [](const float (&v)[4], float& a, float& b, float& cc, float& d) {
+        const float s0 = __fadd_rn(v[0], v[1]), s1 = __fsub_rn(v[0], v[1]);
+        const float d0 = __fadd_rn(v[2], v[3]), d1 = __fsub_rn(v[2], v[3]);
+        a = __fadd_rn(s0, d0); b = __fadd_rn(s1, d1); cc = __fsub_rn(s0, d0); d = __fsub_rn(s1, d1);
+    };
+    float v4[4] = {0.f, 0.f, 0.f, 0.f}, v3[4] = {0.f, 0.f, 0.f, 0.f}, ll2[C], hl2[C], lh2[C], hh2[C];
+    const int row3 = lane / seg3, j3 = lane % seg3;
+    if (L == 4 && lane < 2 * C && ty * 4 + wy < (g.Hp >> 4) && tx * 4 + 2 * wx + lane / C < (g.Wp >> 4))
+        load_quad(4, ty * 4 + wy, tx * 4 + 2 * wx, lane, true, v4);
+    if (L >= 3 && lane < 2 * seg3 && ty * 8 + 2 * wy + row3 < (g.Hp >> 3) && tx * 8 + 4 * wx + j3 / C < (g.Wp >> 3))
+        load_quad(3, ty * 8 + 2 * wy + row3, tx * 8 + 4 * wx, j3, L == 3, v3);
     if (L >= 2) {
-        {
-            const int sh = L - 2;
-            const float* q = g.ll + (int64_t)(gy2 >> sh) * g.ll_stride + (int64_t)(gx2 >> sh) * C;
+        const int h2 = g.Hp >> 2, w2 = g.Wp >> 2;
+        const float* q_hl = g.plane + (int64_t)gy2 * g.pl_stride + (int64_t)(w2 + gx2) * C;
+        const float* q_lh = g.plane + (int64_t)(gy2 + h2) * g.pl_stride + (int64_t)gx2 * C;
+        const float* q_hh = q_lh + (int64_t)w2 * C;
+        const float* q_ll = g.ll + (int64_t)gy2 * g.ll_stride + (int64_t)gx2 * C;
 #pragma unroll
-            for (int c = 0; c < C; ++c) ll2[c] = in2 ? q[c] : 0.f;
+        for (int c = 0; c < C; ++c) {
+            hl2[c] = in2 ? q_hl[c] : 0.f; lh2[c] = in2 ? q_lh[c] : 0.f; hh2[c] = in2 ? q_hh[c] : 0.f;
+            ll2[c] = (in2 && L == 2) ? q_ll[c] : 0.f;
         }
-#pragma unroll
-        for (int T = 4; T >= 3; --T) {
-            if (T > L) continue;
-            const int sh = T - 2;
-            const int gy = gy2 >> sh, gx = gx2 >> sh, hT = g.Hp >> T, wT = g.Wp >> T;
-            const bool qy = (gy2 >> (sh - 1)) & 1, qx = (gx2 >> (sh - 1)) & 1;
-            const float* q_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(wT + gx) * C;
-            const float* q_lh = g.plane + (int64_t)(gy + hT) * g.pl_stride + (int64_t)gx * C;
-            const float* q_hh = q_lh + (int64_t)wT * C;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float vhl = in2 ? q_hl[c] : 0.f, vlh = in2 ? q_lh[c] : 0.f, vhh = in2 ? q_hh[c] : 0.f;
-                // a = (ll+hl)+(lh+hh)  b = (ll-hl)+(lh-hh)  c = (ll+hl)-(lh+hh)  d = (ll-hl)-(lh-hh): pick the quadrant
-                const float s = __fadd_rn(ll2[c], qx ? -vhl : vhl);
-                const float dd = __fadd_rn(vlh, qx ? -vhh : vhh);
-                ll2[c] = __fadd_rn(s, qy ? -dd : dd);
+    }
+    if (L > 2) {
+        float* st3 = stage;                                       // LL_3 of the warp's 2 x 4 blocks
+        float* st2 = stage + 2 * seg3;                            // LL_2 of the warp's 4 x 8 blocks
+        if (L == 4) {
+            if (lane < 2 * C) {
+                float a, b, cc, d;
+                expand(v4, a, b, cc, d);
+                float* q = st3 + 2 * (lane / C) * C + (lane % C);
+                q[0] = a; q[C] = b; q[seg3] = cc; q[seg3 + C] = d;
             }
+            __syncwarp();
         }
+        if (lane < 2 * seg3) {
+            if (L == 4) v3[0] = st3[lane];
+            float a, b, cc, d;
+            expand(v3, a, b, cc, d);
+            float* q = st2 + 2 * row3 * seg2 + 2 * (j3 / C) * C + (j3 % C);
+            q[0] = a; q[C] = b; q[seg2] = cc; q[seg2 + C] = d;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < C; ++c) ll2[c] = st2[ly * seg2 + lx * C + c];
+        __syncwarp();                                             // the stage carries output rows from here on
     }
     // ---- level 2 -> the four LL_1 values of the patch (or LL_1 itself when only one level is fused)
     float ll1[2][2][C];
@@ -389,15 +465,10 @@ inverse_patch_kernel(TileGeom g, float* __restrict__ out, int64_t out_stride) {
 #pragma unroll
         for (int ix = 0; ix < 2; ++ix) in1[iy][ix] = (2 * gy2 + iy < h1) && (2 * gx2 + ix < w1);
     if (L >= 2) {
-        const int h2 = g.Hp >> 2, w2 = g.Wp >> 2;
-        const float* q_hl = g.plane + (int64_t)gy2 * g.pl_stride + (int64_t)(w2 + gx2) * C;
-        const float* q_lh = g.plane + (int64_t)(gy2 + h2) * g.pl_stride + (int64_t)gx2 * C;
-        const float* q_hh = q_lh + (int64_t)w2 * C;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const float vhl = in2 ? q_hl[c] : 0.f, vlh = in2 ? q_lh[c] : 0.f, vhh = in2 ? q_hh[c] : 0.f;
-            const float s0 = __fadd_rn(ll2[c], vhl), s1 = __fsub_rn(ll2[c], vhl);
-            const float d0 = __fadd_rn(vlh, vhh), d1 = __fsub_rn(vlh, vhh);
+            const float s0 = __fadd_rn(ll2[c], hl2[c]), s1 = __fsub_rn(ll2[c], hl2[c]);
+            const float d0 = __fadd_rn(lh2[c], hh2[c]), d1 = __fsub_rn(lh2[c], hh2[c]);
             ll1[0][0][c] = __fadd_rn(s0, d0); ll1[0][1][c] = __fadd_rn(s1, d1);
             ll1[1][0][c] = __fsub_rn(s0, d0); ll1[1][1][c] = __fsub_rn(s1, d1);
         }
@@ -425,7 +496,15 @@ inverse_patch_kernel(TileGeom g, float* __restrict__ out, int64_t out_stride) {
         const float* q_hl = g.plane + (int64_t)gy1 * g.pl_stride + (int64_t)(w1 + 2 * gx2) * C;
         const float* q_lh = g.plane + (int64_t)(gy1 + h1) * g.pl_stride + (int64_t)(2 * gx2) * C;
         const float* q_hh = q_lh + (int64_t)w1 * C;
-        if (in1[iy][0] && in1[iy][1]) {
+        if (full) {
+            if (iy == 0) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();                                     // every lane's copies have landed
+            }
+            const float* d = det + (2 * ly + iy) * kDetPitch + lx * 2 * C;
+            load_run<2 * C>(d, true, true, hl); load_run<2 * C>(d + 8 * kDetPitch, true, true, lh);
+            load_run<2 * C>(d + 16 * kDetPitch, true, true, hh);
+        } else if (in1[iy][0] && in1[iy][1]) {
             load_run<2 * C>(q_hl, vec, rin, hl); load_run<2 * C>(q_lh, vec, rin, lh); load_run<2 * C>(q_hh, vec, rin, hh);
         } else {
 #pragma unroll
@@ -469,7 +548,15 @@ static cudaError_t launch_forward_tiles(const uint8_t* d_src, int64_t pitch, int
 }
 template <int C>
 static cudaError_t launch_inverse_tiles(const TileGeom& g, float* out, int64_t out_stride, cudaStream_t stream) {
-    inverse_patch_kernel<C><<<dim3(g.tiles_x, g.tiles_y), kTileThreads, 0, stream>>>(g, out, out_stride);
+    static thread_local int configured_dev = -1;                  // > 48 KB of dynamic shared memory: opt in once per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(inverse_patch_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)InvSmem<C>::kBytes);
+        if (e != cudaSuccess) return e;
+        configured_dev = dev;
+    }
+    inverse_patch_kernel<C><<<dim3(g.tiles_x, g.tiles_y), kTileThreads, InvSmem<C>::kBytes, stream>>>(g, out, out_stride);
     return cudaGetLastError();
 }
 
