@@ -66,7 +66,7 @@ def row_icons():
             def src_resize():
                 _capi.check(lib.wicca_resize_norm_dev(ptrs, (C.c_int * n)(*[H] * n), (C.c_int * n)(*[W] * n), (C.c_int64 * n)(*[pitch] * n),
                                                       n, 224, 224, 1, out_s.data_ptr(), None, 0, C.c_void_p(stream)), "resize_norm_dev")
-            ms_s = timed(src_resize, reps=3, warm=1)
+            ms_s = timed(src_resize, reps=20, warm=2)
             emit(row="N1 source-image resize", config=f"30 x ({H},{W},3) -> 224x224 tf, device-resident", ms=ms_s,
                  MP_per_s=n * H * W / ms_s / 1e3, GBps=n * H * W * 3 / ms_s / 1e6, frac_of_measured_peak=n * H * W * 3 / ms_s / 1e6 / PEAK)
             # fused epilogue on the resident icons (configs[3])
