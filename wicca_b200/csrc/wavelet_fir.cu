@@ -103,33 +103,80 @@ fir_cols_kernel(const float* __restrict__ t, int h, int w2, int C, FirTaps taps,
 //           pixels it loads are shared by the four outputs, the sums run tap by tap as in the oracle;
 //   cols    each thread filters one output element down the column of row results.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kTileH = 16, kTileW = 64, kTileThreads = 256, kOutPerThread = 4;
+constexpr int kTileH = 16, kTileThreads = 256, kOutPerThread = 4;
+
+// Tile geometry by input type: float planes (levels >= 2) take half the width, so that four CTAs fit an SM.
+template <typename TIn, int C, int L>
+struct FirTile {
+    static constexpr int kW = sizeof(TIn) == 1 ? 64 : 32;                   // low-pass samples per tile row
+    static constexpr int rows = 2 * kTileH + L - 2, cols = 2 * kW + L - 2;   // input window
+    // staged row: up to 15 bytes of alignment slack, the window, rounded up to whole 16-byte chunks
+    static constexpr int kRowBytes = (15 + cols * C * (int)sizeof(TIn) + 15) / 16 * 16;
+    static constexpr size_t kInBytes = (size_t)rows * kRowBytes;
+    static constexpr size_t kSmem = kInBytes + (size_t)rows * kW * C * sizeof(float);
+};
+
+template <int CB>
+__device__ __forceinline__ void fir_cp_async(uint32_t dst, const void* src) {
+    if (CB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    else if (CB == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// All rows of an interior window, as CB-byte chunks from the aligned-down start of each row: fire and forget.
+template <int CB>
+__device__ __forceinline__ void fir_fetch_window(unsigned char* s_raw, int row_pitch_smem, const unsigned char* g_first,
+                                                 int64_t g_pitch_bytes, int rows, int chunks) {
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(s_raw);
+    for (int q = threadIdx.x; q < rows * chunks; q += kTileThreads) {
+        const int r = q / chunks, ch = q - r * chunks;
+        fir_cp_async<CB>(s0 + (uint32_t)(r * row_pitch_smem + ch * CB), g_first + (int64_t)r * g_pitch_bytes + ch * CB);
+    }
+}
 
 template <typename TIn, int C, int L>
 __global__ void __launch_bounds__(kTileThreads)
 fir_tile_kernel(const TIn* __restrict__ src, int64_t pitch_elems, int H, int W, int border_type, int border_const, int h, int w,
                 FirTaps taps, float* __restrict__ out, uint8_t* __restrict__ icon, int64_t icon_pitch) {
+    using G = FirTile<TIn, C, L>;
+    constexpr int kTileW = G::kW, rows = G::rows, cols = G::cols, kRowBytes = G::kRowBytes;
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ float s_g[16];
     if (threadIdx.x < 16) s_g[threadIdx.x] = taps.g[threadIdx.x];
-    constexpr int rows = 2 * kTileH + L - 2, cols = 2 * kTileW + L - 2;
-    TIn* s_in = reinterpret_cast<TIn*>(s_raw);                                       // [rows][cols][C]
-    float* s_t = reinterpret_cast<float*>(s_raw + (((size_t)rows * cols * C * sizeof(TIn) + 15) & ~(size_t)15));   // [rows][kTileW][C]
+    float* s_t = reinterpret_cast<float*>(s_raw + G::kInBytes);                      // [rows][kTileW][C]
     const int h2 = h >> 1, w2 = w >> 1;
     const int oy0 = blockIdx.y * kTileH, ox0 = blockIdx.x * kTileW;
     constexpr bool kU8 = sizeof(TIn) == 1;
-    // ---- stage
+    // ---- stage: row r of the window lives at s_raw + r * kRowBytes + lead
     const int y0 = 2 * oy0 - taps.c, x0 = 2 * ox0 - taps.c;
-    const bool interior = y0 >= 0 && x0 >= 0 && y0 + rows <= (kU8 ? min(h, H) : h) && x0 + cols <= (kU8 ? min(w, W) : w);
+    bool interior = y0 >= 0 && x0 >= 0 && y0 + rows <= (kU8 ? min(h, H) : h) && x0 + cols <= (kU8 ? min(w, W) : w);
+    int lead = 0;
     if (interior) {
-        // no wrap-around and no border rule anywhere in the window: whole rows are contiguous in the source
-        const int row_elems = cols * C;
-        for (int r = threadIdx.x >> 5; r < rows; r += kTileThreads / 32) {
-            const TIn* p = src + (int64_t)(y0 + r) * pitch_elems + (int64_t)x0 * C;
-            TIn* d = s_in + (size_t)r * row_elems;
-            for (int b = threadIdx.x & 31; b < row_elems; b += 32) d[b] = p[b];
+        // no wrap-around and no border rule anywhere in the window: whole rows are contiguous in the source and go to
+        // shared memory as aligned chunks (cp.async: every copy of the tile is in flight before the first wait)
+        const int64_t pitch_bytes = pitch_elems * (int64_t)sizeof(TIn);
+        const uintptr_t al = (uintptr_t)src | (uintptr_t)pitch_bytes;
+        const int cb = (al & 15) == 0 ? 16 : (al & 7) == 0 ? 8 : (al & 3) == 0 ? 4 : 0;
+        const int64_t first = (int64_t)x0 * C * (int64_t)sizeof(TIn);               // byte offset of the window in its row
+        if (cb) {
+            lead = (int)(first & (cb - 1));
+            const int chunks = (lead + cols * C * (int)sizeof(TIn) + cb - 1) / cb;
+            // the rounded-up chunk range must stay inside the row (pitch padding included)
+            if (first - lead + (int64_t)chunks * cb <= pitch_bytes) {
+                const unsigned char* g0 = reinterpret_cast<const unsigned char*>(src) + (int64_t)y0 * pitch_bytes + (first - lead);
+                if (cb == 16) fir_fetch_window<16>(s_raw, kRowBytes, g0, pitch_bytes, rows, chunks);
+                else if (cb == 8) fir_fetch_window<8>(s_raw, kRowBytes, g0, pitch_bytes, rows, chunks);
+                else fir_fetch_window<4>(s_raw, kRowBytes, g0, pitch_bytes, rows, chunks);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            } else {
+                interior = false; lead = 0;
+            }
+        } else {
+            interior = false;
         }
-    } else {
+    }
+    if (!interior) {
         for (int e = threadIdx.x; e < rows * cols; e += kTileThreads) {
             const int r = e / cols, k = e - r * cols;
             int y = (y0 + r) % h;
@@ -138,7 +185,7 @@ fir_tile_kernel(const TIn* __restrict__ src, int64_t pitch_elems, int H, int W, 
             x += x < 0 ? w : 0;
             const int ym = kU8 ? (y < H ? y : border_index(y, H, border_type)) : y;
             const int xm = kU8 ? (x < W ? x : border_index(x, W, border_type)) : x;
-            TIn* d = s_in + (size_t)e * C;
+            TIn* d = reinterpret_cast<TIn*>(s_raw + (size_t)r * kRowBytes) + (size_t)k * C;
             if (ym < 0 || xm < 0) {
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) d[ch] = (TIn)border_const;
@@ -154,7 +201,7 @@ fir_tile_kernel(const TIn* __restrict__ src, int64_t pitch_elems, int H, int W, 
     constexpr int groups = kTileW / kOutPerThread;
     for (int e = threadIdx.x; e < rows * groups; e += kTileThreads) {
         const int r = e / groups, jg = e - r * groups;
-        const TIn* p = s_in + ((size_t)r * cols + 2 * kOutPerThread * jg) * C;
+        const TIn* p = reinterpret_cast<const TIn*>(s_raw + (size_t)r * kRowBytes + lead) + (size_t)(2 * kOutPerThread * jg) * C;
         // the 2*4 + L - 2 pixels the four outputs share, converted once
         constexpr int kPix = 2 * kOutPerThread + L - 2;
         float px[kPix][C];
@@ -203,8 +250,8 @@ fir_tile_kernel(const TIn* __restrict__ src, int64_t pitch_elems, int H, int W, 
 template <typename TIn, int C, int L>
 cudaError_t launch_tile_l(const TIn* src, int64_t pitch_elems, int H, int W, int border_type, int border_const, int h, int w,
                           const FirTaps& taps, float* out, uint8_t* icon, int64_t icon_pitch, cudaStream_t stream) {
-    constexpr int rows = 2 * kTileH + L - 2, cols = 2 * kTileW + L - 2;
-    constexpr size_t smem = (((size_t)rows * cols * C * sizeof(TIn) + 15) & ~(size_t)15) + (size_t)rows * kTileW * C * sizeof(float);
+    using G = FirTile<TIn, C, L>;
+    constexpr size_t smem = G::kSmem;
     static thread_local int configured_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -213,7 +260,7 @@ cudaError_t launch_tile_l(const TIn* src, int64_t pitch_elems, int H, int W, int
         if (e != cudaSuccess) return e;
         configured_dev = dev;
     }
-    const dim3 grid((w / 2 + kTileW - 1) / kTileW, (h / 2 + kTileH - 1) / kTileH);
+    const dim3 grid((w / 2 + G::kW - 1) / G::kW, (h / 2 + kTileH - 1) / kTileH);
     fir_tile_kernel<TIn, C, L><<<grid, kTileThreads, smem, stream>>>(src, pitch_elems, H, W, border_type, border_const, h, w, taps,
                                                                     out, icon, icon_pitch);
     return cudaGetLastError();
