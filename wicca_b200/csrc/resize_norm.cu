@@ -47,19 +47,20 @@ __device__ __forceinline__ void emit_value(uint8_t v, int c, int64_t i, int norm
 }
 
 // skip_area != 0: images in the general-area regime are left to resize_area_rows_kernel.
-__global__ void resize_norm_kernel(ResizeTables t, int n, int out_h, int out_w, int norm_mode, float* __restrict__ out,
+__global__ void resize_norm_kernel(ResizeTables t, int img0, int out_h, int out_w, int norm_mode, float* __restrict__ out,
                                    uint8_t* __restrict__ out_u8, int skip_area) {
-    const int64_t per = (int64_t)out_h * out_w * 3;
-    const int64_t total = per * n;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int img = (int)(i / per);
-        int64_t r = i - (int64_t)img * per;
-        const int c = (int)(r % 3);
-        r /= 3;
-        const int dx = (int)(r % out_w);
-        const int dy = (int)(r / out_w);
-        const ResizeJob j = t.jobs[img];
-        if (skip_area && j.regime == 2) continue;
+    // one image per blockIdx.y; the element index inside an image fits 32 bits (the launcher checks), which keeps
+    // the index arithmetic off the 64-bit division path
+    const uint32_t per = (uint32_t)out_h * (uint32_t)out_w * 3u;
+    const int img = img0 + blockIdx.y;
+    const ResizeJob j = t.jobs[img];
+    if (skip_area && j.regime == 2) return;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < per; e += gridDim.x * blockDim.x) {
+        const uint32_t px = e / 3u;
+        const int c = (int)(e - px * 3u);
+        const int dy = (int)(px / (uint32_t)out_w);
+        const int dx = (int)(px - (uint32_t)dy * (uint32_t)out_w);
+        const int64_t i = (int64_t)img * per + e;
         const int64_t srow = j.pitch;
         const uint8_t* s = j.src + c;
         uint8_t v;
@@ -292,9 +293,15 @@ cudaError_t launch_resize_norm(const ResizeTables& t, int n, int out_h, int out_
         if (e != cudaSuccess) return e;
         if (n_other == 0) return cudaSuccess;
     }
-    int64_t blocks = (total + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    resize_norm_kernel<<<(int)blocks, 256, 0, stream>>>(t, n, out_h, out_w, norm_mode, d_out, d_out_u8, rows_ok ? 1 : 0);
+    const int64_t per = (int64_t)out_h * out_w * 3;
+    if (per > 0x7FFFFFFF) return cudaErrorInvalidValue;                    // 32-bit element index inside an image
+    for (int img0 = 0; img0 < n; img0 += 65535) {                          // one image per blockIdx.y
+        const int m = n - img0 < 65535 ? n - img0 : 65535;
+        int64_t blocks = (per + 255) / 256;
+        const int64_t cap = (148 * 32 + m - 1) / m;                        // enough CTAs in all to fill the GPU a few times
+        if (blocks > cap) blocks = cap;
+        resize_norm_kernel<<<dim3((unsigned)blocks, (unsigned)m), 256, 0, stream>>>(t, img0, out_h, out_w, norm_mode, d_out, d_out_u8, rows_ok ? 1 : 0);
+    }
     return cudaGetLastError();
 }
 
