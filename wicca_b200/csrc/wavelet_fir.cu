@@ -103,17 +103,22 @@ fir_cols_kernel(const float* __restrict__ t, int h, int w2, int C, FirTaps taps,
 //           pixels it loads are shared by the four outputs, the sums run tap by tap as in the oracle;
 //   cols    each thread filters one output element down the column of row results.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kTileH = 16, kTileThreads = 256, kOutPerThread = 4;
+constexpr int kTileThreads = 256, kOutPerThread = 4;
 
 // Tile geometry by input type: float planes (levels >= 2) take half the width, so that four CTAs fit an SM.
 template <typename TIn, int C, int L>
 struct FirTile {
     static constexpr int kW = sizeof(TIn) == 1 ? 64 : 32;                   // low-pass samples per tile row
-    static constexpr int rows = 2 * kTileH + L - 2, cols = 2 * kW + L - 2;   // input window
-    // staged row: up to 15 bytes of alignment slack, the window, rounded up to whole 16-byte chunks
-    static constexpr int kRowBytes = (15 + cols * C * (int)sizeof(TIn) + 15) / 16 * 16;
+    static constexpr int kH = sizeof(TIn) == 1 ? 16 : 14;                   // tile rows
+    static constexpr int rows = 2 * kH + L - 2, cols = 2 * kW + L - 2;      // input window
+    // staged row: up to 15 bytes of alignment slack, the window, rounded up to whole 16-byte chunks; float rows are
+    // padded to a pitch of 4 words mod 8 (a warp of the row pass reads 4 rows x 8 runs 24 words apart: 8-way bank
+    // conflicts on a pitch of 0 mod 8 words, 4-way - the best a multiple of 16 bytes allows - on 4 mod 8)
+    static constexpr int kRowBytesMin = (15 + cols * C * (int)sizeof(TIn) + 15) / 16 * 16;
+    static constexpr int kRowBytes = (sizeof(TIn) == 1 || kRowBytesMin % 32 == 16) ? kRowBytesMin : kRowBytesMin + 16;
     static constexpr size_t kInBytes = (size_t)rows * kRowBytes;
-    static constexpr size_t kSmem = kInBytes + (size_t)rows * kW * C * sizeof(float);
+    static constexpr int kTPitch = kW * C + 4;                               // row results: rows start 4 banks apart, 16-byte stores stay aligned
+    static constexpr size_t kSmem = kInBytes + (size_t)rows * kTPitch * sizeof(float);
 };
 
 template <int CB>
@@ -139,11 +144,11 @@ __global__ void __launch_bounds__(kTileThreads)
 fir_tile_kernel(const TIn* __restrict__ src, int64_t pitch_elems, int H, int W, int border_type, int border_const, int h, int w,
                 FirTaps taps, float* __restrict__ out, uint8_t* __restrict__ icon, int64_t icon_pitch) {
     using G = FirTile<TIn, C, L>;
-    constexpr int kTileW = G::kW, rows = G::rows, cols = G::cols, kRowBytes = G::kRowBytes;
+    constexpr int kTileW = G::kW, kTileH = G::kH, rows = G::rows, cols = G::cols, kRowBytes = G::kRowBytes;
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ float s_g[16];
     if (threadIdx.x < 16) s_g[threadIdx.x] = taps.g[threadIdx.x];
-    float* s_t = reinterpret_cast<float*>(s_raw + G::kInBytes);                      // [rows][kTileW][C]
+    float* s_t = reinterpret_cast<float*>(s_raw + G::kInBytes);                      // [rows][kTPitch]
     const int h2 = h >> 1, w2 = w >> 1;
     const int oy0 = blockIdx.y * kTileH, ox0 = blockIdx.x * kTileW;
     constexpr bool kU8 = sizeof(TIn) == 1;
@@ -221,7 +226,7 @@ fir_tile_kernel(const TIn* __restrict__ src, int64_t pitch_elems, int H, int W, 
                     acc[o][ch] = n == 0 ? v : __fadd_rn(acc[o][ch], v);
                 }
         }
-        float* d = s_t + ((size_t)r * kTileW + kOutPerThread * jg) * C;
+        float* d = s_t + (size_t)r * G::kTPitch + kOutPerThread * jg * C;
 #pragma unroll
         for (int o = 0; o < kOutPerThread; ++o)
 #pragma unroll
@@ -234,11 +239,11 @@ fir_tile_kernel(const TIn* __restrict__ src, int64_t pitch_elems, int H, int W, 
         const int i = e / seg, q = e - i * seg;
         const int oi = oy0 + i, oj = ox0 + q / C;
         if (oi >= h2 || oj >= w2) continue;
-        const float* p = s_t + (size_t)(2 * i) * seg + q;
+        const float* p = s_t + (size_t)(2 * i) * G::kTPitch + q;
         float acc = 0.0f;
 #pragma unroll
         for (int m = 0; m < L; ++m) {
-            const float v = __fmul_rn(p[m * seg], s_g[m]);
+            const float v = __fmul_rn(p[m * G::kTPitch], s_g[m]);
             acc = m == 0 ? v : __fadd_rn(acc, v);
         }
         const int64_t o = (int64_t)ox0 * C + q;
@@ -260,7 +265,7 @@ cudaError_t launch_tile_l(const TIn* src, int64_t pitch_elems, int H, int W, int
         if (e != cudaSuccess) return e;
         configured_dev = dev;
     }
-    const dim3 grid((w / 2 + G::kW - 1) / G::kW, (h / 2 + kTileH - 1) / kTileH);
+    const dim3 grid((w / 2 + G::kW - 1) / G::kW, (h / 2 + G::kH - 1) / G::kH);
     fir_tile_kernel<TIn, C, L><<<grid, kTileThreads, smem, stream>>>(src, pitch_elems, H, W, border_type, border_const, h, w, taps,
                                                                     out, icon, icon_pitch);
     return cudaGetLastError();
