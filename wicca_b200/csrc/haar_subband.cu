@@ -164,6 +164,14 @@ __device__ __forceinline__ void store_rows(const float* stage, int lane, float* 
     else store_rows_impl<SEG, ROWS, PITCH, true>(stage, lane, base, stride, rows_valid, seg_valid);
 }
 
+// Store that asks L2 to keep the line for a while (evict_last): the level-3/4 sub-band rows are written as 48- and
+// 24-byte runs by different warps and CTAs, and should meet their neighbours in L2 before they travel to HBM.
+__device__ __forceinline__ void store_keep(float* p, float v) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+
 template <int C>
 __global__ void __launch_bounds__(kTileThreads, C <= 3 ? 4 : 3)
 forward_patch_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int W, int border_type, int border_const,
@@ -289,10 +297,10 @@ forward_patch_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int 
             if (gy < h3 && gx0 + j / C < w3) {
                 float* q_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(w3 + gx0) * C + j;
                 float* q_lh = g.plane + (int64_t)(gy + h3) * g.pl_stride + (int64_t)gx0 * C + j;
-                q_hl[0] = __fmul_rn(__fsub_rn(rs0, rs1), 0.25f);
-                q_lh[0] = __fmul_rn(__fadd_rn(rd0, rd1), 0.25f);
-                q_lh[(int64_t)w3 * C] = __fmul_rn(__fsub_rn(rd0, rd1), 0.25f);
-                if (g.levels == 3) g.ll[(int64_t)gy * g.ll_stride + (int64_t)gx0 * C + j] = ll3;
+                store_keep(q_hl, __fmul_rn(__fsub_rn(rs0, rs1), 0.25f));
+                store_keep(q_lh, __fmul_rn(__fadd_rn(rd0, rd1), 0.25f));
+                store_keep(q_lh + (int64_t)w3 * C, __fmul_rn(__fsub_rn(rd0, rd1), 0.25f));
+                if (g.levels == 3) store_keep(g.ll + (int64_t)gy * g.ll_stride + (int64_t)gx0 * C + j, ll3);
             }
         }
         if (g.levels == 3) return;
@@ -308,10 +316,10 @@ forward_patch_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int 
             if (gy < h4 && gx0 + lane / C < w4) {
                 float* q_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(w4 + gx0) * C + lane;
                 float* q_lh = g.plane + (int64_t)(gy + h4) * g.pl_stride + (int64_t)gx0 * C + lane;
-                q_hl[0] = __fmul_rn(__fsub_rn(rs0, rs1), 0.25f);
-                q_lh[0] = __fmul_rn(__fadd_rn(rd0, rd1), 0.25f);
-                q_lh[(int64_t)w4 * C] = __fmul_rn(__fsub_rn(rd0, rd1), 0.25f);
-                g.ll[(int64_t)gy * g.ll_stride + (int64_t)gx0 * C + lane] = __fmul_rn(__fadd_rn(rs0, rs1), 0.25f);   // levels == 4 here
+                store_keep(q_hl, __fmul_rn(__fsub_rn(rs0, rs1), 0.25f));
+                store_keep(q_lh, __fmul_rn(__fadd_rn(rd0, rd1), 0.25f));
+                store_keep(q_lh + (int64_t)w4 * C, __fmul_rn(__fsub_rn(rd0, rd1), 0.25f));
+                store_keep(g.ll + (int64_t)gy * g.ll_stride + (int64_t)gx0 * C + lane, __fmul_rn(__fadd_rn(rs0, rs1), 0.25f));   // levels == 4 here
             }
         }
     }
