@@ -1,5 +1,6 @@
-python -m pytest tests/test_gpu_resize_norm.py tests/test_gpu_device_api.py -x -q 2>&1 | tail -2
-python tools/bench_rows.py icons 2>&1 | grep -E "epilogue|N1|fused" | cut -c1-175
+#!/bin/bash
+# Recapture the ncu evidence of the secondary kernels under gpurun_out/ (copied to profiles/ by hand):
+#   bash tools/refresh_profiles.sh
 ncu --set full --clock-control none --import-source on -k regex:patch -s 2 -c 2 -o gpurun_out/sub6 python tools/profile_subband.py 6 > /dev/null 2>&1; ncu -i gpurun_out/sub6.ncu-rep --page raw --csv > gpurun_out/sub6_raw.csv
 ncu --set full --clock-control none --import-source on -k regex:patch -s 2 -c 2 -o gpurun_out/sub3 python tools/profile_subband.py 3 > /dev/null 2>&1; ncu -i gpurun_out/sub3.ncu-rep --page raw --csv > gpurun_out/sub3_raw.csv
 ncu --set full --clock-control none --import-source on -k regex:fir_tile -s 6 -c 3 -o gpurun_out/fir2 python tools/profile_fir.py > /dev/null 2>&1; ncu -i gpurun_out/fir2.ncu-rep --page raw --csv > gpurun_out/fir2_raw.csv
