@@ -37,6 +37,19 @@ def test_round_trip_is_exact(coder, depth):
     assert rec.shape == pad.shape and np.max(np.abs(rec - pad)) == 0.0
 
 
+@pytest.mark.parametrize("w", [769, 770, 772, 776])
+def test_round_trip_row_alignments(coder, w):
+    """Depth 1 on widths whose sub-band rows start 4-, 8- and 16-byte aligned: the inverse kernel fetches its level-1
+    details with cp.async in chunks of that size."""
+    img = gen_input("noise", w, 200, w, 3)
+    co = coder.forward(img, 1)
+    exp = ho.haar_forward(img, 1)
+    assert all(np.array_equal(a, b) for a, b in zip(co[1], exp[1])) and np.array_equal(co[0], exp[0])
+    rec = coder.inverse(co)
+    pad = ho.get_padded_copy(img, 2).astype(np.float32)
+    assert rec.shape == pad.shape and np.array_equal(rec, pad)
+
+
 def test_inverse_matches_oracle_on_arbitrary_coefficients(coder):
     rng = np.random.default_rng(7)
     ll = rng.integers(-512, 512, (5, 7, 3)).astype(np.float32) / 4
