@@ -131,9 +131,10 @@ __device__ __forceinline__ void analyse(const float (&a)[C], const float (&b)[C]
 // ------------------------------------------------------------------------------------------
 // Forward: a CTA covers a 64 x 64-pixel tile, a warp a 16-row x 32-pixel region of it, and a lane
 // one 4 x 4-pixel patch (one level-2 block; lane = 8*ly + lx inside the warp's 4 x 8 level-2 blocks).
-// Levels 1 and 2 are computed in registers, levels 3 and 4 with warp shuffles: nothing crosses a warp,
-// so there is no barrier and no shared-memory pyramid.  Sub-band rows leave through a per-warp stage
-// so that every store instruction writes 128 contiguous bytes of one row.
+// Levels 1 and 2 are computed in registers; for levels 3 and 4 the warp's level-2 LLs pass through the per-warp
+// stage and a lane owns one (block, channel) element (see below).  Nothing crosses a warp, so there is no
+// barrier and no CTA-wide pyramid.  Sub-band rows leave through the per-warp stage so that every store
+// instruction writes 128 contiguous bytes of one row.
 // ------------------------------------------------------------------------------------------
 // Store ROWS staged rows of SEG floats (row pitch PITCH in the stage) to rows of a sub-band.  One store
 // instruction covers 32 consecutive floats of one row (or 32/SEG whole rows when SEG is 8 or 16); the row pointer
@@ -326,11 +327,12 @@ forward_patch_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int 
 }
 
 // ------------------------------------------------------------------------------------------
-// Inverse, the mirror image: a lane owns one level-2 block = a 4 x 4 patch of the output.  It walks
-// down from the top fused level reading the detail coefficients of its own ancestors (lanes that share
-// an ancestor read the same address: one broadcast transaction) and keeps only its own quadrant, so no
-// level needs another lane's result: no shared-memory pyramid, no barrier, no shuffle.  Levels 2 and 1
-// are expanded in registers and the 4 x 4 x C patch leaves through the per-warp stage as whole rows.
+// Inverse, the mirror image: a lane owns one level-2 block = a 4 x 4 patch of the output.  The LL of that block is
+// walked down from the top fused level inside the warp (levels 4 and 3: one (block, channel) element per lane,
+// handed down through the per-warp stage), while the level-1 details - most of the input - are already on their
+// way to shared memory (cp.async issued first thing); every global load of the walk is issued before the first
+// wait, because a second serial trip to HBM per warp is what this kernel cannot afford.  Levels 2 and 1 are
+// expanded in registers and the 4 x 4 x C patch leaves through the per-warp stage as whole rows.  No barrier.
 // ------------------------------------------------------------------------------------------
 template <int N>
 __device__ __forceinline__ void load_run(const float* p, bool vec, bool inside, float (&v)[N]) {
