@@ -95,6 +95,73 @@ __global__ void inverse_level_f32_kernel(const float* __restrict__ ll, int64_t l
     }
 }
 
+// Two levels per launch for the levels above the fused ones (a plane at least 256 times smaller than the image, where
+// a launch costs more than its work): a thread takes one (block of the upper level, channel) = 4 x 4 values of the
+// input LL.  o1: the lower of the two levels (its LL is not stored, nobody reads it), o2: the upper one.
+__global__ void forward_level2x_f32_kernel(const float* __restrict__ in, int64_t in_stride, SubbandOut o1, SubbandOut o2) {
+    const int64_t n = (int64_t)o2.h * o2.w * o2.C;
+    const int C = o2.C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t t = i / C;
+        const int ox = (int)(t % o2.w);
+        const int oy = (int)(t / o2.w);
+        float ll1[2][2];
+#pragma unroll
+        for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+            for (int ix = 0; ix < 2; ++ix) {
+                const int by = 2 * oy + iy, bx = 2 * ox + ix;                   // block of the lower level
+                const float* p = in + (int64_t)(2 * by) * in_stride + (int64_t)(2 * bx) * C + c;
+                const float a = p[0], b = p[C], cc = p[in_stride], d = p[in_stride + C];
+                const float rs0 = __fadd_rn(a, cc), rs1 = __fadd_rn(b, d), rd0 = __fsub_rn(a, cc), rd1 = __fsub_rn(b, d);
+                ll1[iy][ix] = __fmul_rn(__fadd_rn(rs0, rs1), 0.25f);
+                const int64_t e = (int64_t)bx * C + c;
+                o1.plane[(int64_t)by * o1.pl_stride + (int64_t)o1.w * C + e] = __fmul_rn(__fsub_rn(rs0, rs1), 0.25f);
+                o1.plane[(int64_t)(by + o1.h) * o1.pl_stride + e] = __fmul_rn(__fadd_rn(rd0, rd1), 0.25f);
+                o1.plane[(int64_t)(by + o1.h) * o1.pl_stride + (int64_t)o1.w * C + e] = __fmul_rn(__fsub_rn(rd0, rd1), 0.25f);
+            }
+        analyse_store(o2, oy, ox, c, ll1[0][0], ll1[0][1], ll1[1][0], ll1[1][1]);
+    }
+}
+
+// Two synthesis levels per launch: LL_l (h x w) + details of levels l and l - 1 -> LL_{l-2} (4h x 4w).
+__global__ void inverse_level2x_f32_kernel(const float* __restrict__ ll, int64_t ll_stride, const float* __restrict__ plane,
+                                           int64_t pl_stride, float* __restrict__ out, int64_t out_stride, int h, int w, int C) {
+    const int64_t n = (int64_t)h * w * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t t = i / C;
+        const int ox = (int)(t % w);
+        const int oy = (int)(t / w);
+        float ll1[2][2];
+        {
+            const int64_t e = (int64_t)ox * C + c;
+            const float vll = ll[(int64_t)oy * ll_stride + e];
+            const float vhl = plane[(int64_t)oy * pl_stride + (int64_t)w * C + e];
+            const float vlh = plane[(int64_t)(oy + h) * pl_stride + e];
+            const float vhh = plane[(int64_t)(oy + h) * pl_stride + (int64_t)w * C + e];
+            const float s0 = __fadd_rn(vll, vhl), s1 = __fsub_rn(vll, vhl), d0 = __fadd_rn(vlh, vhh), d1 = __fsub_rn(vlh, vhh);
+            ll1[0][0] = __fadd_rn(s0, d0); ll1[0][1] = __fadd_rn(s1, d1); ll1[1][0] = __fsub_rn(s0, d0); ll1[1][1] = __fsub_rn(s1, d1);
+        }
+        const int h1 = 2 * h, w1 = 2 * w;
+#pragma unroll
+        for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+            for (int ix = 0; ix < 2; ++ix) {
+                const int by = 2 * oy + iy, bx = 2 * ox + ix;
+                const int64_t e = (int64_t)bx * C + c;
+                const float vll = ll1[iy][ix];
+                const float vhl = plane[(int64_t)by * pl_stride + (int64_t)w1 * C + e];
+                const float vlh = plane[(int64_t)(by + h1) * pl_stride + e];
+                const float vhh = plane[(int64_t)(by + h1) * pl_stride + (int64_t)w1 * C + e];
+                const float s0 = __fadd_rn(vll, vhl), s1 = __fsub_rn(vll, vhl), d0 = __fadd_rn(vlh, vhh), d1 = __fsub_rn(vlh, vhh);
+                float* q = out + (int64_t)(2 * by) * out_stride + (int64_t)(2 * bx) * C + c;
+                q[0] = __fadd_rn(s0, d0); q[C] = __fadd_rn(s1, d1); q[out_stride] = __fsub_rn(s0, d0); q[out_stride + C] = __fsub_rn(s1, d1);
+            }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Fused kernels: levels 1..min(depth, 4) of one 64 x 64-pixel tile in one pass (the per-level
 // kernels above finish depths > 4 on a plane that is 256 times smaller).  Forward: the uint8 tile is
@@ -609,7 +676,22 @@ cudaError_t launch_forward(const uint8_t* d_src, int64_t pitch, int H, int W, in
         SubbandOut o;
         o.h = Hp >> l; o.w = Wp >> l; o.C = C;
         o.plane = d_coeffs; o.pl_stride = pl_stride;
+        if (first > kFusedLevels && l + 1 <= depth) {
+            // above the fused levels: two levels per launch (the planes are tiny, both scratch buffers hold any of them)
+            SubbandOut o2 = o;
+            o2.h = Hp >> (l + 1); o2.w = Wp >> (l + 1);
+            if (l + 1 == depth) { o2.ll = d_coeffs; o2.ll_stride = pl_stride; }
+            else { o2.ll = (in == workA) ? workB : workA; o2.ll_stride = (int64_t)o2.w * C; }
+            o.ll = nullptr; o.ll_stride = 0;
+            forward_level2x_f32_kernel<<<grid_for((int64_t)o2.h * o2.w * C), 256, 0, stream>>>(in, in_stride, o, o2);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            in = o2.ll; in_stride = o2.ll_stride;
+            ++l;
+            continue;
+        }
         if (l == depth) { o.ll = d_coeffs; o.ll_stride = pl_stride; }
+        else if (first > kFusedLevels) { o.ll = (in == workA) ? workB : workA; o.ll_stride = (int64_t)o.w * C; }
         else { o.ll = (l & 1) ? workA : workB; o.ll_stride = (int64_t)o.w * C; }
         const int64_t n = (int64_t)o.h * o.w * C;
         if (l == 1) forward_level1_u8_kernel<<<grid_for(n), 256, 0, stream>>>(d_src, pitch, H, W, border_type, border_const, o);
@@ -633,10 +715,22 @@ cudaError_t launch_inverse(const float* d_coeffs, int Hp, int Wp, int C, int dep
     // levels depth .. fused_levels+1 one by one (only when depth > kFusedLevels or C > 4)
     for (int l = depth; l > fused_levels; --l) {
         const int h = Hp >> l, w = Wp >> l;
+        const int64_t n = (int64_t)h * w * C;
+        if (fused_levels == kFusedLevels && l - 1 > fused_levels) {
+            // above the fused levels: two levels per launch (tiny planes: either scratch buffer holds any of them)
+            float* out = (ll == workA) ? workB : workA;
+            const int64_t out_stride = (int64_t)(4 * w) * C;
+            inverse_level2x_f32_kernel<<<grid_for(n), 256, 0, stream>>>(ll, ll_stride, d_coeffs, pl_stride, out, out_stride, h, w, C);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            ll = out; ll_stride = out_stride;
+            --l;
+            continue;
+        }
         float* out; int64_t out_stride;
         if (l == 1) { out = d_image; out_stride = pl_stride; }
+        else if (fused_levels == kFusedLevels) { out = (ll == workA) ? workB : workA; out_stride = (int64_t)(2 * w) * C; }
         else { out = ((l - 1) & 1) ? workA : workB; out_stride = (int64_t)(2 * w) * C; }
-        const int64_t n = (int64_t)h * w * C;
         inverse_level_f32_kernel<<<grid_for(n), 256, 0, stream>>>(ll, ll_stride, d_coeffs, pl_stride, out, out_stride, h, w, C);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
