@@ -2,7 +2,7 @@
 """Headline benchmark: MP/s of the multi-level Haar DWT + LL icon path (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
-    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (NumPy port)
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path (oracle/_ref)
 
 Workload (BASELINE.json configs[1]): a batch of 30 synthetic (6393, 8284, 3) uint8 images
 (8284 x 6393 px, 52.96 MP each); one STEP = every image of the batch -> its six icons at depths
@@ -50,16 +50,31 @@ def workload_config(n_gpus: int) -> dict:
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the NumPy port of the reference (oracle/haar_oracle.py)
+# reference arm / cpu baseline: the UNMODIFIED reference HaarCoder staged under oracle/_ref
+# (wicca/wavelet_coder.py:50-67, padding by cv2.copyMakeBorder, wicca/data_loader.py:116-117);
+# the NumPy port of oracle/haar_oracle.py only when that import fails.  Always full 6393 x 8284 images.
 # ----------------------------------------------------------------------------------------------
-def _cpu_sample(job) -> float:
-    """Six get_small_copy-equivalents (depths 1..6) on one synthetic (rows, 8284, 3) image; seconds."""
-    seed, rows = job
-    from oracle import haar_oracle as ho
-    img = ho.synthetic_image(seed, rows, W, CH)
+_CPU_IMAGES: list = []          # filled before the worker pool forks (copy-on-write, read only)
+_CPU_CODER = None
+
+
+def reference_coder():
+    """(callable get_small_copy(image, depth), kind, description)."""
+    try:
+        from oracle import ref_loader
+        cls, _ = ref_loader.load_haar_coder()
+        return cls().get_small_copy, "reference", ("oracle/_ref: the unmodified wicca/wavelet_coder.py HaarCoder.get_small_copy "
+                                                   "(validate_image, cv2.copyMakeBorder padding, float32 NumPy levels)")
+    except Exception as exc:  # noqa: BLE001
+        from oracle import haar_oracle as ho
+        return ho.haar_icon_fp32, "port", f"oracle.haar_icon_fp32, NumPy restatement of wavelet_coder.py:50-67 (oracle/_ref unavailable: {exc})"
+
+
+def _cpu_task(job) -> float:
+    """One get_small_copy(image, depth) of the reference on one full-size image; seconds."""
+    idx, depth = job
     t0 = time.perf_counter()
-    for d in DEPTHS:
-        ho.haar_icon_fp32(img, d)
+    _CPU_CODER(_CPU_IMAGES[idx], depth)
     return time.perf_counter() - t0
 
 
@@ -71,53 +86,64 @@ def host_cores() -> int:
 
 
 def cpu_baseline_single(budget_images: int = 2) -> dict:
-    """1 core, bounded sample: `budget_images` full-size images x 6 depths (about 6 s per image)."""
-    secs = [_cpu_sample((i, H)) for i in range(budget_images)]
+    """1 core (the reference is single-threaded), bounded sample: `budget_images` full-size images x depths 1-6."""
+    from oracle import haar_oracle as ho
+    fn, kind, what = reference_coder()
+    secs = []
+    for i in range(budget_images):
+        img = ho.synthetic_image(i, H, W, CH)
+        t0 = time.perf_counter()
+        for d in DEPTHS:
+            fn(img, d)
+        secs.append(time.perf_counter() - t0)
     best = min(secs)
-    return {"value": MP_PER_IMAGE / best, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{budget_images} image(s) of {H}x{W}x3 x depths 1-6 through oracle.haar_icon_fp32 (NumPy "
-                      f"restatement of wavelet_coder.py:50-67), best image: {best:.2f} s"}
+    return {"value": MP_PER_IMAGE / best, "unit": UNIT, "cores": 1, "kind": kind, "source": what,
+            "sample": f"{budget_images} image(s) of {H}x{W}x3, get_small_copy at each of depths 1-6 (six calls per image, "
+                      f"as classifying_tools.py:546-551 does), best image: {best:.2f} s"}
 
 
 def run_reference(args) -> int:
-    """bench.py --impl reference: the reference's CPU algorithm (NumPy port) on all host cores, one
-    image per worker process per step.  Each step is a bounded sample: full-width images whose
-    height is sized so that the whole --steps/--warmup run stays within a few minutes."""
+    """bench.py --impl reference: the reference's own CPU implementation on every host core.  One step = M full-size
+    (6393, 8284, 3) images x depths 1-6 = 6M get_small_copy calls spread over one worker process per core; M is the
+    bounded sample (a step of the GPU arm is 30 such images), sized so that the run ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import multiprocessing as mp
+    from oracle import haar_oracle as ho
+    global _CPU_CODER
+    _CPU_CODER, kind, what = reference_coder()
     cores = host_cores()
-    workers = max(1, min(cores, 64))            # each worker holds up to ~1 GB of NumPy temporaries
-    budget_s = float(os.environ.get("WICCA_REF_BUDGET_S", "150"))
+    workers = max(1, min(cores, 64))
+    budget_s = float(os.environ.get("WICCA_REF_BUDGET_S", "200"))
+    m_images = int(os.environ.get("WICCA_REF_IMAGES", "0")) or max(1, workers // 2)      # 3 calls per worker and step
+    for i in range(m_images):
+        _CPU_IMAGES.append(ho.synthetic_image(i, H, W, CH))
     ctx = mp.get_context("fork")
     with ctx.Pool(workers) as pool:
-        def step(base, rows):
+        def step(m):
+            jobs = [(i, d) for d in DEPTHS for i in range(m)]
             t0 = time.perf_counter()
-            pool.map(_cpu_sample, [(base + i, rows) for i in range(workers)])
+            pool.map(_cpu_task, jobs, chunksize=1)
             return time.perf_counter() - t0
-        step(0, 64)                                                    # spin the pool up
-        cal_rows = 512
-        cal = step(100, cal_rows)                                      # aggregate rate with every core busy
-        per_step = budget_s / max(1, args.steps + args.warmup)
-        rows = int(cal_rows * per_step / max(cal, 1e-6))
-        rows = max(64, min(H, rows // 64 * 64))
-        if rows >= H - 64:
-            rows = H
-        for w in range(args.warmup):
-            step(1000 * (w + 1), rows)
-        times = [step(100_000 + 1000 * k, rows) for k in range(args.steps)]
+        cal = step(m_images)                                           # spins the pool up, and calibrates
+        n_steps = max(1, args.steps + args.warmup)
+        if cal * n_steps > budget_s and not os.environ.get("WICCA_REF_IMAGES"):
+            m_images = max(1, min(m_images, int(m_images * budget_s / (cal * n_steps))))
+        for _ in range(args.warmup):
+            step(m_images)
+        times = [step(m_images) for _ in range(args.steps)]
     total = sum(times)
-    mp_per_step = workers * rows * W / 1e6
-    value = args.steps * mp_per_step / total
+    value = args.steps * m_images * MP_PER_IMAGE / total
+    used = min(workers, 6 * m_images)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
-                             "sample": f"each step: {workers} images of {rows}x{W}x3 (one per worker process) x depths "
-                                       "1-6 through oracle.haar_icon_fp32, the NumPy restatement of the reference "
-                                       "(the reference itself is Python; /root/reference does not exist on the GPU box)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "source": what,
+                             "sample": f"each step: {m_images} full-size images of {H}x{W}x3 x depths 1-6 = {6 * m_images} "
+                                       f"get_small_copy calls over {workers} worker processes (one per host core); "
+                                       "never cropped - a step of the GPU arm is 30 such images"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     return 0
@@ -174,6 +200,256 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+def _pinned(lib, _capi, nbytes: int, device: int):
+    """(ctypes pointer, flat uint8 view) of page-locked memory placed next to `device`."""
+    p = C.c_void_p()
+    _capi.check(lib.wicca_host_alloc_near(C.byref(p), max(1, nbytes), device), "wicca_host_alloc_near")
+    return p, np.ctypeslib.as_array((C.c_uint8 * max(1, nbytes)).from_address(p.value))
+
+
+def _peak():
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "6650 GB/s (of fallback)"
+
+
+def host_link_ceiling(torch, dist, dev, world, host_flat, out_flat, h2d_bytes, d2h_bytes, barrier):
+    """What the host side of the PCIe links gives this job, measured with plain large copies on every rank at once:
+    (i) H2D only, (ii) one e2e step's traffic - h2d_bytes up on one stream, d2h_bytes down on another - with no
+    kernels, no 2-D pitch, no per-image synchronisation.  An e2e step cannot finish faster than (ii)."""
+    n_up = max(1, round(h2d_bytes / host_flat.numel()))
+    n_down = max(1, round(d2h_bytes / out_flat.numel()))
+    d_up = torch.empty(host_flat.numel(), dtype=torch.uint8, device=dev)
+    d_down = torch.zeros(out_flat.numel(), dtype=torch.uint8, device=dev)
+    s_up, s_down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def run(up: bool, down: bool) -> float:
+        barrier()
+        t0 = time.perf_counter()
+        if up:
+            with torch.cuda.stream(s_up):
+                for _ in range(n_up):
+                    d_up.copy_(host_flat, non_blocking=True)
+        if down:
+            with torch.cuda.stream(s_down):
+                for _ in range(n_down):
+                    out_flat.copy_(d_down, non_blocking=True)
+        s_up.synchronize(); s_down.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item())
+
+    run(True, True)                                   # warm-up
+    t_up = min(run(True, False) for _ in range(2))
+    t_both = min(run(True, True) for _ in range(2))
+    up_b, down_b = n_up * host_flat.numel(), n_down * out_flat.numel()
+    del d_up, d_down
+    return {"h2d_only_GBps": world * up_b / t_up / 1e9, "step_traffic_s": t_both,
+            "h2d_GBps_with_d2h": world * up_b / t_both / 1e9, "d2h_GBps_with_h2d": world * down_b / t_both / 1e9,
+            "method": f"every rank at once, page-locked buffers: {n_up} x {host_flat.numel() / 1e6:.0f} MB cudaMemcpyAsync up on one "
+                      f"stream + {n_down} x {out_flat.numel() / 1e6:.0f} MB down on another (the byte counts of one e2e step), max over ranks"}
+
+
+def extra_subbands(torch, lib, _capi, dev, local, stream, all_max, peak):
+    """configs[2]: full forward + inverse sub-band transform of a 16384 x 16384 x 3 image, depths 1 / 3 / 6."""
+    from wicca_b200.plan import pitch_bytes
+    S = 16384
+    pitch = pitch_bytes(S, 3)
+    g = torch.Generator(device=dev); g.manual_seed(7)
+    img = torch.randint(0, 256, (S, pitch), dtype=torch.uint8, device=dev, generator=g)
+    coeffs = torch.empty((S, S, 3), dtype=torch.float32, device=dev)
+    work = torch.empty((S * S * 3 * 5 // 16 + 64,), dtype=torch.float32, device=dev)
+    rec = torch.empty((S, S, 3), dtype=torch.float32, device=dev)
+    rows, px = [], S * S
+
+    def timed(fn, reps=3, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return all_max(e0.elapsed_time(e1) / reps)
+
+    for depth in (1, 3, 6):
+        def fwd():
+            _capi.check(lib.wicca_haar_forward_dev(img.data_ptr(), S, S, 3, pitch, depth, 1, 0.0, coeffs.data_ptr(),
+                                                   work.data_ptr(), local, C.c_void_p(stream)), "forward_dev")
+
+        def inv():
+            _capi.check(lib.wicca_haar_inverse_dev(coeffs.data_ptr(), S, S, 3, depth, rec.data_ptr(), work.data_ptr(), local,
+                                                   C.c_void_p(stream)), "inverse_dev")
+        ms_f, ms_i = timed(fwd), timed(inv)
+        coeffs.zero_(); rec.zero_()
+        fwd(); inv(); torch.cuda.synchronize()
+        err = 0.0
+        for r0 in range(0, S, 2048):                   # max |rec - x| over the whole image, in bands (no 3 GB temporary)
+            band = rec[r0:r0 + 2048] - img[r0:r0 + 2048, : S * 3].reshape(-1, S, 3).float()
+            err = max(err, float(band.abs().max().item()))
+        rows.append({"depth": depth, "forward_ms": ms_f, "inverse_ms": ms_i, "max_abs_rec_minus_x": err,
+                     "forward_frac": 15 * px / ms_f / 1e6 / peak, "inverse_frac": 24 * px / ms_i / 1e6 / peak,
+                     "forward_MP_per_s": px / ms_f / 1e3, "inverse_MP_per_s": px / ms_i / 1e3})
+    del img, coeffs, work, rec
+    torch.cuda.empty_cache()
+    return {"workload": "configs[2]: 16384x16384x3 u8 -> float32 Mallat plane (all sub-bands kept) -> float32 image, per GPU",
+            "algorithmic_bytes_per_px": {"forward": 15, "inverse": 24}, "rows": rows}
+
+
+def extra_epilogue(torch, plan_cls, imgs, pitch, local, stream, dev, all_max, peak):
+    """configs[3]: icon + cv2.resize(INTER_AREA) to 224 / 331 + preprocess_input('tf'), batches of 30 from the
+    resident images; the icon never leaves the GPU (wicca_plan_resize_norm after wicca_plan_launch)."""
+    n = len(imgs)
+    rows = []
+
+    def timed(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return all_max(e0.elapsed_time(e1) / reps)
+
+    for depth in (1, 3):
+        plan = plan_cls(local, [t.data_ptr() for t in imgs], [H] * n, [W] * n, [pitch] * n, [depth])
+        info = plan.info()
+        _, ih, iw, _ = plan.icon_info(0, 0)
+        for target in (224, 331):
+            out = torch.empty((n, target, target, 3), dtype=torch.float32, device=dev)
+            ms_all = timed(lambda: (plan.launch(stream), plan.resize_norm(0, target, target, 1, out.data_ptr(), 0, stream)))
+            ms_epi = timed(lambda: plan.resize_norm(0, target, target, 1, out.data_ptr(), 0, stream))
+            byt_epi = n * (ih * iw * 3 + target * target * 3 * 4)
+            byt_all = info["bytes_read"] + n * target * target * 3 * 4      # the icon stays on the GPU: not counted
+            rows.append({"depth": depth, "target": target, "icon_hw": [ih, iw], "icon_plus_epilogue_ms": ms_all,
+                         "epilogue_ms": ms_epi, "epilogue_frac": byt_epi / ms_epi / 1e6 / peak,
+                         "icon_plus_epilogue_frac": byt_all / ms_all / 1e6 / peak,
+                         "MP_per_s": n * MP_PER_IMAGE / ms_all * 1e3, "batches_of_30_per_s": 1e3 / ms_all})
+            del out
+        plan.close()
+    return {"workload": "configs[3]: 30 resident 8284x6393x3 images -> depth-d icon -> INTER_AREA 224 / 331 -> preprocess_input "
+                        "'tf' -> (30, t, t, 3) float32, per GPU", "rows": rows}
+
+
+def extra_sharded(torch, dist, lib, _capi, local, rank, world, barrier):
+    """configs[4]: 130 ragged ~52 MP host images, depths 2-6, STRONG-scaled over the ranks (image i -> rank i % world,
+    classifying_tools.py:312-321), icons gathered on the host through the shared-memory arena; wall clock."""
+    from wicca_b200 import HaarCoder
+    from wicca_b200.sharding import IconArena, shard_indices, sharded_small_copies
+    n, distinct, depths = 130, 13, [2, 3, 4, 5, 6]
+    rng = np.random.default_rng(0)
+    shapes = [(H + int(rng.integers(-256, 257)), W + int(rng.integers(-256, 257)), 3) for _ in range(distinct)]
+    mine = shard_indices(n, rank, world)
+    need = sorted({i % distinct for i in mine} | (set(range(distinct)) if rank == 0 else set()))
+    ptrs, arrs = {}, {}
+    for k in need:                                   # image i is distinct image i % 13 (seeded by k: every rank agrees)
+        h, w, _ = shapes[k]
+        p, flat = _pinned(lib, _capi, h * w * 3, local)
+        a = flat[: h * w * 3].reshape(h, w, 3)
+        a[:] = np.random.default_rng(1000 + k).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ptrs[k], arrs[k] = p, a
+    coder = HaarCoder()
+    coder.device = local
+    transform = lambda images, ds, out=None: coder.get_small_copies_batch(images, ds, devices=[local], out=out)  # noqa: E731
+    arena = IconArena([shapes[i % distinct] for i in range(n)], depths)
+    get = lambda i: arrs[i % distinct]  # noqa: E731
+    sharded_small_copies(get, min(n, 2 * world), depths, transform, arena=arena)        # warm-up: contexts, buffers
+    times = []
+    for _ in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        icons = sharded_small_copies(get, n, depths, transform, arena=arena)            # ends with the gather barrier
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        times.append(float(dt.item()))
+    res = None
+    if rank == 0:
+        # order / bit equality: everything the ranks gathered against this rank's own single-GPU run, and a sample
+        # against the C oracle (checker only, outside the timed region)
+        from oracle import c_oracle
+        single = coder.get_small_copies_batch([get(i) for i in range(n)], depths, devices=[local])
+        equal = all(np.array_equal(a, b) for ra, rb in zip(icons, single) for a, b in zip(ra, rb))
+        for i in (0, 57, 129):
+            exp = c_oracle.haar_icons_multi(get(i), depths)
+            equal = equal and all(np.array_equal(a, b) for a, b in zip(icons[i], exp))
+        mp_total = sum(shapes[i % distinct][0] * shapes[i % distinct][1] for i in range(n)) / 1e6
+        best = min(times)
+        res = {"workload": "configs[4]: 130 ragged ~52 MP page-locked host images (13 distinct shapes, H/W = 6393/8284 +- 256), "
+                           "depths 2-6, image i on rank i % N, double-buffered H2D, icons gathered into a shared-memory arena",
+               "scaling": "strong", "n_gpus": world, "seconds": best, "MP_per_s": mp_total / best,
+               "h2d_GBps": mp_total * 3e6 / best / 1e9, "gathered_equals_single_gpu_and_oracle": bool(equal)}
+        del single
+    del icons
+    arena.close()
+    for p in ptrs.values():
+        lib.wicca_host_free(p)
+    return res
+
+
+def extra_jpeg(torch, dist, lib, _capi, local, rank, world, barrier):
+    """Row N2 as the e2e branch that is not bound by the host side of PCIe: 30 baseline JPEG files of 53 MP per GPU ->
+    icons at depths 1-6 on the host (load_image + get_small_copy, data_loader.py:53-58 + wavelet_coder.py:50-67); only
+    the 12 MB files cross the link."""
+    try:
+        import cv2
+    except Exception as exc:  # noqa: BLE001
+        return {"skipped": f"cv2 (the encoder of the synthetic files) not importable: {exc}"} if rank == 0 else None
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    img = np.empty((H, W, 3), np.float32)
+    for c in range(3):
+        img[:, :, c] = 128 + 90 * np.sin(xx / (37.0 + 9 * c) + c) + 70 * np.cos(yy / (23.0 + 5 * c) - c)
+    del yy, xx
+    img += np.random.default_rng(3).normal(0, 6, (H, W, 1)).astype(np.float32)
+    img = np.clip(img, 0, 255).astype(np.uint8)
+    ok, enc = cv2.imencode(".jpg", img[:, :, ::-1], [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
+                                                    cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420])
+    data = bytes(enc)
+    n = BATCH
+    nd = len(DEPTHS)
+    outs = [[np.empty((lib.wicca_icon_dim(H, d), lib.wicca_icon_dim(W, d), 3), np.uint8) for d in DEPTHS] for _ in range(n)]
+    datas = (C.c_void_p * n)(*[C.cast(C.c_char_p(data), C.c_void_p).value] * n)
+    lens = (C.c_size_t * n)(*[len(data)] * n)
+    dsts = (C.c_void_p * (n * nd))(*[o.ctypes.data for per in outs for o in per])
+    threads = max(2, min(16, host_cores() // world))
+    hm = C.c_float()
+
+    def step():
+        _capi.check(lib.wicca_batch_icons_from_jpeg(datas, lens, n, (C.c_int * nd)(*DEPTHS), nd, 1, 0.0, dsts,
+                                                    (C.c_int * 1)(local), 1, threads, C.byref(hm)), "wicca_batch_icons_from_jpeg")
+    step()
+    times = []
+    for _ in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        step()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        times.append(float(dt.item()))
+    if rank != 0:
+        return None
+    from oracle import c_oracle
+    ref = cv2.cvtColor(cv2.imdecode(enc, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)      # what load_image returns
+    exp = c_oracle.haar_icons_multi(ref, DEPTHS)
+    equal = all(np.array_equal(a, b) for k in (0, n - 1) for a, b in zip(outs[k], exp))
+    best = min(times)
+    return {"value": world * n * MP_PER_IMAGE / best, "unit": UNIT, "seconds_per_step": best,
+            "h2d_bytes_per_step": n * len(data), "d2h_bytes_per_step": n * sum(o.nbytes for o in outs[0]),
+            "workload": f"30 JPEG files per GPU ({H}x{W}, q90 4:2:0, {len(data) / 1e6:.1f} MB each, photo-like synthetic content) -> "
+                        f"icons depths 1-6 on the host; Huffman decoding, IDCT, colour and icons on the GPU; {threads} host "
+                        "threads per rank strip the byte stuffing",
+            "equals_cv2_imdecode_then_oracle": bool(equal), "api": "wicca_batch_icons_from_jpeg"}
+
+
 def run_ours(args) -> int:
     import torch
     import torch.distributed as dist
@@ -190,14 +466,22 @@ def run_ours(args) -> int:
     dev = torch.device(f"cuda:{local}")
     distributed = world > 1
     if distributed:
-        if not os.environ.get("WICCA_KEEP_NCCL_DEBUG"):
-            os.environ.pop("NCCL_DEBUG", None)      # NCCL prints its banner on stdout; keep stdout to the one JSON line
+        # NCCL writes its NCCL_DEBUG lines to stdout by default; stdout carries the one JSON line, so they go to stderr
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if distributed:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def all_max(x: float) -> float:
+        if not distributed:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     lib = _capi.load()
     pitch = pitch_bytes(W, CH)
@@ -209,6 +493,7 @@ def run_ours(args) -> int:
     info = plan.info()
     alg_bytes = info["bytes_read"] + info["bytes_written"]
     stream = torch.cuda.current_stream().cuda_stream
+    peak, peak_src = _peak()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -226,37 +511,29 @@ def run_ours(args) -> int:
     e1.record()
     barrier()
     t_clk1 = time.perf_counter()
-    ms = e0.elapsed_time(e1)
-    ms_t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if distributed:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms_max = float(ms_t.item())
-    ms_per_step = ms_max / args.steps
+    ms_per_step = all_max(e0.elapsed_time(e1)) / args.steps
     value = world * BATCH * MP_PER_IMAGE / (ms_per_step / 1e3)
 
     # ---- end to end through the C ABI with host buffers -------------------------------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    n_host = min(BATCH, args.e2e_host_images)           # distinct pinned host images, cycled
-    host_ptrs, host_arrays = [], []
+    n_host = min(BATCH, args.e2e_host_images)           # distinct page-locked host images, cycled through the batch
+    host_ptrs, host_arrays, host_flats = [], [], []
     rng = np.random.default_rng(99 + rank)
     for i in range(n_host):
-        p = C.c_void_p()
-        _capi.check(lib.wicca_host_alloc_near(C.byref(p), H * W * CH, local), "wicca_host_alloc_near")
-        arr = np.ctypeslib.as_array((C.c_uint8 * (H * W * CH)).from_address(p.value)).reshape(H, W, CH)
+        p, flat = _pinned(lib, _capi, H * W * CH, local)
+        arr = flat.reshape(H, W, CH)
         arr[:] = rng.integers(0, 256, (H, W, CH), dtype=np.uint8)
-        host_ptrs.append(p)
-        host_arrays.append(arr)
+        host_ptrs.append(p); host_arrays.append(arr); host_flats.append(flat)
     icon_shapes = [(-(-H // (1 << d)), -(-W // (1 << d)), CH) for d in DEPTHS]
-    out_ptrs = []
-
-    def pinned_array(shape):
-        n = int(np.prod(shape))
-        q = C.c_void_p()
-        _capi.check(lib.wicca_host_alloc_near(C.byref(q), n, local), "wicca_host_alloc_near")
+    icon_sizes = [int(np.prod(s)) for s in icon_shapes]
+    out_ptrs, outs = [], []
+    for _ in range(BATCH):                              # one page-locked block per image, the six icons back to back
+        q, flat = _pinned(lib, _capi, sum(icon_sizes), local)
         out_ptrs.append(q)
-        return np.ctypeslib.as_array((C.c_uint8 * n).from_address(q.value)).reshape(shape)
-
-    outs = [[pinned_array(s) for s in icon_shapes] for _ in range(BATCH)]
+        row, off = [], 0
+        for s, nb in zip(icon_shapes, icon_sizes):
+            row.append(flat[off:off + nb].reshape(s)); off += nb
+        outs.append(row)
     nd = len(DEPTHS)
     srcs = (C.c_void_p * BATCH)(*[host_ptrs[i % n_host].value for i in range(BATCH)])
     hs = (C.c_int * BATCH)(*[H] * BATCH)
@@ -277,32 +554,50 @@ def run_ours(args) -> int:
     for _ in range(e2e_steps):
         e2e_step()
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if distributed:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_t.item())
+    e2e_s = all_max(time.perf_counter() - t0)
     e2e_value = world * BATCH * e2e_steps * MP_PER_IMAGE / e2e_s
     h2d_bytes = BATCH * H * W * CH
-    d2h_bytes = BATCH * sum(int(np.prod(s)) for s in icon_shapes)
+    d2h_bytes = BATCH * sum(icon_sizes)
     stage_ms = tim.as_dict()                               # sums over the 30 images of the last step
 
-    # parity spot check of the e2e outputs against the device-resident plan (same kernel, other data path)
+    # the host's measured limit for the same traffic, all ranks at once
+    out_flat_t = torch.from_numpy(np.ctypeslib.as_array((C.c_uint8 * sum(icon_sizes)).from_address(out_ptrs[0].value)))
+    ceiling = host_link_ceiling(torch, dist, dev, world, torch.from_numpy(host_flats[0]), out_flat_t, h2d_bytes, d2h_bytes, barrier)
+    ceiling_value = world * BATCH * MP_PER_IMAGE / ceiling["step_traffic_s"]
+
+    # parity of EVERY icon of the last e2e step (30 images x 6 depths) against the C oracle, outside the timed region
+    e2e_checked = 0
     if rank == 0:
-        from oracle import haar_oracle as ho  # noqa: PLC0415  (checker only, outside every timed region)
-        chk = ho.haar_icon_blocksum(host_arrays[0], 6)
-        assert np.array_equal(outs[0][5], chk), "e2e icon mismatch vs oracle"
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import c_oracle  # noqa: PLC0415  (checker only)
+        with ThreadPoolExecutor(min(8, n_host)) as ex:
+            expected = list(ex.map(lambda a: c_oracle.haar_icons_multi(a, DEPTHS), host_arrays))
+        for i in range(BATCH):
+            for got, exp in zip(outs[i], expected[i % n_host]):
+                assert got.shape == exp.shape and np.array_equal(got, exp), f"e2e icon mismatch vs oracle (image {i})"
+                e2e_checked += 1
+        del expected
+    for p in host_ptrs + out_ptrs:
+        lib.wicca_host_free(p)
+    del host_arrays, host_flats, outs, out_flat_t
+    t_clk2 = time.perf_counter()
+
+    # ---- the other configs of BASELINE.json, bounded (about 20 s) ---------------------------
+    extra = {}
+    if not args.no_extra:
+        for name, fn in (("configs3_icon_resize_norm", lambda: extra_epilogue(torch, IconPlan, imgs, pitch, local, stream, dev, all_max, peak)),):
+            extra[name] = fn()
+    plan.close()
+    del imgs
+    torch.cuda.empty_cache()
+    if not args.no_extra:
+        extra["configs2_subband_round_trip"] = extra_subbands(torch, lib, _capi, dev, local, stream, all_max, peak)
+        extra["configs4_sharded_ragged_batch"] = extra_sharded(torch, dist, lib, _capi, local, rank, world, barrier)
+    e2e_jpeg = None if args.no_extra else extra_jpeg(torch, dist, lib, _capi, local, rank, world, barrier)
 
     sampler.stop()
     line = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-        except Exception:  # noqa: BLE001
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
         achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
         traffic = None
         try:
@@ -322,17 +617,21 @@ def run_ours(args) -> int:
                          "note": "achieved = (30 x H*W*3 read + sum of the six icons written) / mean launch time, "
                                  "K launches back to back between two CUDA events on the launch stream"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                    "api": "wicca_batch_icons_u8 (pinned host images and icons, two upload slots per GPU so H2D(i+1) overlaps kernel/D2H(i))",
+                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "distinct_host_images": n_host,
+                    "api": "wicca_batch_icons_u8 (page-locked host images and icons; upload slots per GPU so H2D(i+1) overlaps kernel/D2H(i))",
                     "stage_ms_sum_over_images": stage_ms,
-                    "h2d_GBps": h2d_bytes / max(stage_ms["h2d_ms"], 1e-9) / 1e6},
-            "clocks": sampler.summary(t_clk0, t_clk1 + e2e_s + 5.0),
+                    "h2d_GBps": world * h2d_bytes * e2e_steps / e2e_s / 1e9,
+                    "host_ceiling_GBps": ceiling["h2d_GBps_with_d2h"], "host_ceiling_MP_per_s": ceiling_value,
+                    "frac_of_ceiling": e2e_value / ceiling_value, "host_ceiling": ceiling,
+                    "icons_checked_against_oracle": e2e_checked},
+            "clocks": sampler.summary(t_clk0, t_clk2),
         }
+        if e2e_jpeg is not None:
+            line["e2e_jpeg"] = e2e_jpeg
+        if extra:
+            line["extra"] = extra
         if cpu is not None:
             line["cpu_baseline"] = cpu
-    for p in host_ptrs + out_ptrs:
-        lib.wicca_host_free(p)
-    plan.close()
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
@@ -350,6 +649,7 @@ def main() -> int:
     ap.add_argument("--e2e-steps", type=int, default=3, help="end-to-end (host buffer) steps, each ~4.8 GB of H2D")
     ap.add_argument("--e2e-host-images", type=int, default=10, help="distinct pinned host images cycled through the batch")
     ap.add_argument("--cpu-images", type=int, default=2, help="images of the bounded cpu_baseline sample (0 = skip)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[2..4] / e2e_jpeg block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -89,9 +89,15 @@ WICCA_API int     wicca_icon_dim(int n, int depth);
 /* Page-locked host memory for inputs/outputs that should be DMA'd without a bounce copy. */
 WICCA_API int wicca_host_alloc(void** ptr, size_t bytes);
 /* Same, with the pages placed on the NUMA node of `device` (its PCIe root's local CPUs, from sysfs),
- * so the DMA does not cross the socket interconnect.  device < 0: no placement. */
+ * so the DMA does not cross the socket interconnect: by first touch when the process may run there, else by
+ * mmap + mbind + cudaHostRegister (memory policy needs no CPU on the node).  device < 0: no placement.
+ * WICCA_HOST_ALLOC=cuda disables the placement. */
 WICCA_API int wicca_host_alloc_near(void** ptr, size_t bytes, int device);
 WICCA_API int wicca_host_free(void* ptr);
+/* Page-lock memory the caller owns (e.g. a POSIX shared-memory segment that several single-GPU processes gather
+ * their icons into - wicca_b200/sharding.py), so results are DMA'd straight into it.  Undo with _unregister. */
+WICCA_API int wicca_host_register(void* ptr, size_t bytes);
+WICCA_API int wicca_host_unregister(void* ptr);
 
 /* ---- HaarCoder.get_small_copy  (host buffers in, host buffers out) ----- */
 /* dst must hold wicca_icon_dim(H,depth) * wicca_icon_dim(W,depth) * C bytes (tight HWC).

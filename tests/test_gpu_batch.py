@@ -53,3 +53,43 @@ def test_pinned_host_buffers_round_trip():
     assert np.array_equal(got, ho.haar_icon_blocksum(np.array(buf), 3))
     del buf
     _capi.check(lib.wicca_host_free(p))
+
+
+def test_batch_over_every_gpu_of_the_box():
+    """The multi-GPU code path proper: image i -> GPU i % n for every GPU the box has (skips only on a
+    one-GPU box), ragged shapes, compared image by image with the single-GPU result and the oracle."""
+    ndev = _capi.load().wicca_device_count()
+    if ndev < 2:
+        pytest.skip("needs at least two GPUs")
+    coder = HaarCoder()
+    imgs = ragged_images(4 * ndev + 3, seed=9)
+    depths = [1, 2, 3, 4, 5, 6]
+    multi = coder.get_small_copies_batch(imgs, depths, devices=list(range(ndev)))
+    single = coder.get_small_copies_batch(imgs, depths, devices=[0])
+    for im, rm, rs in zip(imgs, multi, single):
+        for d, a, b in zip(depths, rm, rs):
+            assert np.array_equal(a, b) and np.array_equal(a, ho.haar_icon_blocksum(im, d)), (im.shape, d)
+    # every GPU can also be addressed on its own
+    for dev in range(ndev):
+        coder.device = dev
+        assert np.array_equal(coder.get_small_copy(imgs[dev], 3), ho.haar_icon_blocksum(imgs[dev], 3))
+
+
+def test_batch_writes_into_caller_arrays_and_registered_memory():
+    """`out=`: icons land in arrays the caller owns - here views of an IconArena segment page-locked with
+    wicca_host_register, as the one-node gather of wicca_b200/sharding.py uses them."""
+    from wicca_b200.sharding import IconArena, sharded_small_copies
+    coder = HaarCoder()
+    imgs = ragged_images(7, seed=2)
+    depths = [0, 2, 5]
+    arena = IconArena([im.shape for im in imgs], depths, pin=True)
+    out = sharded_small_copies(lambda i: imgs[i], len(imgs), depths,
+                               lambda images, ds, out=None: coder.get_small_copies_batch(images, ds, out=out), arena=arena)
+    for i, (im, row) in enumerate(zip(imgs, out)):
+        for d, ic, view in zip(depths, row, arena.views(i)):
+            assert ic.shape == view.shape and np.shares_memory(ic, view)
+            assert np.array_equal(ic, ho.haar_icon_blocksum(im, d)), (im.shape, d)
+    with pytest.raises(ValueError):
+        coder.get_small_copies_batch(imgs[:1], depths, out=[[np.empty((3, 3, 3), np.uint8)] * 3])
+    del out, row, ic, view
+    arena.close()

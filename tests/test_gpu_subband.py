@@ -103,3 +103,31 @@ def test_config3_device_resident_16384():
         crop = ref[: 64 << depth, : 64 << depth].cpu().numpy()
         assert np.array_equal(ll.astype(np.uint8), ho.haar_icon_blocksum(crop, depth)), depth
         assert n * (1 << depth) == S
+
+
+@pytest.mark.parametrize("depth", [1, 6])
+def test_every_subband_of_a_large_image_against_the_c_oracle(coder, depth):
+    """configs[2] scale: EVERY coefficient of every sub-band of an 8192 x 8192 x 3 image against the C oracle
+    (oracle/haar_oracle.c: oracle_haar_forward_f32), not just the round trip - a forward and an inverse that agree with
+    each other but mis-place a detail band at a tile seam would fail here."""
+    from oracle import c_oracle
+    from wicca_b200.wavelet_coder import list_to_mallat
+    img = gen_input("noise", 17 + depth, 8192, 8192, 3)
+    got, _ = list_to_mallat(coder.forward(img, depth))
+    exp = c_oracle.haar_forward_plane(img, depth)
+    assert got.shape == exp.shape and np.array_equal(got, exp)
+    rec = coder.inverse(coder.forward(img, depth))
+    assert np.array_equal(rec, c_oracle.haar_inverse_plane(exp, depth))
+
+
+@pytest.mark.parametrize("border", [0, 1, 2, 3, 4])
+def test_every_subband_of_a_ragged_53mp_image_all_borders(coder, border):
+    """The headline shape (6393, 8284, 3) needs padding in both axes at depth 6 (-> 6400 x 8320): all five cv2 border
+    rules, every sub-band of every level against the C oracle."""
+    from oracle import c_oracle
+    from wicca_b200.wavelet_coder import list_to_mallat
+    img = gen_input("noise", 90 + border, 6393, 8284, 3)
+    got, _ = list_to_mallat(coder.forward(img, 6, border, 201))
+    exp = c_oracle.haar_forward_plane(img, 6, border, 201)
+    assert got.shape == exp.shape == (6400, 8320, 3)
+    assert np.array_equal(got, exp)

@@ -43,6 +43,8 @@ SIGNATURES = {
     "wicca_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "wicca_host_alloc_near": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]),
     "wicca_host_free": (C.c_int, [C.c_void_p]),
+    "wicca_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "wicca_host_unregister": (C.c_int, [C.c_void_p]),
     "wicca_haar_icon_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double,
                                      C.c_void_p, C.c_int, C.POINTER(Timing)]),
     "wicca_haar_icons_multi_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, c_intp, C.c_int, C.c_int,

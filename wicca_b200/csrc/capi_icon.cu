@@ -256,23 +256,6 @@ int wicca_shutdown(void) { destroy_all_ctx(); return 0; }
 int64_t wicca_pitch_bytes(int W, int C) { return align_up((int64_t)W * C, 128); }
 int wicca_icon_dim(int n, int depth) { return icon_dim(n, depth); }
 
-int wicca_host_alloc_near(void** ptr, size_t bytes, int device) {
-    if (!ptr) return fail(WICCA_EINVAL, "ptr is NULL");
-    *ptr = nullptr;
-    int rc = check_device(device < 0 ? 0 : device);
-    if (rc) return rc;
-    // the pages are faulted in by this thread while it is bound to the GPU's own NUMA node
-    ScopedAffinity bind(device);
-    WICCA_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
-    return 0;
-}
-int wicca_host_alloc(void** ptr, size_t bytes) { return wicca_host_alloc_near(ptr, bytes, -1); }
-int wicca_host_free(void* ptr) {
-    if (!ptr) return 0;
-    WICCA_CUDA(cudaFreeHost(ptr));
-    return 0;
-}
-
 int wicca_haar_icons_multi_u8(const uint8_t* src, int H, int W, int C, int64_t src_row_stride, const int* depths,
                               int n_depths, int border_type, double border_const, uint8_t* const* dsts, int device,
                               wicca_timing* t) {

@@ -170,10 +170,13 @@ class HaarCoder(WaveletCoder):
 
     def get_small_copies_batch(self, images: Sequence[np.ndarray], transform_depths: Iterable[int],
                                border_type: int = BORDER_REPLICATE, border_constant: int = 0,
-                               devices: Sequence[int] | None = None) -> list[list[np.ndarray]]:
+                               devices: Sequence[int] | None = None,
+                               out: Sequence[Sequence[np.ndarray]] | None = None) -> list[list[np.ndarray]]:
         """Icons of many images, sharded image-by-image over ``devices`` (default: every visible
         GPU) with double-buffered uploads; ``result[i][k]`` is image ``i`` at ``depths[k]`` - the
-        per-image loop of ``classifying_tools.py:312-321`` without the Python overhead."""
+        per-image loop of ``classifying_tools.py:312-321`` without the Python overhead.
+        ``out[i][k]`` (optional): preallocated C-contiguous uint8 arrays of the icon shapes to
+        write into (e.g. views of a ``sharding.IconArena``); they are returned instead of new arrays."""
         depths = [_as_depth(d) for d in transform_depths]
         views = []
         for img in images:
@@ -193,10 +196,20 @@ class HaarCoder(WaveletCoder):
         if devices is None:
             devices = list(range(max(1, lib.wicca_device_count())))
         outs: list[list[np.ndarray]] = []
-        for v, _ in views:
+        for i, (v, _) in enumerate(views):
             h, w, _c = v.shape
-            outs.append([np.empty(((h, w) if d <= 0 else (-(-h // (1 << d)), -(-w // (1 << d)))) + (c,), np.uint8)
-                         for d in depths])
+            shapes = [((h, w) if d <= 0 else (-(-h // (1 << d)), -(-w // (1 << d)))) + (c,) for d in depths]
+            if out is None:
+                outs.append([np.empty(sh, np.uint8) for sh in shapes])
+                continue
+            row = list(out[i])
+            if len(row) != nd:
+                raise ValueError(f"out[{i}] holds {len(row)} arrays for {nd} depths")
+            for o, sh in zip(row, shapes):
+                if not isinstance(o, np.ndarray) or o.dtype != np.uint8 or o.shape != sh or not o.flags.c_contiguous \
+                        or not o.flags.writeable:
+                    raise ValueError(f"out[{i}] must hold writable C-contiguous uint8 arrays of shapes {shapes}")
+            outs.append(row)
         srcs = (C.c_void_p * n)(*[v.ctypes.data for v, _ in views])
         hs = (C.c_int * n)(*[v.shape[0] for v, _ in views])
         ws = (C.c_int * n)(*[v.shape[1] for v, _ in views])
