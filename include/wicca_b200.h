@@ -240,26 +240,22 @@ WICCA_API int wicca_wavelet_icon_u8(const uint8_t* src, int H, int W, int C, int
 
 /* ---- JPEG ingest (row N2 of the hot-path table) -------------------------
  * Replaces `cv2.imread(file_path)` + `cv2.cvtColor(image, cv2.COLOR_BGR2RGB)` in load_image
- * (wicca/data_loader.py:53-58) for baseline JPEG files.  The entropy-coded scan is Huffman-decoded on the host
- * (serial by construction); dequantisation, the inverse DCT, chroma upsampling and YCbCr->RGB run on the GPU with
+ * (wicca/data_loader.py:53-58) for baseline JPEG files.  The host parses the markers and strips the byte stuffing;
+ * Huffman decoding, dequantisation, the inverse DCT, chroma upsampling and YCbCr->RGB run on the GPU with
  * libjpeg-turbo's default arithmetic (islow IDCT, fancy upsampling), so the result is bit-identical to cv2's.
- * Decoded subset: SOF0/SOF1 (Huffman decoding on the GPU) and SOF2 progressive / multi-scan files (entropy decoding
- * on the host, the rest on the GPU), 8-bit, 1 (grey, returned as 3 equal channels like IMREAD_COLOR) or
- * 3 (YCbCr) components, integral sampling ratios, restart intervals; the EXIF orientation
- * is applied as cv2.imread applies it (H and W below are those of the oriented image).
+ * Decoded subset: SOF0/SOF1 single-scan Huffman files, 8-bit, 1 (grey, returned as 3 equal channels like
+ * IMREAD_COLOR) or 3 (YCbCr) components, integral sampling ratios, restart intervals; the EXIF orientation
+ * is applied as cv2.imread applies it (H and W below are those of the oriented image).  Progressive (SOF2) and
+ * multi-scan files are not decoded: WICCA_EUNSUPPORTED, from wicca_jpeg_probe already.
  * Everything else returns WICCA_EUNSUPPORTED with the reason in wicca_last_error() - nothing is ever decoded
  * approximately and there is no CPU fallback: route such files through cv2.imread as before. */
 WICCA_API int wicca_jpeg_probe(const uint8_t* data, size_t len, int* H, int* W, int* n_components,
                                int* h_max, int* v_max);
-/* Host-only helpers (no GPU): number of int16 coefficients of the dense coefficient array (negative = error code),
- * and the Huffman decoder itself - per component, blocks in raster order, 64 quantised coefficients each in
- * natural order; blocks_w/blocks_h [n_components], qt [n_components * 64] (natural order) are optional outputs. */
+/* Number of int16 coefficients of the dense coefficient array (negative = error code): per component, blocks in
+ * raster order, 64 quantised coefficients each in natural order. */
 WICCA_API int64_t wicca_jpeg_coeff_count(const uint8_t* data, size_t len);
-WICCA_API int wicca_jpeg_decode_coeffs(const uint8_t* data, size_t len, int16_t* dst, int64_t dst_count,
-                                       int* blocks_w, int* blocks_h, uint16_t* qt);
-/* The same coefficients from the GPU Huffman decoder (the default first stage of every entry point below;
- * WICCA_JPEG_HUFFMAN=host selects the host decoder).  passes (nullable): re-synchronisation
- * passes it took.  For tests and measurements. */
+/* Those coefficients from the GPU Huffman decoder (the first stage of every entry point below).  passes (nullable):
+ * re-synchronisation passes it took.  For tests and measurements. */
 WICCA_API int wicca_jpeg_decode_coeffs_gpu(const uint8_t* data, size_t len, int16_t* dst, int64_t dst_count, int device,
                                            int* passes);
 /* JPEG bytes -> host RGB image (H, W, 3), rows dst_stride bytes apart (0 = tight).  host_decode_ms (nullable):

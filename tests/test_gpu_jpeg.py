@@ -97,14 +97,17 @@ def test_decode_to_device_buffer():
     assert (host[:info["height"], (info["width"] * 3 + 3) // 4 * 4:] == 0xAB).all()  # and so is the row padding
 
 
-@pytest.mark.parametrize("sampling", ["444", "422", "420"])
-def test_progressive_files_match_cv2(sampling):
-    from wicca_b200 import decode_jpeg
+@pytest.mark.parametrize("sampling", ["444", "420"])
+def test_progressive_files_are_refused_not_decoded_on_the_cpu(sampling):
+    """Progressive scans depend on each other and are not decoded on the GPU; the product has no host entropy decoder
+    behind it (no CPU fallback), so these files are reported, never decoded approximately."""
+    from wicca_b200 import UnsupportedImageError, decode_jpeg, icons_from_jpeg
     rng = np.random.default_rng(27)
-    for (h, w, q, r) in [(8, 8, 90, 0), (37, 53, 35, 0), (255, 257, 90, 4), (600, 401, 100, 0), (1200, 900, 85, 0)]:
-        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if q == 35 else photo_like(rng, h, w)
-        data = encode(img, q, sampling, r, progressive=True)
-        assert np.array_equal(decode_jpeg(data), reference_rgb(data)), (h, w, q, sampling, r)
+    data = encode(photo_like(rng, 255, 257), 90, sampling, 0, progressive=True)
+    with pytest.raises(UnsupportedImageError):
+        decode_jpeg(data)
+    with pytest.raises(UnsupportedImageError):
+        icons_from_jpeg(data, [2])
 
 
 def test_unsupported_files_fail_loudly():
@@ -134,16 +137,6 @@ def test_gpu_huffman_decoder_matches_host_decoder(sampling):
         passes = C.c_int()
         _capi.check(lib.wicca_jpeg_decode_coeffs_gpu(data, len(data), got.ctypes.data, got.size, 0, C.byref(passes)), "coeffs_gpu")
         assert np.array_equal(got, exp), (h, w, q, sampling, restart, passes.value)
-
-
-def test_both_huffman_stages_give_the_same_image(monkeypatch):
-    from wicca_b200 import decode_jpeg
-    rng = np.random.default_rng(32)
-    data = encode(photo_like(rng, 1111, 1777), 90, "420")
-    a = decode_jpeg(data)
-    monkeypatch.setenv("WICCA_JPEG_HUFFMAN", "host")
-    b = decode_jpeg(data)
-    assert np.array_equal(a, b) and np.array_equal(a, reference_rgb(data))
 
 
 @pytest.mark.parametrize("orientation", [1, 2, 3, 4, 5, 6, 7, 8])
@@ -191,8 +184,16 @@ def test_decode_matches_reference_goldens():
     """Committed fixtures from the reference's own load_image (no OpenCV needed at test time)."""
     from tests.test_oracle_jpeg import jpeg_golden
     from wicca_b200 import decode_jpeg
+    from wicca_b200 import UnsupportedImageError
+    n_ok = 0
     for case, data, rgb in jpeg_golden():
+        if len(case) > 8 and case[8]:                    # progressive fixture: refused, never decoded on the CPU
+            with pytest.raises(UnsupportedImageError):
+                decode_jpeg(data)
+            continue
         assert np.array_equal(decode_jpeg(data), rgb), case
+        n_ok += 1
+    assert n_ok >= 14
 
 
 def test_gpu_decoder_survives_corrupt_scans():

@@ -105,20 +105,46 @@ def test_host_progressive_decoder_matches_oracle(sampling):
             off += cf.size
 
 
+def emul_jpeg():
+    """tests/cpu_emul/jpeg_entropy_host.cpp (host entropy decoders: the checker of the GPU Huffman decoder) built with
+    the product's marker parser compiled as C++.  Never part of libwicca_b200.so."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    out = root / "tests" / "cpu_emul" / "_build"
+    out.mkdir(parents=True, exist_ok=True)
+    so = out / "libemul_jpeg.so"
+    srcs = [root / "tests" / "cpu_emul" / "jpeg_entropy_host.cpp", root / "wicca_b200" / "csrc" / "jpeg_host.cu"]
+    deps = srcs + [root / "wicca_b200" / "csrc" / "jpeg_host.h"]
+    if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I/usr/local/cuda/include",
+                        f"-I{root / 'wicca_b200' / 'csrc'}", str(srcs[0]), "-x", "c++", str(srcs[1]), "-o", str(so)], check=True)
+    lib = C.CDLL(str(so))
+    lib.emul_jpeg_coeff_count.restype = C.c_longlong
+    lib.emul_jpeg_coeff_count.argtypes = [C.c_char_p, C.c_size_t]
+    lib.emul_jpeg_decode_coeffs.restype = C.c_int
+    lib.emul_jpeg_decode_coeffs.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_char_p]
+    return lib
+
+
 def host_coefficients(data):
-    lib = _capi.load()
-    n = lib.wicca_jpeg_coeff_count(data, len(data))
-    assert n > 0, _capi.last_error()
+    lib = emul_jpeg()
+    n = lib.emul_jpeg_coeff_count(data, len(data))
+    assert n > 0, n
     dst = np.empty(n, np.int16)
     bw, bh = (C.c_int * 3)(), (C.c_int * 3)()
     qt = np.empty(192, np.uint16)
-    _capi.check(lib.wicca_jpeg_decode_coeffs(data, len(data), dst.ctypes.data, n, bw, bh, qt.ctypes.data), "decode_coeffs")
+    why = C.create_string_buffer(256)
+    rc = lib.emul_jpeg_decode_coeffs(data, len(data), dst.ctypes.data, n, bw, bh, qt.ctypes.data, why)
+    assert rc == 0, why.value
     return dst, list(bw), list(bh), qt
 
 
 @pytest.mark.parametrize("sampling", list(SAMPLING))
 def test_host_huffman_decoder_matches_oracle(sampling):
-    """The product's host stage (parser + Huffman decoder) against the oracle's, coefficient by coefficient."""
+    """The product's marker parser + the host Huffman decoder that checks the GPU one (tests/cpu_emul), against the
+    oracle's, coefficient by coefficient."""
     rng = np.random.default_rng(7)
     for (h, w, q, s, r) in CASES + [(130, 97, 90, sampling, 5)]:
         if s != sampling:
@@ -143,7 +169,8 @@ def test_probe_and_unsupported_flavours():
     info = jpeg_info(encode(img, 90, "420"))
     assert info == {"height": 33, "width": 47, "components": 3, "h_max": 2, "v_max": 2}
     assert jpeg_info(encode(img[:, :, 0], 90))["components"] == 1
-    assert jpeg_info(encode(img, progressive=True))["height"] == 33      # progressive files are decoded too
+    with pytest.raises(UnsupportedImageError):                          # progressive: not decoded on the GPU, no CPU fallback
+        jpeg_info(encode(img, progressive=True))
     ok, png = cv2.imencode(".png", img)
     with pytest.raises(UnsupportedImageError):
         jpeg_info(bytes(png))
@@ -167,7 +194,7 @@ def with_exif_orientation(data, orientation):
 def test_host_decoder_survives_corrupt_files():
     """Ingest reads untrusted files: mutated headers and scans must end in an error code or a decode, never a crash
     (the same driver ran 24,000 mutations under ASan/UBSan during development)."""
-    lib = _capi.load()
+    lib = emul_jpeg()
     rng = np.random.default_rng(99)
     base = bytearray(encode(photo_like(rng, 61, 83), 85, "420", restart=4))
     outcomes = set()
@@ -180,7 +207,8 @@ def test_host_decoder_survives_corrupt_files():
         if kind == 2:
             d = d[:1 + int(rng.integers(0, len(d)))]
         data = bytes(d)
-        n = lib.wicca_jpeg_coeff_count(data, len(data))
+        n = lib.emul_jpeg_coeff_count(data, len(data))
+        assert n == _capi.load().wicca_jpeg_coeff_count(data, len(data))          # same parser on both sides
         if n <= 0:
             assert n in (_capi.EINVAL, _capi.EUNSUPPORTED), n
             outcomes.add(int(n))
@@ -188,7 +216,7 @@ def test_host_decoder_survives_corrupt_files():
         if n > 1 << 24:
             continue
         dst = np.empty(n, np.int16)
-        rc = lib.wicca_jpeg_decode_coeffs(data, len(data), dst.ctypes.data, n, None, None, None)
+        rc = lib.emul_jpeg_decode_coeffs(data, len(data), dst.ctypes.data, n, None, None, None, None)
         assert rc in (0, _capi.EINVAL), rc
         outcomes.add(int(rc))
     assert 0 in outcomes and _capi.EINVAL in outcomes

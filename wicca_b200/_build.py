@@ -48,7 +48,8 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every ``csrc/*.cu`` and link the shared library.  Returns its path."""
+    """Compile every ``csrc/*.cu`` and link the shared library.  Returns its path.
+    ``WICCA_DEV=1`` in the environment adds ``-DWICCA_DEV`` (kernel knobs for ``tools/``; never for a release)."""
     lib = lib_path()
     if not force and not is_stale():
         return lib
@@ -62,7 +63,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         obj = OBJDIR / (src.stem + ".o")
         if (not force) and obj.exists() and obj.stat().st_mtime >= max(src.stat().st_mtime, hdr_mtime):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, "-Xptxas", "-v", "-c", str(src), "-o", str(obj)]
+        dev = ["-DWICCA_DEV"] if os.environ.get("WICCA_DEV") == "1" else []
+        cmd = [nvcc, *NVCC_FLAGS, *dev, "-Xptxas", "-v", "-c", str(src), "-o", str(obj)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or res.returncode != 0:
             print(" ".join(cmd))

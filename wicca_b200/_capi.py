@@ -80,7 +80,6 @@ SIGNATURES = {
                                         C.POINTER(C.c_float), C.c_int, C.c_void_p, C.c_int, C.POINTER(Timing)]),
     "wicca_jpeg_probe": (C.c_int, [C.c_void_p, C.c_size_t, c_intp, c_intp, c_intp, c_intp, c_intp]),
     "wicca_jpeg_coeff_count": (C.c_int64, [C.c_void_p, C.c_size_t]),
-    "wicca_jpeg_decode_coeffs": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, c_intp, c_intp, C.c_void_p]),
     "wicca_jpeg_decode_coeffs_gpu": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.c_int, c_intp]),
     "wicca_jpeg_decode_u8": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.c_int, C.POINTER(Timing),
                                        C.POINTER(C.c_float)]),

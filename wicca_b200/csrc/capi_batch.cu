@@ -1,7 +1,8 @@
 // capi_batch.cu - sharded host batch: images are independent units (the per-image loop of
 // wicca/classifying_tools.py:312-321), so image i goes to devices[i % n_devices] and nothing
-// crosses between GPUs.  One worker thread per device; two upload slots (stream + buffers) per
-// worker so the H2D copy of image j+1 overlaps the kernel and icon D2H of image j.
+// crosses between GPUs.  One worker thread per device; three upload slots (stream + buffers) per
+// worker so the H2D copies of images j+1, j+2 overlap the kernel and icon D2H of image j.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -39,11 +40,21 @@ void add_times(WorkerResult& r, Ctx& c) {
     r.h2d += a; r.kernel += b; r.d2h += d; r.total += e;
 }
 
+// Upload slots per worker: slot s owns a stream, a device image buffer and icon buffers.  Three keep the H2D engine
+// busy across the host's synchronise-and-enqueue gap (two leave a bubble whenever the kernel + icon read-back of one
+// slot ends while the other slot's upload is already draining).  WICCA_UPLOAD_SLOTS=2..4 overrides.
+int upload_slots() {
+    int n = 3;
+    if (const char* e = getenv("WICCA_UPLOAD_SLOTS")) n = atoi(e);
+    return n < 2 ? 2 : (n > 4 ? 4 : n);
+}
+
 int worker_body(const BatchArgs& a, int device, int first, int step, WorkerResult& res) {
     ScopedAffinity bind(device);         // this worker (and the buffers it allocates) stays on the GPU's NUMA node
-    CtxLease slot[2];
-    bool busy[2] = {false, false};
-    for (int s = 0; s < 2; ++s) {
+    const int n_slots = upload_slots();
+    CtxLease slot[4];
+    bool busy[4] = {false, false, false, false};
+    for (int s = 0; s < n_slots; ++s) {
         int rc = acquire_ctx(device, &slot[s].c);
         if (rc) return rc;
     }
@@ -52,9 +63,9 @@ int worker_body(const BatchArgs& a, int device, int first, int step, WorkerResul
     size_t max_src = 0;
     for (int i = first; i < a.n_images; i += step)
         max_src = std::max(max_src, (size_t)wicca_pitch_bytes(a.Ws[i], a.C) * a.Hs[i] + 256);
-    for (int s = 0; s < 2; ++s) WICCA_CUDA(slot[s].c->d_src.reserve(max_src));
+    for (int s = 0; s < n_slots; ++s) WICCA_CUDA(slot[s].c->d_src.reserve(max_src));
     int j = 0;
-    for (int i = first; i < a.n_images; i += step, ++j) {
+    for (int i = first; i < a.n_images; i += step) {
         const int H = a.Hs[i], W = a.Ws[i];
         const int64_t rowb = (int64_t)W * a.C;
         const int64_t stride = (a.strides && a.strides[i]) ? a.strides[i] : rowb;
@@ -68,8 +79,10 @@ int worker_body(const BatchArgs& a, int device, int first, int step, WorkerResul
             }
         }
         if (!device_work) continue;
-        Ctx& c = *slot[j & 1].c;
-        if (busy[j & 1]) {
+        const int s = j % n_slots;
+        ++j;
+        Ctx& c = *slot[s].c;
+        if (busy[s]) {
             WICCA_CUDA(cudaStreamSynchronize(c.stream));
             c.flush_pending();
             add_times(res, c);
@@ -82,14 +95,17 @@ int worker_body(const BatchArgs& a, int device, int first, int step, WorkerResul
         WICCA_CUDA(cudaEventRecord(c.ev[1], c.stream));
         rc = icons_from_resident(c, H, W, a.C, pitch, a.depths, a.n_depths, a.border_type, a.bconst, dsts);
         if (rc) { cudaStreamSynchronize(c.stream); c.pending.clear(); return rc; }
-        busy[j & 1] = true;
+        busy[s] = true;
     }
-    for (int s = 0; s < 2; ++s)
+    // drain in issue order
+    for (int k = 0; k < n_slots; ++k) {
+        const int s = (j + k) % n_slots;
         if (busy[s]) {
             WICCA_CUDA(cudaStreamSynchronize(slot[s].c->stream));
             slot[s].c->flush_pending();
             add_times(res, *slot[s].c);
         }
+    }
     return 0;
 }
 

@@ -1,7 +1,7 @@
 // capi_jpeg.cu - C entry points of the JPEG ingest path (row N2).  Replaces `cv2.imread(path)` +
-// `cv2.cvtColor(image, cv2.COLOR_BGR2RGB)` (wicca/data_loader.py:53-58) for baseline JPEG files: Huffman
-// decoding on the host, everything else on the GPU, the RGB image lands directly in the pitched device
-// buffer the icon kernel reads.
+// `cv2.cvtColor(image, cv2.COLOR_BGR2RGB)` (wicca/data_loader.py:53-58) for baseline JPEG files: the host parses
+// the markers and strips the byte stuffing; Huffman decoding and everything after it run on the GPU, and the RGB
+// image lands directly in the pitched device buffer the icon kernel reads.
 #include <string.h>
 
 #include <atomic>
@@ -39,26 +39,9 @@ int upsample_mode(const JpegFrame& f, const JpegComponent& q) {
     return 4;
 }
 
-// Host stage: Huffman-decode the scan into c.h_in (page-locked), before anything is enqueued.
-int jpeg_host_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFrame& f, float* host_ms) {
-    WICCA_CUDA(c.h_in.reserve((size_t)f.total_coefs * sizeof(int16_t)));
-    const double t0 = now_ms();
-    std::string why;
-    int rc = f.multiscan ? jpeg_decode_multiscan(data, len, f, (int16_t*)c.h_in.p, why)
-                         : jpeg_decode_coefficients(data, len, f, (int16_t*)c.h_in.p, why);
-    if (rc) return fail(rc, "%s", why.c_str());
-    if (host_ms) *host_ms += (float)(now_ms() - t0);
-    return 0;
-}
-
-bool gpu_huffman_wanted(const JpegFrame& f) {
-    if (f.multiscan) return false;                           // progressive / several scans: host entropy decoder
-    const char* e = getenv("WICCA_JPEG_HUFFMAN");
-    return !(e && e[0] == 'h');                              // WICCA_JPEG_HUFFMAN=host forces the CPU stage
-}
-
 // Huffman stage on the GPU: the host only strips the byte stuffing; coefficients end up in c.d_f32a.
-// Returns 1 when the fixed point was not reached within the pass budget (the caller falls back to the host stage).
+// Returns 1 when the scan cannot be decoded here (damaged restart structure, no fixed point within the pass budget):
+// the caller reports the file as WICCA_EUNSUPPORTED - there is no host decoder behind this one.
 int jpeg_gpu_huffman_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFrame& f, cudaStream_t stream, float* host_ms,
                            int* passes_out) {
     const size_t cap = len - f.scan_offset + 32;
@@ -69,7 +52,7 @@ int jpeg_gpu_huffman_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFr
     if (host_ms) *host_ms += (float)(now_ms() - t0);
     if (n_bytes == 0 || n_bytes >= ((size_t)1 << 28)) return 1;
     if (f.restart_interval) {
-        // exactly one marker between consecutive intervals, or the file is damaged: the host decoder copes better
+        // exactly one marker between consecutive intervals, or the file is damaged
         const int64_t mcus = (int64_t)f.mcux * f.mcuy;
         if ((int64_t)starts.size() != (mcus + f.restart_interval - 1) / f.restart_interval - 1) return 1;
     } else if (!starts.empty()) {
@@ -155,9 +138,9 @@ int jpeg_gpu_huffman_stage(Ctx& c, const uint8_t* data, size_t len, const JpegFr
     return 0;
 }
 
-// Device stage: coefficients (in c.h_in, or already in c.d_f32a when `resident`) -> d_dst (RGB, rows d_pitch bytes
-// apart) on `stream`, through c's scratch.
-int jpeg_device_stage(Ctx& c, const JpegFrame& f, uint8_t* d_dst, int64_t d_pitch, cudaStream_t stream, bool resident = false) {
+// Device stage: coefficients (in c.d_f32a, left there by the Huffman stage) -> d_dst (RGB, rows d_pitch bytes apart)
+// on `stream`, through c's scratch.
+int jpeg_device_stage(Ctx& c, const JpegFrame& f, uint8_t* d_dst, int64_t d_pitch, cudaStream_t stream) {
     const size_t coef_bytes = (size_t)f.total_coefs * sizeof(int16_t);
     size_t plane_bytes = 0;
     JpegImageDesc d;
@@ -186,10 +169,6 @@ int jpeg_device_stage(Ctx& c, const JpegFrame& f, uint8_t* d_dst, int64_t d_pitc
         p.mode = upsample_mode(f, q);
         memcpy(p.qt, f.qt[q.tq], sizeof p.qt);
     }
-    if (!resident) {
-        WICCA_CUDA(cudaMemcpyAsync(c.d_f32a.p, c.h_in.p, coef_bytes, cudaMemcpyHostToDevice, stream));
-        WICCA_CUDA(cudaEventRecord(c.ev[4], stream));             // coefficients resident
-    }
     cudaError_t e = launch_jpeg_decode(d, stream);
     if (e == cudaSuccess && f.orientation != 1)
         e = launch_jpeg_orient(d.dst, d.dst_pitch, f.height, f.width, f.orientation, d_dst, d_pitch, stream);
@@ -201,15 +180,15 @@ int jpeg_device_stage(Ctx& c, const JpegFrame& f, uint8_t* d_dst, int64_t d_pitc
 // (scan bytes or coefficients) is resident.
 int jpeg_to_device(Ctx& c, const uint8_t* data, size_t len, const JpegFrame& f, uint8_t* d_dst, int64_t d_pitch,
                    cudaStream_t stream, float* host_ms) {
-    if (gpu_huffman_wanted(f)) {
-        int rc = jpeg_gpu_huffman_stage(c, data, len, f, stream, host_ms, nullptr);
-        if (rc < 0 || rc > 1) return rc;
-        if (rc == 0) return jpeg_device_stage(c, f, d_dst, d_pitch, stream, true);
-        WICCA_CUDA(cudaStreamSynchronize(stream));            // no fixed point within the budget: host stage instead
+    if (f.multiscan)
+        return fail(WICCA_EUNSUPPORTED, "progressive / multi-scan JPEG: its scans depend on each other and are not decoded on "
+                                        "the GPU (read this file with cv2.imread)");
+    int rc = jpeg_gpu_huffman_stage(c, data, len, f, stream, host_ms, nullptr);
+    if (rc == 1) {
+        cudaStreamSynchronize(stream);
+        return fail(WICCA_EUNSUPPORTED, "JPEG scan with a damaged restart structure / no decoder fixed point (read this file with cv2.imread)");
     }
-    int rc = jpeg_host_stage(c, data, len, f, host_ms);
     if (rc) return rc;
-    WICCA_CUDA(cudaEventRecord(c.ev[0], stream));
     return jpeg_device_stage(c, f, d_dst, d_pitch, stream);
 }
 
@@ -243,6 +222,7 @@ int wicca_jpeg_probe(const uint8_t* data, size_t len, int* H, int* W, int* n_com
     JpegFrame f;
     int rc = parse_or_fail(data, len, f);
     if (rc) return rc;
+    if (f.multiscan) return fail(WICCA_EUNSUPPORTED, "progressive / multi-scan JPEG (not decoded on the GPU; read it with cv2.imread)");
     int oh, ow;
     jpeg_output_size(f, &oh, &ow);
     if (H) *H = oh;
@@ -259,29 +239,12 @@ int64_t wicca_jpeg_coeff_count(const uint8_t* data, size_t len) {
     return rc ? (int64_t)rc : f.total_coefs;
 }
 
-int wicca_jpeg_decode_coeffs(const uint8_t* data, size_t len, int16_t* dst, int64_t dst_count, int* blocks_w, int* blocks_h,
-                             uint16_t* qt) {
-    JpegFrame f;
-    int rc = parse_or_fail(data, len, f);
-    if (rc) return rc;
-    if (!dst || dst_count < f.total_coefs) return fail(WICCA_EINVAL, "coefficient buffer too small (%lld needed)", (long long)f.total_coefs);
-    for (int k = 0; k < f.ncomp; ++k) {
-        if (blocks_w) blocks_w[k] = f.comp[k].blocks_w;
-        if (blocks_h) blocks_h[k] = f.comp[k].blocks_h;
-        if (qt) memcpy(qt + 64 * k, f.qt[f.comp[k].tq], 64 * sizeof(uint16_t));
-    }
-    std::string why;
-    rc = f.multiscan ? jpeg_decode_multiscan(data, len, f, dst, why) : jpeg_decode_coefficients(data, len, f, dst, why);
-    if (rc) return fail(rc, "%s", why.c_str());
-    return 0;
-}
-
 int wicca_jpeg_decode_coeffs_gpu(const uint8_t* data, size_t len, int16_t* dst, int64_t dst_count, int device, int* passes) {
     JpegFrame f;
     int rc = parse_or_fail(data, len, f);
     if (rc) return rc;
     if (!dst || dst_count < f.total_coefs) return fail(WICCA_EINVAL, "coefficient buffer too small (%lld needed)", (long long)f.total_coefs);
-    if (f.multiscan) return fail(WICCA_EUNSUPPORTED, "progressive / multi-scan files are entropy-decoded on the host");
+    if (f.multiscan) return fail(WICCA_EUNSUPPORTED, "progressive / multi-scan files are not decoded on the GPU");
     rc = check_device(device);
     if (rc) return rc;
     CtxLease lease;

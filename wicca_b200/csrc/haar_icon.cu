@@ -100,8 +100,9 @@ __device__ __forceinline__ int item_index(int k, int run_len) {
 }
 
 // ------------------------------------------------------------------------------------------
-// The one-pass kernel.  debug: 0 = normal; 1 = consumers skip the arithmetic (load path only);
-// 2 = arithmetic but no level 1..3 output (developer instrumentation, see tools/bench_variants.py).
+// The one-pass kernel.  dev_mode exists only in -DWICCA_DEV builds (tools/bench_variants.py: 1 = consumers skip the
+// arithmetic, 2 = arithmetic but no level 1..3 output); the release library compiles it to the constant 0, so no
+// environment variable or argument can make the product kernel skip work.
 // Two consumer warps per stage: warp pair p owns stage p; the upper warp reduces rows 0..31 of the
 // 128 x 64 item, the lower warp rows 32..63 (8 rows per lane), so a stage is held half as long and
 // twice as many warps hide each other's latencies.  Levels 1..5 are complete inside a warp; the
@@ -112,8 +113,14 @@ __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0
 template <int kStages>
 __global__ void __launch_bounds__(32 * (1 + 2 * kStages), 1)
 haar_icon_tma2_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* __restrict__ strips, int n_images,
-                      int total_items, int border_type, int border_const, int debug, int run_len, int stream_hint) {
+                      int total_items, int border_type, int border_const, int dev_mode, int run_len, int stream_hint) {
     static_assert(kStages <= 15, "one named barrier per warp pair");
+#ifdef WICCA_DEV
+    const int debug = dev_mode;
+#else
+    constexpr int debug = 0;
+    (void)dev_mode;
+#endif
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* stages = smem_raw;
     uint8_t* out_tiles = smem_raw + (size_t)kStages * kStageBytes;
@@ -379,7 +386,7 @@ static cudaError_t launch_tma2_variant(const IconImage* d_imgs, const uint8_t* c
 }
 
 // variant 0 (default): 6 stages, runs of up to 16 horizontally adjacent items per CTA (shorter when
-// the launch is small, to keep the CTAs balanced).  Developer knobs (WICCA_ICON_VARIANT):
+// the launch is small, to keep the CTAs balanced).  Developer knobs (WICCA_ICON_VARIANT, -DWICCA_DEV builds only):
 // variant % 100 in {20,21,22,23} = 7/6/5/4 stages, + 100 * debug mode, + 1000 * (1 + log2(run length)).
 cudaError_t launch_icon_tma(const IconImage* d_imgs, const uint8_t* const* d_strips, int n_images, int total_items,
                             int border_type, int border_const, int sm_count, int variant, int stream_hint,
@@ -395,6 +402,7 @@ cudaError_t launch_icon_tma(const IconImage* d_imgs, const uint8_t* const* d_str
         while (run_len > 1 && (int64_t)8 * run_len * grid > total_items) run_len >>= 1;
     }
     if ((int64_t)run_len * grid > total_items) run_len = 1;
+#ifdef WICCA_DEV
     const int debug = (variant / 100) % 10;
     switch (variant % 100) {
         case 20: return launch_tma2_variant<7>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, run_len, stream_hint, stream);
@@ -402,6 +410,9 @@ cudaError_t launch_icon_tma(const IconImage* d_imgs, const uint8_t* const* d_str
         case 23: return launch_tma2_variant<4>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, run_len, stream_hint, stream);
         default: return launch_tma2_variant<6>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, debug, run_len, stream_hint, stream);
     }
+#else
+    return launch_tma2_variant<6>(d_imgs, d_strips, n_images, total_items, border_type, border_const, grid, 0, run_len, stream_hint, stream);
+#endif
 }
 
 cudaError_t launch_edge_strips(const IconImage* d_imgs, uint8_t* const* d_strips, int n_images, int max_rows,

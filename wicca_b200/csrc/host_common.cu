@@ -384,9 +384,13 @@ int encode_icon_tmap(CUtensorMap* tm, const void* d_icon, int h, int64_t w_bytes
 }
 
 int icon_variant_from_env() {
-    const char* e = getenv("WICCA_ICON_VARIANT");   // developer knob, see haar_icon.cu launch_icon_tma
+#ifdef WICCA_DEV
+    const char* e = getenv("WICCA_ICON_VARIANT");   // developer knob (tools/), see haar_icon.cu launch_icon_tma
     const int v = e ? atoi(e) : 0;
     return v < 0 ? 0 : v;
+#else
+    return 0;                                       // the release library has no kernel knobs
+#endif
 }
 
 }  // namespace wicca

@@ -1,7 +1,7 @@
-// jpeg_host.h - host half of the JPEG ingest path (row N2: cv2.imread + BGR2RGB, wicca/data_loader.py:53-58).
-// The entropy-coded segment is decoded on the CPU into dense quantised coefficients (the serial part of a
-// JPEG); dequantisation, the inverse DCT, chroma upsampling and the colour transform run on the GPU
-// (jpeg_kernels.cu), bit-exact with libjpeg-turbo's defaults, which is what cv2.imread uses.
+// jpeg_host.h - host half of the JPEG ingest path (row N2: cv2.imread + BGR2RGB, wicca/data_loader.py:53-58):
+// marker parsing and byte un-stuffing only.  Huffman decoding (jpeg_huffman.cu), dequantisation, the inverse DCT,
+// chroma upsampling and the colour transform (jpeg_kernels.cu) run on the GPU, bit-exact with libjpeg-turbo's
+// defaults, which is what cv2.imread uses.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -65,6 +65,8 @@ inline void jpeg_output_size(const JpegFrame& f, int* H, int* W) {
 // JPEGs outside the subset (progressive, arithmetic coding, 12-bit, CMYK, several scans ...).
 int jpeg_parse(const uint8_t* data, size_t len, JpegFrame& f, std::string& why);
 
+// --- the two host entropy decoders below are NOT part of libwicca_b200.so: they are implemented in
+// --- tests/cpu_emul/jpeg_entropy_host.cpp and exist only as the checker of the GPU Huffman decoder.
 // All scans of a progressive / multi-scan file accumulated into dst[total_coefs] (same layout as below); this is
 // what libjpeg holds when the whole file has been read, before it outputs the first row.
 int jpeg_decode_multiscan(const uint8_t* data, size_t len, const JpegFrame& f, int16_t* dst, std::string& why);

@@ -1,10 +1,10 @@
 """GPU ingest for the image files the reference reads with OpenCV (row N2 of the hot-path table).
 
 Mirror of ``wicca.data_loader.load_image`` (wicca/data_loader.py:27-63): ``cv2.imread(file_path)`` followed by
-``cv2.cvtColor(image, cv2.COLOR_BGR2RGB)``.  For JPEG files the entropy decoding runs on the GPU (baseline files)
-or on the host (progressive files) and the rest of the decoder (dequantisation, inverse DCT, chroma upsampling,
-YCbCr -> RGB, EXIF orientation) on the GPU with libjpeg-turbo's default arithmetic, so the returned array is
-bit-identical to the reference's.  Files outside that subset raise
+``cv2.cvtColor(image, cv2.COLOR_BGR2RGB)``.  For baseline (single-scan Huffman) JPEG files the whole decoder - entropy
+decoding, dequantisation, inverse DCT, chroma upsampling, YCbCr -> RGB, EXIF orientation - runs on the GPU with
+libjpeg-turbo's default arithmetic, so the returned array is bit-identical to the reference's; the host only parses
+markers and strips the byte stuffing.  Files outside that subset (progressive JPEG, PNG, ...) raise
 :class:`UnsupportedImageError` - there is no CPU fallback in this package; read those with ``cv2.imread``.
 """
 from __future__ import annotations
