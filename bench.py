@@ -560,11 +560,6 @@ def run_ours(args) -> int:
     d2h_bytes = BATCH * sum(icon_sizes)
     stage_ms = tim.as_dict()                               # sums over the 30 images of the last step
 
-    # the host's measured limit for the same traffic (SURVEY.md 8(e)), all ranks at once
-    out_flat_t = torch.from_numpy(np.ctypeslib.as_array((C.c_uint8 * sum(icon_sizes)).from_address(out_ptrs[0].value)))
-    ceiling = host_link_ceiling(torch, dist, dev, world, torch.from_numpy(host_flats[0]), out_flat_t, h2d_bytes, d2h_bytes, barrier)
-    ceiling_value = world * BATCH * MP_PER_IMAGE / ceiling["step_traffic_s"]
-
     # parity of EVERY icon of the last e2e step (30 images x 6 depths) against the C oracle, outside the timed region
     e2e_checked = 0
     if rank == 0:
@@ -577,6 +572,12 @@ def run_ours(args) -> int:
                 assert got.shape == exp.shape and np.array_equal(got, exp), f"e2e icon mismatch vs oracle (image {i})"
                 e2e_checked += 1
         del expected
+    # the host's measured limit for the same traffic (SURVEY.md 8(e)), all ranks at once
+    # (after the parity check: the probe's downward copies overwrite the first image's icons)
+    out_flat_t = torch.from_numpy(np.ctypeslib.as_array((C.c_uint8 * sum(icon_sizes)).from_address(out_ptrs[0].value)))
+    ceiling = host_link_ceiling(torch, dist, dev, world, torch.from_numpy(host_flats[0]), out_flat_t, h2d_bytes, d2h_bytes, barrier)
+    ceiling_value = world * BATCH * MP_PER_IMAGE / ceiling["step_traffic_s"]
+
     for p in host_ptrs + out_ptrs:
         lib.wicca_host_free(p)
     del host_arrays, host_flats, outs, out_flat_t

@@ -24,8 +24,9 @@ extern "C" {
 // src: tight (H, W, 3) uint8.  mask bit (d-1) requests depth d.  outs[d-1]: tight icon buffers
 // (may be NULL when not requested).  Returns 0, or a positive code when a guard byte around an
 // icon was overwritten (out-of-bounds store).
+// sum6_out (nullable): receives the (ceil(H/64), ceil(W/64), 3) plane of exact level-6 block sums that feeds depths > 6.
 int emul_fused_icons(const uint8_t* src, int H, int W, int border_type, int border_const, unsigned mask,
-                     uint8_t** outs) {
+                     uint8_t** outs, uint32_t* sum6_out) {
     const int64_t pitch = ((int64_t)W * 3 + 127) / 128 * 128;
     std::vector<uint8_t> img((size_t)pitch * H + 64, 0xA5);      // pad bytes are garbage on purpose
     for (int y = 0; y < H; ++y) memcpy(&img[(size_t)y * pitch], src + (size_t)y * W * 3, (size_t)W * 3);
@@ -43,6 +44,7 @@ int emul_fused_icons(const uint8_t* src, int H, int W, int border_type, int bord
         icons[d - 1].assign((size_t)ip * h + 2 * guard, 0xEE);
         icon_image_add_level(&im, d, icons[d - 1].data() + guard, ip);
     }
+    if (sum6_out) icon_image_add_sum6(&im, sum6_out);
     const int Wa = W & ~(kChunkPx - 1);
     const int npx = im.Wp_max - Wa;
     std::vector<uint8_t> strip;

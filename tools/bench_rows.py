@@ -91,6 +91,39 @@ def row_icons():
     torch.cuda.empty_cache()
 
 
+def row_deep():
+    """Depths 7-8 and other channel counts (verdict r1 item 6): one 53 MP image, device-resident, through the
+    device-pointer ABI (wicca_haar_icons_multi_dev)."""
+    g = torch.Generator(device=dev); g.manual_seed(2)
+    for ch, depth_sets in ((3, ([8], [7], [7, 8], [1, 2, 3, 4, 5, 6, 7, 8], [6])), (4, ([1], [3], [6], [8])), (1, ([3], [8]))):
+        pitch = pitch_bytes(W, ch)
+        img = torch.randint(0, 256, (H, pitch), dtype=torch.uint8, device=dev, generator=g)
+        host = img[:, : W * ch].reshape(H, W, ch).cpu().numpy()
+        for ds in depth_sets:
+            outs, ptrs, pitches = [], [], []
+            for d in ds:
+                oh, ow = -(-H // (1 << d)), -(-W // (1 << d))
+                op = -(-ow * ch // 128) * 128
+                t = torch.zeros((oh, op), dtype=torch.uint8, device=dev)
+                outs.append((t, oh, ow)); ptrs.append(t.data_ptr()); pitches.append(op)
+            n = len(ds)
+
+            def run():
+                _capi.check(lib.wicca_haar_icons_multi_dev(img.data_ptr(), H, W, ch, pitch, (C.c_int * n)(*ds), n, 1, 0.0,
+                                                           (C.c_void_p * n)(*ptrs), (C.c_int64 * n)(*pitches), 0,
+                                                           C.c_void_p(stream)), "icons_multi_dev")
+            ms = timed(run, reps=10, warm=2)
+            from oracle import c_oracle
+            exp = c_oracle.haar_icons_multi(host, ds)
+            ok = all(np.array_equal(t[:, : ow * ch].reshape(oh, ow, ch).cpu().numpy(), e) for (t, oh, ow), e in zip(outs, exp))
+            byt = H * W * ch + sum(oh * ow * ch for _, oh, ow in outs)
+            emit(row="A3 beyond the one-pass domain", config=f"one ({H},{W},{ch}) image, depths {ds}, device-resident", ms=ms,
+                 MP_per_s=H * W / ms / 1e3, GBps_if_one_pass=byt / ms / 1e6, frac_of_measured_peak_if_one_pass=byt / ms / 1e6 / PEAK,
+                 equals_oracle=bool(ok), lib=os.environ.get("WICCA_B200_LIB", "in-tree"))
+        del img
+    torch.cuda.empty_cache()
+
+
 def row_subbands():
     S = 16384
     pitch = pitch_bytes(S, 3)
@@ -314,6 +347,8 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["icons", "subbands", "batch", "jpeg", "wavelets", "oneshot", "cpu"]
     if "icons" in which:
         row_icons()
+    if "deep" in which:
+        row_deep()
     if "subbands" in which:
         row_subbands()
     if "batch" in which:

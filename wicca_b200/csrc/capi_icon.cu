@@ -46,12 +46,14 @@ bool fused_eligible(const void* d_src, int64_t pitch, int C) {
 
 // Fill one IconImage (including its tensor map).  outs: the fused outputs (depth 1..6) of this image.
 int fill_icon_image(IconImage* im, const uint8_t* d_src, int H, int W, int64_t pitch, const IconOut* outs, int n_outs,
-                    int item_base) {
+                    int item_base, uint32_t* sum6 = nullptr) {
     memset(im, 0, sizeof(*im));
     int rc = encode_image_tmap(&im->tmap, d_src, H, pitch);
     if (rc) return rc;
     icon_image_geometry(im, d_src, H, W, pitch, item_base);
+    if (sum6) icon_image_add_sum6(im, sum6);
     for (int i = 0; i < n_outs; ++i) {
+        if (outs[i].depth > kMaxFused) continue;     // finished from the level-6 plane by haar_tail_kernel
         icon_image_add_level(im, outs[i].depth, outs[i].d_ptr, outs[i].pitch);
         const int d = outs[i].depth;
         if (d <= 3) {   // levels 1..3 leave the kernel through TMA store
@@ -115,6 +117,40 @@ int enqueue_generic(const uint8_t* d_src, int64_t pitch, int H, int W, int C, in
     return 0;
 }
 
+// Depth 7..WICCA_MAX_DEPTH of a 3-channel image whose exact level-6 block sums the one-pass kernel has left in
+// `sum6` ((ceil(H/64), ceil(W/64), 3) uint32): no second pass over the image.  f32a/f32b as in enqueue_generic.
+size_t sum6_bytes(int H, int W) { return (size_t)icon_dim(H, 6) * icon_dim(W, 6) * 3 * sizeof(uint32_t); }
+int enqueue_tail(const uint8_t* d_src, int64_t pitch, int H, int W, int depth, int border_type, int bconst,
+                 const uint32_t* sum6, uint8_t* d_dst, int64_t dst_pitch, float* f32a, float* f32b, cudaStream_t stream) {
+    TailArgs a;
+    a.src = d_src; a.pitch = pitch; a.H = H; a.W = W;
+    a.border_type = border_base(border_type); a.border_const = bconst;
+    a.sum6 = sum6; a.s6_h = icon_dim(H, 6); a.s6_w = icon_dim(W, 6);
+    if (depth <= 8) {
+        a.depth = depth; a.out_h = icon_dim(H, depth); a.out_w = icon_dim(W, depth);
+        a.dst_u8 = d_dst; a.dst_pitch = dst_pitch; a.dst_f32 = nullptr;
+        cudaError_t e = launch_icon_tail(a, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "icon tail kernel");
+        return 0;
+    }
+    const int oh = icon_dim(H, depth), ow = icon_dim(W, depth);
+    int lh = oh << (depth - 8), lw = ow << (depth - 8);
+    a.depth = 8; a.out_h = lh; a.out_w = lw; a.dst_u8 = nullptr; a.dst_pitch = 0; a.dst_f32 = f32a;
+    cudaError_t e = launch_icon_tail(a, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "icon tail kernel (level 8)");
+    float* in = f32a;
+    float* out = f32b;
+    for (int l = 9; l <= depth; ++l) {
+        lh >>= 1; lw >>= 1;
+        const bool last = (l == depth);
+        if (last && dst_pitch != (int64_t)lw * 3) return fail(WICCA_EINVAL, "depth > 8 needs a tight destination");
+        e = launch_level_f32(in, out, last ? d_dst : nullptr, lh, lw, 3, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "fp32 level kernel");
+        std::swap(in, out);
+    }
+    return 0;
+}
+
 size_t level8_elems(int H, int W, int C, int depth) {
     if (depth <= 8) return 0;
     const int64_t oh = icon_dim(H, depth), ow = icon_dim(W, depth);
@@ -145,7 +181,7 @@ int enqueue_icons_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int
                            int bconst, std::vector<IconOut>& outs) {
     const uint8_t* d_src = (const uint8_t*)c.d_src.p;
     outs.assign(n_depths, IconOut());
-    std::vector<int> fused, generic;
+    std::vector<int> fused, tail, generic;
     const bool can_fuse = fused_eligible(d_src, pitch, C);
     size_t icon_bytes = 0, f32_elems = 0;
     for (int i = 0; i < n_depths; ++i) {
@@ -160,6 +196,7 @@ int enqueue_icons_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int
         bool dup = false;   // the fused kernel has one slot per level: duplicates go the general way
         for (int j : fused) dup |= (depths[j] == d);
         if (can_fuse && d <= kMaxFused && !dup) fused.push_back(i);
+        else if (can_fuse && d > kMaxFused) { tail.push_back(i); f32_elems = std::max(f32_elems, level8_elems(H, W, C, d)); }
         else { generic.push_back(i); f32_elems = std::max(f32_elems, level8_elems(H, W, C, d)); }
     }
     WICCA_CUDA(c.d_icons.reserve(icon_bytes + 256));
@@ -167,6 +204,7 @@ int enqueue_icons_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int
         WICCA_CUDA(c.d_f32a.reserve(f32_elems * sizeof(float)));
         WICCA_CUDA(c.d_f32b.reserve(f32_elems * sizeof(float) / 4 + 16));
     }
+    if (!tail.empty()) WICCA_CUDA(c.d_sum6.reserve(sum6_bytes(H, W)));
     size_t off = 0;
     for (int i = 0; i < n_depths; ++i) {
         if (depths[i] <= 0) continue;
@@ -174,13 +212,13 @@ int enqueue_icons_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int
         outs[i].d_ptr = (uint8_t*)c.d_icons.p + off;
         off += (size_t)outs[i].pitch * outs[i].h;
     }
-    if (!fused.empty()) {
+    if (!fused.empty() || !tail.empty()) {
         std::vector<IconOut> fo;
         for (int i : fused) fo.push_back(outs[i]);
         WICCA_CUDA(c.h_desc.reserve(sizeof(IconImage) + 64));
         WICCA_CUDA(c.d_desc.reserve(sizeof(IconImage) + 64));
         IconImage* him = (IconImage*)c.h_desc.p;
-        int rc = fill_icon_image(him, d_src, H, W, pitch, fo.data(), (int)fo.size(), 0);
+        int rc = fill_icon_image(him, d_src, H, W, pitch, fo.data(), (int)fo.size(), 0, tail.empty() ? nullptr : (uint32_t*)c.d_sum6.p);
         if (rc) return rc;
         uint8_t** h_strip = (uint8_t**)((uint8_t*)c.h_desc.p + sizeof(IconImage));
         *h_strip = nullptr;
@@ -200,6 +238,11 @@ int enqueue_icons_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int
                                         device_info(c.device).sm_count, icon_variant_from_env(),
                                         stream_hint_for(fo.data(), (int)fo.size()), c.stream);
         if (e != cudaSuccess) return cuda_fail(e, "fused icon kernel");
+        for (int i : tail) {
+            rc = enqueue_tail(d_src, pitch, H, W, depths[i], border_type, bconst, (const uint32_t*)c.d_sum6.p, outs[i].d_ptr,
+                              outs[i].pitch, (float*)c.d_f32a.p, (float*)c.d_f32b.p, c.stream);
+            if (rc) return rc;
+        }
     }
     for (int i : generic) {
         int rc = enqueue_generic(d_src, pitch, H, W, C, depths[i], border_type, bconst, outs[i].d_ptr, outs[i].pitch,
@@ -320,7 +363,7 @@ int wicca_haar_icons_multi_dev(const uint8_t* d_src, int H, int W, int C, int64_
     const int bconst = saturate_u8(border_const);
 
     std::vector<IconOut> fo;
-    std::vector<int> generic;
+    std::vector<int> generic, tail;
     size_t f32_elems = 0;
     const bool can_fuse = fused_eligible(d_src, src_pitch, C);
     for (int i = 0; i < n_depths; ++i) {
@@ -335,6 +378,9 @@ int wicca_haar_icons_multi_dev(const uint8_t* d_src, int H, int W, int C, int64_
             IconOut o;
             o.depth = d; o.h = icon_dim(H, d); o.w = w; o.d_ptr = d_dsts[i]; o.pitch = dst_pitches[i];
             fo.push_back(o);
+        } else if (can_fuse && d > kMaxFused) {
+            tail.push_back(i);
+            f32_elems = std::max(f32_elems, level8_elems(H, W, C, d));
         } else {
             generic.push_back(i);
             f32_elems = std::max(f32_elems, level8_elems(H, W, C, d));
@@ -358,9 +404,11 @@ int wicca_haar_icons_multi_dev(const uint8_t* d_src, int H, int W, int C, int64_
         WICCA_CUDA(scratch.get((void**)&f32a, f32_elems * sizeof(float)));
         WICCA_CUDA(scratch.get((void**)&f32b, f32_elems * sizeof(float) / 4 + 16));
     }
-    if (!fo.empty()) {
+    if (!fo.empty() || !tail.empty()) {
+        uint32_t* sum6 = nullptr;
+        if (!tail.empty()) WICCA_CUDA(scratch.get((void**)&sum6, sum6_bytes(H, W)));
         IconImage him;
-        rc = fill_icon_image(&him, d_src, H, W, src_pitch, fo.data(), (int)fo.size(), 0);
+        rc = fill_icon_image(&him, d_src, H, W, src_pitch, fo.data(), (int)fo.size(), 0, sum6);
         if (rc) return rc;
         uint8_t* strip = nullptr;
         if (border_needs_strip(border_type) && strip_px(W, him.Wp_max) > 0)
@@ -380,6 +428,11 @@ int wicca_haar_icons_multi_dev(const uint8_t* d_src, int H, int W, int C, int64_
                                         device_info(device).sm_count, icon_variant_from_env(),
                                         stream_hint_for(fo.data(), (int)fo.size()), stream);
         if (e != cudaSuccess) return cuda_fail(e, "fused icon kernel");
+        for (int i : tail) {
+            rc = enqueue_tail(d_src, src_pitch, H, W, depths[i], border_type, bconst, sum6, d_dsts[i], dst_pitches[i], f32a, f32b,
+                              stream);
+            if (rc) return rc;
+        }
     }
     for (int i : generic) {
         rc = enqueue_generic(d_src, src_pitch, H, W, C, depths[i], border_type, bconst, d_dsts[i], dst_pitches[i], f32a,
@@ -401,7 +454,8 @@ struct wicca_plan {
     std::vector<IconOut> outs;                 // n * n_depths
     std::vector<IconImage> h_imgs;
     std::vector<GenericIconArgs> gen;          // general path launches
-    DevBuf d_imgs, d_strip_ptrs, d_strips, d_icons;
+    std::vector<TailArgs> tails;               // depths 7, 8 of a fused plan, from the level-6 planes
+    DevBuf d_imgs, d_strip_ptrs, d_strips, d_icons, d_sum6;
     int total_items = 0, max_rows = 0, sm_count = 148;
     bool need_strips = false;
     int launches = 0;
@@ -425,7 +479,6 @@ int wicca_plan_create(int device, int n_images, const uint8_t* const* d_srcs, co
     bool all_fusable = (C == 3);
     for (int k = 0; k < n_depths; ++k) {
         if (depths[k] < 1 || depths[k] > 8) return fail(WICCA_EDEPTH, "plans support depths 1..8, got %d", depths[k]);
-        if (depths[k] > kMaxFused) all_fusable = false;
         for (int j = 0; j < k; ++j)
             if (depths[j] == depths[k]) return fail(WICCA_EDEPTH, "duplicate depth %d in plan", depths[k]);
     }
@@ -444,7 +497,7 @@ int wicca_plan_create(int device, int n_images, const uint8_t* const* d_srcs, co
     p->outs.resize((size_t)n_images * n_depths);
 
     auto cleanup = [&](int code) {
-        p->d_imgs.release(); p->d_strip_ptrs.release(); p->d_strips.release(); p->d_icons.release();
+        p->d_imgs.release(); p->d_strip_ptrs.release(); p->d_strips.release(); p->d_icons.release(); p->d_sum6.release();
         delete p;
         return code;
     };
@@ -476,10 +529,29 @@ int wicca_plan_create(int device, int n_images, const uint8_t* const* d_srcs, co
         std::vector<uint8_t*> strip_ptrs(n_images, nullptr);
         size_t strip_bytes = 0;
         int base = 0;
+        bool deep = false;
+        for (int k = 0; k < n_depths; ++k) deep |= depths[k] > kMaxFused;
+        std::vector<size_t> s6_off(n_images + 1, 0);
+        if (deep) {
+            for (int i = 0; i < n_images; ++i) s6_off[i + 1] = s6_off[i] + (size_t)align_up((int64_t)sum6_bytes(Hs[i], Ws[i]), 256);
+            e = p->d_sum6.reserve(s6_off[n_images]);
+            if (e != cudaSuccess) return cleanup(cuda_fail(e, "level-6 plane allocation"));
+        }
         for (int i = 0; i < n_images; ++i) {
+            uint32_t* sum6 = deep ? (uint32_t*)((uint8_t*)p->d_sum6.p + s6_off[i]) : nullptr;
             rc = fill_icon_image(&p->h_imgs[i], d_srcs[i], Hs[i], Ws[i], src_pitches[i], &p->outs[(size_t)i * n_depths],
-                                 n_depths, base);
+                                 n_depths, base, sum6);
             if (rc) return cleanup(rc);
+            for (int k = 0; k < n_depths && deep; ++k) {
+                const IconOut& o = p->outs[(size_t)i * n_depths + k];
+                if (o.depth <= kMaxFused) continue;
+                TailArgs t;
+                t.src = d_srcs[i]; t.pitch = src_pitches[i]; t.H = Hs[i]; t.W = Ws[i];
+                t.border_type = p->border; t.border_const = p->bconst;
+                t.sum6 = sum6; t.s6_h = icon_dim(Hs[i], 6); t.s6_w = icon_dim(Ws[i], 6);
+                t.depth = o.depth; t.out_h = o.h; t.out_w = o.w; t.dst_u8 = o.d_ptr; t.dst_pitch = o.pitch; t.dst_f32 = nullptr;
+                p->tails.push_back(t);
+            }
             base += p->h_imgs[i].items_x * p->h_imgs[i].items_y;
             p->max_rows = std::max(p->max_rows, Hs[i]);
             if (border_needs_strip(border_type) && strip_px(Ws[i], p->h_imgs[i].Wp_max) > 0) strip_bytes += (size_t)Hs[i] * kStripPitch;
@@ -501,7 +573,7 @@ int wicca_plan_create(int device, int n_images, const uint8_t* const* d_srcs, co
         if (e == cudaSuccess) e = cudaMemcpy(p->d_imgs.p, p->h_imgs.data(), sizeof(IconImage) * n_images, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(p->d_strip_ptrs.p, strip_ptrs.data(), sizeof(uint8_t*) * n_images, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return cleanup(cuda_fail(e, "plan descriptor upload"));
-        p->launches = 1 + (p->need_strips ? 1 : 0);
+        p->launches = 1 + (p->need_strips ? 1 : 0) + (int)p->tails.size();
     } else {
         for (int i = 0; i < n_images; ++i)
             for (int k = 0; k < n_depths; ++k) {
@@ -532,6 +604,10 @@ int wicca_plan_launch(wicca_plan* p, void* stream_v) {
         cudaError_t e = launch_icon_tma(d_im, d_strips, p->n, p->total_items, p->border, p->bconst, p->sm_count,
                                         icon_variant_from_env(), stream_hint_for(p->outs.data(), p->n_depths), stream);
         if (e != cudaSuccess) return cuda_fail(e, "fused icon kernel");
+        for (const auto& t : p->tails) {
+            e = launch_icon_tail(t, stream);
+            if (e != cudaSuccess) return cuda_fail(e, "icon tail kernel");
+        }
     } else {
         for (const auto& a : p->gen) {
             cudaError_t e = launch_icon_generic(a, stream);
@@ -611,7 +687,7 @@ int wicca_plan_destroy(wicca_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     for (auto& kv : p->epilogues) { kv.second->d_tables.release(); delete kv.second; }
-    p->d_imgs.release(); p->d_strip_ptrs.release(); p->d_strips.release(); p->d_icons.release();
+    p->d_imgs.release(); p->d_strip_ptrs.release(); p->d_strips.release(); p->d_icons.release(); p->d_sum6.release();
     delete p;
     return 0;
 }

@@ -268,7 +268,7 @@ haar_icon_tma2_kernel(const IconImage* __restrict__ imgs, const uint8_t* const* 
             s5[c] = b;
             s6[c] = b + __shfl_xor_sync(0xFFFFFFFFu, b, 2);
         }
-        if (sk.icon[5] != nullptr && debug != 1) {
+        if ((sk.icon[5] != nullptr || sk.sum6 != nullptr) && debug != 1) {
             uint32_t* slot = box + (k / kStages & 1) * 8;        // double-buffered per item parity
             if (half == 1 && (cx & 3) == 0 && ry == 0) {
                 uint32_t* q = slot + (cx >> 2) * 3;
@@ -428,6 +428,9 @@ cudaError_t launch_edge_strips(const IconImage* d_imgs, uint8_t* const* d_strips
 cudaError_t launch_icon_generic(const GenericIconArgs& a, cudaStream_t stream) {
     const int64_t n = (int64_t)a.out_h * a.out_w * a.C;
     if (n <= 0) return cudaSuccess;
+    // coalesced row-streaming kernel (haar_rows.cu) whenever one output pixel's row segment fits a tile;
+    // the scalar kernel below remains for absurd channel counts only
+    if (rows_kernel_groups(a.C, a.depth) > 0) return launch_icon_rows(a, stream);
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     haar_icon_generic_kernel<<<(int)blocks, 256, 0, stream>>>(a);

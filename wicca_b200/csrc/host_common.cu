@@ -129,7 +129,7 @@ void Ctx::destroy() {
     if (device < 0) return;
     cudaSetDevice(device);
     d_src.release(); d_icons.release(); d_desc.release(); d_strip.release();
-    d_f32a.release(); d_f32b.release(); d_misc.release(); d_tmp.release();
+    d_f32a.release(); d_f32b.release(); d_misc.release(); d_tmp.release(); d_sum6.release();
     h_desc.release(); h_bounce.release(); h_in.release(); h_out.release(); h_jpeg.release();
     for (auto& x : ev) if (x) { cudaEventDestroy(x); x = nullptr; }
     if (stream) { cudaStreamDestroy(stream); stream = nullptr; }

@@ -52,7 +52,7 @@ struct Ctx {
     int device = -1;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};                // start, h2d done, kernels done, d2h done, spare x2
-    DevBuf d_src, d_icons, d_desc, d_strip, d_f32a, d_f32b, d_misc, d_tmp;
+    DevBuf d_src, d_icons, d_desc, d_strip, d_f32a, d_f32b, d_misc, d_tmp, d_sum6;
     PinBuf h_desc, h_bounce, h_in, h_out, h_jpeg;
     // Results bound for pageable host memory are DMA'd into h_bounce (so the copy is truly
     // asynchronous) and moved to their destination after the stream has been synchronised.

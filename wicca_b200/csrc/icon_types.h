@@ -31,6 +31,8 @@ struct alignas(128) IconImage {
     uint8_t* icon[kMaxFused];    // per level (index = depth-1); nullptr = not emitted
     int64_t icon_pitch[kMaxFused];
     int icon_h[kMaxFused], icon_w[kMaxFused];
+    uint32_t* sum6;              // nullptr, or (sum6_h, sum6_w, 3) exact 64 x 64 block sums for the levels above 6
+    int sum6_h, sum6_w;          // ceil(H/64), ceil(W/64)
 };
 
 // Geometry part of an IconImage (everything except the tensor map).  Host side.
@@ -41,6 +43,14 @@ inline void icon_image_geometry(IconImage* im, const uint8_t* src, int H, int W,
     im->item_base = item_base;
     im->Hp_max = 0; im->Wp_max = 0;
     for (int l = 0; l < kMaxFused; ++l) { im->icon[l] = nullptr; im->icon_pitch[l] = 0; im->icon_h[l] = 0; im->icon_w[l] = 0; }
+    im->sum6 = nullptr; im->sum6_h = 0; im->sum6_w = 0;
+}
+// Request the plane of exact level-6 block sums (haar_tail_kernel finishes depths > 6 from it).
+inline void icon_image_add_sum6(IconImage* im, uint32_t* plane) {
+    im->sum6 = plane;
+    im->sum6_h = (im->H + 63) >> 6; im->sum6_w = (im->W + 63) >> 6;
+    if (im->sum6_h * 64 > im->Hp_max) im->Hp_max = im->sum6_h * 64;
+    if (im->sum6_w * 64 > im->Wp_max) im->Wp_max = im->sum6_w * 64;
 }
 // Request level `depth` (1..6) of the image; icon rows are `pitch` bytes apart.
 inline void icon_image_add_level(IconImage* im, int depth, uint8_t* icon, int64_t pitch) {
@@ -60,6 +70,18 @@ struct GenericIconArgs {
     int out_h, out_w;
     uint8_t* dst_u8; int64_t dst_pitch;      // used when depth is the final depth
     float* dst_f32;                          // else: exact level value as fp32 (tight, out_w*C per row)
+};
+
+// Arguments of haar_tail_kernel: depth 7 / 8 (uint8) or the exact level-8 plane (float32) of a 3-channel image from
+// the level-6 sums; out_h x out_w may exceed the depth's own icon when the plane feeds still deeper levels.
+struct TailArgs {
+    const uint8_t* src; int64_t pitch; int H, W;
+    int border_type, border_const;
+    const uint32_t* sum6; int s6_h, s6_w;
+    int depth;                   // 7 or 8
+    int out_h, out_w;
+    uint8_t* dst_u8; int64_t dst_pitch;
+    float* dst_f32;
 };
 
 }  // namespace wicca
