@@ -44,7 +44,7 @@ int emul_fused_icons(const uint8_t* src, int H, int W, int border_type, int bord
         icons[d - 1].assign((size_t)ip * h + 2 * guard, 0xEE);
         icon_image_add_level(&im, d, icons[d - 1].data() + guard, ip);
     }
-    if (sum6_out) icon_image_add_sum6(&im, sum6_out);
+    if (sum6_out) icon_image_add_sum6(&im, sum6_out, 0);
     const int Wa = W & ~(kChunkPx - 1);
     const int npx = im.Wp_max - Wa;
     std::vector<uint8_t> strip;

@@ -46,12 +46,12 @@ bool fused_eligible(const void* d_src, int64_t pitch, int C) {
 
 // Fill one IconImage (including its tensor map).  outs: the fused outputs (depth 1..6) of this image.
 int fill_icon_image(IconImage* im, const uint8_t* d_src, int H, int W, int64_t pitch, const IconOut* outs, int n_outs,
-                    int item_base, uint32_t* sum6 = nullptr) {
+                    int item_base, uint32_t* sum6 = nullptr, int sum6_stride = 0) {
     memset(im, 0, sizeof(*im));
     int rc = encode_image_tmap(&im->tmap, d_src, H, pitch);
     if (rc) return rc;
     icon_image_geometry(im, d_src, H, W, pitch, item_base);
-    if (sum6) icon_image_add_sum6(im, sum6);
+    if (sum6) icon_image_add_sum6(im, sum6, sum6_stride);
     for (int i = 0; i < n_outs; ++i) {
         if (outs[i].depth > kMaxFused) continue;     // finished from the level-6 plane by haar_tail_kernel
         icon_image_add_level(im, outs[i].depth, outs[i].d_ptr, outs[i].pitch);
@@ -119,21 +119,33 @@ int enqueue_generic(const uint8_t* d_src, int64_t pitch, int H, int W, int C, in
 
 // Depth 7..WICCA_MAX_DEPTH of a 3-channel image whose exact level-6 block sums the one-pass kernel has left in
 // `sum6` ((ceil(H/64), ceil(W/64), 3) uint32): no second pass over the image.  f32a/f32b as in enqueue_generic.
-size_t sum6_bytes(int H, int W) { return (size_t)icon_dim(H, 6) * icon_dim(W, 6) * 3 * sizeof(uint32_t); }
-int enqueue_tail(const uint8_t* d_src, int64_t pitch, int H, int W, int depth, int border_type, int bconst,
-                 const uint32_t* sum6, uint8_t* d_dst, int64_t dst_pitch, float* f32a, float* f32b, cudaStream_t stream) {
+struct TailGeom { int s6_h, s6_w, ext_h, ext_w; };
+// level-6 blocks the one-pass kernel produces (s6_*) and those of the padded grid of `max_depth` (ext_*)
+TailGeom tail_geom(int H, int W, int max_depth) {
+    TailGeom g;
+    g.s6_h = icon_dim(H, 6); g.s6_w = icon_dim(W, 6);
+    g.ext_h = icon_dim(H, max_depth) << (max_depth - 6); g.ext_w = icon_dim(W, max_depth) << (max_depth - 6);
+    return g;
+}
+size_t sum6_bytes(const TailGeom& g) { return (size_t)g.ext_h * g.ext_w * 3 * sizeof(uint32_t); }
+TailArgs tail_base(const uint8_t* d_src, int64_t pitch, int H, int W, int border_type, int bconst, uint32_t* sum6, const TailGeom& g) {
     TailArgs a;
+    memset(&a, 0, sizeof a);
     a.src = d_src; a.pitch = pitch; a.H = H; a.W = W;
     a.border_type = border_base(border_type); a.border_const = bconst;
-    a.sum6 = sum6; a.s6_h = icon_dim(H, 6); a.s6_w = icon_dim(W, 6);
+    a.sum6 = sum6; a.s6_h = g.s6_h; a.s6_w = g.s6_w; a.ext_h = g.ext_h; a.ext_w = g.ext_w;
+    return a;
+}
+int enqueue_tail(const TailArgs& base, int depth, uint8_t* d_dst, int64_t dst_pitch, float* f32a, float* f32b, cudaStream_t stream) {
+    TailArgs a = base;
     if (depth <= 8) {
-        a.depth = depth; a.out_h = icon_dim(H, depth); a.out_w = icon_dim(W, depth);
+        a.depth = depth; a.out_h = icon_dim(a.H, depth); a.out_w = icon_dim(a.W, depth);
         a.dst_u8 = d_dst; a.dst_pitch = dst_pitch; a.dst_f32 = nullptr;
         cudaError_t e = launch_icon_tail(a, stream);
         if (e != cudaSuccess) return cuda_fail(e, "icon tail kernel");
         return 0;
     }
-    const int oh = icon_dim(H, depth), ow = icon_dim(W, depth);
+    const int oh = icon_dim(a.H, depth), ow = icon_dim(a.W, depth);
     int lh = oh << (depth - 8), lw = ow << (depth - 8);
     a.depth = 8; a.out_h = lh; a.out_w = lw; a.dst_u8 = nullptr; a.dst_pitch = 0; a.dst_f32 = f32a;
     cudaError_t e = launch_icon_tail(a, stream);
@@ -204,7 +216,10 @@ int enqueue_icons_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int
         WICCA_CUDA(c.d_f32a.reserve(f32_elems * sizeof(float)));
         WICCA_CUDA(c.d_f32b.reserve(f32_elems * sizeof(float) / 4 + 16));
     }
-    if (!tail.empty()) WICCA_CUDA(c.d_sum6.reserve(sum6_bytes(H, W)));
+    int tail_max = 0;
+    for (int i : tail) tail_max = std::max(tail_max, depths[i]);
+    const TailGeom tg = tail_geom(H, W, tail.empty() ? 6 : tail_max);
+    if (!tail.empty()) WICCA_CUDA(c.d_sum6.reserve(sum6_bytes(tg)));
     size_t off = 0;
     for (int i = 0; i < n_depths; ++i) {
         if (depths[i] <= 0) continue;
@@ -218,7 +233,8 @@ int enqueue_icons_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int
         WICCA_CUDA(c.h_desc.reserve(sizeof(IconImage) + 64));
         WICCA_CUDA(c.d_desc.reserve(sizeof(IconImage) + 64));
         IconImage* him = (IconImage*)c.h_desc.p;
-        int rc = fill_icon_image(him, d_src, H, W, pitch, fo.data(), (int)fo.size(), 0, tail.empty() ? nullptr : (uint32_t*)c.d_sum6.p);
+        int rc = fill_icon_image(him, d_src, H, W, pitch, fo.data(), (int)fo.size(), 0, tail.empty() ? nullptr : (uint32_t*)c.d_sum6.p,
+                                 tg.ext_w);
         if (rc) return rc;
         uint8_t** h_strip = (uint8_t**)((uint8_t*)c.h_desc.p + sizeof(IconImage));
         *h_strip = nullptr;
@@ -238,10 +254,14 @@ int enqueue_icons_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int
                                         device_info(c.device).sm_count, icon_variant_from_env(),
                                         stream_hint_for(fo.data(), (int)fo.size()), c.stream);
         if (e != cudaSuccess) return cuda_fail(e, "fused icon kernel");
-        for (int i : tail) {
-            rc = enqueue_tail(d_src, pitch, H, W, depths[i], border_type, bconst, (const uint32_t*)c.d_sum6.p, outs[i].d_ptr,
-                              outs[i].pitch, (float*)c.d_f32a.p, (float*)c.d_f32b.p, c.stream);
-            if (rc) return rc;
+        if (!tail.empty()) {
+            const TailArgs tb = tail_base(d_src, pitch, H, W, border_type, bconst, (uint32_t*)c.d_sum6.p, tg);
+            e = launch_icon_tail_fill(tb, c.stream);
+            if (e != cudaSuccess) return cuda_fail(e, "icon tail fill kernel");
+            for (int i : tail) {
+                rc = enqueue_tail(tb, depths[i], outs[i].d_ptr, outs[i].pitch, (float*)c.d_f32a.p, (float*)c.d_f32b.p, c.stream);
+                if (rc) return rc;
+            }
         }
     }
     for (int i : generic) {
@@ -406,9 +426,12 @@ int wicca_haar_icons_multi_dev(const uint8_t* d_src, int H, int W, int C, int64_
     }
     if (!fo.empty() || !tail.empty()) {
         uint32_t* sum6 = nullptr;
-        if (!tail.empty()) WICCA_CUDA(scratch.get((void**)&sum6, sum6_bytes(H, W)));
+        int tail_max = 6;
+        for (int i : tail) tail_max = std::max(tail_max, depths[i]);
+        const TailGeom tg = tail_geom(H, W, tail_max);
+        if (!tail.empty()) WICCA_CUDA(scratch.get((void**)&sum6, sum6_bytes(tg)));
         IconImage him;
-        rc = fill_icon_image(&him, d_src, H, W, src_pitch, fo.data(), (int)fo.size(), 0, sum6);
+        rc = fill_icon_image(&him, d_src, H, W, src_pitch, fo.data(), (int)fo.size(), 0, sum6, tg.ext_w);
         if (rc) return rc;
         uint8_t* strip = nullptr;
         if (border_needs_strip(border_type) && strip_px(W, him.Wp_max) > 0)
@@ -428,10 +451,14 @@ int wicca_haar_icons_multi_dev(const uint8_t* d_src, int H, int W, int C, int64_
                                         device_info(device).sm_count, icon_variant_from_env(),
                                         stream_hint_for(fo.data(), (int)fo.size()), stream);
         if (e != cudaSuccess) return cuda_fail(e, "fused icon kernel");
-        for (int i : tail) {
-            rc = enqueue_tail(d_src, src_pitch, H, W, depths[i], border_type, bconst, sum6, d_dsts[i], dst_pitches[i], f32a, f32b,
-                              stream);
-            if (rc) return rc;
+        if (!tail.empty()) {
+            const TailArgs tb = tail_base(d_src, src_pitch, H, W, border_type, bconst, sum6, tg);
+            e = launch_icon_tail_fill(tb, stream);
+            if (e != cudaSuccess) return cuda_fail(e, "icon tail fill kernel");
+            for (int i : tail) {
+                rc = enqueue_tail(tb, depths[i], d_dsts[i], dst_pitches[i], f32a, f32b, stream);
+                if (rc) return rc;
+            }
         }
     }
     for (int i : generic) {
@@ -455,6 +482,7 @@ struct wicca_plan {
     std::vector<IconImage> h_imgs;
     std::vector<GenericIconArgs> gen;          // general path launches
     std::vector<TailArgs> tails;               // depths 7, 8 of a fused plan, from the level-6 planes
+    std::vector<TailArgs> tail_fills;          // one per image whose deeper padding reaches past the depth-6 extents
     DevBuf d_imgs, d_strip_ptrs, d_strips, d_icons, d_sum6;
     int total_items = 0, max_rows = 0, sm_count = 148;
     bool need_strips = false;
@@ -529,28 +557,32 @@ int wicca_plan_create(int device, int n_images, const uint8_t* const* d_srcs, co
         std::vector<uint8_t*> strip_ptrs(n_images, nullptr);
         size_t strip_bytes = 0;
         int base = 0;
-        bool deep = false;
-        for (int k = 0; k < n_depths; ++k) deep |= depths[k] > kMaxFused;
+        int tail_max = 6;
+        for (int k = 0; k < n_depths; ++k) tail_max = std::max(tail_max, depths[k]);
+        const bool deep = tail_max > kMaxFused;
         std::vector<size_t> s6_off(n_images + 1, 0);
         if (deep) {
-            for (int i = 0; i < n_images; ++i) s6_off[i + 1] = s6_off[i] + (size_t)align_up((int64_t)sum6_bytes(Hs[i], Ws[i]), 256);
+            for (int i = 0; i < n_images; ++i)
+                s6_off[i + 1] = s6_off[i] + (size_t)align_up((int64_t)sum6_bytes(tail_geom(Hs[i], Ws[i], tail_max)), 256);
             e = p->d_sum6.reserve(s6_off[n_images]);
             if (e != cudaSuccess) return cleanup(cuda_fail(e, "level-6 plane allocation"));
         }
         for (int i = 0; i < n_images; ++i) {
             uint32_t* sum6 = deep ? (uint32_t*)((uint8_t*)p->d_sum6.p + s6_off[i]) : nullptr;
+            const TailGeom tg = tail_geom(Hs[i], Ws[i], tail_max);
             rc = fill_icon_image(&p->h_imgs[i], d_srcs[i], Hs[i], Ws[i], src_pitches[i], &p->outs[(size_t)i * n_depths],
-                                 n_depths, base, sum6);
+                                 n_depths, base, sum6, tg.ext_w);
             if (rc) return cleanup(rc);
-            for (int k = 0; k < n_depths && deep; ++k) {
-                const IconOut& o = p->outs[(size_t)i * n_depths + k];
-                if (o.depth <= kMaxFused) continue;
-                TailArgs t;
-                t.src = d_srcs[i]; t.pitch = src_pitches[i]; t.H = Hs[i]; t.W = Ws[i];
-                t.border_type = p->border; t.border_const = p->bconst;
-                t.sum6 = sum6; t.s6_h = icon_dim(Hs[i], 6); t.s6_w = icon_dim(Ws[i], 6);
-                t.depth = o.depth; t.out_h = o.h; t.out_w = o.w; t.dst_u8 = o.d_ptr; t.dst_pitch = o.pitch; t.dst_f32 = nullptr;
-                p->tails.push_back(t);
+            if (deep) {
+                const TailArgs tb = tail_base(d_srcs[i], src_pitches[i], Hs[i], Ws[i], p->border, p->bconst, sum6, tg);
+                if ((int64_t)tg.ext_h * tg.ext_w > (int64_t)tg.s6_h * tg.s6_w) p->tail_fills.push_back(tb);
+                for (int k = 0; k < n_depths; ++k) {
+                    const IconOut& o = p->outs[(size_t)i * n_depths + k];
+                    if (o.depth <= kMaxFused) continue;
+                    TailArgs t = tb;
+                    t.depth = o.depth; t.out_h = o.h; t.out_w = o.w; t.dst_u8 = o.d_ptr; t.dst_pitch = o.pitch; t.dst_f32 = nullptr;
+                    p->tails.push_back(t);
+                }
             }
             base += p->h_imgs[i].items_x * p->h_imgs[i].items_y;
             p->max_rows = std::max(p->max_rows, Hs[i]);
@@ -573,7 +605,7 @@ int wicca_plan_create(int device, int n_images, const uint8_t* const* d_srcs, co
         if (e == cudaSuccess) e = cudaMemcpy(p->d_imgs.p, p->h_imgs.data(), sizeof(IconImage) * n_images, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(p->d_strip_ptrs.p, strip_ptrs.data(), sizeof(uint8_t*) * n_images, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return cleanup(cuda_fail(e, "plan descriptor upload"));
-        p->launches = 1 + (p->need_strips ? 1 : 0) + (int)p->tails.size();
+        p->launches = 1 + (p->need_strips ? 1 : 0) + (int)p->tails.size() + (int)p->tail_fills.size();
     } else {
         for (int i = 0; i < n_images; ++i)
             for (int k = 0; k < n_depths; ++k) {
@@ -604,6 +636,10 @@ int wicca_plan_launch(wicca_plan* p, void* stream_v) {
         cudaError_t e = launch_icon_tma(d_im, d_strips, p->n, p->total_items, p->border, p->bconst, p->sm_count,
                                         icon_variant_from_env(), stream_hint_for(p->outs.data(), p->n_depths), stream);
         if (e != cudaSuccess) return cuda_fail(e, "fused icon kernel");
+        for (const auto& t : p->tail_fills) {
+            e = launch_icon_tail_fill(t, stream);
+            if (e != cudaSuccess) return cuda_fail(e, "icon tail fill kernel");
+        }
         for (const auto& t : p->tails) {
             e = launch_icon_tail(t, stream);
             if (e != cudaSuccess) return cuda_fail(e, "icon tail kernel");

@@ -148,8 +148,8 @@ struct IconSink {
     uint8_t* icon[6];      // index = depth-1; nullptr = level not requested
     int64_t pitch[6];
     int h[6], w[6];        // icon extents: ceil(H / 2^d), ceil(W / 2^d)
-    uint32_t* sum6;        // nullptr, or the (sum6_h, sum6_w, 3) plane of exact level-6 block sums (depths > 6)
-    int sum6_h, sum6_w;
+    uint32_t* sum6;        // nullptr, or the plane of exact level-6 block sums (depths > 6), sum6_stride blocks per row
+    int sum6_h, sum6_w, sum6_stride;
 };
 
 // ---------------------------------------------------------------------------
@@ -255,7 +255,7 @@ WHD void emit_tail_half(const IconSink& sk, int x0, int y0, int cx, int ry, bool
     if (sk.sum6 != nullptr && upper && (cx & 3) == 0 && ry == 0) {
         const int oy = y0 >> 6, ox = x0 >> 6;
         if (oy < sk.sum6_h && ox < sk.sum6_w) {
-            uint32_t* p = sk.sum6 + ((int64_t)oy * sk.sum6_w + ox) * 3;
+            uint32_t* p = sk.sum6 + ((int64_t)oy * sk.sum6_stride + ox) * 3;
             p[0] = s6[0]; p[1] = s6[1]; p[2] = s6[2];
         }
     }
@@ -449,7 +449,7 @@ WHD IconSink make_sink(const IconImage& im) {
     for (int l = 0; l < kMaxFused; ++l) {
         sk.icon[l] = im.icon[l]; sk.pitch[l] = im.icon_pitch[l]; sk.h[l] = im.icon_h[l]; sk.w[l] = im.icon_w[l];
     }
-    sk.sum6 = im.sum6; sk.sum6_h = im.sum6_h; sk.sum6_w = im.sum6_w;
+    sk.sum6 = im.sum6; sk.sum6_h = im.sum6_h; sk.sum6_w = im.sum6_w; sk.sum6_stride = im.sum6_stride;
     return sk;
 }
 

@@ -12,9 +12,9 @@
 //                           (replaces a kernel that gave every output element to one thread with r^2 serial byte loads).
 //   haar_tail_kernel        depths 7, 8 (and the exact level-8 plane from which depths > 8 continue in float32) from
 //                           the exact uint32 level-6 block sums the one-pass kernel leaves in a scratch plane, so
-//                           depths 1..8 of an RGB image still cost ONE pass over it.  Level-6 blocks that lie entirely
-//                           in the padding of the deeper level (beyond the depth-6 extents) are summed directly from
-//                           the image through the border index map, a warp per output pixel.
+//                           depths 1..8 of an RGB image still cost ONE pass over it.
+//   haar_tail_fill_kernel   the level-6 blocks that lie entirely in the padding of the deeper level (beyond the depth-6
+//                           extents), summed directly from the image through the border index map, a warp per block.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -37,11 +37,15 @@ __device__ __forceinline__ uint32_t padded_byte(const GenericIconArgs& a, const 
     return xm < 0 ? (uint32_t)a.border_const : (uint32_t)row[(int64_t)xm * a.C + c];
 }
 
+// WPT words per thread and row; U = 8 / WPT rows are fetched before the first of them is consumed, so every thread keeps
+// eight independent 32-bit loads in flight (a row loop that consumes each word as it arrives serialises on the HBM
+// latency: 0.9 TB/s measured; the batched form is what makes the kernel bandwidth bound).
 template <int WPT>
 __global__ void __launch_bounds__(kRowsThreads)
 haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int aligned) {
+    constexpr int U = WPT >= 8 ? 1 : 8 / WPT;
     __shared__ __align__(16) uint16_t colsum[kRowsMaxTileBytes];
-    __shared__ uint32_t outsum[1024];
+    __shared__ uint32_t outsum[kRowsThreads / 2];   // used only when nseg > 1, i.e. n_out <= 128
     const int tid = threadIdx.x;
     const int r = 1 << a.depth;
     const int gb = a.C << a.depth;                    // bytes of one output pixel's input row segment
@@ -51,10 +55,13 @@ haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int align
     const int64_t row_bytes = (int64_t)a.W * a.C;     // bytes of an image row that exist
     const int64_t b0 = (int64_t)blockIdx.x * tile_bytes;
     const uint32_t fill = (uint32_t)a.border_const * 0x01010101u;
-    // horizontal stage: nseg threads share one output
+    const bool interior = aligned && (b0 + tile_bytes <= row_bytes);       // CTA-uniform: no right border in this tile
+    // horizontal stage: nseg threads share one output when there are few outputs and many pixels per output
     int nseg = 1;
     while (nseg * 2 * n_out <= kRowsThreads && nseg * 2 <= r) nseg *= 2;
     const int seg_len = r / nseg;
+    const int64_t ob0 = (int64_t)blockIdx.x * n_out;  // first output byte (of the icon row) of this tile
+    const int64_t out_row_bytes = (int64_t)a.out_w * a.C;
 
     for (int rr = 0; rr < rows_per_cta; ++rr) {
         const int oy = blockIdx.y * rows_per_cta + rr;
@@ -62,28 +69,52 @@ haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int align
         uint32_t accE[WPT], accO[WPT];
 #pragma unroll
         for (int k = 0; k < WPT; ++k) accE[k] = accO[k] = 0u;
-        for (int o = tid; o < n_out; o += kRowsThreads) outsum[o] = 0u;
-#pragma unroll 4
-        for (int dy = 0; dy < r; ++dy) {
-            const int ym = border_index((oy << a.depth) + dy, a.H, a.border_type);       // uniform over the CTA
-            const uint8_t* row = ym < 0 ? nullptr : a.src + (int64_t)ym * a.pitch;
+        if (nseg > 1)
+            for (int o = tid; o < n_out; o += kRowsThreads) outsum[o] = 0u;
+        if (interior) {
+            for (int dy0 = 0; dy0 < r; dy0 += U) {
+                uint32_t v[U][WPT];
 #pragma unroll
-            for (int k = 0; k < WPT; ++k) {
-                const int w = tid + k * kRowsThreads;
-                if (w >= n_words) break;
-                const int64_t b = b0 + 4 * (int64_t)w;
-                uint32_t v;
-                if (row == nullptr) {
-                    v = fill;
-                } else if (b + 4 <= row_bytes) {
-                    if (aligned) v = __ldg(reinterpret_cast<const uint32_t*>(row + b));
-                    else v = (uint32_t)row[b] | ((uint32_t)row[b + 1] << 8) | ((uint32_t)row[b + 2] << 16) | ((uint32_t)row[b + 3] << 24);
-                } else {
-                    v = padded_byte(a, row, b) | (padded_byte(a, row, b + 1) << 8) | (padded_byte(a, row, b + 2) << 16) |
-                        (padded_byte(a, row, b + 3) << 24);
+                for (int u = 0; u < U; ++u) {
+                    const int dy = dy0 + u;
+                    const int ym = dy < r ? border_index((oy << a.depth) + dy, a.H, a.border_type) : -2;
+                    const uint32_t* row = ym < 0 ? nullptr : reinterpret_cast<const uint32_t*>(a.src + (int64_t)ym * a.pitch + b0);
+#pragma unroll
+                    for (int k = 0; k < WPT; ++k) {
+                        const int w = tid + k * kRowsThreads;
+                        v[u][k] = (ym == -2 || w >= n_words) ? 0u : (row == nullptr ? fill : __ldg(row + w));
+                    }
                 }
-                accE[k] += prmt(v, 0u, 0x4240u);      // bytes 0 and 2 in 16-bit lanes
-                accO[k] += prmt(v, 0u, 0x4341u);      // bytes 1 and 3
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int k = 0; k < WPT; ++k) {
+                        accE[k] += prmt(v[u][k], 0u, 0x4240u);      // bytes 0 and 2 in 16-bit lanes
+                        accO[k] += prmt(v[u][k], 0u, 0x4341u);      // bytes 1 and 3
+                    }
+            }
+        } else {
+            for (int dy = 0; dy < r; ++dy) {
+                const int ym = border_index((oy << a.depth) + dy, a.H, a.border_type);       // uniform over the CTA
+                const uint8_t* row = ym < 0 ? nullptr : a.src + (int64_t)ym * a.pitch;
+#pragma unroll
+                for (int k = 0; k < WPT; ++k) {
+                    const int w = tid + k * kRowsThreads;
+                    if (w >= n_words) break;
+                    const int64_t b = b0 + 4 * (int64_t)w;
+                    uint32_t v;
+                    if (row == nullptr) {
+                        v = fill;
+                    } else if (b + 4 <= row_bytes) {
+                        if (aligned) v = __ldg(reinterpret_cast<const uint32_t*>(row + b));
+                        else v = (uint32_t)row[b] | ((uint32_t)row[b + 1] << 8) | ((uint32_t)row[b + 2] << 16) | ((uint32_t)row[b + 3] << 24);
+                    } else {
+                        v = padded_byte(a, row, b) | (padded_byte(a, row, b + 1) << 8) | (padded_byte(a, row, b + 2) << 16) |
+                            (padded_byte(a, row, b + 3) << 24);
+                    }
+                    accE[k] += prmt(v, 0u, 0x4240u);
+                    accO[k] += prmt(v, 0u, 0x4341u);
+                }
             }
         }
 #pragma unroll
@@ -96,67 +127,100 @@ haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int align
             *reinterpret_cast<uint2*>(&colsum[4 * w]) = pk;
         }
         __syncthreads();
-        const int total = n_out * nseg;
-        for (int i = tid; i < total; i += kRowsThreads) {
-            const int o = i % n_out, seg = i / n_out;
-            const int g = o / a.C, c = o - g * a.C;
-            const uint16_t* p = colsum + g * gb + (seg * seg_len) * a.C + c;
-            uint32_t s = 0;
-            for (int q = 0; q < seg_len; ++q) s += p[q * a.C];
-            if (nseg == 1) outsum[o] = s;
-            else atomicAdd(&outsum[o], s);            // integer: exact and order-independent
+        if (nseg > 1) {
+            const int total = n_out * nseg;
+            for (int i = tid; i < total; i += kRowsThreads) {
+                const int o = i % n_out, seg = i / n_out;
+                const int g = o / a.C, c = o - g * a.C;
+                const uint16_t* p = colsum + g * gb + (seg * seg_len) * a.C + c;
+                uint32_t s = 0;
+                for (int q = 0; q < seg_len; ++q) s += p[q * a.C];
+                atomicAdd(&outsum[o], s);             // integer: exact and order-independent
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        for (int o = tid; o < n_out; o += kRowsThreads) {
-            const int g = o / a.C, c = o - g * a.C;
-            const int ox = blockIdx.x * groups + g;
-            if (ox >= a.out_w) continue;
-            const uint32_t s = outsum[o];
-            if (a.dst_u8 != nullptr) a.dst_u8[(int64_t)oy * a.dst_pitch + (int64_t)ox * a.C + c] = (uint8_t)(s >> (2 * a.depth));
-            else a.dst_f32[((int64_t)oy * a.out_w + ox) * a.C + c] = __uint2float_rn(s) * (1.0f / (float)(1u << (2 * a.depth)));
+        // four consecutive output bytes (or floats) per thread
+        for (int o4 = 4 * tid; o4 < n_out; o4 += 4 * kRowsThreads) {
+            uint32_t sv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int o = o4 + j;
+                sv[j] = 0u;
+                if (o >= n_out) continue;
+                if (nseg > 1) { sv[j] = outsum[o]; continue; }
+                const int g = o / a.C, c = o - g * a.C;
+                const uint16_t* p = colsum + g * gb + c;
+                uint32_t s = 0;
+                for (int q = 0; q < r; ++q) s += p[q * a.C];
+                sv[j] = s;
+            }
+            const int64_t ob = ob0 + o4;
+            if (a.dst_u8 != nullptr) {
+                uint8_t* q = a.dst_u8 + (int64_t)oy * a.dst_pitch + ob;
+                const uint32_t word = (sv[0] >> (2 * a.depth)) | ((sv[1] >> (2 * a.depth)) << 8) | ((sv[2] >> (2 * a.depth)) << 16) |
+                                      ((sv[3] >> (2 * a.depth)) << 24);
+                if (o4 + 4 <= n_out && ob + 4 <= out_row_bytes && ((uintptr_t)q & 3) == 0) {
+                    *reinterpret_cast<uint32_t*>(q) = word;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (o4 + j < n_out && ob + j < out_row_bytes) q[j] = (uint8_t)(word >> (8 * j));
+                }
+            } else {
+                const float scale = 1.0f / (float)(1u << (2 * a.depth));
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (o4 + j < n_out && ob + j < out_row_bytes) a.dst_f32[(int64_t)oy * out_row_bytes + ob + j] = __uint2float_rn(sv[j]) * scale;
+            }
         }
         __syncthreads();
     }
 }
 
 // ---- levels above 6 of a fused run --------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) haar_tail_kernel(TailArgs a) {
+// Level-6 blocks of the deeper level's padded grid that the one-pass kernel did not produce (they lie entirely in the
+// padding beyond the depth-6 extents): a warp per block, straight from the image through the border index map.
+__global__ void __launch_bounds__(256) haar_tail_fill_kernel(TailArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int nb = 1 << (a.depth - 6);                  // level-6 blocks per output pixel and axis
-    for (int64_t o = warp; o < (int64_t)a.out_h * a.out_w; o += n_warps) {
-        const int oy = (int)(o / a.out_w), ox = (int)(o - (int64_t)oy * a.out_w);
+    const int right_w = a.ext_w - a.s6_w;                               // columns right of the valid region
+    const int64_t n_right = (int64_t)right_w * a.s6_h;
+    const int64_t n_missing = n_right + (int64_t)(a.ext_h - a.s6_h) * a.ext_w;
+    for (int64_t m = warp; m < n_missing; m += n_warps) {
+        int by, bx;
+        if (m < n_right) { by = (int)(m / right_w); bx = a.s6_w + (int)(m - (int64_t)by * right_w); }
+        else { const int64_t q = m - n_right; by = a.s6_h + (int)(q / a.ext_w); bx = (int)(q - (int64_t)(by - a.s6_h) * a.ext_w); }
         uint32_t s[3] = {0u, 0u, 0u};
-        for (int j = 0; j < nb * nb; ++j) {
-            const int by = oy * nb + j / nb, bx = ox * nb + j % nb;
-            if (by < a.s6_h && bx < a.s6_w) {           // inside the depth-6 extents: the one-pass kernel's exact sums
-                if (lane == 0) {
-                    const uint32_t* p = a.sum6 + ((int64_t)by * a.s6_w + bx) * 3;
-                    s[0] += p[0]; s[1] += p[1]; s[2] += p[2];
-                }
-                continue;
-            }
-            // a 64 x 64 block entirely in the padding of the deeper level: straight from the image
-            for (int i = lane; i < 64 * 64; i += 32) {
-                const int ym = border_index(by * 64 + (i >> 6), a.H, a.border_type);
-                const int xm = border_index(bx * 64 + (i & 63), a.W, a.border_type);
-                if (ym < 0 || xm < 0) { s[0] += a.border_const; s[1] += a.border_const; s[2] += a.border_const; continue; }
-                const uint8_t* p = a.src + (int64_t)ym * a.pitch + (int64_t)xm * 3;
-                s[0] += p[0]; s[1] += p[1]; s[2] += p[2];
-            }
+        for (int i = lane; i < 64 * 64; i += 32) {
+            const int ym = border_index(by * 64 + (i >> 6), a.H, a.border_type);
+            const int xm = border_index(bx * 64 + (i & 63), a.W, a.border_type);
+            if (ym < 0 || xm < 0) { s[0] += a.border_const; s[1] += a.border_const; s[2] += a.border_const; continue; }
+            const uint8_t* p = a.src + (int64_t)ym * a.pitch + (int64_t)xm * 3;
+            s[0] += p[0]; s[1] += p[1]; s[2] += p[2];
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) s[c] += __shfl_xor_sync(0xFFFFFFFFu, s[c], off);
-        if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                if (a.dst_u8 != nullptr) a.dst_u8[(int64_t)oy * a.dst_pitch + (int64_t)ox * 3 + c] = (uint8_t)(s[c] >> (2 * a.depth));
-                else a.dst_f32[((int64_t)oy * a.out_w + ox) * 3 + c] = __uint2float_rn(s[c]) * (1.0f / (float)(1u << (2 * a.depth)));
-            }
-        }
+        if (lane < 3) a.sum6[((int64_t)by * a.ext_w + bx) * 3 + lane] = lane == 0 ? s[0] : (lane == 1 ? s[1] : s[2]);
+    }
+}
+
+// One thread per output element: the 2^(d-6) x 2^(d-6) level-6 block sums of its pixel, shifted once.
+__global__ void __launch_bounds__(256) haar_tail_kernel(TailArgs a) {
+    const int nb = 1 << (a.depth - 6);
+    const int64_t n = (int64_t)a.out_h * a.out_w * 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % 3);
+        const int64_t t = i / 3;
+        const int ox = (int)(t % a.out_w), oy = (int)(t / a.out_w);
+        const uint32_t* p = a.sum6 + ((int64_t)oy * nb * a.ext_w + (int64_t)ox * nb) * 3 + c;
+        uint32_t s = 0;
+        for (int y = 0; y < nb; ++y)
+            for (int x = 0; x < nb; ++x) s += p[((int64_t)y * a.ext_w + x) * 3];
+        if (a.dst_u8 != nullptr) a.dst_u8[(int64_t)oy * a.dst_pitch + (int64_t)ox * 3 + c] = (uint8_t)(s >> (2 * a.depth));
+        else a.dst_f32[i] = __uint2float_rn(s) * (1.0f / (float)(1u << (2 * a.depth)));
     }
 }
 
@@ -167,7 +231,9 @@ __global__ void __launch_bounds__(256) haar_tail_kernel(TailArgs a) {
 int rows_kernel_groups(int C, int depth) {
     const int64_t gb = (int64_t)C << depth;            // even, because depth >= 1
     if (depth < 1 || gb > kRowsMaxTileBytes) return 0;
-    int g = (int)(1024 / gb);
+    // eight loads in flight per thread: 1 KB tiles when an output row has >= 8 input rows, wider tiles below that
+    const int target = depth >= 3 ? 1024 : (depth == 2 ? 2048 : 4096);
+    int g = (int)(target / gb);
     if (gb % 4 == 0) return g < 1 ? 1 : g;
     g &= ~1;                                           // depth 1, odd channel count: pairs of output pixels
     return g < 2 ? 2 : g;
@@ -191,10 +257,19 @@ cudaError_t launch_icon_rows(const GenericIconArgs& a, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+cudaError_t launch_icon_tail_fill(const TailArgs& a, cudaStream_t stream) {
+    const int64_t missing = (int64_t)a.ext_h * a.ext_w - (int64_t)a.s6_h * a.s6_w;
+    if (missing <= 0) return cudaSuccess;
+    int64_t blocks = (missing + 7) / 8;              // a warp per missing block, 8 warps per CTA
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    haar_tail_fill_kernel<<<(int)blocks, 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_icon_tail(const TailArgs& a, cudaStream_t stream) {
-    const int64_t n = (int64_t)a.out_h * a.out_w;
+    const int64_t n = (int64_t)a.out_h * a.out_w * 3;
     if (n <= 0) return cudaSuccess;
-    int64_t blocks = (n + 7) / 8;                    // a warp per output pixel, 8 warps per CTA
+    int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     haar_tail_kernel<<<(int)blocks, 256, 0, stream>>>(a);
     return cudaGetLastError();

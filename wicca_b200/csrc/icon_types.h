@@ -31,8 +31,9 @@ struct alignas(128) IconImage {
     uint8_t* icon[kMaxFused];    // per level (index = depth-1); nullptr = not emitted
     int64_t icon_pitch[kMaxFused];
     int icon_h[kMaxFused], icon_w[kMaxFused];
-    uint32_t* sum6;              // nullptr, or (sum6_h, sum6_w, 3) exact 64 x 64 block sums for the levels above 6
-    int sum6_h, sum6_w;          // ceil(H/64), ceil(W/64)
+    uint32_t* sum6;              // nullptr, or the plane of exact 64 x 64 block sums for the levels above 6:
+    int sum6_h, sum6_w;          // this kernel fills rows < ceil(H/64), columns < ceil(W/64) of it,
+    int sum6_stride;             // blocks per plane row (>= sum6_w: the deeper level's padded grid)
 };
 
 // Geometry part of an IconImage (everything except the tensor map).  Host side.
@@ -43,12 +44,13 @@ inline void icon_image_geometry(IconImage* im, const uint8_t* src, int H, int W,
     im->item_base = item_base;
     im->Hp_max = 0; im->Wp_max = 0;
     for (int l = 0; l < kMaxFused; ++l) { im->icon[l] = nullptr; im->icon_pitch[l] = 0; im->icon_h[l] = 0; im->icon_w[l] = 0; }
-    im->sum6 = nullptr; im->sum6_h = 0; im->sum6_w = 0;
+    im->sum6 = nullptr; im->sum6_h = 0; im->sum6_w = 0; im->sum6_stride = 0;
 }
-// Request the plane of exact level-6 block sums (haar_tail_kernel finishes depths > 6 from it).
-inline void icon_image_add_sum6(IconImage* im, uint32_t* plane) {
+// Request the plane of exact level-6 block sums (haar_tail_kernel finishes depths > 6 from it); `stride` blocks per row.
+inline void icon_image_add_sum6(IconImage* im, uint32_t* plane, int stride) {
     im->sum6 = plane;
     im->sum6_h = (im->H + 63) >> 6; im->sum6_w = (im->W + 63) >> 6;
+    im->sum6_stride = stride < im->sum6_w ? im->sum6_w : stride;
     if (im->sum6_h * 64 > im->Hp_max) im->Hp_max = im->sum6_h * 64;
     if (im->sum6_w * 64 > im->Wp_max) im->Wp_max = im->sum6_w * 64;
 }
@@ -77,7 +79,8 @@ struct GenericIconArgs {
 struct TailArgs {
     const uint8_t* src; int64_t pitch; int H, W;
     int border_type, border_const;
-    const uint32_t* sum6; int s6_h, s6_w;
+    uint32_t* sum6;              // (ext_h, ext_w, 3): rows < s6_h, columns < s6_w come from the one-pass kernel,
+    int s6_h, s6_w, ext_h, ext_w; //                   the rest from haar_tail_fill_kernel
     int depth;                   // 7 or 8
     int out_h, out_w;
     uint8_t* dst_u8; int64_t dst_pitch;

@@ -18,6 +18,7 @@ cudaError_t launch_icon_generic(const GenericIconArgs& a, cudaStream_t stream);
 // haar_rows.cu
 int rows_kernel_groups(int C, int depth);            // 0: haar_icon_rows_kernel cannot take this (C, depth)
 cudaError_t launch_icon_rows(const GenericIconArgs& a, cudaStream_t stream);
+cudaError_t launch_icon_tail_fill(const TailArgs& a, cudaStream_t stream);   // once per image, before the tails
 cudaError_t launch_icon_tail(const TailArgs& a, cudaStream_t stream);
 cudaError_t launch_level_f32(const float* in, float* out, uint8_t* out_u8, int out_h, int out_w, int C,
                              cudaStream_t stream);
