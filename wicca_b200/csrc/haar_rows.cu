@@ -14,7 +14,7 @@
 //                           the exact uint32 level-6 block sums the one-pass kernel leaves in a scratch plane, so
 //                           depths 1..8 of an RGB image still cost ONE pass over it.
 //   haar_tail_fill_kernel   the level-6 blocks that lie entirely in the padding of the deeper level (beyond the depth-6
-//                           extents), summed directly from the image through the border index map, a warp per block.
+//                           extents), summed directly from the image through the border index map, a CTA per block.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -71,20 +71,17 @@ haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int align
         for (int k = 0; k < WPT; ++k) accE[k] = accO[k] = 0u;
         if (nseg > 1)
             for (int o = tid; o < n_out; o += kRowsThreads) outsum[o] = 0u;
-        if (interior) {
+        if (interior && (((int64_t)oy + 1) << a.depth) <= a.H && (r % U) == 0) {
+            // no border anywhere in this tile: a plain strided stream, U x WPT loads issued before the first use
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(a.src + ((int64_t)oy << a.depth) * a.pitch + b0) + tid;
+            const int64_t pw = a.pitch >> 2;
             for (int dy0 = 0; dy0 < r; dy0 += U) {
                 uint32_t v[U][WPT];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int dy = dy0 + u;
-                    const int ym = dy < r ? border_index((oy << a.depth) + dy, a.H, a.border_type) : -2;
-                    const uint32_t* row = ym < 0 ? nullptr : reinterpret_cast<const uint32_t*>(a.src + (int64_t)ym * a.pitch + b0);
+                for (int u = 0; u < U; ++u)
 #pragma unroll
-                    for (int k = 0; k < WPT; ++k) {
-                        const int w = tid + k * kRowsThreads;
-                        v[u][k] = (ym == -2 || w >= n_words) ? 0u : (row == nullptr ? fill : __ldg(row + w));
-                    }
-                }
+                    for (int k = 0; k < WPT; ++k)
+                        v[u][k] = (tid + k * kRowsThreads < n_words) ? __ldg(p + (int64_t)(dy0 + u) * pw + k * kRowsThreads) : 0u;
 #pragma unroll
                 for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -179,31 +176,36 @@ haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int align
 
 // ---- levels above 6 of a fused run --------------------------------------------------------------------------
 // Level-6 blocks of the deeper level's padded grid that the one-pass kernel did not produce (they lie entirely in the
-// padding beyond the depth-6 extents): a warp per block, straight from the image through the border index map.
+// padding beyond the depth-6 extents): a CTA per block, straight from the image through the border index map.
 __global__ void __launch_bounds__(256) haar_tail_fill_kernel(TailArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    __shared__ uint32_t tot[3];
     const int right_w = a.ext_w - a.s6_w;                               // columns right of the valid region
     const int64_t n_right = (int64_t)right_w * a.s6_h;
     const int64_t n_missing = n_right + (int64_t)(a.ext_h - a.s6_h) * a.ext_w;
-    for (int64_t m = warp; m < n_missing; m += n_warps) {
+    for (int64_t m = blockIdx.x; m < n_missing; m += gridDim.x) {       // a CTA per block: 16 pixels per thread
         int by, bx;
         if (m < n_right) { by = (int)(m / right_w); bx = a.s6_w + (int)(m - (int64_t)by * right_w); }
         else { const int64_t q = m - n_right; by = a.s6_h + (int)(q / a.ext_w); bx = (int)(q - (int64_t)(by - a.s6_h) * a.ext_w); }
+        if (threadIdx.x < 3) tot[threadIdx.x] = 0u;
+        __syncthreads();
         uint32_t s[3] = {0u, 0u, 0u};
-        for (int i = lane; i < 64 * 64; i += 32) {
-            const int ym = border_index(by * 64 + (i >> 6), a.H, a.border_type);
-            const int xm = border_index(bx * 64 + (i & 63), a.W, a.border_type);
+        const int xm = border_index(bx * 64 + (threadIdx.x & 63), a.W, a.border_type);
+#pragma unroll 4
+        for (int i = threadIdx.x >> 6; i < 64; i += 4) {
+            const int ym = border_index(by * 64 + i, a.H, a.border_type);
             if (ym < 0 || xm < 0) { s[0] += a.border_const; s[1] += a.border_const; s[2] += a.border_const; continue; }
             const uint8_t* p = a.src + (int64_t)ym * a.pitch + (int64_t)xm * 3;
             s[0] += p[0]; s[1] += p[1]; s[2] += p[2];
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < 3; ++c) {
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) s[c] += __shfl_xor_sync(0xFFFFFFFFu, s[c], off);
-        if (lane < 3) a.sum6[((int64_t)by * a.ext_w + bx) * 3 + lane] = lane == 0 ? s[0] : (lane == 1 ? s[1] : s[2]);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&tot[c], s[c]);      // integer: exact, order-independent
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) a.sum6[((int64_t)by * a.ext_w + bx) * 3 + threadIdx.x] = tot[threadIdx.x];
+        __syncthreads();
     }
 }
 
@@ -260,8 +262,8 @@ cudaError_t launch_icon_rows(const GenericIconArgs& a, cudaStream_t stream) {
 cudaError_t launch_icon_tail_fill(const TailArgs& a, cudaStream_t stream) {
     const int64_t missing = (int64_t)a.ext_h * a.ext_w - (int64_t)a.s6_h * a.s6_w;
     if (missing <= 0) return cudaSuccess;
-    int64_t blocks = (missing + 7) / 8;              // a warp per missing block, 8 warps per CTA
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    int64_t blocks = missing;                        // a CTA per missing block
+    if (blocks > 148 * 8) blocks = 148 * 8;
     haar_tail_fill_kernel<<<(int)blocks, 256, 0, stream>>>(a);
     return cudaGetLastError();
 }

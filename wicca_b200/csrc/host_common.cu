@@ -182,6 +182,15 @@ const DeviceInfo& device_info(int device) {
     DeviceInfo& di = g_info[device];
     if (!di.ok) {
         int v = 0;
+        // the device-pointer entry points take their scratch from the stream-ordered pool: keep a little cached
+        // there instead of handing it back to the driver at every synchronisation (the default threshold is 0)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            uint64_t cur = 0, keep = (uint64_t)64 << 20;
+            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < keep)
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
         cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
         di.sm_count = v > 0 ? v : 148;
         cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);

@@ -160,25 +160,55 @@ __device__ __forceinline__ float byte_times(uint32_t word, float w, float nw) {
     return __fmaf_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440 | K)), w, nw);
 }
 
-// Four taps = 12 bytes = three realigned words; tap t has weight w[t].  Channel chains stay in tap order.
-__device__ __forceinline__ void area_group(const uint32_t*& wp, uint32_t& w0, uint32_t shift, const float (&w)[4],
-                                           const float (&nw)[4], float (&h)[3]) {
-    const uint32_t w1 = wp[1], w2 = wp[2], w3 = wp[3];
-    const uint32_t a0 = __funnelshift_r(w0, w1, shift), a1 = __funnelshift_r(w1, w2, shift), a2 = __funnelshift_r(w2, w3, shift);
-    h[0] = __fadd_rn(h[0], byte_times<0>(a0, w[0], nw[0])); h[1] = __fadd_rn(h[1], byte_times<1>(a0, w[0], nw[0]));
-    h[2] = __fadd_rn(h[2], byte_times<2>(a0, w[0], nw[0])); h[0] = __fadd_rn(h[0], byte_times<3>(a0, w[1], nw[1]));
-    h[1] = __fadd_rn(h[1], byte_times<0>(a1, w[1], nw[1])); h[2] = __fadd_rn(h[2], byte_times<1>(a1, w[1], nw[1]));
-    h[0] = __fadd_rn(h[0], byte_times<2>(a1, w[2], nw[2])); h[1] = __fadd_rn(h[1], byte_times<3>(a1, w[2], nw[2]));
-    h[2] = __fadd_rn(h[2], byte_times<0>(a2, w[2], nw[2])); h[0] = __fadd_rn(h[0], byte_times<1>(a2, w[3], nw[3]));
-    h[1] = __fadd_rn(h[1], byte_times<2>(a2, w[3], nw[3])); h[2] = __fadd_rn(h[2], byte_times<3>(a2, w[3], nw[3]));
-    w0 = w3;
-    wp += 3;
+// Blackwell's packed float32 pair instructions (FFMA2 / FADD2): two independent IEEE operations per issue slot.  The
+// kernel is issue bound, and the accumulation chains of two SOURCE ROWS of the same output pixel are independent
+// (OpenCV finishes a row's x taps before it touches the sum over rows), so a thread walks two rows at once with the
+// chains of row A in the low halves and those of row B in the high halves: 1 PRMT + 1/2 FFMA2 + 1/2 FADD2 per byte
+// instead of PRMT + FFMA + FADD.  Every lane result is the scalar result bit for bit.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
 }
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// (2^23 + byte K of wa, 2^23 + byte K of wb) as a float pair
+template <int K>
+__device__ __forceinline__ uint64_t byte_pair(uint32_t wa, uint32_t wb) {
+    return f2_pack(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7440 | K)), __uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7440 | K)));
+}
+#define WICCA_TAP(K, A, B, T, C) h[C] = f2_add(h[C], f2_fma(byte_pair<K>(A, B), w[T], nw[T]))
+
+// Four taps = 12 bytes = three realigned words of row A and of row B; tap t has weight w[t] (the same in both halves).
+// Channel chains stay in tap order.
+__device__ __forceinline__ void area_group2(const uint32_t*& pa, const uint32_t*& pb, uint32_t& a0, uint32_t& b0, uint32_t shift,
+                                            const uint64_t (&w)[4], const uint64_t (&nw)[4], uint64_t (&h)[3]) {
+    const uint32_t a1 = pa[1], a2 = pa[2], a3 = pa[3];
+    const uint32_t b1 = pb[1], b2 = pb[2], b3 = pb[3];
+    const uint32_t x0 = __funnelshift_r(a0, a1, shift), x1 = __funnelshift_r(a1, a2, shift), x2 = __funnelshift_r(a2, a3, shift);
+    const uint32_t y0 = __funnelshift_r(b0, b1, shift), y1 = __funnelshift_r(b1, b2, shift), y2 = __funnelshift_r(b2, b3, shift);
+    WICCA_TAP(0, x0, y0, 0, 0); WICCA_TAP(1, x0, y0, 0, 1); WICCA_TAP(2, x0, y0, 0, 2);
+    WICCA_TAP(3, x0, y0, 1, 0); WICCA_TAP(0, x1, y1, 1, 1); WICCA_TAP(1, x1, y1, 1, 2);
+    WICCA_TAP(2, x1, y1, 2, 0); WICCA_TAP(3, x1, y1, 2, 1); WICCA_TAP(0, x2, y2, 2, 2);
+    WICCA_TAP(1, x2, y2, 3, 0); WICCA_TAP(2, x2, y2, 3, 1); WICCA_TAP(3, x2, y2, 3, 2);
+    a0 = a3; b0 = b3;
+    pa += 3; pb += 3;
+}
+#undef WICCA_TAP
 
 __global__ void __launch_bounds__(kRowsMaxThreads)
 resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, float* __restrict__ out,
                         uint8_t* __restrict__ out_u8, int buf_bytes) {
-    extern __shared__ __align__(16) uint8_t s_rows[];          // two row buffers of buf_bytes each
+    extern __shared__ __align__(16) uint8_t s_rows[];          // two PAIRS of row buffers, buf_bytes each
     __shared__ __align__(8) uint64_t s_full[2];
     const int img = blockIdx.y, dy = blockIdx.x;
     const ResizeJob j = t.jobs[img];
@@ -203,18 +233,25 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
     // the y taps of this output row, in OpenCV's order: [left partial] + full rows + [right partial]
     const int has_l = ay.w_left != 0.0f, has_r = ay.w_right != 0.0f;
     const int n_rows = has_l + ay.n_full + has_r;
+    const int n_pairs = (n_rows + 1) >> 1;
     auto row_index = [&](int k) { return (has_l && k == 0) ? ay.s_left : (k - has_l < ay.n_full ? ay.s_first + (k - has_l) : ay.s_right); };
     auto row_weight = [&](int k) { return (has_l && k == 0) ? ay.w_left : (k - has_l < ay.n_full ? ay.w_full : ay.w_right); };
-    auto fetch = [&](int k) {
-        const uint8_t* g = j.src + (int64_t)row_index(k) * j.pitch + lo;
-        uint8_t* s = s_rows + (k & 1) * buf_bytes + kRowPadFront;
+    // pair p = source rows 2p and 2p+1 (the last pair of an odd count has one row) into buffers 2(p&1), 2(p&1)+1
+    auto fetch = [&](int p) {
+        const int n_here = (2 * p + 1 < n_rows) ? 2 : 1;
         if (bulk) {
             if (threadIdx.x == 0) {
-                rs_mbar_expect_tx(&s_full[k & 1], (uint32_t)copy_bytes);
-                rs_bulk_load(s, g, (uint32_t)copy_bytes, &s_full[k & 1]);
+                rs_mbar_expect_tx(&s_full[p & 1], (uint32_t)(copy_bytes * n_here));
+                for (int q = 0; q < n_here; ++q)
+                    rs_bulk_load(s_rows + (2 * (p & 1) + q) * buf_bytes + kRowPadFront, j.src + (int64_t)row_index(2 * p + q) * j.pitch + lo,
+                                 (uint32_t)copy_bytes, &s_full[p & 1]);
             }
         } else {
-            for (int b = threadIdx.x; b < seg_bytes; b += blockDim.x) s[b] = g[b];
+            for (int q = 0; q < n_here; ++q) {
+                const uint8_t* g = j.src + (int64_t)row_index(2 * p + q) * j.pitch + lo;
+                uint8_t* s = s_rows + (2 * (p & 1) + q) * buf_bytes + kRowPadFront;
+                for (int b = threadIdx.x; b < seg_bytes; b += blockDim.x) s[b] = g[b];
+            }
         }
     };
     // ---- this thread's x taps (independent of the row)
@@ -224,37 +261,43 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
     const int n_taps = ax.n_full + 2;                          // pixels s_first - 1 .. s_first + n_full
     const int groups = (n_taps + 3) >> 2;
     auto tap_weight = [&](int tp) { return tp == 0 ? ax.w_left : (tp <= ax.n_full ? ax.w_full : (tp == ax.n_full + 1 ? ax.w_right : 0.0f)); };
-    float wa[4], nwa[4], wz[4], nwz[4], wm[4], nwm[4];
+    uint64_t wa[4], nwa[4], wz[4], nwz[4], wm[4], nwm[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        wa[q] = tap_weight(q); nwa[q] = -8388608.0f * wa[q];
-        wz[q] = tap_weight(4 * (groups - 1) + q); nwz[q] = -8388608.0f * wz[q];
-        wm[q] = ax.w_full; nwm[q] = -8388608.0f * ax.w_full;
+        const float fa = tap_weight(q), fz = tap_weight(4 * (groups - 1) + q);
+        wa[q] = f2_pack(fa, fa); nwa[q] = f2_pack(-8388608.0f * fa, -8388608.0f * fa);
+        wz[q] = f2_pack(fz, fz); nwz[q] = f2_pack(-8388608.0f * fz, -8388608.0f * fz);
+        wm[q] = f2_pack(ax.w_full, ax.w_full); nwm[q] = f2_pack(-8388608.0f * ax.w_full, -8388608.0f * ax.w_full);
     }
     const int b_start = (ax.s_first - 1) * 3 - lo + kRowPadFront;   // >= 13
     const uint32_t shift = (uint32_t)(b_start & 3) * 8;
     float acc[3] = {0.0f, 0.0f, 0.0f};
     __syncthreads();                                           // mbarrier init visible
     fetch(0);
-    for (int k = 0; k < n_rows; ++k) {
-        if (k + 1 < n_rows) fetch(k + 1);
-        if (bulk) rs_mbar_wait(&s_full[k & 1], (uint32_t)(k >> 1) & 1u);
+    for (int p = 0; p < n_pairs; ++p) {
+        if (p + 1 < n_pairs) fetch(p + 1);
+        if (bulk) rs_mbar_wait(&s_full[p & 1], (uint32_t)(p >> 1) & 1u);
         else __syncthreads();
         if (active) {
-            const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_rows + (k & 1) * buf_bytes) + (b_start >> 2);
-            uint32_t w0 = wp[0];
-            float h[3] = {0.0f, 0.0f, 0.0f};
-            area_group(wp, w0, shift, wa, nwa, h);
-            for (int g = 1; g < groups - 1; ++g) area_group(wp, w0, shift, wm, nwm, h);
-            if (groups > 1) area_group(wp, w0, shift, wz, nwz, h);
-            const float beta = row_weight(k);
+            const bool two = 2 * p + 1 < n_rows;
+            const uint32_t* pa = reinterpret_cast<const uint32_t*>(s_rows + (2 * (p & 1)) * buf_bytes) + (b_start >> 2);
+            const uint32_t* pb = two ? reinterpret_cast<const uint32_t*>(s_rows + (2 * (p & 1) + 1) * buf_bytes) + (b_start >> 2) : pa;
+            uint32_t a0 = pa[0], b0 = pb[0];
+            uint64_t h[3] = {0ull, 0ull, 0ull};                // (+0.0f, +0.0f)
+            area_group2(pa, pb, a0, b0, shift, wa, nwa, h);
+            for (int g = 1; g < groups - 1; ++g) area_group2(pa, pb, a0, b0, shift, wm, nwm, h);
+            if (groups > 1) area_group2(pa, pb, a0, b0, shift, wz, nwz, h);
+            const float beta_a = row_weight(2 * p), beta_b = two ? row_weight(2 * p + 1) : 0.0f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float bh = __fmul_rn(beta, h[c]);
-                acc[c] = (k == 0) ? bh : __fadd_rn(acc[c], bh);
+                float ha, hb;
+                f2_unpack(h[c], ha, hb);
+                const float ba = __fmul_rn(beta_a, ha);
+                acc[c] = (p == 0) ? ba : __fadd_rn(acc[c], ba);
+                if (two) acc[c] = __fadd_rn(acc[c], __fmul_rn(beta_b, hb));
             }
         }
-        __syncthreads();          // the buffer is refilled two iterations later
+        __syncthreads();          // the buffers are refilled two iterations later
     }
     if (active) {
         const int64_t i = (((int64_t)img * out_h + dy) * out_w + dx) * 3;
@@ -277,7 +320,7 @@ cudaError_t launch_resize_norm(const ResizeTables& t, int n, int out_h, int out_
     // source span of one segment: seg_w target pixels x scale, + the early pixel, the padded last group, alignment slack
     const int64_t span_px = segs == 1 ? (int64_t)max_src_w + 8 : ((int64_t)seg_w * max_src_w + out_w - 1) / out_w + 10;
     const int buf_bytes = kRowPadFront + (int)((span_px * 3 + 16 + 15) / 16 * 16) + kRowPadBack;
-    const size_t smem = (size_t)2 * buf_bytes;
+    const size_t smem = (size_t)4 * buf_bytes;                // two pairs of source rows in flight
     const bool rows_ok = n_area > 0 && out_w <= kRowsMaxThreads && smem <= 200 * 1024 && n <= 65535 && segs <= 65535;
     if (rows_ok) {
         static thread_local int configured_dev = -1;
