@@ -430,7 +430,7 @@ cudaError_t launch_icon_generic(const GenericIconArgs& a, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     // coalesced row-streaming kernel (haar_rows.cu) whenever one output pixel's row segment fits a tile;
     // the scalar kernel below remains for absurd channel counts only
-    if (rows_kernel_groups(a.C, a.depth) > 0) return launch_icon_rows(a, stream);
+    if (rows_kernel_groups(a.C, a.depth) > 0 && (((int64_t)a.out_w << a.depth) + 8) * a.C < 0x7FFFFFFF) return launch_icon_rows(a, stream);
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     haar_icon_generic_kernel<<<(int)blocks, 256, 0, stream>>>(a);

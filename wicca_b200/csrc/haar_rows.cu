@@ -29,18 +29,22 @@ namespace {
 constexpr int kRowsThreads = 256;
 constexpr int kRowsMaxTileBytes = 8192;         // 8 words per thread
 
-// One border-extended byte of image row ym (ym >= 0) at byte offset b of the padded row.
-__device__ __forceinline__ uint32_t padded_byte(const GenericIconArgs& a, const uint8_t* row, int64_t b) {
-    const int x = (int)(b / a.C);
-    const int c = (int)(b - (int64_t)x * a.C);
+// Source byte offset inside an image row of byte b of the border-extended row (b >= W*C is where it matters);
+// -1 when the border rule supplies the constant.  32-bit arithmetic: a padded row is far below 2 GB (launcher).
+__device__ __forceinline__ int padded_offset(const GenericIconArgs& a, int b) {
+    const int x = b / a.C;
+    const int c = b - x * a.C;
     const int xm = border_index(x, a.W, a.border_type);
-    return xm < 0 ? (uint32_t)a.border_const : (uint32_t)row[(int64_t)xm * a.C + c];
+    return xm < 0 ? -1 : xm * a.C + c;
 }
 
 // WPT words per thread and row; U = 8 / WPT rows are fetched before the first of them is consumed, so every thread keeps
 // eight independent 32-bit loads in flight (a row loop that consumes each word as it arrives serialises on the HBM
 // latency: 0.9 TB/s measured; the batched form is what makes the kernel bandwidth bound).
-template <int WPT>
+// BORDER = false: the CTAs whose whole tile lies inside the image (the streaming loop with no selects, few registers);
+// BORDER = true: the others (last tile column, last row block, unaligned sources).  Both are launched over the same
+// grid and each CTA returns at once from the instantiation that is not its own.
+template <int WPT, bool BORDER>
 __global__ void __launch_bounds__(kRowsThreads)
 haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int aligned) {
     constexpr int U = WPT >= 8 ? 1 : 8 / WPT;
@@ -53,9 +57,12 @@ haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int align
     const int n_words = tile_bytes >> 2;
     const int n_out = groups * a.C;
     const int64_t row_bytes = (int64_t)a.W * a.C;     // bytes of an image row that exist
+    const int64_t padded_bytes = ((int64_t)a.out_w << a.depth) * a.C;   // bytes of a border-extended row that feed an output
     const int64_t b0 = (int64_t)blockIdx.x * tile_bytes;
     const uint32_t fill = (uint32_t)a.border_const * 0x01010101u;
-    const bool interior = aligned && (b0 + tile_bytes <= row_bytes);       // CTA-uniform: no right border in this tile
+    const bool interior = aligned && (b0 + tile_bytes <= row_bytes) && (r % U) == 0 &&
+                          ((((int64_t)blockIdx.y + 1) * rows_per_cta) << a.depth) <= a.H;    // CTA-uniform: no border in this tile
+    if (interior == BORDER) return;
     // horizontal stage: nseg threads share one output when there are few outputs and many pixels per output
     int nseg = 1;
     while (nseg * 2 * n_out <= kRowsThreads && nseg * 2 <= r) nseg *= 2;
@@ -71,7 +78,7 @@ haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int align
         for (int k = 0; k < WPT; ++k) accE[k] = accO[k] = 0u;
         if (nseg > 1)
             for (int o = tid; o < n_out; o += kRowsThreads) outsum[o] = 0u;
-        if (interior && (((int64_t)oy + 1) << a.depth) <= a.H && (r % U) == 0) {
+        if (!BORDER) {
             // no border anywhere in this tile: a plain strided stream, U x WPT loads issued before the first use
             const uint32_t* p = reinterpret_cast<const uint32_t*>(a.src + ((int64_t)oy << a.depth) * a.pitch + b0) + tid;
             const int64_t pw = a.pitch >> 2;
@@ -91,26 +98,62 @@ haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int align
                     }
             }
         } else {
-            for (int dy = 0; dy < r; ++dy) {
-                const int ym = border_index((oy << a.depth) + dy, a.H, a.border_type);       // uniform over the CTA
-                const uint8_t* row = ym < 0 ? nullptr : a.src + (int64_t)ym * a.pitch;
+            // A tile that touches the bottom and / or the right border.  Words that lie inside the image horizontally
+            // are still streamed row-major, U rows in flight, with the border row map applied by selects (no branches
+            // between the loads); the few words that touch the right border are walked word-major further down.
+            for (int dy0 = 0; dy0 < r; dy0 += U) {
+                int ymv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) ymv[u] = dy0 + u < r ? border_index((oy << a.depth) + dy0 + u, a.H, a.border_type) : -2;
+                uint32_t v[U][WPT];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint8_t* row = a.src + (int64_t)(ymv[u] < 0 ? 0 : ymv[u]) * a.pitch;
+#pragma unroll
+                    for (int k = 0; k < WPT; ++k) {
+                        const int64_t b = b0 + 4 * (int64_t)(tid + k * kRowsThreads);
+                        const bool in_image = tid + k * kRowsThreads < n_words && b + 4 <= row_bytes;
+                        const int64_t bs = in_image ? b : 0;
+                        uint32_t x;
+                        if (aligned) x = __ldg(reinterpret_cast<const uint32_t*>(row + bs));
+                        else x = (uint32_t)row[bs] | ((uint32_t)row[bs + 1] << 8) | ((uint32_t)row[bs + 2] << 16) | ((uint32_t)row[bs + 3] << 24);
+                        v[u][k] = (!in_image || ymv[u] == -2) ? 0u : (ymv[u] < 0 ? fill : x);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int k = 0; k < WPT; ++k) {
+                        accE[k] += prmt(v[u][k], 0u, 0x4240u);
+                        accO[k] += prmt(v[u][k], 0u, 0x4341u);
+                    }
+            }
+            if (b0 + tile_bytes > row_bytes) {
 #pragma unroll
                 for (int k = 0; k < WPT; ++k) {
-                    const int w = tid + k * kRowsThreads;
-                    if (w >= n_words) break;
-                    const int64_t b = b0 + 4 * (int64_t)w;
-                    uint32_t v;
-                    if (row == nullptr) {
-                        v = fill;
-                    } else if (b + 4 <= row_bytes) {
-                        if (aligned) v = __ldg(reinterpret_cast<const uint32_t*>(row + b));
-                        else v = (uint32_t)row[b] | ((uint32_t)row[b + 1] << 8) | ((uint32_t)row[b + 2] << 16) | ((uint32_t)row[b + 3] << 24);
-                    } else {
-                        v = padded_byte(a, row, b) | (padded_byte(a, row, b + 1) << 8) | (padded_byte(a, row, b + 2) << 16) |
-                            (padded_byte(a, row, b + 3) << 24);
+                    const int64_t b = b0 + 4 * (int64_t)(tid + k * kRowsThreads);
+                    if (tid + k * kRowsThreads >= n_words || b + 4 <= row_bytes || b >= padded_bytes) continue;
+                    int off[4];                       // source byte of each of the word's four columns (-1: the constant)
+#pragma unroll
+                    for (int jb = 0; jb < 4; ++jb) off[jb] = padded_offset(a, (int)b + jb);
+                    for (int dy0 = 0; dy0 < r; dy0 += 8) {
+                        uint32_t by[8][4];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int ym = dy0 + u < r ? border_index((oy << a.depth) + dy0 + u, a.H, a.border_type) : -2;
+                            const uint8_t* row = a.src + (int64_t)(ym < 0 ? 0 : ym) * a.pitch;
+#pragma unroll
+                            for (int jb = 0; jb < 4; ++jb) {
+                                const uint32_t x = row[off[jb] < 0 ? 0 : off[jb]];
+                                by[u][jb] = ym == -2 ? 0u : ((ym < 0 || off[jb] < 0) ? (uint32_t)a.border_const : x);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            accE[k] += by[u][0] | (by[u][2] << 16);
+                            accO[k] += by[u][1] | (by[u][3] << 16);
+                        }
                     }
-                    accE[k] += prmt(v, 0u, 0x4240u);
-                    accO[k] += prmt(v, 0u, 0x4341u);
                 }
             }
         }
@@ -244,7 +287,7 @@ int rows_kernel_groups(int C, int depth) {
 cudaError_t launch_icon_rows(const GenericIconArgs& a, cudaStream_t stream) {
     if ((int64_t)a.out_h * a.out_w <= 0) return cudaSuccess;
     const int groups = rows_kernel_groups(a.C, a.depth);
-    if (groups <= 0 || a.depth > 8) return cudaErrorInvalidValue;
+    if (groups <= 0 || a.depth > 8 || (((int64_t)a.out_w << a.depth) + 8) * a.C >= 0x7FFFFFFF) return cudaErrorInvalidValue;
     const int64_t tile_bytes = (int64_t)groups * ((int64_t)a.C << a.depth);
     const int wpt = (int)((tile_bytes / 4 + kRowsThreads - 1) / kRowsThreads);
     int rows_per_cta = 32 >> a.depth;
@@ -252,10 +295,16 @@ cudaError_t launch_icon_rows(const GenericIconArgs& a, cudaStream_t stream) {
     const int aligned = (((uintptr_t)a.src & 3) == 0 && (a.pitch & 3) == 0) ? 1 : 0;
     while ((a.out_h + rows_per_cta - 1) / rows_per_cta > 65535) rows_per_cta *= 2;
     dim3 grid((unsigned)((a.out_w + groups - 1) / groups), (unsigned)((a.out_h + rows_per_cta - 1) / rows_per_cta));
-    if (wpt <= 1) haar_icon_rows_kernel<1><<<grid, kRowsThreads, 0, stream>>>(a, groups, rows_per_cta, aligned);
-    else if (wpt <= 2) haar_icon_rows_kernel<2><<<grid, kRowsThreads, 0, stream>>>(a, groups, rows_per_cta, aligned);
-    else if (wpt <= 4) haar_icon_rows_kernel<4><<<grid, kRowsThreads, 0, stream>>>(a, groups, rows_per_cta, aligned);
-    else haar_icon_rows_kernel<8><<<grid, kRowsThreads, 0, stream>>>(a, groups, rows_per_cta, aligned);
+#define WICCA_ROWS_LAUNCH(N)                                                                                              \
+    do {                                                                                                                  \
+        haar_icon_rows_kernel<N, false><<<grid, kRowsThreads, 0, stream>>>(a, groups, rows_per_cta, aligned);                 \
+        haar_icon_rows_kernel<N, true><<<grid, kRowsThreads, 0, stream>>>(a, groups, rows_per_cta, aligned);                  \
+    } while (0)
+    if (wpt <= 1) WICCA_ROWS_LAUNCH(1);
+    else if (wpt <= 2) WICCA_ROWS_LAUNCH(2);
+    else if (wpt <= 4) WICCA_ROWS_LAUNCH(4);
+    else WICCA_ROWS_LAUNCH(8);
+#undef WICCA_ROWS_LAUNCH
     return cudaGetLastError();
 }
 
