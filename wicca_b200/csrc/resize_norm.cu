@@ -205,79 +205,59 @@ __device__ __forceinline__ void area_group2(const uint32_t*& pa, const uint32_t*
 }
 #undef WICCA_TAP
 
-__device__ __forceinline__ void rs_mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rs_smem_u32(bar)) : "memory");
-}
-
-// Warp 0 is the producer: it alone knows where source rows live and keeps two PAIRS of rows in flight (full / empty
-// mbarriers per pair slot).  The consumer warps (one thread per output pixel) never meet at a CTA barrier inside the
-// loop: a warp that has finished a pair releases the slot and goes straight on to wait for the next one.
-__global__ void __launch_bounds__(kRowsMaxThreads + 32)
+__global__ void __launch_bounds__(kRowsMaxThreads)
 resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, float* __restrict__ out,
                         uint8_t* __restrict__ out_u8, int buf_bytes) {
     extern __shared__ __align__(16) uint8_t s_rows[];          // two PAIRS of row buffers, buf_bytes each
-    __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+    __shared__ __align__(8) uint64_t s_full[2];
     const int img = blockIdx.y, dy = blockIdx.x;
     const ResizeJob j = t.jobs[img];
     if (j.regime != 2) return;
-    const int seg_w = (int)blockDim.x - 32;                    // consumer threads = output pixels per CTA
-    const int x0 = blockIdx.z * seg_w;
-    if (x0 >= out_w) return;
     const AreaDesc ay = t.area[j.yoff + dy];
+    // this CTA's segment of the output row (blockIdx.z) and the source bytes that feed it
+    const int x0 = blockIdx.z * blockDim.x;
+    if (x0 >= out_w) return;
+    const int x_last = min(x0 + (int)blockDim.x, out_w) - 1;
+    const AreaDesc a_first = t.area[j.xoff + x0], a_last = t.area[j.xoff + x_last];
+    const int row_bytes = j.sw * 3;
+    const int lo = max(0, (a_first.s_first - 1) * 3) & ~15;                            // first byte fetched
+    const int hi = min(row_bytes, (a_last.s_first + a_last.n_full + 1) * 3);           // one past the last byte needed
+    const int seg_bytes = hi - lo;
+    const int copy_bytes = (seg_bytes + 15) & ~15;
+    // a segment can be bulk-copied when it starts on a 16-byte boundary and its rounded-up length stays inside the pitch
+    const bool bulk = (((uintptr_t)j.src | (uintptr_t)j.pitch) & 15) == 0 && lo + copy_bytes <= j.pitch;
+    if (threadIdx.x == 0) {
+        rs_mbar_init(&s_full[0], 1); rs_mbar_init(&s_full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     // the y taps of this output row, in OpenCV's order: [left partial] + full rows + [right partial]
     const int has_l = ay.w_left != 0.0f, has_r = ay.w_right != 0.0f;
     const int n_rows = has_l + ay.n_full + has_r;
     const int n_pairs = (n_rows + 1) >> 1;
-    // the source bytes that feed this CTA's segment of the output row
-    const int x_last = min(x0 + seg_w, out_w) - 1;
-    const int s_lo = t.area[j.xoff + x0].s_first;
-    const int lo = max(0, (s_lo - 1) * 3) & ~15;                                       // first byte fetched
-    if (threadIdx.x == 0) {
-        rs_mbar_init(&s_full[0], 1); rs_mbar_init(&s_full[1], 1);
-        rs_mbar_init(&s_empty[0], (uint32_t)(seg_w >> 5)); rs_mbar_init(&s_empty[1], (uint32_t)(seg_w >> 5));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (threadIdx.x < 32) {
-        // ---------------------------------------------------------------- producer warp
-        const AreaDesc a_last = t.area[j.xoff + x_last];
-        const int row_bytes = j.sw * 3;
-        const int hi = min(row_bytes, (a_last.s_first + a_last.n_full + 1) * 3);       // one past the last byte needed
-        const int seg_bytes = hi - lo;
-        const int copy_bytes = (seg_bytes + 15) & ~15;
-        // a segment can be bulk-copied when it starts on a 16-byte boundary and its rounded-up length stays inside the pitch
-        const bool bulk = (((uintptr_t)j.src | (uintptr_t)j.pitch) & 15) == 0 && lo + copy_bytes <= j.pitch;
-        auto row_index = [&](int k) { return (has_l && k == 0) ? ay.s_left : (k - has_l < ay.n_full ? ay.s_first + (k - has_l) : ay.s_right); };
-        for (int p = 0; p < n_pairs; ++p) {
-            const int slot = p & 1;
-            if (p >= 2) rs_mbar_wait(&s_empty[slot], (uint32_t)((p >> 1) - 1) & 1u);
-            const int n_here = (2 * p + 1 < n_rows) ? 2 : 1;
-            if (bulk) {
-                if (threadIdx.x == 0) {
-                    rs_mbar_expect_tx(&s_full[slot], (uint32_t)(copy_bytes * n_here));
-                    for (int q = 0; q < n_here; ++q)
-                        rs_bulk_load(s_rows + (2 * slot + q) * buf_bytes + kRowPadFront,
-                                     j.src + (int64_t)row_index(2 * p + q) * j.pitch + lo, (uint32_t)copy_bytes, &s_full[slot]);
-                }
-            } else {
-                for (int q = 0; q < n_here; ++q) {
-                    const uint8_t* g = j.src + (int64_t)row_index(2 * p + q) * j.pitch + lo;
-                    uint8_t* s = s_rows + (2 * slot + q) * buf_bytes + kRowPadFront;
-                    for (int b = threadIdx.x; b < seg_bytes; b += 32) s[b] = g[b];
-                }
-                __syncwarp();
-                if (threadIdx.x == 0) rs_mbar_arrive(&s_full[slot]);       // release: the copies above are visible to the waiters
+    auto row_index = [&](int k) { return (has_l && k == 0) ? ay.s_left : (k - has_l < ay.n_full ? ay.s_first + (k - has_l) : ay.s_right); };
+    auto row_weight = [&](int k) { return (has_l && k == 0) ? ay.w_left : (k - has_l < ay.n_full ? ay.w_full : ay.w_right); };
+    // pair p = source rows 2p and 2p+1 (the last pair of an odd count has one row) into buffers 2(p&1), 2(p&1)+1
+    auto fetch = [&](int p) {
+        const int n_here = (2 * p + 1 < n_rows) ? 2 : 1;
+        if (bulk) {
+            if (threadIdx.x == 0) {
+                rs_mbar_expect_tx(&s_full[p & 1], (uint32_t)(copy_bytes * n_here));
+                for (int q = 0; q < n_here; ++q)
+                    rs_bulk_load(s_rows + (2 * (p & 1) + q) * buf_bytes + kRowPadFront, j.src + (int64_t)row_index(2 * p + q) * j.pitch + lo,
+                                 (uint32_t)copy_bytes, &s_full[p & 1]);
+            }
+        } else {
+            for (int q = 0; q < n_here; ++q) {
+                const uint8_t* g = j.src + (int64_t)row_index(2 * p + q) * j.pitch + lo;
+                uint8_t* s = s_rows + (2 * (p & 1) + q) * buf_bytes + kRowPadFront;
+                for (int b = threadIdx.x; b < seg_bytes; b += blockDim.x) s[b] = g[b];
             }
         }
-        return;
-    }
-
-    // -------------------------------------------------------------------- consumer warps
-    auto row_weight = [&](int k) { return (has_l && k == 0) ? ay.w_left : (k - has_l < ay.n_full ? ay.w_full : ay.w_right); };
-    const int dx = x0 + (int)threadIdx.x - 32;
+    };
+    // ---- this thread's x taps (independent of the row)
+    const int dx = x0 + threadIdx.x;
     const bool active = dx < out_w;
-    const AreaDesc ax = t.area[j.xoff + (active ? dx : x_last)];
+    const AreaDesc ax = t.area[j.xoff + (active ? dx : 0)];
     const int n_taps = ax.n_full + 2;                          // pixels s_first - 1 .. s_first + n_full
     const int groups = (n_taps + 3) >> 2;
     auto tap_weight = [&](int tp) { return tp == 0 ? ax.w_left : (tp <= ax.n_full ? ax.w_full : (tp == ax.n_full + 1 ? ax.w_right : 0.0f)); };
@@ -291,31 +271,33 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
     }
     const int b_start = (ax.s_first - 1) * 3 - lo + kRowPadFront;   // >= 13
     const uint32_t shift = (uint32_t)(b_start & 3) * 8;
-    const uint32_t* base_a = reinterpret_cast<const uint32_t*>(s_rows) + (b_start >> 2);
-    const int buf_words = buf_bytes >> 2;
     float acc[3] = {0.0f, 0.0f, 0.0f};
+    __syncthreads();                                           // mbarrier init visible
+    fetch(0);
     for (int p = 0; p < n_pairs; ++p) {
-        const int slot = p & 1;
-        rs_mbar_wait(&s_full[slot], (uint32_t)(p >> 1) & 1u);
-        const bool two = 2 * p + 1 < n_rows;
-        const uint32_t* pa = base_a + (2 * slot) * buf_words;
-        const uint32_t* pb = two ? pa + buf_words : pa;
-        uint32_t a0 = pa[0], b0 = pb[0];
-        uint64_t h[3] = {0ull, 0ull, 0ull};                    // (+0.0f, +0.0f)
-        area_group2(pa, pb, a0, b0, shift, wa, nwa, h);
-        for (int g = 1; g < groups - 1; ++g) area_group2(pa, pb, a0, b0, shift, wm, nwm, h);
-        if (groups > 1) area_group2(pa, pb, a0, b0, shift, wz, nwz, h);
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) rs_mbar_arrive(&s_empty[slot]);        // this warp is done with the slot
-        const float beta_a = row_weight(2 * p), beta_b = two ? row_weight(2 * p + 1) : 0.0f;
+        if (p + 1 < n_pairs) fetch(p + 1);
+        if (bulk) rs_mbar_wait(&s_full[p & 1], (uint32_t)(p >> 1) & 1u);
+        else __syncthreads();
+        if (active) {
+            const bool two = 2 * p + 1 < n_rows;
+            const uint32_t* pa = reinterpret_cast<const uint32_t*>(s_rows + (2 * (p & 1)) * buf_bytes) + (b_start >> 2);
+            const uint32_t* pb = two ? reinterpret_cast<const uint32_t*>(s_rows + (2 * (p & 1) + 1) * buf_bytes) + (b_start >> 2) : pa;
+            uint32_t a0 = pa[0], b0 = pb[0];
+            uint64_t h[3] = {0ull, 0ull, 0ull};                // (+0.0f, +0.0f)
+            area_group2(pa, pb, a0, b0, shift, wa, nwa, h);
+            for (int g = 1; g < groups - 1; ++g) area_group2(pa, pb, a0, b0, shift, wm, nwm, h);
+            if (groups > 1) area_group2(pa, pb, a0, b0, shift, wz, nwz, h);
+            const float beta_a = row_weight(2 * p), beta_b = two ? row_weight(2 * p + 1) : 0.0f;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float ha, hb;
-            f2_unpack(h[c], ha, hb);
-            const float ba = __fmul_rn(beta_a, ha);
-            acc[c] = (p == 0) ? ba : __fadd_rn(acc[c], ba);
-            if (two) acc[c] = __fadd_rn(acc[c], __fmul_rn(beta_b, hb));
+            for (int c = 0; c < 3; ++c) {
+                float ha, hb;
+                f2_unpack(h[c], ha, hb);
+                const float ba = __fmul_rn(beta_a, ha);
+                acc[c] = (p == 0) ? ba : __fadd_rn(acc[c], ba);
+                if (two) acc[c] = __fadd_rn(acc[c], __fmul_rn(beta_b, hb));
+            }
         }
+        __syncthreads();          // the buffers are refilled two iterations later
     }
     if (active) {
         const int64_t i = (((int64_t)img * out_h + dy) * out_w + dx) * 3;
@@ -349,8 +331,7 @@ cudaError_t launch_resize_norm(const ResizeTables& t, int n, int out_h, int out_
             if (e != cudaSuccess) return e;
             configured_dev = dev;
         }
-        // + 32: the producer warp
-        resize_area_rows_kernel<<<dim3(out_h, n, segs), seg_w + 32, smem, stream>>>(t, out_h, out_w, norm_mode, d_out, d_out_u8, buf_bytes);
+        resize_area_rows_kernel<<<dim3(out_h, n, segs), seg_w, smem, stream>>>(t, out_h, out_w, norm_mode, d_out, d_out_u8, buf_bytes);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_other == 0) return cudaSuccess;
