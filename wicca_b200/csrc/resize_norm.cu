@@ -203,18 +203,6 @@ __device__ __forceinline__ void area_group2(const uint32_t*& pa, const uint32_t*
     a0 = a3; b0 = b3;
     pa += 3; pb += 3;
 }
-
-// Two taps = 6 bytes of row A and of row B: the tail of a run whose tap count is 1 or 2 past a multiple of four
-// (a 331-pixel target of a depth-1 icon has 13-14 taps per output pixel: three groups and this instead of four groups).
-__device__ __forceinline__ void area_half_group2(const uint32_t* pa, const uint32_t* pb, uint32_t a0, uint32_t b0, uint32_t shift,
-                                                 const uint64_t (&w)[4], const uint64_t (&nw)[4], uint64_t (&h)[3]) {
-    const uint32_t a1 = pa[1], a2 = pa[2];
-    const uint32_t b1 = pb[1], b2 = pb[2];
-    const uint32_t x0 = __funnelshift_r(a0, a1, shift), x1 = __funnelshift_r(a1, a2, shift);
-    const uint32_t y0 = __funnelshift_r(b0, b1, shift), y1 = __funnelshift_r(b1, b2, shift);
-    WICCA_TAP(0, x0, y0, 0, 0); WICCA_TAP(1, x0, y0, 0, 1); WICCA_TAP(2, x0, y0, 0, 2);
-    WICCA_TAP(3, x0, y0, 1, 0); WICCA_TAP(0, x1, y1, 1, 1); WICCA_TAP(1, x1, y1, 1, 2);
-}
 #undef WICCA_TAP
 
 __global__ void __launch_bounds__(kRowsMaxThreads)
@@ -270,27 +258,14 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
     const int dx = x0 + threadIdx.x;
     const bool active = dx < out_w;
     const AreaDesc ax = t.area[j.xoff + (active ? dx : 0)];
-    // Tap slots: pixels s_first - 1 .. s_first + n_full, padded with weight-0 taps to whole groups of four plus, when
-    // that saves a group, one half group of two.  The structure is chosen per WARP (from its longest run) so that the
-    // lanes never diverge; every lane's weights are by tap index, so any structure with enough slots is exact for it.
-    const int n_taps = __reduce_max_sync(0xFFFFFFFFu, ax.n_full + 2);
-    const int rem = n_taps & 3;
-    const bool half_tail = rem == 1 || rem == 2;
-    const int groups = half_tail ? (n_taps >> 2) : ((n_taps + 3) >> 2);     // full groups
-    // chunks: [first: per-tap weights a] [middle: w_full] [second to last full group: per-tap weights y] [last chunk,
-    // a full or a half group: per-tap weights z].  Two per-tap chunks at the end, because a lane whose run is a tap or
-    // two shorter than the warp's longest has its right partial pixel one chunk earlier.
-    const int z_base = half_tail ? 4 * groups : 4 * (groups - 1);          // first tap of the last chunk
-    const int n_y = (half_tail ? groups >= 2 : groups >= 3) ? 1 : 0;       // is there a y chunk (between first and last)
-    const int y_base = z_base - 4;
-    const int n_mid = (half_tail ? groups - 2 : groups - 3);               // w_full groups (<= 0: none)
+    const int n_taps = ax.n_full + 2;                          // pixels s_first - 1 .. s_first + n_full
+    const int groups = (n_taps + 3) >> 2;
     auto tap_weight = [&](int tp) { return tp == 0 ? ax.w_left : (tp <= ax.n_full ? ax.w_full : (tp == ax.n_full + 1 ? ax.w_right : 0.0f)); };
-    uint64_t wa[4], nwa[4], wy[4], nwy[4], wz[4], nwz[4], wm[4], nwm[4];
+    uint64_t wa[4], nwa[4], wz[4], nwz[4], wm[4], nwm[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const float fa = tap_weight(q), fy = tap_weight(y_base + q), fz = tap_weight(z_base + q);
+        const float fa = tap_weight(q), fz = tap_weight(4 * (groups - 1) + q);
         wa[q] = f2_pack(fa, fa); nwa[q] = f2_pack(-8388608.0f * fa, -8388608.0f * fa);
-        wy[q] = f2_pack(fy, fy); nwy[q] = f2_pack(-8388608.0f * fy, -8388608.0f * fy);
         wz[q] = f2_pack(fz, fz); nwz[q] = f2_pack(-8388608.0f * fz, -8388608.0f * fz);
         wm[q] = f2_pack(ax.w_full, ax.w_full); nwm[q] = f2_pack(-8388608.0f * ax.w_full, -8388608.0f * ax.w_full);
     }
@@ -309,12 +284,9 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
             const uint32_t* pb = two ? reinterpret_cast<const uint32_t*>(s_rows + (2 * (p & 1) + 1) * buf_bytes) + (b_start >> 2) : pa;
             uint32_t a0 = pa[0], b0 = pb[0];
             uint64_t h[3] = {0ull, 0ull, 0ull};                // (+0.0f, +0.0f)
-            const bool has_first = half_tail ? groups >= 1 : true;
-            if (has_first) area_group2(pa, pb, a0, b0, shift, wa, nwa, h);
-            for (int g = 0; g < n_mid; ++g) area_group2(pa, pb, a0, b0, shift, wm, nwm, h);
-            if (n_y) area_group2(pa, pb, a0, b0, shift, wy, nwy, h);
-            if (half_tail) area_half_group2(pa, pb, a0, b0, shift, wz, nwz, h);
-            else if (groups >= 2) area_group2(pa, pb, a0, b0, shift, wz, nwz, h);
+            area_group2(pa, pb, a0, b0, shift, wa, nwa, h);
+            for (int g = 1; g < groups - 1; ++g) area_group2(pa, pb, a0, b0, shift, wm, nwm, h);
+            if (groups > 1) area_group2(pa, pb, a0, b0, shift, wz, nwz, h);
             const float beta_a = row_weight(2 * p), beta_b = two ? row_weight(2 * p + 1) : 0.0f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
