@@ -228,20 +228,31 @@ def host_link_ceiling(torch, dist, dev, world, host_flat, out_flat, h2d_bytes, d
     def run(up: bool, down: bool) -> float:
         barrier()
         t0 = time.perf_counter()
-        if up:
-            with torch.cuda.stream(s_up):
-                for _ in range(n_up):
+        # the downward copies are paced by the upward ones (copy i down waits for copy i-1 up), as in the real
+        # pipeline where an image's icons can only flow back after the image has arrived; unpaced, the 1:3 traffic
+        # mix degenerates into a burst of writes followed by reads and the host memory system does worse
+        n = max(n_up if up else 0, n_down if down else 0)
+        for i in range(n):
+            ev = None
+            if up and i < n_up:
+                with torch.cuda.stream(s_up):
                     d_up.copy_(host_flat, non_blocking=True)
-        if down:
-            with torch.cuda.stream(s_down):
-                for _ in range(n_down):
+                    ev = torch.cuda.Event()
+                    ev.record(s_up)
+            if down and i < n_down:
+                with torch.cuda.stream(s_down):
+                    if up and prev[0] is not None:
+                        s_down.wait_event(prev[0])
                     out_flat.copy_(d_down, non_blocking=True)
+            prev[0] = ev
         s_up.synchronize(); s_down.synchronize()
+        prev[0] = None
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         return float(dt.item())
 
+    prev = [None]
     run(True, True)                                   # warm-up
     t_up = min(run(True, False) for _ in range(2))
     t_both = min(run(True, True) for _ in range(2))
@@ -480,10 +491,13 @@ def run_ours(args) -> int:
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     distributed = world > 1
+    # stdout carries exactly ONE line, the JSON record.  NCCL prints its banner / NCCL_DEBUG lines on stdout (whatever
+    # NCCL_DEBUG is set to is left alone: the driver reads those lines), so file descriptor 1 is pointed at stderr for
+    # the duration of the run and the record is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if distributed:
-        # NCCL writes its NCCL_DEBUG lines to stdout by default; stdout carries the one JSON line, so they go to stderr
-        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
-            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -651,6 +665,9 @@ def run_ours(args) -> int:
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
     if line is not None:
         print(json.dumps(line), flush=True)
     return 0
