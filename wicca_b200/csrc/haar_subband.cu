@@ -170,7 +170,8 @@ __global__ void inverse_level2x_f32_kernel(const float* __restrict__ ll, int64_t
 // ------------------------------------------------------------------------------------------
 constexpr int kTile = 64;
 constexpr int kTileThreads = 256;
-constexpr int kFusedLevels = 4;
+constexpr int kFusedLevels = 4;          // inverse: levels expanded inside a tile
+constexpr int kFwdFusedLevels = 6;       // forward: a 64 x 64 tile holds one whole level-6 block, so the tile finishes it
 
 struct TileGeom {
     int Hp, Wp;                 // padded extents (multiples of 2^depth)
@@ -199,8 +200,9 @@ __device__ __forceinline__ void analyse(const float (&a)[C], const float (&b)[C]
 // Forward: a CTA covers a 64 x 64-pixel tile, a warp a 16-row x 32-pixel region of it, and a lane
 // one 4 x 4-pixel patch (one level-2 block; lane = 8*ly + lx inside the warp's 4 x 8 level-2 blocks).
 // Levels 1 and 2 are computed in registers; for levels 3 and 4 the warp's level-2 LLs pass through the per-warp
-// stage and a lane owns one (block, channel) element (see below).  Nothing crosses a warp, so there is no
-// barrier and no CTA-wide pyramid.  Sub-band rows leave through the per-warp stage so that every store
+// stage and a lane owns one (block, channel) element (see below).  Up to level 4 nothing crosses a warp: no barrier,
+// no CTA-wide pyramid.  Depths 5 and 6 end with ONE barrier, after which warp 0 finishes the tile from its sixteen
+// level-4 LLs (all d levels of depth <= 6 in one pass over the image, one launch).  Sub-band rows leave through the per-warp stage so that every store
 // instruction writes 128 contiguous bytes of one row.
 // ------------------------------------------------------------------------------------------
 // Store ROWS staged rows of SEG floats (row pitch PITCH in the stage) to rows of a sub-band.  One store
@@ -246,6 +248,7 @@ forward_patch_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int 
                      TileGeom g) {
     constexpr int kPitch1 = 16 * C + 8;                        // staged level-1 row (+8: float2 writes hit every bank once)
     __shared__ __align__(16) float s_st[kTileThreads / 32][8 * kPitch1];   // per-warp staging of one sub-band of one level
+    __shared__ float s_ll4[4][4 * C];                                      // the tile's level-4 LLs (levels 5 and 6)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wy = warp >> 1, wx = warp & 1, ly = lane >> 3, lx = lane & 7;
     const int ty = blockIdx.y, tx = blockIdx.x;
@@ -379,6 +382,7 @@ forward_patch_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int 
         const float cc = __shfl_sync(0xFFFFFFFFu, ll3, s0 + seg), d = __shfl_sync(0xFFFFFFFFu, ll3, s0 + seg + C);
         if (lane < 2 * C) {
             const float rs0 = __fadd_rn(a, cc), rs1 = __fadd_rn(b, d), rd0 = __fsub_rn(a, cc), rd1 = __fsub_rn(b, d);
+            const float ll4 = __fmul_rn(__fadd_rn(rs0, rs1), 0.25f);
             const int h4 = g.Hp >> 4, w4 = g.Wp >> 4;
             const int gy = ty * 4 + wy, gx0 = tx * 4 + 2 * wx;
             if (gy < h4 && gx0 + lane / C < w4) {
@@ -387,8 +391,49 @@ forward_patch_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int 
                 store_keep(q_hl, __fmul_rn(__fsub_rn(rs0, rs1), 0.25f));
                 store_keep(q_lh, __fmul_rn(__fadd_rn(rd0, rd1), 0.25f));
                 store_keep(q_lh + (int64_t)w4 * C, __fmul_rn(__fsub_rn(rd0, rd1), 0.25f));
-                store_keep(g.ll + (int64_t)gy * g.ll_stride + (int64_t)gx0 * C + lane, __fmul_rn(__fadd_rn(rs0, rs1), 0.25f));   // levels == 4 here
+                if (g.levels == 4) store_keep(g.ll + (int64_t)gy * g.ll_stride + (int64_t)gx0 * C + lane, ll4);
             }
+            s_ll4[wy][2 * wx * C + lane] = ll4;                   // lane = block * C + channel
+        }
+    }
+    if (g.levels == 4) return;
+    // ---- levels 5 and 6: the tile's 4 x 4 level-4 LLs meet in shared memory - the only CTA-wide step, a few dozen
+    // values - and warp 0 finishes the tile's 2 x 2 level-5 blocks and its one level-6 block (a 64 x 64 tile IS a
+    // level-6 block), so depths 5 and 6 need no second launch over a scratch plane.
+    __syncthreads();
+    if (warp != 0) return;
+    float ll5 = 0.f;
+    {
+        const int blk = (lane / C) & 3, c = lane % C, by = blk >> 1, bx = blk & 1;
+        const float a = s_ll4[2 * by][(2 * bx) * C + c], b = s_ll4[2 * by][(2 * bx + 1) * C + c];
+        const float cc = s_ll4[2 * by + 1][(2 * bx) * C + c], d = s_ll4[2 * by + 1][(2 * bx + 1) * C + c];
+        const float rs0 = __fadd_rn(a, cc), rs1 = __fadd_rn(b, d), rd0 = __fsub_rn(a, cc), rd1 = __fsub_rn(b, d);
+        ll5 = __fmul_rn(__fadd_rn(rs0, rs1), 0.25f);
+        const int h5 = g.Hp >> 5, w5 = g.Wp >> 5;
+        const int gy = ty * 2 + by, gx = tx * 2 + bx;
+        if (lane < 4 * C && gy < h5 && gx < w5) {
+            float* q_hl = g.plane + (int64_t)gy * g.pl_stride + (int64_t)(w5 + gx) * C + c;
+            float* q_lh = g.plane + (int64_t)(gy + h5) * g.pl_stride + (int64_t)gx * C + c;
+            store_keep(q_hl, __fmul_rn(__fsub_rn(rs0, rs1), 0.25f));
+            store_keep(q_lh, __fmul_rn(__fadd_rn(rd0, rd1), 0.25f));
+            store_keep(q_lh + (int64_t)w5 * C, __fmul_rn(__fsub_rn(rd0, rd1), 0.25f));
+            if (g.levels == 5) store_keep(g.ll + (int64_t)gy * g.ll_stride + (int64_t)gx * C + c, ll5);
+        }
+    }
+    if (g.levels == 5) return;
+    {
+        const int c = lane % C;
+        const float a = __shfl_sync(0xFFFFFFFFu, ll5, c), b = __shfl_sync(0xFFFFFFFFu, ll5, C + c);
+        const float cc = __shfl_sync(0xFFFFFFFFu, ll5, 2 * C + c), d = __shfl_sync(0xFFFFFFFFu, ll5, 3 * C + c);
+        const float rs0 = __fadd_rn(a, cc), rs1 = __fadd_rn(b, d), rd0 = __fsub_rn(a, cc), rd1 = __fsub_rn(b, d);
+        const int h6 = g.Hp >> 6, w6 = g.Wp >> 6;
+        if (lane < C && ty < h6 && tx < w6) {
+            float* q_hl = g.plane + (int64_t)ty * g.pl_stride + (int64_t)(w6 + tx) * C + c;
+            float* q_lh = g.plane + (int64_t)(ty + h6) * g.pl_stride + (int64_t)tx * C + c;
+            store_keep(q_hl, __fmul_rn(__fsub_rn(rs0, rs1), 0.25f));
+            store_keep(q_lh, __fmul_rn(__fadd_rn(rd0, rd1), 0.25f));
+            store_keep(q_lh + (int64_t)w6 * C, __fmul_rn(__fsub_rn(rd0, rd1), 0.25f));
+            store_keep(g.ll + (int64_t)ty * g.ll_stride + (int64_t)tx * C + c, __fmul_rn(__fadd_rn(rs0, rs1), 0.25f));   // levels == 6
         }
     }
 }
@@ -654,9 +699,9 @@ cudaError_t launch_forward(const uint8_t* d_src, int64_t pitch, int H, int W, in
     int64_t in_stride = 0;
     int first = 1;
     if (C <= 4) {
-        // levels 1..min(depth, kFusedLevels) in one pass per 64 x 64 tile
+        // levels 1..min(depth, kFwdFusedLevels) in one pass per 64 x 64 tile
         TileGeom g;
-        g.Hp = Hp; g.Wp = Wp; g.levels = depth < kFusedLevels ? depth : kFusedLevels;
+        g.Hp = Hp; g.Wp = Wp; g.levels = depth < kFwdFusedLevels ? depth : kFwdFusedLevels;
         g.tiles_x = (Wp + kTile - 1) / kTile; g.tiles_y = (Hp + kTile - 1) / kTile;
         g.plane = d_coeffs; g.pl_stride = pl_stride;
         if (depth <= g.levels) { g.ll = d_coeffs; g.ll_stride = pl_stride; }
@@ -676,7 +721,7 @@ cudaError_t launch_forward(const uint8_t* d_src, int64_t pitch, int H, int W, in
         SubbandOut o;
         o.h = Hp >> l; o.w = Wp >> l; o.C = C;
         o.plane = d_coeffs; o.pl_stride = pl_stride;
-        if (first > kFusedLevels && l + 1 <= depth) {
+        if (first > kFwdFusedLevels && l + 1 <= depth) {
             // above the fused levels: two levels per launch (the planes are tiny, both scratch buffers hold any of them)
             SubbandOut o2 = o;
             o2.h = Hp >> (l + 1); o2.w = Wp >> (l + 1);
@@ -691,7 +736,7 @@ cudaError_t launch_forward(const uint8_t* d_src, int64_t pitch, int H, int W, in
             continue;
         }
         if (l == depth) { o.ll = d_coeffs; o.ll_stride = pl_stride; }
-        else if (first > kFusedLevels) { o.ll = (in == workA) ? workB : workA; o.ll_stride = (int64_t)o.w * C; }
+        else if (first > kFwdFusedLevels) { o.ll = (in == workA) ? workB : workA; o.ll_stride = (int64_t)o.w * C; }
         else { o.ll = (l & 1) ? workA : workB; o.ll_stride = (int64_t)o.w * C; }
         const int64_t n = (int64_t)o.h * o.w * C;
         if (l == 1) forward_level1_u8_kernel<<<grid_for(n), 256, 0, stream>>>(d_src, pitch, H, W, border_type, border_const, o);
