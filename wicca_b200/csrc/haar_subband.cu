@@ -201,8 +201,8 @@ __device__ __forceinline__ void analyse(const float (&a)[C], const float (&b)[C]
 // one 4 x 4-pixel patch (one level-2 block; lane = 8*ly + lx inside the warp's 4 x 8 level-2 blocks).
 // Levels 1 and 2 are computed in registers; for levels 3 and 4 the warp's level-2 LLs pass through the per-warp
 // stage and a lane owns one (block, channel) element (see below).  Up to level 4 nothing crosses a warp: no barrier,
-// no CTA-wide pyramid.  At depths 5 and 6 the warp that delivers its level-4 LLs last finishes the tile from all sixteen
-// of them (all d levels of depth <= 6 in one pass over the image, one launch, nobody waits).  Sub-band rows leave through the per-warp stage so that every store
+// no CTA-wide pyramid.  Depths 5 and 6 end with ONE barrier, after which warp 0 finishes the tile from its sixteen
+// level-4 LLs (all d levels of depth <= 6 in one pass over the image, one launch).  Sub-band rows leave through the per-warp stage so that every store
 // instruction writes 128 contiguous bytes of one row.
 // ------------------------------------------------------------------------------------------
 // Store ROWS staged rows of SEG floats (row pitch PITCH in the stage) to rows of a sub-band.  One store
@@ -249,11 +249,6 @@ forward_patch_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int 
     constexpr int kPitch1 = 16 * C + 8;                        // staged level-1 row (+8: float2 writes hit every bank once)
     __shared__ __align__(16) float s_st[kTileThreads / 32][8 * kPitch1];   // per-warp staging of one sub-band of one level
     __shared__ float s_ll4[4][4 * C];                                      // the tile's level-4 LLs (levels 5 and 6)
-    __shared__ int s_arrived;                                              // warps that have delivered theirs
-    if (g.levels > 4) {                                                    // uniform; every warp has only just started
-        if (threadIdx.x == 0) s_arrived = 0;
-        __syncthreads();
-    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wy = warp >> 1, wx = warp & 1, ly = lane >> 3, lx = lane & 7;
     const int ty = blockIdx.y, tx = blockIdx.x;
@@ -403,18 +398,10 @@ forward_patch_kernel(const uint8_t* __restrict__ src, int64_t pitch, int H, int 
     }
     if (g.levels == 4) return;
     // ---- levels 5 and 6: the tile's 4 x 4 level-4 LLs meet in shared memory - the only CTA-wide step, a few dozen
-    // values - and the LAST warp to arrive finishes the tile's 2 x 2 level-5 blocks and its one level-6 block (a
-    // 64 x 64 tile IS a level-6 block), so depths 5 and 6 need no second launch over a scratch plane and no warp
-    // waits for another (a barrier here keeps seven finished warps resident until the slowest one is done).
-    __syncwarp();
-    int last = 0;
-    if (lane == 0) {
-        __threadfence_block();
-        last = atomicAdd(&s_arrived, 1) == kTileThreads / 32 - 1;
-    }
-    last = __shfl_sync(0xFFFFFFFFu, last, 0);
-    if (!last) return;
-    __threadfence_block();
+    // values - and warp 0 finishes the tile's 2 x 2 level-5 blocks and its one level-6 block (a 64 x 64 tile IS a
+    // level-6 block), so depths 5 and 6 need no second launch over a scratch plane.
+    __syncthreads();
+    if (warp != 0) return;
     float ll5 = 0.f;
     {
         const int blk = (lane / C) & 3, c = lane % C, by = blk >> 1, bx = blk & 1;
