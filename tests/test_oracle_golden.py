@@ -68,3 +68,19 @@ def test_preprocess_modes():
     assert np.allclose(caffe[..., 0], x[..., 2].astype(np.float32) - 103.939)
     torch_ = ro.preprocess_input(x, "torch")
     assert np.allclose(torch_[..., 1], (x[..., 1] / 255.0 - 0.456) / 0.224, atol=1e-5)
+
+
+def test_torch_mode_agrees_with_torchvision_normalize():
+    """Row A6 stays UNPINNED (Keras 3.11.3 is not installed, vendored or in the wheelhouse).  The one independent
+    implementation this image holds is torchvision's `normalize`, the convention Keras' "torch" mode copies
+    (x / 255, then (x - mean) / std per channel, float32): corroboration of one of the four modes, not a pin."""
+    import pytest
+    torch = pytest.importorskip("torch")
+    tvf = pytest.importorskip("torchvision.transforms.functional")
+    from oracle import resize_oracle as ro
+    batch = np.random.default_rng(4).integers(0, 256, (3, 17, 23, 3), dtype=np.uint8)
+    batch[0, :16, :16, 0] = np.arange(256, dtype=np.uint8).reshape(16, 16)          # every byte value at least once
+    exp = ro.preprocess_input(batch, "torch")
+    x = torch.from_numpy(batch).permute(0, 3, 1, 2).to(torch.float32) / 255.0          # to_tensor's scaling, NCHW
+    got = tvf.normalize(x, mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225]).permute(0, 2, 3, 1).numpy()
+    assert got.dtype == np.float32 and np.array_equal(got, exp)
