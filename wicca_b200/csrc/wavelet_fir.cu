@@ -96,58 +96,28 @@ fir_cols_kernel(const float* __restrict__ t, int h, int w2, int C, FirTaps taps,
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Tiled level kernel (C <= 4): a CTA produces kH x 32 low-pass samples from a window of R = 2*kH + L - 2 input rows.
-//   stage   the R x (64 + L - 2) input pixels the tile needs go to shared memory; the periodic wrap-around and
-//           (level 1) the border rule are resolved here, once per pixel;
-//   rows    a thread filters TWO staged rows for four neighbouring outputs, channel by channel.  The kernel is issue
-//           bound (2L - 1 separately rounded float operations per output, by definition), so the two rows ride in the
-//           two halves of Blackwell's packed float32 pair instructions (FMUL2 / FFMA2 / FADD2: two IEEE operations per
-//           issue slot, each half bit-identical to the scalar instruction).  uint8 input is never converted: PRMT builds
-//           the float 2^23 + byte, and fma(2^23 + byte, g, -2^23 g) rounds the exact product byte * g once, i.e. it IS
-//           fmul(byte, g) (2^23 g is exact) - no LDS.U8, no quarter-rate I2F;
-//   cols    a thread filters two neighbouring output elements down the columns of row results (8-byte shared loads
-//           feed the packed pairs directly).
-// Tile geometry: R rows = one row pair per 8 threads x 8 groups of four outputs = exactly one item per thread in the
-// row pass (256 threads and R = 64 for uint8, 128 threads and R = 32 for the float planes of the deeper levels).
+// Tiled level kernel (C <= 4): a CTA produces kTileH x kTileW low-pass samples.
+//   stage   the (2*kTileH + L - 2) x (2*kTileW + L - 2) input pixels the tile needs go to shared memory; the
+//           periodic wrap-around and (level 1) the border rule are resolved here, once per pixel;
+//   rows    each thread filters one staged row for four neighbouring outputs and all channels: the 2*4 + L - 2
+//           pixels it loads are shared by the four outputs, the sums run tap by tap as in the oracle;
+//   cols    each thread filters one output element down the column of row results.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kOutPerThread = 4, kFirTileW = 32;
+constexpr int kTileThreads = 256, kOutPerThread = 4;
 
-__device__ __forceinline__ uint64_t fir_pack(float lo, float hi) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void fir_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ uint64_t fir_mul2(uint64_t a, uint64_t b) {
-    uint64_t r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ uint64_t fir_fma2(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ uint64_t fir_add2(uint64_t a, uint64_t b) {
-    uint64_t r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-
+// Tile geometry by input type: float planes (levels >= 2) take half the width, so that four CTAs fit an SM.
 template <typename TIn, int C, int L>
 struct FirTile {
-    static constexpr bool kU8 = sizeof(TIn) == 1;
-    static constexpr int kThreads = kU8 ? 256 : 128;
-    static constexpr int kW = kFirTileW;                                    // low-pass samples per tile row
-    static constexpr int rows = kThreads / 4;                               // input window rows: 64 / 32
-    static constexpr int kH = (rows + 2 - L) / 2;                           // tile rows: 2*kH + L - 2 == rows
-    static constexpr int cols = 2 * kW + L - 2;                             // input window columns
-    // staged row: up to 15 bytes of alignment slack, the window, rounded up to whole 16-byte chunks (+16: the row pass
-    // reads whole words past the last pixel); float rows are padded to a pitch of 4 words mod 8 against bank conflicts
-    static constexpr int kRowBytesMin = (15 + cols * C * (int)sizeof(TIn) + 15) / 16 * 16 + 16;
-    static constexpr int kRowBytes = (kU8 || kRowBytesMin % 32 == 16) ? kRowBytesMin : kRowBytesMin + 16;
+    static constexpr int kW = sizeof(TIn) == 1 ? 64 : 32;                   // low-pass samples per tile row
+    static constexpr int kH = sizeof(TIn) == 1 ? 16 : 14;                   // tile rows
+    static constexpr int rows = 2 * kH + L - 2, cols = 2 * kW + L - 2;      // input window
+    // staged row: up to 15 bytes of alignment slack, the window, rounded up to whole 16-byte chunks; float rows are
+    // padded to a pitch of 4 words mod 8 (a warp of the row pass reads 4 rows x 8 runs 24 words apart: 8-way bank
+    // conflicts on a pitch of 0 mod 8 words, 4-way - the best a multiple of 16 bytes allows - on 4 mod 8)
+    static constexpr int kRowBytesMin = (15 + cols * C * (int)sizeof(TIn) + 15) / 16 * 16;
+    static constexpr int kRowBytes = (sizeof(TIn) == 1 || kRowBytesMin % 32 == 16) ? kRowBytesMin : kRowBytesMin + 16;
     static constexpr size_t kInBytes = (size_t)rows * kRowBytes;
-    static constexpr int kTPitch = kW * C + 4;                               // row results: rows start 4 banks apart, 8-byte loads stay aligned
+    static constexpr int kTPitch = kW * C + 4;                               // row results: rows start 4 banks apart, 16-byte stores stay aligned
     static constexpr size_t kSmem = kInBytes + (size_t)rows * kTPitch * sizeof(float);
 };
 
@@ -159,29 +129,29 @@ __device__ __forceinline__ void fir_cp_async(uint32_t dst, const void* src) {
 }
 
 // All rows of an interior window, as CB-byte chunks from the aligned-down start of each row: fire and forget.
-template <int CB, int THREADS>
+template <int CB>
 __device__ __forceinline__ void fir_fetch_window(unsigned char* s_raw, int row_pitch_smem, const unsigned char* g_first,
                                                  int64_t g_pitch_bytes, int rows, int chunks) {
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(s_raw);
-    for (int q = threadIdx.x; q < rows * chunks; q += THREADS) {
+    for (int q = threadIdx.x; q < rows * chunks; q += kTileThreads) {
         const int r = q / chunks, ch = q - r * chunks;
         fir_cp_async<CB>(s0 + (uint32_t)(r * row_pitch_smem + ch * CB), g_first + (int64_t)r * g_pitch_bytes + ch * CB);
     }
 }
 
 template <typename TIn, int C, int L>
-__global__ void __launch_bounds__(FirTile<TIn, C, L>::kThreads)
+__global__ void __launch_bounds__(kTileThreads)
 fir_tile_kernel(const TIn* __restrict__ src, int64_t pitch_elems, int H, int W, int border_type, int border_const, int h, int w,
                 FirTaps taps, float* __restrict__ out, uint8_t* __restrict__ icon, int64_t icon_pitch) {
     using G = FirTile<TIn, C, L>;
-    constexpr int kTileW = G::kW, kTileH = G::kH, rows = G::rows, cols = G::cols, kRowBytes = G::kRowBytes, kThreads = G::kThreads;
-    constexpr bool kU8 = G::kU8;
+    constexpr int kTileW = G::kW, kTileH = G::kH, rows = G::rows, cols = G::cols, kRowBytes = G::kRowBytes;
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ float s_g[16];
     if (threadIdx.x < 16) s_g[threadIdx.x] = taps.g[threadIdx.x];
     float* s_t = reinterpret_cast<float*>(s_raw + G::kInBytes);                      // [rows][kTPitch]
     const int h2 = h >> 1, w2 = w >> 1;
     const int oy0 = blockIdx.y * kTileH, ox0 = blockIdx.x * kTileW;
+    constexpr bool kU8 = sizeof(TIn) == 1;
     // ---- stage: row r of the window lives at s_raw + r * kRowBytes + lead
     const int y0 = 2 * oy0 - taps.c, x0 = 2 * ox0 - taps.c;
     bool interior = y0 >= 0 && x0 >= 0 && y0 + rows <= (kU8 ? min(h, H) : h) && x0 + cols <= (kU8 ? min(w, W) : w);
@@ -199,9 +169,9 @@ fir_tile_kernel(const TIn* __restrict__ src, int64_t pitch_elems, int H, int W, 
             // the rounded-up chunk range must stay inside the row (pitch padding included)
             if (first - lead + (int64_t)chunks * cb <= pitch_bytes) {
                 const unsigned char* g0 = reinterpret_cast<const unsigned char*>(src) + (int64_t)y0 * pitch_bytes + (first - lead);
-                if (cb == 16) fir_fetch_window<16, kThreads>(s_raw, kRowBytes, g0, pitch_bytes, rows, chunks);
-                else if (cb == 8) fir_fetch_window<8, kThreads>(s_raw, kRowBytes, g0, pitch_bytes, rows, chunks);
-                else fir_fetch_window<4, kThreads>(s_raw, kRowBytes, g0, pitch_bytes, rows, chunks);
+                if (cb == 16) fir_fetch_window<16>(s_raw, kRowBytes, g0, pitch_bytes, rows, chunks);
+                else if (cb == 8) fir_fetch_window<8>(s_raw, kRowBytes, g0, pitch_bytes, rows, chunks);
+                else fir_fetch_window<4>(s_raw, kRowBytes, g0, pitch_bytes, rows, chunks);
                 asm volatile("cp.async.commit_group;" ::: "memory");
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
             } else {
@@ -212,7 +182,7 @@ fir_tile_kernel(const TIn* __restrict__ src, int64_t pitch_elems, int H, int W, 
         }
     }
     if (!interior) {
-        for (int e = threadIdx.x; e < rows * cols; e += kThreads) {
+        for (int e = threadIdx.x; e < rows * cols; e += kTileThreads) {
             const int r = e / cols, k = e - r * cols;
             int y = (y0 + r) % h;
             y += y < 0 ? h : 0;
@@ -232,107 +202,53 @@ fir_tile_kernel(const TIn* __restrict__ src, int64_t pitch_elems, int H, int W, 
         }
     }
     __syncthreads();
-    // ---- rows: (rows 2 rp and 2 rp + 1, outputs 4 jg .. 4 jg + 3, all channels) = exactly one item per thread
-    {
-        constexpr int groups = kTileW / kOutPerThread;                          // 8
-        constexpr int kPix = 2 * kOutPerThread + L - 2;                         // pixels the four outputs share
-        const int rp = threadIdx.x / groups, jg = threadIdx.x - rp * groups;
-        const unsigned char* row_a = s_raw + (size_t)(2 * rp) * kRowBytes + lead + (size_t)(2 * kOutPerThread * jg) * C * sizeof(TIn);
-        const unsigned char* row_b = row_a + kRowBytes;
-        float* d_a = s_t + (size_t)(2 * rp) * G::kTPitch + kOutPerThread * jg * C;
-        float* d_b = d_a + G::kTPitch;
-        uint64_t g2[L], ng2[L];
+    // ---- rows: (row r, outputs 4 jg .. 4 jg + 3, all channels) per work item
+    constexpr int groups = kTileW / kOutPerThread;
+    for (int e = threadIdx.x; e < rows * groups; e += kTileThreads) {
+        const int r = e / groups, jg = e - r * groups;
+        const TIn* p = reinterpret_cast<const TIn*>(s_raw + (size_t)r * kRowBytes + lead) + (size_t)(2 * kOutPerThread * jg) * C;
+        // the 2*4 + L - 2 pixels the four outputs share, converted once
+        constexpr int kPix = 2 * kOutPerThread + L - 2;
+        float px[kPix][C];
+#pragma unroll
+        for (int k = 0; k < kPix; ++k)
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) px[k][ch] = (float)p[k * C + ch];
+        float acc[kOutPerThread][C];
 #pragma unroll
         for (int n = 0; n < L; ++n) {
-            g2[n] = fir_pack(s_g[n], s_g[n]);
-            ng2[n] = fir_pack(-8388608.0f * s_g[n], -8388608.0f * s_g[n]);      // exact: a power of two times g
+            const float g = s_g[n];
+#pragma unroll
+            for (int o = 0; o < kOutPerThread; ++o)
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    const float v = __fmul_rn(px[2 * o + n][ch], g);
+                    acc[o][ch] = n == 0 ? v : __fadd_rn(acc[o][ch], v);
+                }
         }
-        if (kU8) {
-            // the kPix * C bytes of both rows as realigned words
-            constexpr int kWords = (kPix * C + 3) / 4;
-            const uint32_t sh = (uint32_t)((uintptr_t)row_a & 3) * 8;
-            const uint32_t* wa = reinterpret_cast<const uint32_t*>((uintptr_t)row_a & ~(uintptr_t)3);
-            const uint32_t* wb = reinterpret_cast<const uint32_t*>((uintptr_t)row_b & ~(uintptr_t)3);
-            uint32_t xa[kWords], xb[kWords];
-            {
-                uint32_t pa = wa[0], pb = wb[0];
+        float* d = s_t + (size_t)r * G::kTPitch + kOutPerThread * jg * C;
 #pragma unroll
-                for (int i = 0; i < kWords; ++i) {
-                    const uint32_t na = wa[i + 1], nb = wb[i + 1];
-                    xa[i] = __funnelshift_r(pa, na, sh);
-                    xb[i] = __funnelshift_r(pb, nb, sh);
-                    pa = na; pb = nb;
-                }
-            }
+        for (int o = 0; o < kOutPerThread; ++o)
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-                uint64_t px[kPix];                                              // (2^23 + byte of row a, 2^23 + byte of row b)
-#pragma unroll
-                for (int k = 0; k < kPix; ++k) {
-                    const int b = k * C + ch;
-                    px[k] = fir_pack(__uint_as_float(__byte_perm(xa[b >> 2], 0x4B000000u, 0x7440 | (b & 3))),
-                                     __uint_as_float(__byte_perm(xb[b >> 2], 0x4B000000u, 0x7440 | (b & 3))));
-                }
-#pragma unroll
-                for (int o = 0; o < kOutPerThread; ++o) {
-                    uint64_t acc = fir_fma2(px[2 * o], g2[0], ng2[0]);
-#pragma unroll
-                    for (int n = 1; n < L; ++n) acc = fir_add2(acc, fir_fma2(px[2 * o + n], g2[n], ng2[n]));
-                    float ta, tb;
-                    fir_unpack(acc, ta, tb);
-                    d_a[o * C + ch] = ta;
-                    d_b[o * C + ch] = tb;
-                }
-            }
-        } else {
-            const float* fa = reinterpret_cast<const float*>(row_a);
-            const float* fb = reinterpret_cast<const float*>(row_b);
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-                uint64_t px[kPix];
-#pragma unroll
-                for (int k = 0; k < kPix; ++k) px[k] = fir_pack(fa[k * C + ch], fb[k * C + ch]);
-#pragma unroll
-                for (int o = 0; o < kOutPerThread; ++o) {
-                    uint64_t acc = fir_mul2(px[2 * o], g2[0]);
-#pragma unroll
-                    for (int n = 1; n < L; ++n) acc = fir_add2(acc, fir_mul2(px[2 * o + n], g2[n]));
-                    float ta, tb;
-                    fir_unpack(acc, ta, tb);
-                    d_a[o * C + ch] = ta;
-                    d_b[o * C + ch] = tb;
-                }
-            }
-        }
+            for (int ch = 0; ch < C; ++ch) d[o * C + ch] = acc[o][ch];
     }
     __syncthreads();
-    // ---- columns: two neighbouring elements of an output row per work item
-    constexpr int seg = kTileW * C, seg2 = seg / 2;                              // kTileW is even
-    for (int e = threadIdx.x; e < kTileH * seg2; e += kThreads) {
-        const int i = e / seg2, q = 2 * (e - i * seg2);
-        const int oi = oy0 + i;
-        if (oi >= h2) continue;
+    // ---- columns
+    constexpr int seg = kTileW * C;
+    for (int e = threadIdx.x; e < kTileH * seg; e += kTileThreads) {
+        const int i = e / seg, q = e - i * seg;
+        const int oi = oy0 + i, oj = ox0 + q / C;
+        if (oi >= h2 || oj >= w2) continue;
         const float* p = s_t + (size_t)(2 * i) * G::kTPitch + q;
-        uint64_t acc = 0;
+        float acc = 0.0f;
 #pragma unroll
         for (int m = 0; m < L; ++m) {
-            const float2 v = *reinterpret_cast<const float2*>(p + m * G::kTPitch);
-            const uint64_t pr = fir_mul2(fir_pack(v.x, v.y), fir_pack(s_g[m], s_g[m]));
-            acc = m == 0 ? pr : fir_add2(acc, pr);
+            const float v = __fmul_rn(p[m * G::kTPitch], s_g[m]);
+            acc = m == 0 ? v : __fadd_rn(acc, v);
         }
-        float r0, r1;
-        fir_unpack(acc, r0, r1);
-        const bool in0 = ox0 + q / C < w2, in1 = ox0 + (q + 1) / C < w2;
         const int64_t o = (int64_t)ox0 * C + q;
-        if (icon) {
-            uint8_t* d = icon + (int64_t)oi * icon_pitch + o;
-            if (in0) d[0] = (uint8_t)fminf(fmaxf(r0, 0.0f), 255.0f);          // clip, then truncate
-            if (in1) d[1] = (uint8_t)fminf(fmaxf(r1, 0.0f), 255.0f);
-        } else {
-            float* d = out + (int64_t)oi * w2 * C + o;
-            if (in0) d[0] = r0;
-            if (in1) d[1] = r1;
-        }
+        if (icon) icon[(int64_t)oi * icon_pitch + o] = (uint8_t)fminf(fmaxf(acc, 0.0f), 255.0f);      // clip, then truncate
+        else out[(int64_t)oi * w2 * C + o] = acc;
     }
 }
 
@@ -350,8 +266,8 @@ cudaError_t launch_tile_l(const TIn* src, int64_t pitch_elems, int H, int W, int
         configured_dev = dev;
     }
     const dim3 grid((w / 2 + G::kW - 1) / G::kW, (h / 2 + G::kH - 1) / G::kH);
-    fir_tile_kernel<TIn, C, L><<<grid, G::kThreads, smem, stream>>>(src, pitch_elems, H, W, border_type, border_const, h, w, taps,
-                                                                   out, icon, icon_pitch);
+    fir_tile_kernel<TIn, C, L><<<grid, kTileThreads, smem, stream>>>(src, pitch_elems, H, W, border_type, border_const, h, w, taps,
+                                                                    out, icon, icon_pitch);
     return cudaGetLastError();
 }
 
