@@ -630,16 +630,25 @@ def run_ours(args) -> int:
 
     # ---- the other configs of BASELINE.json, bounded (about 20 s) ---------------------------
     extra = {}
+
+    def guarded(name, fn):
+        """The headline record must not be lost to a failure in a side measurement: report it instead."""
+        try:
+            return fn()
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] extra '{name}' failed on rank {rank}: {exc!r}", file=sys.stderr, flush=True)
+            return {"error": repr(exc)[:300]}
+
     if not args.no_extra:
-        for name, fn in (("configs3_icon_resize_norm", lambda: extra_epilogue(torch, IconPlan, imgs, pitch, local, stream, dev, all_max, peak)),):
-            extra[name] = fn()
+        extra["configs3_icon_resize_norm"] = guarded("configs3", lambda: extra_epilogue(torch, IconPlan, imgs, pitch, local, stream, dev, all_max, peak))
     plan.close()
     del imgs
     torch.cuda.empty_cache()
+    e2e_jpeg = None
     if not args.no_extra:
-        extra["configs2_subband_round_trip"] = extra_subbands(torch, lib, _capi, dev, local, stream, all_max, peak)
-        extra["configs4_sharded_ragged_batch"] = extra_sharded(torch, dist, lib, _capi, local, rank, world, barrier)
-    e2e_jpeg = None if args.no_extra else extra_jpeg(torch, dist, lib, _capi, local, rank, world, barrier)
+        extra["configs2_subband_round_trip"] = guarded("configs2", lambda: extra_subbands(torch, lib, _capi, dev, local, stream, all_max, peak))
+        extra["configs4_sharded_ragged_batch"] = guarded("configs4", lambda: extra_sharded(torch, dist, lib, _capi, local, rank, world, barrier))
+        e2e_jpeg = guarded("e2e_jpeg", lambda: extra_jpeg(torch, dist, lib, _capi, local, rank, world, barrier))
 
     sampler.stop()
     line = None
