@@ -120,3 +120,29 @@ def test_plan_with_depths_1_to_8():
             for k, d in enumerate(ds):
                 assert np.array_equal(plan.read_icon(i, k), ho.haar_icon_fp32(im, d, border)), (i, d, border)
         plan.close()
+
+
+def test_concurrent_callers_share_one_coder_across_all_paths():
+    """The reference calls one coder instance from a ThreadPoolExecutor (classifying_tools.py:414-418).  Twelve
+    threads hammer the three kernel families at once - one-pass (depths <= 6), level-6 plane + tail (depths 7-10) and the
+    row-streaming kernel (RGBA, grey) - each call must still equal the oracle (per-call streams, planes and scratch)."""
+    from concurrent.futures import ThreadPoolExecutor
+    coder = HaarCoder()
+    rng = np.random.default_rng(77)
+    jobs = []
+    for k in range(36):
+        c = (3, 3, 4, 1)[k % 4]
+        h, w = int(rng.integers(200, 900)), int(rng.integers(200, 1300))
+        depths = ([1, 4, 6], [8, 3], [7, 9], [2, 5])[k % 4] if c == 3 else ([3, 6], [8])[k % 2]
+        if c == 1:                                   # grey images must not need padding (the reference fails there)
+            h, w = h // 256 * 256 + 256, w // 256 * 256 + 256
+        jobs.append((rng.integers(0, 256, (h, w, c), dtype=np.uint8), depths, (1, 4, 2)[k % 3]))
+
+    def run(job):
+        img, depths, border = job
+        got = coder.get_small_copies(img, depths, border, 5)
+        return all(np.array_equal(g, ho.haar_icon_fp32(img, d, border, 5)) for g, d in zip(got, depths))
+
+    with ThreadPoolExecutor(12) as ex:
+        for rep in range(3):
+            assert all(ex.map(run, jobs)), rep

@@ -344,7 +344,7 @@ def cpu_side():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["icons", "subbands", "batch", "jpeg", "wavelets", "oneshot", "cpu"]
+    which = sys.argv[1:] or ["icons", "deep", "subbands", "batch", "jpeg", "wavelets", "oneshot", "cpu"]
     if "icons" in which:
         row_icons()
     if "deep" in which:
