@@ -69,6 +69,30 @@ haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int align
     const int seg_len = r / nseg;
     const int64_t ob0 = (int64_t)blockIdx.x * n_out;  // first output byte (of the icon row) of this tile
     const int64_t out_row_bytes = (int64_t)a.out_w * a.C;
+    // Where this thread's outputs live in the column sums: the same for every output row of the CTA, so the divisions
+    // by the (run-time) channel count are done once here, not per row (they were most of the kernel's instructions).
+    constexpr int kMaxO4 = kRowsMaxTileBytes / 2 / (4 * kRowsThreads);    // n_out <= tile / 2 (depth >= 1): 4 groups of 4
+    int off[kMaxO4][4];
+    int hs_off = -1, hs_o = 0;
+    if (nseg > 1) {
+        if (tid < n_out * nseg) {
+            const int o = tid % n_out, seg = tid / n_out;
+            const int g = o / a.C, c = o - g * a.C;
+            hs_off = g * gb + (seg * seg_len) * a.C + c;
+            hs_o = o;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kMaxO4; ++k) {
+            const int o4 = 4 * tid + k * 4 * kRowsThreads;
+            int g = o4 / a.C, c = o4 - g * a.C;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                off[k][j] = g * gb + c;
+                if (++c == a.C) { c = 0; ++g; }
+            }
+        }
+    }
 
     for (int rr = 0; rr < rows_per_cta; ++rr) {
         const int oy = blockIdx.y * rows_per_cta + rr;
@@ -168,28 +192,26 @@ haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int align
         }
         __syncthreads();
         if (nseg > 1) {
-            const int total = n_out * nseg;
-            for (int i = tid; i < total; i += kRowsThreads) {
-                const int o = i % n_out, seg = i / n_out;
-                const int g = o / a.C, c = o - g * a.C;
-                const uint16_t* p = colsum + g * gb + (seg * seg_len) * a.C + c;
+            if (hs_off >= 0) {
+                const uint16_t* p = colsum + hs_off;
                 uint32_t s = 0;
                 for (int q = 0; q < seg_len; ++q) s += p[q * a.C];
-                atomicAdd(&outsum[o], s);             // integer: exact and order-independent
+                atomicAdd(&outsum[hs_o], s);          // integer: exact and order-independent
             }
             __syncthreads();
         }
-        // four consecutive output bytes (or floats) per thread
-        for (int o4 = 4 * tid; o4 < n_out; o4 += 4 * kRowsThreads) {
+        // four consecutive output bytes (or floats) per thread and group
+#pragma unroll
+        for (int k = 0; k < kMaxO4; ++k) {
+            const int o4 = 4 * tid + k * 4 * kRowsThreads;
+            if (o4 >= n_out) break;
             uint32_t sv[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int o = o4 + j;
                 sv[j] = 0u;
-                if (o >= n_out) continue;
-                if (nseg > 1) { sv[j] = outsum[o]; continue; }
-                const int g = o / a.C, c = o - g * a.C;
-                const uint16_t* p = colsum + g * gb + c;
+                if (o4 + j >= n_out) continue;
+                if (nseg > 1) { sv[j] = outsum[o4 + j]; continue; }
+                const uint16_t* p = colsum + off[k][j];
                 uint32_t s = 0;
                 for (int q = 0; q < r; ++q) s += p[q * a.C];
                 sv[j] = s;
