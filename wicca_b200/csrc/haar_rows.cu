@@ -69,29 +69,17 @@ haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int align
     const int seg_len = r / nseg;
     const int64_t ob0 = (int64_t)blockIdx.x * n_out;  // first output byte (of the icon row) of this tile
     const int64_t out_row_bytes = (int64_t)a.out_w * a.C;
-    // Where this thread's outputs live in the column sums: the same for every output row of the CTA, so the divisions
-    // by the (run-time) channel count are done once here, not per row (they were most of the kernel's instructions).
-    constexpr int kMaxO4 = kRowsMaxTileBytes / 2 / (4 * kRowsThreads);    // n_out <= tile / 2 (depth >= 1): 4 groups of 4
-    int off[kMaxO4][4];
+    // Where this thread's outputs live in the column sums.  The divisions by the (run-time) channel count were most of
+    // the kernel's instructions: the few-outputs case (nseg > 1) resolves its one (output, segment) here, once per CTA;
+    // the many-outputs case divides by multiplication (exact for the 13-bit indices of a tile) instead of keeping
+    // sixteen offsets in registers - at 52 registers the kernel lost more to occupancy than the divisions had cost.
+    const uint32_t inv_c = a.C > 1 ? 0xFFFFFFFFu / (uint32_t)a.C + 1u : 0u;
     int hs_off = -1, hs_o = 0;
-    if (nseg > 1) {
-        if (tid < n_out * nseg) {
-            const int o = tid % n_out, seg = tid / n_out;
-            const int g = o / a.C, c = o - g * a.C;
-            hs_off = g * gb + (seg * seg_len) * a.C + c;
-            hs_o = o;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < kMaxO4; ++k) {
-            const int o4 = 4 * tid + k * 4 * kRowsThreads;
-            int g = o4 / a.C, c = o4 - g * a.C;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                off[k][j] = g * gb + c;
-                if (++c == a.C) { c = 0; ++g; }
-            }
-        }
+    if (nseg > 1 && tid < n_out * nseg) {
+        const int o = tid % n_out, seg = tid / n_out;
+        const int g = o / a.C, c = o - g * a.C;
+        hs_off = g * gb + (seg * seg_len) * a.C + c;
+        hs_o = o;
     }
 
     for (int rr = 0; rr < rows_per_cta; ++rr) {
@@ -201,20 +189,25 @@ haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int align
             __syncthreads();
         }
         // four consecutive output bytes (or floats) per thread and group
-#pragma unroll
-        for (int k = 0; k < kMaxO4; ++k) {
-            const int o4 = 4 * tid + k * 4 * kRowsThreads;
-            if (o4 >= n_out) break;
+#pragma unroll 1
+        for (int o4 = 4 * tid; o4 < n_out; o4 += 4 * kRowsThreads) {
             uint32_t sv[4];
+            int g = a.C > 1 ? (int)__umulhi((uint32_t)o4, inv_c) : o4, c = o4 - g * a.C;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 sv[j] = 0u;
-                if (o4 + j >= n_out) continue;
-                if (nseg > 1) { sv[j] = outsum[o4 + j]; continue; }
-                const uint16_t* p = colsum + off[k][j];
-                uint32_t s = 0;
-                for (int q = 0; q < r; ++q) s += p[q * a.C];
-                sv[j] = s;
+                if (o4 + j < n_out) {
+                    if (nseg > 1) {
+                        sv[j] = outsum[o4 + j];
+                    } else {
+                        const uint16_t* p = colsum + g * gb + c;
+                        uint32_t s = 0;
+#pragma unroll 2
+                        for (int q = 0; q < r; ++q) s += p[q * a.C];
+                        sv[j] = s;
+                    }
+                }
+                if (++c == a.C) { c = 0; ++g; }
             }
             const int64_t ob = ob0 + o4;
             if (a.dst_u8 != nullptr) {
