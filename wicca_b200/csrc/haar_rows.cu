@@ -48,7 +48,6 @@ template <int WPT, bool BORDER>
 __global__ void __launch_bounds__(kRowsThreads)
 haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int aligned) {
     constexpr int U = WPT >= 8 ? 1 : 8 / WPT;
-    constexpr int UB = WPT >= 8 ? 4 : 32 / WPT;      // border tiles are few (at most one CTA per SM): four times the loads in flight
     __shared__ __align__(16) uint16_t colsum[kRowsMaxTileBytes];
     __shared__ uint32_t outsum[kRowsThreads / 2];   // used only when nseg > 1, i.e. n_out <= 128
     const int tid = threadIdx.x;
@@ -114,13 +113,13 @@ haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int align
             // A tile that touches the bottom and / or the right border.  Words that lie inside the image horizontally
             // are still streamed row-major, U rows in flight, with the border row map applied by selects (no branches
             // between the loads); the few words that touch the right border are walked word-major further down.
-            for (int dy0 = 0; dy0 < r; dy0 += UB) {
-                int ymv[UB];
+            for (int dy0 = 0; dy0 < r; dy0 += U) {
+                int ymv[U];
 #pragma unroll
-                for (int u = 0; u < UB; ++u) ymv[u] = dy0 + u < r ? border_index((oy << a.depth) + dy0 + u, a.H, a.border_type) : -2;
-                uint32_t v[UB][WPT];
+                for (int u = 0; u < U; ++u) ymv[u] = dy0 + u < r ? border_index((oy << a.depth) + dy0 + u, a.H, a.border_type) : -2;
+                uint32_t v[U][WPT];
 #pragma unroll
-                for (int u = 0; u < UB; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const uint8_t* row = a.src + (int64_t)(ymv[u] < 0 ? 0 : ymv[u]) * a.pitch;
 #pragma unroll
                     for (int k = 0; k < WPT; ++k) {
@@ -134,7 +133,7 @@ haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int align
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < UB; ++u)
+                for (int u = 0; u < U; ++u)
 #pragma unroll
                     for (int k = 0; k < WPT; ++k) {
                         accE[k] += prmt(v[u][k], 0u, 0x4240u);
