@@ -110,10 +110,36 @@ haar_icon_rows_kernel(GenericIconArgs a, int groups, int rows_per_cta, int align
                     }
             }
         } else {
-            // A tile that touches the bottom and / or the right border.  Words that lie inside the image horizontally
-            // are still streamed row-major, U rows in flight, with the border row map applied by selects (no branches
+            // A tile that touches the bottom and / or the right border.  The rows of this output row that exist in
+            // the image are streamed exactly like an interior tile (only the words that lie inside the image
+            // horizontally); the rows below the image follow with the border row map applied by selects (no branches
             // between the loads); the few words that touch the right border are walked word-major further down.
-            for (int dy0 = 0; dy0 < r; dy0 += U) {
+            int n_fast = 0;
+            if (aligned && (r % U) == 0) {
+                const int64_t left = (int64_t)a.H - ((int64_t)oy << a.depth);      // image rows at and below this output row's first
+                n_fast = left >= r ? r : (left <= 0 ? 0 : (int)left / U * U);
+                const uint32_t* p = reinterpret_cast<const uint32_t*>(a.src + ((int64_t)oy << a.depth) * a.pitch + b0) + tid;
+                const int64_t pw = a.pitch >> 2;
+                for (int dy0 = 0; dy0 < n_fast; dy0 += U) {
+                    uint32_t v[U][WPT];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int k = 0; k < WPT; ++k) {
+                            const int w = tid + k * kRowsThreads;
+                            const bool in_image = w < n_words && b0 + 4 * (int64_t)w + 4 <= row_bytes;
+                            v[u][k] = in_image ? __ldg(p + (int64_t)(dy0 + u) * pw + k * kRowsThreads) : 0u;
+                        }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int k = 0; k < WPT; ++k) {
+                            accE[k] += prmt(v[u][k], 0u, 0x4240u);
+                            accO[k] += prmt(v[u][k], 0u, 0x4341u);
+                        }
+                }
+            }
+            for (int dy0 = n_fast; dy0 < r; dy0 += U) {
                 int ymv[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) ymv[u] = dy0 + u < r ? border_index((oy << a.depth) + dy0 + u, a.H, a.border_type) : -2;
