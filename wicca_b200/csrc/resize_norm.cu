@@ -205,38 +205,16 @@ __device__ __forceinline__ void area_group2(const uint32_t*& pa, const uint32_t*
 }
 #undef WICCA_TAP
 
-// The y taps of one output row, in OpenCV's order: [left partial] + full rows + [right partial].
-struct RowTaps {
-    AreaDesc ay;
-    int has_l, n_rows, n_pairs;
-    __device__ __forceinline__ void set(const AreaDesc& d) {
-        ay = d;
-        has_l = d.w_left != 0.0f;
-        n_rows = has_l + d.n_full + (d.w_right != 0.0f ? 1 : 0);
-        n_pairs = (n_rows + 1) >> 1;
-    }
-    __device__ __forceinline__ int index(int k) const {
-        return (has_l && k == 0) ? ay.s_left : (k - has_l < ay.n_full ? ay.s_first + (k - has_l) : ay.s_right);
-    }
-    __device__ __forceinline__ float weight(int k) const {
-        return (has_l && k == 0) ? ay.w_left : (k - has_l < ay.n_full ? ay.w_full : ay.w_right);
-    }
-};
-
-// A CTA produces rows_per_cta consecutive output rows of one image (one when the launch is small): the x-tap set-up
-// of a thread does not depend on the row, and the pairs of source rows of consecutive output rows form ONE stream with
-// a pair always in flight - small icons (a depth-3 icon gives an output row three pairs of 3 KB rows) were bound by
-// the set-up and the first fetch of every CTA.
 __global__ void __launch_bounds__(kRowsMaxThreads)
 resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, float* __restrict__ out,
-                        uint8_t* __restrict__ out_u8, int buf_bytes, int rows_per_cta) {
+                        uint8_t* __restrict__ out_u8, int buf_bytes) {
     extern __shared__ __align__(16) uint8_t s_rows[];          // two PAIRS of row buffers, buf_bytes each
     __shared__ __align__(8) uint64_t s_full[2];
-    const int img = blockIdx.y;
-    const int dy_begin = blockIdx.x * rows_per_cta, dy_end = min(dy_begin + rows_per_cta, out_h);
+    const int img = blockIdx.y, dy = blockIdx.x;
     const ResizeJob j = t.jobs[img];
     if (j.regime != 2) return;
-    // this CTA's segment of the output rows (blockIdx.z) and the source bytes that feed it
+    const AreaDesc ay = t.area[j.yoff + dy];
+    // this CTA's segment of the output row (blockIdx.z) and the source bytes that feed it
     const int x0 = blockIdx.z * blockDim.x;
     if (x0 >= out_w) return;
     const int x_last = min(x0 + (int)blockDim.x, out_w) - 1;
@@ -252,21 +230,26 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
         rs_mbar_init(&s_full[0], 1); rs_mbar_init(&s_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // pair p of an output row = its source rows 2p and 2p+1 (the last pair of an odd count has one row); the k-th pair
-    // of the CTA's stream goes into buffers 2(k&1), 2(k&1)+1
-    auto fetch = [&](const RowTaps& rt, int p, int k) {
-        const int n_here = (2 * p + 1 < rt.n_rows) ? 2 : 1;
+    // the y taps of this output row, in OpenCV's order: [left partial] + full rows + [right partial]
+    const int has_l = ay.w_left != 0.0f, has_r = ay.w_right != 0.0f;
+    const int n_rows = has_l + ay.n_full + has_r;
+    const int n_pairs = (n_rows + 1) >> 1;
+    auto row_index = [&](int k) { return (has_l && k == 0) ? ay.s_left : (k - has_l < ay.n_full ? ay.s_first + (k - has_l) : ay.s_right); };
+    auto row_weight = [&](int k) { return (has_l && k == 0) ? ay.w_left : (k - has_l < ay.n_full ? ay.w_full : ay.w_right); };
+    // pair p = source rows 2p and 2p+1 (the last pair of an odd count has one row) into buffers 2(p&1), 2(p&1)+1
+    auto fetch = [&](int p) {
+        const int n_here = (2 * p + 1 < n_rows) ? 2 : 1;
         if (bulk) {
             if (threadIdx.x == 0) {
-                rs_mbar_expect_tx(&s_full[k & 1], (uint32_t)(copy_bytes * n_here));
+                rs_mbar_expect_tx(&s_full[p & 1], (uint32_t)(copy_bytes * n_here));
                 for (int q = 0; q < n_here; ++q)
-                    rs_bulk_load(s_rows + (2 * (k & 1) + q) * buf_bytes + kRowPadFront, j.src + (int64_t)rt.index(2 * p + q) * j.pitch + lo,
-                                 (uint32_t)copy_bytes, &s_full[k & 1]);
+                    rs_bulk_load(s_rows + (2 * (p & 1) + q) * buf_bytes + kRowPadFront, j.src + (int64_t)row_index(2 * p + q) * j.pitch + lo,
+                                 (uint32_t)copy_bytes, &s_full[p & 1]);
             }
         } else {
             for (int q = 0; q < n_here; ++q) {
-                const uint8_t* g = j.src + (int64_t)rt.index(2 * p + q) * j.pitch + lo;
-                uint8_t* s = s_rows + (2 * (k & 1) + q) * buf_bytes + kRowPadFront;
+                const uint8_t* g = j.src + (int64_t)row_index(2 * p + q) * j.pitch + lo;
+                uint8_t* s = s_rows + (2 * (p & 1) + q) * buf_bytes + kRowPadFront;
                 for (int b = threadIdx.x; b < seg_bytes; b += blockDim.x) s[b] = g[b];
             }
         }
@@ -289,46 +272,37 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
     const int b_start = (ax.s_first - 1) * 3 - lo + kRowPadFront;   // >= 13
     const uint32_t shift = (uint32_t)(b_start & 3) * 8;
     float acc[3] = {0.0f, 0.0f, 0.0f};
-    RowTaps cur, nxt;
-    cur.set(t.area[j.yoff + dy_begin]);
     __syncthreads();                                           // mbarrier init visible
-    fetch(cur, 0, 0);
-    int k = 0;                                                 // pairs consumed so far by this CTA
-    for (int dy = dy_begin; dy < dy_end; ++dy) {
-        const bool more_rows = dy + 1 < dy_end;
-        if (more_rows) nxt.set(t.area[j.yoff + dy + 1]);
-        for (int p = 0; p < cur.n_pairs; ++p, ++k) {
-            if (p + 1 < cur.n_pairs) fetch(cur, p + 1, k + 1);
-            else if (more_rows) fetch(nxt, 0, k + 1);
-            if (bulk) rs_mbar_wait(&s_full[k & 1], (uint32_t)(k >> 1) & 1u);
-            else __syncthreads();
-            if (active) {
-                const bool two = 2 * p + 1 < cur.n_rows;
-                const uint32_t* pa = reinterpret_cast<const uint32_t*>(s_rows + (2 * (k & 1)) * buf_bytes) + (b_start >> 2);
-                const uint32_t* pb = two ? reinterpret_cast<const uint32_t*>(s_rows + (2 * (k & 1) + 1) * buf_bytes) + (b_start >> 2) : pa;
-                uint32_t a0 = pa[0], b0 = pb[0];
-                uint64_t h[3] = {0ull, 0ull, 0ull};            // (+0.0f, +0.0f)
-                area_group2(pa, pb, a0, b0, shift, wa, nwa, h);
-                for (int g = 1; g < groups - 1; ++g) area_group2(pa, pb, a0, b0, shift, wm, nwm, h);
-                if (groups > 1) area_group2(pa, pb, a0, b0, shift, wz, nwz, h);
-                const float beta_a = cur.weight(2 * p), beta_b = two ? cur.weight(2 * p + 1) : 0.0f;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    float ha, hb;
-                    f2_unpack(h[c], ha, hb);
-                    const float ba = __fmul_rn(beta_a, ha);
-                    acc[c] = (p == 0) ? ba : __fadd_rn(acc[c], ba);
-                    if (two) acc[c] = __fadd_rn(acc[c], __fmul_rn(beta_b, hb));
-                }
-            }
-            __syncthreads();      // the buffers are refilled two iterations later
-        }
+    fetch(0);
+    for (int p = 0; p < n_pairs; ++p) {
+        if (p + 1 < n_pairs) fetch(p + 1);
+        if (bulk) rs_mbar_wait(&s_full[p & 1], (uint32_t)(p >> 1) & 1u);
+        else __syncthreads();
         if (active) {
-            const int64_t i = (((int64_t)img * out_h + dy) * out_w + dx) * 3;
+            const bool two = 2 * p + 1 < n_rows;
+            const uint32_t* pa = reinterpret_cast<const uint32_t*>(s_rows + (2 * (p & 1)) * buf_bytes) + (b_start >> 2);
+            const uint32_t* pb = two ? reinterpret_cast<const uint32_t*>(s_rows + (2 * (p & 1) + 1) * buf_bytes) + (b_start >> 2) : pa;
+            uint32_t a0 = pa[0], b0 = pb[0];
+            uint64_t h[3] = {0ull, 0ull, 0ull};                // (+0.0f, +0.0f)
+            area_group2(pa, pb, a0, b0, shift, wa, nwa, h);
+            for (int g = 1; g < groups - 1; ++g) area_group2(pa, pb, a0, b0, shift, wm, nwm, h);
+            if (groups > 1) area_group2(pa, pb, a0, b0, shift, wz, nwz, h);
+            const float beta_a = row_weight(2 * p), beta_b = two ? row_weight(2 * p + 1) : 0.0f;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) emit_value(sat_rint_u8(acc[c]), c, i + c, norm_mode, out, out_u8);
+            for (int c = 0; c < 3; ++c) {
+                float ha, hb;
+                f2_unpack(h[c], ha, hb);
+                const float ba = __fmul_rn(beta_a, ha);
+                acc[c] = (p == 0) ? ba : __fadd_rn(acc[c], ba);
+                if (two) acc[c] = __fadd_rn(acc[c], __fmul_rn(beta_b, hb));
+            }
         }
-        cur = nxt;
+        __syncthreads();          // the buffers are refilled two iterations later
+    }
+    if (active) {
+        const int64_t i = (((int64_t)img * out_h + dy) * out_w + dx) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) emit_value(sat_rint_u8(acc[c]), c, i + c, norm_mode, out, out_u8);
     }
 }
 
@@ -357,11 +331,7 @@ cudaError_t launch_resize_norm(const ResizeTables& t, int n, int out_h, int out_
             if (e != cudaSuccess) return e;
             configured_dev = dev;
         }
-        // consecutive output rows per CTA: as many as still leave the GPU ~8 CTAs per SM (1 for a lone image)
-        int rows_per_cta = (int)((int64_t)out_h * n_area * segs / (148 * 8));
-        rows_per_cta = rows_per_cta < 1 ? 1 : (rows_per_cta > 8 ? 8 : rows_per_cta);
-        resize_area_rows_kernel<<<dim3((out_h + rows_per_cta - 1) / rows_per_cta, n, segs), seg_w, smem, stream>>>(
-            t, out_h, out_w, norm_mode, d_out, d_out_u8, buf_bytes, rows_per_cta);
+        resize_area_rows_kernel<<<dim3(out_h, n, segs), seg_w, smem, stream>>>(t, out_h, out_w, norm_mode, d_out, d_out_u8, buf_bytes);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_other == 0) return cudaSuccess;
