@@ -325,6 +325,19 @@ int rows_kernel_groups(int C, int depth) {
     return g < 2 ? 2 : g;
 }
 
+// One non-blocking side stream per device and host thread, created on first use (nullptr if that fails: the border
+// instantiation then simply follows the interior one on the caller's stream).
+static cudaStream_t rows_side_stream() {
+    static thread_local cudaStream_t streams[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return nullptr; }
+    if (streams[dev] == nullptr && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        streams[dev] = nullptr;
+    }
+    return streams[dev];
+}
+
 cudaError_t launch_icon_rows(const GenericIconArgs& a, cudaStream_t stream) {
     if ((int64_t)a.out_h * a.out_w <= 0) return cudaSuccess;
     const int groups = rows_kernel_groups(a.C, a.depth);
@@ -336,16 +349,40 @@ cudaError_t launch_icon_rows(const GenericIconArgs& a, cudaStream_t stream) {
     const int aligned = (((uintptr_t)a.src & 3) == 0 && (a.pitch & 3) == 0) ? 1 : 0;
     while ((a.out_h + rows_per_cta - 1) / rows_per_cta > 65535) rows_per_cta *= 2;
     dim3 grid((unsigned)((a.out_w + groups - 1) / groups), (unsigned)((a.out_h + rows_per_cta - 1) / rows_per_cta));
+    // The border instantiation is a few dozen long-running CTAs (one output row's 2^d input rows each): it runs next to
+    // the interior one on a side stream, forked from and joined back into the caller's stream with events (the pattern
+    // is capture-safe), instead of after it.
+    cudaStream_t side = rows_side_stream();
+    cudaEvent_t fork = nullptr, join = nullptr;
+    if (side != nullptr) {
+        if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) {
+            if (fork) cudaEventDestroy(fork);
+            cudaGetLastError();
+            fork = join = nullptr;
+            side = nullptr;
+        }
+    }
+    cudaStream_t bstream = side ? side : stream;
+    if (side) { cudaEventRecord(fork, stream); cudaStreamWaitEvent(side, fork, 0); }
 #define WICCA_ROWS_LAUNCH(N)                                                                                              \
     do {                                                                                                                  \
+        haar_icon_rows_kernel<N, true><<<grid, kRowsThreads, 0, bstream>>>(a, groups, rows_per_cta, aligned);                 \
         haar_icon_rows_kernel<N, false><<<grid, kRowsThreads, 0, stream>>>(a, groups, rows_per_cta, aligned);                 \
-        haar_icon_rows_kernel<N, true><<<grid, kRowsThreads, 0, stream>>>(a, groups, rows_per_cta, aligned);                  \
     } while (0)
     if (wpt <= 1) WICCA_ROWS_LAUNCH(1);
     else if (wpt <= 2) WICCA_ROWS_LAUNCH(2);
     else if (wpt <= 4) WICCA_ROWS_LAUNCH(4);
     else WICCA_ROWS_LAUNCH(8);
 #undef WICCA_ROWS_LAUNCH
+    const cudaError_t launched = cudaGetLastError();
+    if (side) {
+        cudaEventRecord(join, side);
+        cudaStreamWaitEvent(stream, join, 0);
+        cudaEventDestroy(fork);                       // destruction is deferred until the events have completed
+        cudaEventDestroy(join);
+    }
+    if (launched != cudaSuccess) return launched;
     return cudaGetLastError();
 }
 
