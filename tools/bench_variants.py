@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
 """Developer microbenchmark: device-resident fused icon kernel, per variant / depth set.
-Not the graded bench (that is bench.py); used to pick kernel parameters on the GPU box."""
+Not the graded bench (that is bench.py); used to pick kernel parameters on the GPU box.
+Needs a developer build of the library (`WICCA_DEV=1 python -m wicca_b200._build --force`): the release build
+compiles the kernel variants out and ignores WICCA_ICON_VARIANT."""
 import json
 import os
 import sys

@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
 """Launch each (variant, depth set) twice; run under `ncu --metrics gpu__time_duration.sum` to get
-kernel-only durations without host launch gaps."""
+kernel-only durations without host launch gaps.
+Needs a developer build of the library (`WICCA_DEV=1 python -m wicca_b200._build --force`): the release build
+compiles the kernel variants out and ignores WICCA_ICON_VARIANT."""
 import json, os, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))

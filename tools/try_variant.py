@@ -1,5 +1,7 @@
 #!/usr/bin/env python3
-"""Developer check: run one kernel variant (WICCA_ICON_VARIANT) through the host API against the oracle."""
+"""Developer check: run one kernel variant (WICCA_ICON_VARIANT) through the host API against the oracle.
+Needs a developer build of the library (`WICCA_DEV=1 python -m wicca_b200._build --force`): the release build
+compiles the kernel variants out and ignores WICCA_ICON_VARIANT."""
 import os, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
