@@ -220,7 +220,9 @@ WICCA_API int wicca_batch_classifier_inputs_multi_f32(const uint8_t* const* srcs
 
 /* Device-resident variant for sources that already live in HBM - icons, or the full-size source images of
  * the reference's other branch, cv2.resize(image, shape, interpolation) (classifying_tools.py:315).
- * d_srcs[i]: device uint8 (hs[i], ws[i], 3), rows pitches[i] bytes apart.  Enqueues on `stream`. */
+ * d_srcs[i]: device uint8 (hs[i], ws[i], 3), rows pitches[i] bytes apart.  Enqueues on `stream`.  The tap tables of a
+ * (sources, target) combination are kept on the device (keyed by pointers and geometry, not by content), so repeating the
+ * call on a resident batch is the kernel launch alone; the first call of a combination uploads them synchronously. */
 WICCA_API int wicca_resize_norm_dev(const uint8_t* const* d_srcs, const int* hs, const int* ws, const int64_t* pitches,
                                     int n, int out_h, int out_w, int norm_mode, float* d_dst, uint8_t* d_dst_u8,
                                     int device, void* stream);

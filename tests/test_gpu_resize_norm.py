@@ -93,6 +93,24 @@ def test_source_image_branch_n1(coder):
     torch.cuda.synchronize()
     assert np.array_equal(out8.cpu().numpy(), exp)
     assert np.array_equal(out.cpu().numpy(), ro.preprocess_input(exp, "tf"))
+    # The tap tables of a resident batch are cached on the device (keyed by pointers and geometry, never by content):
+    # new pixels behind the same pointers, another target in between, a second stream - every call must see the data.
+    side = torch.cuda.Stream()
+    for rep, target in enumerate((224, 331, 224, 224)):
+        new = [gen_input("noise", 900 + 10 * rep + i, *im.shape) for i, im in enumerate(imgs)]
+        for t, im in zip(dev, new):
+            t[:, : im.shape[1] * 3].copy_(torch.from_numpy(im.reshape(im.shape[0], -1)))
+        torch.cuda.synchronize()
+        o8 = torch.empty((3, target, target, 3), dtype=torch.uint8, device="cuda:0")
+        of = torch.empty((3, target, target, 3), dtype=torch.float32, device="cuda:0")
+        st = side if rep % 2 else torch.cuda.current_stream()
+        rc = _capi.load().wicca_resize_norm_dev((C.c_void_p * n)(*[t.data_ptr() for t in dev]), (C.c_int * n)(*[im.shape[0] for im in imgs]),
+                                                (C.c_int * n)(*[im.shape[1] for im in imgs]), (C.c_int64 * n)(*[t.shape[1] for t in dev]),
+                                                n, target, target, 0, of.data_ptr(), o8.data_ptr(), 0, C.c_void_p(st.cuda_stream))
+        _capi.check(rc, "wicca_resize_norm_dev")
+        torch.cuda.synchronize()
+        assert np.array_equal(o8.cpu().numpy(), np.stack([ro.resize_area(im, target, target) for im in new])), (rep, target)
+    assert _capi.load().wicca_shutdown() == 0           # drops the cached tables; the next call rebuilds them
 
 
 @pytest.mark.parametrize("depth,shape,mode", [(2, (224, 224), "tf"), (3, (331, 331), "caffe"), (5, (224, 224), "torch"),

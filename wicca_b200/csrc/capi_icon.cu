@@ -314,7 +314,7 @@ extern "C" {
 const char* wicca_version(void) { return "wicca_b200 0.1.0 (sm_100a)"; }
 const char* wicca_last_error(void) { return last_error_ref().c_str(); }
 int wicca_device_count(void) { return device_count_cached(); }
-int wicca_shutdown(void) { destroy_all_ctx(); return 0; }
+int wicca_shutdown(void) { resize_table_cache_clear(); destroy_all_ctx(); return 0; }
 
 int64_t wicca_pitch_bytes(int W, int C) { return align_up((int64_t)W * C, 128); }
 int wicca_icon_dim(int n, int depth) { return icon_dim(n, depth); }

@@ -1,6 +1,9 @@
 // capi_resize.cu - C ABI of the resize + normalise epilogue (rows A5/A6), host-buffer variant.
 #include <string.h>
 
+#include <list>
+#include <memory>
+#include <mutex>
 #include <vector>
 
 #include "host_common.h"
@@ -8,6 +11,23 @@
 #include "resize_tables.h"
 
 using namespace wicca;
+
+namespace {
+// Device-resident tap tables of wicca_resize_norm_dev, most recently used first.  An evicted entry frees its tables with
+// cudaFree, which waits for any kernel still reading them.
+struct TableCacheEntry {
+    std::vector<int64_t> key;
+    int device = 0;
+    ResizeTableBlob blob;          // offsets and launch hints (the bytes themselves are dropped after the upload)
+    DevBuf d_tables;
+    ~TableCacheEntry() {
+        if (d_tables.p) { int cur = 0; cudaGetDevice(&cur); cudaSetDevice(device); d_tables.release(); cudaSetDevice(cur); }
+    }
+};
+constexpr size_t kTableCacheEntries = 16;
+std::mutex g_table_mu;
+std::list<std::shared_ptr<TableCacheEntry>> g_table_cache;
+}  // namespace
 
 extern "C" int wicca_icon_resize_norm_f32(const uint8_t* const* icons, const int* hs, const int* ws, int n, int out_h,
                                           int out_w, int norm_mode, float* dst, uint8_t* dst_u8, int device,
@@ -85,15 +105,43 @@ extern "C" int wicca_resize_norm_dev(const uint8_t* const* d_srcs, const int* hs
     if (rc) return rc;
     WICCA_CUDA(cudaSetDevice(device));
     cudaStream_t stream = (cudaStream_t)stream_v;
-    const ResizeTableBlob blob = build_resize_tables(srcs, out_h, out_w);
-    void* d_tables = nullptr;
-    WICCA_CUDA(cudaMallocAsync(&d_tables, blob.bytes.size(), stream));          // stream-ordered scratch
-    // pageable source: staged by the runtime before the call returns, so `blob` may go out of scope
-    cudaError_t e = cudaMemcpyAsync(d_tables, blob.bytes.data(), blob.bytes.size(), cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess) e = launch_resize_norm(blob.view(d_tables), n, out_h, out_w, norm_mode, d_dst, d_dst_u8,
-                                                      blob.max_src_w, blob.n_area, blob.n_other, stream);
-    cudaError_t e2 = cudaFreeAsync(d_tables, stream);
+    // The tap tables depend only on (sources, target): a batch that stays resident and is resized again - the reference
+    // does it once per classifier and depth, classifying_tools.py:546-551 - finds them on the device and the call is the
+    // kernel launch alone.  A miss builds them on the host and uploads them synchronously (they are read by kernels on
+    // whatever stream later calls pass, so the upload must not be ordered on this call's stream only).
+    std::vector<int64_t> key;
+    key.reserve(4 + 4 * (size_t)n);
+    key.push_back(device); key.push_back(out_h); key.push_back(out_w); key.push_back(n);
+    for (int i = 0; i < n; ++i) { key.push_back((int64_t)(uintptr_t)d_srcs[i]); key.push_back(hs[i]); key.push_back(ws[i]); key.push_back(pitches[i]); }
+    std::shared_ptr<TableCacheEntry> entry;
+    {
+        std::lock_guard<std::mutex> lk(g_table_mu);
+        for (auto it = g_table_cache.begin(); it != g_table_cache.end(); ++it)
+            if ((*it)->key == key) { entry = *it; g_table_cache.erase(it); g_table_cache.push_front(entry); break; }
+    }
+    if (!entry) {
+        entry = std::make_shared<TableCacheEntry>();
+        entry->key = key;
+        entry->device = device;
+        entry->blob = build_resize_tables(srcs, out_h, out_w);
+        cudaError_t e = entry->d_tables.reserve(entry->blob.bytes.size());
+        if (e == cudaSuccess) e = cudaMemcpy(entry->d_tables.p, entry->blob.bytes.data(), entry->blob.bytes.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { entry->d_tables.release(); return cuda_fail(e, "resize table upload"); }
+        entry->blob.bytes.clear();
+        entry->blob.bytes.shrink_to_fit();
+        std::lock_guard<std::mutex> lk(g_table_mu);
+        g_table_cache.push_front(entry);
+        while (g_table_cache.size() > kTableCacheEntries) g_table_cache.pop_back();     // ~TableCacheEntry frees the device tables
+    }
+    cudaError_t e = launch_resize_norm(entry->blob.view(entry->d_tables.p), n, out_h, out_w, norm_mode, d_dst, d_dst_u8,
+                                       entry->blob.max_src_w, entry->blob.n_area, entry->blob.n_other, stream);
     if (e != cudaSuccess) return cuda_fail(e, "resize/normalise kernel");
-    if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFreeAsync");
     return 0;
 }
+
+namespace wicca {
+void resize_table_cache_clear() {
+    std::lock_guard<std::mutex> lk(g_table_mu);
+    g_table_cache.clear();
+}
+}  // namespace wicca

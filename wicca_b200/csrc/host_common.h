@@ -75,6 +75,7 @@ const DeviceInfo& device_info(int device);
 int acquire_ctx(int device, Ctx** out);             // sets the calling thread's current device
 void release_ctx(Ctx* c);
 void destroy_all_ctx();
+void resize_table_cache_clear();                        // capi_resize.cu: cached tap tables of wicca_resize_norm_dev
 
 struct CtxLease {
     Ctx* c = nullptr;
