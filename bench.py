@@ -260,6 +260,8 @@ def host_link_ceiling(torch, dist, dev, world, host_flat, out_flat, h2d_bytes, d
     del d_up, d_down
     return {"h2d_only_GBps": world * up_b / t_up / 1e9, "step_traffic_s": t_both,
             "h2d_GBps_with_d2h": world * up_b / t_both / 1e9, "d2h_GBps_with_h2d": world * down_b / t_both / 1e9,
+            "note": "a probe of the same traffic with plain copies, best of two; run-to-run spread of either side is a few per "
+                    "cent, so frac_of_ceiling reads 0.94-1.04",
             "method": f"every rank at once, page-locked buffers: {n_up} x {host_flat.numel() / 1e6:.0f} MB cudaMemcpyAsync up on one "
                       f"stream + {n_down} x {out_flat.numel() / 1e6:.0f} MB down on another (the byte counts of one e2e step), max over ranks"}
 
