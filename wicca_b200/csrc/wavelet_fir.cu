@@ -233,22 +233,39 @@ fir_tile_kernel(const TIn* __restrict__ src, int64_t pitch_elems, int H, int W, 
             for (int ch = 0; ch < C; ++ch) d[o * C + ch] = acc[o][ch];
     }
     __syncthreads();
-    // ---- columns
-    constexpr int seg = kTileW * C;
-    for (int e = threadIdx.x; e < kTileH * seg; e += kTileThreads) {
-        const int i = e / seg, q = e - i * seg;
-        const int oi = oy0 + i, oj = ox0 + q / C;
-        if (oi >= h2 || oj >= w2) continue;
-        const float* p = s_t + (size_t)(2 * i) * G::kTPitch + q;
-        float acc = 0.0f;
+    // ---- columns: two neighbouring elements of an output row per work item - an 8-byte shared load feeds both halves
+    // of Blackwell's packed float32 pair instructions (mul.rn.f32x2 / add.rn.f32x2: two IEEE operations per issue slot,
+    // each half bit-identical to the scalar instruction), which halves the issue slots of this pass
+    constexpr int seg = kTileW * C, seg2 = seg / 2;                              // kTileW is even
+    for (int e = threadIdx.x; e < kTileH * seg2; e += kTileThreads) {
+        const int i = e / seg2, q = 2 * (e - i * seg2);
+        const int oi = oy0 + i;
+        if (oi >= h2) continue;
+        const float* p = s_t + (size_t)(2 * i) * G::kTPitch + q;               // 8-byte aligned: kTPitch and q are even
+        uint64_t acc = 0;
 #pragma unroll
         for (int m = 0; m < L; ++m) {
-            const float v = __fmul_rn(p[m * G::kTPitch], s_g[m]);
-            acc = m == 0 ? v : __fadd_rn(acc, v);
+            const float2 v = *reinterpret_cast<const float2*>(p + m * G::kTPitch);
+            uint64_t v2, g2, pr;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(v2) : "f"(v.x), "f"(v.y));
+            asm("mov.b64 %0, {%1, %1};" : "=l"(g2) : "f"(s_g[m]));
+            asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(v2), "l"(g2));
+            if (m == 0) acc = pr;
+            else asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc) : "l"(acc), "l"(pr));
         }
+        float r0, r1;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(acc));
+        const bool in0 = ox0 + q / C < w2, in1 = ox0 + (q + 1) / C < w2;
         const int64_t o = (int64_t)ox0 * C + q;
-        if (icon) icon[(int64_t)oi * icon_pitch + o] = (uint8_t)fminf(fmaxf(acc, 0.0f), 255.0f);      // clip, then truncate
-        else out[(int64_t)oi * w2 * C + o] = acc;
+        if (icon) {
+            uint8_t* d = icon + (int64_t)oi * icon_pitch + o;
+            if (in0) d[0] = (uint8_t)fminf(fmaxf(r0, 0.0f), 255.0f);          // clip, then truncate
+            if (in1) d[1] = (uint8_t)fminf(fmaxf(r1, 0.0f), 255.0f);
+        } else {
+            float* d = out + (int64_t)oi * w2 * C + o;
+            if (in0) d[0] = r0;
+            if (in1) d[1] = r1;
+        }
     }
 }
 
