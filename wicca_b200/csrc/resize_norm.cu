@@ -316,10 +316,17 @@ cudaError_t launch_resize_norm(const ResizeTables& t, int n, int out_h, int out_
     // the GPU a few times over (a lone 53 MP image would otherwise run on 224 CTAs, each streaming 0.7 MB)
     int seg_w = (out_w + 31) / 32 * 32;
     while (seg_w > 32 && (int64_t)out_h * (n_area > 0 ? n_area : 1) * ((out_w + seg_w - 1) / seg_w) < 148 * 8) seg_w = (seg_w / 2 + 31) / 32 * 32;
-    const int segs = (out_w + seg_w - 1) / seg_w;
     // source span of one segment: seg_w target pixels x scale, + the early pixel, the padded last group, alignment slack
-    const int64_t span_px = segs == 1 ? (int64_t)max_src_w + 8 : ((int64_t)seg_w * max_src_w + out_w - 1) / out_w + 10;
-    const int buf_bytes = kRowPadFront + (int)((span_px * 3 + 16 + 15) / 16 * 16) + kRowPadBack;
+    auto buf_for = [&](int sw) {
+        const int sg = (out_w + sw - 1) / sw;
+        const int64_t span_px = sg == 1 ? (int64_t)max_src_w + 8 : ((int64_t)sw * max_src_w + out_w - 1) / out_w + 10;
+        return kRowPadFront + (int)((span_px * 3 + 16 + 15) / 16 * 16) + kRowPadBack;
+    };
+    // ... and no wider than lets four CTAs share an SM's shared memory (two pairs of rows each): the rows of a 53 MP
+    // source image are 25 KB, and whole-row CTAs ran two to an SM (0.83 ms for 30 images; 0.79 ms in two segments)
+    while (seg_w > 64 && (size_t)4 * buf_for(seg_w) > 64 * 1024) seg_w = (seg_w / 2 + 31) / 32 * 32;
+    const int segs = (out_w + seg_w - 1) / seg_w;
+    const int buf_bytes = buf_for(seg_w);
     const size_t smem = (size_t)4 * buf_bytes;                // two pairs of source rows in flight
     const bool rows_ok = n_area > 0 && out_w <= kRowsMaxThreads && smem <= 200 * 1024 && n <= 65535 && segs <= 65535;
     if (rows_ok) {
