@@ -171,7 +171,7 @@ def row_batch():
     images = [arrs[i % distinct] for i in range(n)]
     depths = [2, 3, 4, 5, 6]
     for devices in ([0], list(range(ndev))) if ndev > 1 else ([0],):
-        coder.get_small_copies_batch(images[:4], depths, devices=devices)          # warm-up
+        coder.get_small_copies_batch(images[: 6 * len(devices)], depths, devices=devices)   # warm-up: every device, every upload slot
         t0 = time.perf_counter()
         out = coder.get_small_copies_batch(images, depths, devices=devices)
         dt = time.perf_counter() - t0
