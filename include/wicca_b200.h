@@ -152,11 +152,10 @@ WICCA_API int wicca_plan_destroy(wicca_plan* plan);
 /* ---- sharded host batch: images are independent units ------------------ */
 /* srcs[i]: host image i, (Hs[i], Ws[i], C) uint8 with row stride strides[i] (0 = tight).
  * dsts[i * n_depths + k]: tight host icon of image i at depths[k].
- * Every image runs on exactly one of `devices` (devices == NULL: ordinals 0..n_devices-1): each device has its
- * own worker thread, streams and three upload slots, so H2D of images i+1, i+2 overlaps the kernel and read-back of
- * image i, and a worker takes the next untaken image whenever a slot is free - GPUs behind a slower host link take
- * fewer images, ragged sizes balance themselves, and dsts stays in input order whoever did the work.  No inter-GPU
- * traffic.  t (nullable) receives the SUM over images of the per-stage device times. */
+ * Image i runs on devices[i % n_devices] (devices == NULL: ordinals 0..n_devices-1); each
+ * device has its own worker thread, streams and double-buffered upload slots, so H2D of
+ * image i+1 overlaps the kernel of image i.  No inter-GPU traffic.  t (nullable) receives the
+ * SUM over images of the per-stage device times. */
 WICCA_API int wicca_batch_icons_u8(const uint8_t* const* srcs, const int* Hs, const int* Ws,
                                    const int64_t* strides, int n_images, int C,
                                    const int* depths, int n_depths,

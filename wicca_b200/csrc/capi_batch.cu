@@ -1,5 +1,5 @@
 // capi_batch.cu - sharded host batch: images are independent units (the per-image loop of
-// wicca/classifying_tools.py:312-321), so every image goes to exactly one device and nothing
+// wicca/classifying_tools.py:312-321), so image i goes to devices[i % n_devices] and nothing
 // crosses between GPUs.  One worker thread per device; three upload slots (stream + buffers) per
 // worker so the H2D copies of images j+1, j+2 overlap the kernel and icon D2H of image j.
 #include <stdlib.h>
@@ -23,8 +23,6 @@ struct BatchArgs {
     const uint8_t* const* srcs; const int* Hs; const int* Ws; const int64_t* strides;
     int n_images, C; const int* depths; int n_depths; int border_type, bconst;
     uint8_t* const* dsts;
-    std::atomic<int>* next;        // next image nobody has taken yet (shared by the workers)
-    size_t max_src;                // device bytes of the largest image of the batch
 };
 
 struct WorkerResult {
@@ -51,11 +49,7 @@ int upload_slots() {
     return n < 2 ? 2 : (n > 4 ? 4 : n);
 }
 
-// Images are handed out dynamically: a worker takes the next untaken image whenever one of its upload slots is free, so
-// a GPU behind a slower host link (on the 8-GPU boxes measured here, GPUs 0-3 share a path to host memory that GPUs
-// 4-7 do not, profiles/r2_calib_link_n8.log) simply takes fewer images instead of holding the batch up, and ragged
-// sizes balance themselves.  Results are indexed by image, so the output order never depends on who did what.
-int worker_body(const BatchArgs& a, int device, WorkerResult& res) {
+int worker_body(const BatchArgs& a, int device, int first, int step, WorkerResult& res) {
     ScopedAffinity bind(device);         // this worker (and the buffers it allocates) stays on the GPU's NUMA node
     const int n_slots = upload_slots();
     CtxLease slot[4];
@@ -64,21 +58,14 @@ int worker_body(const BatchArgs& a, int device, WorkerResult& res) {
         int rc = acquire_ctx(device, &slot[s].c);
         if (rc) return rc;
     }
-    // one allocation per slot, sized for the largest image of the batch (ragged batches would
+    // one allocation per slot, sized for the largest image of this worker (ragged batches would
     // otherwise grow the buffer - and synchronise the device - several times)
-    for (int s = 0; s < n_slots; ++s) WICCA_CUDA(slot[s].c->d_src.reserve(a.max_src));
+    size_t max_src = 0;
+    for (int i = first; i < a.n_images; i += step)
+        max_src = std::max(max_src, (size_t)wicca_pitch_bytes(a.Ws[i], a.C) * a.Hs[i] + 256);
+    for (int s = 0; s < n_slots; ++s) WICCA_CUDA(slot[s].c->d_src.reserve(max_src));
     int j = 0;
-    for (;;) {
-        const int s = j % n_slots;
-        Ctx& c = *slot[s].c;
-        if (busy[s]) {                   // free the slot first, THEN take an image: a waiting worker hoards nothing
-            WICCA_CUDA(cudaStreamSynchronize(c.stream));
-            c.flush_pending();
-            add_times(res, c);
-            busy[s] = false;
-        }
-        const int i = a.next->fetch_add(1, std::memory_order_relaxed);
-        if (i >= a.n_images) break;
+    for (int i = first; i < a.n_images; i += step) {
         const int H = a.Hs[i], W = a.Ws[i];
         const int64_t rowb = (int64_t)W * a.C;
         const int64_t stride = (a.strides && a.strides[i]) ? a.strides[i] : rowb;
@@ -92,7 +79,14 @@ int worker_body(const BatchArgs& a, int device, WorkerResult& res) {
             }
         }
         if (!device_work) continue;
+        const int s = j % n_slots;
         ++j;
+        Ctx& c = *slot[s].c;
+        if (busy[s]) {
+            WICCA_CUDA(cudaStreamSynchronize(c.stream));
+            c.flush_pending();
+            add_times(res, c);
+        }
         const int64_t pitch = wicca_pitch_bytes(W, a.C);
         WICCA_CUDA(c.d_src.reserve((size_t)pitch * H + 256));
         WICCA_CUDA(cudaEventRecord(c.ev[0], c.stream));
@@ -140,16 +134,13 @@ extern "C" int wicca_batch_icons_u8(const uint8_t* const* srcs, const int* Hs, c
         int rc = check_device(devs[k]);
         if (rc) return rc;
     }
-    std::atomic<int> next{0};
-    size_t max_src = 0;
-    for (int i = 0; i < n_images; ++i) max_src = std::max(max_src, (size_t)wicca_pitch_bytes(Ws[i], C) * Hs[i] + 256);
-    BatchArgs a{srcs, Hs, Ws, strides, n_images, C, depths, n_depths, border_type, saturate_u8(border_const), dsts, &next, max_src};
+    BatchArgs a{srcs, Hs, Ws, strides, n_images, C, depths, n_depths, border_type, saturate_u8(border_const), dsts};
     const int nw = n_devices < n_images ? n_devices : n_images;
     std::vector<WorkerResult> results(nw);
     std::vector<std::thread> threads;
     for (int k = 0; k < nw; ++k)
         threads.emplace_back([&, k] {
-            results[k].rc = worker_body(a, devs[k], results[k]);
+            results[k].rc = worker_body(a, devs[k], k, nw, results[k]);
             if (results[k].rc) results[k].msg = last_error_ref();
         });
     for (auto& th : threads) th.join();
