@@ -148,6 +148,26 @@ __device__ __forceinline__ void rs_mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(rs_smem_u32(bar)), "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ void rs_mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rs_mbar_wait_a(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void rs_bulk_load_a(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ void rs_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      rs_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(rs_smem_u32(bar))
@@ -203,9 +223,25 @@ __device__ __forceinline__ void area_group2(const uint32_t*& pa, const uint32_t*
     a0 = a3; b0 = b3;
     pa += 3; pb += 3;
 }
+// The last one or two taps of a run as a half group: two taps = 6 bytes (weights w[0], w[1]).  A run is walked as
+// [first group, per-tap weights] + whole groups of the uniform weight + [a whole or a half group, per-tap weights], so at
+// most one padded (weight-0) tap is ever walked instead of up to three.
+__device__ __forceinline__ void area_half2(const uint32_t* pa, const uint32_t* pb, uint32_t a0, uint32_t b0, uint32_t shift,
+                                           const uint64_t (&w)[4], const uint64_t (&nw)[4], uint64_t (&h)[3]) {
+    const uint32_t a1 = pa[1], a2 = pa[2];
+    const uint32_t b1 = pb[1], b2 = pb[2];
+    const uint32_t x0 = __funnelshift_r(a0, a1, shift), x1 = __funnelshift_r(a1, a2, shift);
+    const uint32_t y0 = __funnelshift_r(b0, b1, shift), y1 = __funnelshift_r(b1, b2, shift);
+    WICCA_TAP(0, x0, y0, 0, 0); WICCA_TAP(1, x0, y0, 0, 1); WICCA_TAP(2, x0, y0, 0, 2);
+    WICCA_TAP(3, x0, y0, 1, 0); WICCA_TAP(0, x1, y1, 1, 1); WICCA_TAP(1, x1, y1, 1, 2);
+}
 #undef WICCA_TAP
 
-__global__ void __launch_bounds__(kRowsMaxThreads)
+// kMaxRegs: the register cap of the instantiation.  Shared memory admits four CTAs per SM on the headline shapes; whether
+// the registers do depends on the CTA size (one thread per output pixel), and the kernel wants them when it can have
+// them: 64 for up to 256 threads, 48 up to 320, 40 above (331 px: 4 CTAs of 352 threads; with 54 registers only three).
+template <int kMaxRegs>
+__global__ void __maxnreg__(kMaxRegs)
 resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, float* __restrict__ out,
                         uint8_t* __restrict__ out_u8, int buf_bytes) {
     extern __shared__ __align__(16) uint8_t s_rows[];          // two PAIRS of row buffers, buf_bytes each
@@ -230,71 +266,96 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
         rs_mbar_init(&s_full[0], 1); rs_mbar_init(&s_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // the y taps of this output row, in OpenCV's order: [left partial] + full rows + [right partial]
+    // the y taps of this output row, in OpenCV's order: [left partial] + full rows + [right partial].  computeResizeAreaTab
+    // lists consecutive source rows (the left partial row is s_first - 1, the right one s_first + n_full), so tap k is
+    // row row0 + k; its weight is w_left / w_full / w_right by position and 0 for the pad row of an odd count.
     const int has_l = ay.w_left != 0.0f, has_r = ay.w_right != 0.0f;
     const int n_rows = has_l + ay.n_full + has_r;
     const int n_pairs = (n_rows + 1) >> 1;
-    auto row_index = [&](int k) { return (has_l && k == 0) ? ay.s_left : (k - has_l < ay.n_full ? ay.s_first + (k - has_l) : ay.s_right); };
-    auto row_weight = [&](int k) { return (has_l && k == 0) ? ay.w_left : (k - has_l < ay.n_full ? ay.w_full : ay.w_right); };
+    const int k_right = has_r ? n_rows - 1 : -1;
+    auto row_weight = [&](int k) {
+        float b = k < n_rows ? ay.w_full : 0.0f;
+        if (has_l && k == 0) b = ay.w_left;
+        if (k == k_right) b = ay.w_right;
+        return b;
+    };
+    const uint8_t* g_rows = j.src + (int64_t)(ay.s_first - has_l) * j.pitch + lo;     // row 2p of pair p: + 2p * pitch
     // pair p = source rows 2p and 2p+1 (the last pair of an odd count has one row) into buffers 2(p&1), 2(p&1)+1
+    const uint32_t bar0 = rs_smem_u32(&s_full[0]), rows0 = rs_smem_u32(s_rows);
     auto fetch = [&](int p) {
         const int n_here = (2 * p + 1 < n_rows) ? 2 : 1;
+        const uint8_t* g = g_rows + (int64_t)(2 * p) * j.pitch;
+        uint8_t* s = s_rows + (2 * (p & 1)) * buf_bytes + kRowPadFront;
         if (bulk) {
             if (threadIdx.x == 0) {
-                rs_mbar_expect_tx(&s_full[p & 1], (uint32_t)(copy_bytes * n_here));
-                for (int q = 0; q < n_here; ++q)
-                    rs_bulk_load(s_rows + (2 * (p & 1) + q) * buf_bytes + kRowPadFront, j.src + (int64_t)row_index(2 * p + q) * j.pitch + lo,
-                                 (uint32_t)copy_bytes, &s_full[p & 1]);
+                const uint32_t bar = bar0 + 8u * (p & 1), dst = rows0 + (2 * (p & 1)) * buf_bytes + kRowPadFront;
+                rs_mbar_expect_tx_a(bar, (uint32_t)(copy_bytes * n_here));
+                rs_bulk_load_a(dst, g, (uint32_t)copy_bytes, bar);
+                if (n_here == 2) rs_bulk_load_a(dst + buf_bytes, g + j.pitch, (uint32_t)copy_bytes, bar);
             }
         } else {
-            for (int q = 0; q < n_here; ++q) {
-                const uint8_t* g = j.src + (int64_t)row_index(2 * p + q) * j.pitch + lo;
-                uint8_t* s = s_rows + (2 * (p & 1) + q) * buf_bytes + kRowPadFront;
-                for (int b = threadIdx.x; b < seg_bytes; b += blockDim.x) s[b] = g[b];
-            }
+            for (int q = 0; q < n_here; ++q)
+                for (int b = threadIdx.x; b < seg_bytes; b += blockDim.x) s[q * buf_bytes + b] = g[q * j.pitch + b];
         }
     };
-    // ---- this thread's x taps (independent of the row)
+    fetch(0);      // thread 0 initialised the barriers itself: the first rows travel while the x taps are set up
+    // ---- this thread's x taps (independent of the row): pixels s_first - 1 .. s_first + n_full.  Lanes beyond the end of
+    // the output row walk the last pixel's taps again and store nothing, so the row loop has no per-lane branch.
     const int dx = x0 + threadIdx.x;
     const bool active = dx < out_w;
-    const AreaDesc ax = t.area[j.xoff + (active ? dx : 0)];
-    const int n_taps = ax.n_full + 2;                          // pixels s_first - 1 .. s_first + n_full
-    const int groups = (n_taps + 3) >> 2;
+    const bool warp_active = x0 + (int)(threadIdx.x & ~31u) < out_w;          // a segment's last CTA can hold idle warps
+    const AreaDesc ax = t.area[j.xoff + min(dx, out_w - 1)];
+    const int n_taps = ax.n_full + 2;
     auto tap_weight = [&](int tp) { return tp == 0 ? ax.w_left : (tp <= ax.n_full ? ax.w_full : (tp == ax.n_full + 1 ? ax.w_right : 0.0f)); };
+    // A run of more than four taps: first group (w_left, then the uniform weight), `mid` whole groups of the uniform weight,
+    // and the last `tail_halves` half groups (one for an odd count of half groups, two for an even one) with per-tap
+    // weights.  A run of at most four taps is a tail of two half groups and nothing else.
+    const bool has_first = n_taps > 4;
+    const int halves = has_first ? (n_taps - 3) >> 1 : 2;
+    const int own_tail = 2 - (halves & 1);
+    const int mid = (halves - own_tail) >> 1;
+    // ... and a whole group for the entire warp as soon as one lane needs it (the two extra taps of the others have
+    // weight 0), so that the lanes of a warp never take the two tail forms one after the other
+    const int tail_halves = __any_sync(0xFFFFFFFFu, own_tail == 2) ? 2 : 1;
+    const int tail_tap = has_first ? 4 + 4 * mid : 0;
     uint64_t wa[4], nwa[4], wz[4], nwz[4], wm[4], nwm[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const float fa = tap_weight(q), fz = tap_weight(4 * (groups - 1) + q);
+        const float fa = q == 0 ? ax.w_left : ax.w_full, fz = tap_weight(tail_tap + q);
         wa[q] = f2_pack(fa, fa); nwa[q] = f2_pack(-8388608.0f * fa, -8388608.0f * fa);
         wz[q] = f2_pack(fz, fz); nwz[q] = f2_pack(-8388608.0f * fz, -8388608.0f * fz);
         wm[q] = f2_pack(ax.w_full, ax.w_full); nwm[q] = f2_pack(-8388608.0f * ax.w_full, -8388608.0f * ax.w_full);
     }
     const int b_start = (ax.s_first - 1) * 3 - lo + kRowPadFront;   // >= 13
     const uint32_t shift = (uint32_t)(b_start & 3) * 8;
-    float acc[3] = {0.0f, 0.0f, 0.0f};
+    const uint8_t* s_mine = s_rows + (b_start & ~3);
+    const int lane = threadIdx.x & 31;
+    float my_beta_a = 0.0f, my_beta_b = 0.0f;
+    float acc[3] = {0.0f, 0.0f, 0.0f};                          // 0 + x == x: the first y tap needs no special case
     __syncthreads();                                           // mbarrier init visible
-    fetch(0);
     for (int p = 0; p < n_pairs; ++p) {
+        if ((p & 31) == 0) {          // lane l keeps the y weights of pair p + l for the next 32 pairs
+            my_beta_a = row_weight(2 * (p + lane)); my_beta_b = row_weight(2 * (p + lane) + 1);
+        }
         if (p + 1 < n_pairs) fetch(p + 1);
-        if (bulk) rs_mbar_wait(&s_full[p & 1], (uint32_t)(p >> 1) & 1u);
+        if (bulk) rs_mbar_wait_a(bar0 + 8u * (p & 1), (uint32_t)(p >> 1) & 1u);
         else __syncthreads();
-        if (active) {
-            const bool two = 2 * p + 1 < n_rows;
-            const uint32_t* pa = reinterpret_cast<const uint32_t*>(s_rows + (2 * (p & 1)) * buf_bytes) + (b_start >> 2);
-            const uint32_t* pb = two ? reinterpret_cast<const uint32_t*>(s_rows + (2 * (p & 1) + 1) * buf_bytes) + (b_start >> 2) : pa;
+        if (warp_active) {
+            const uint32_t* pa = reinterpret_cast<const uint32_t*>(s_mine + (2 * (p & 1)) * buf_bytes);
+            const uint32_t* pb = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(pa) + (2 * p + 1 < n_rows ? buf_bytes : 0));
             uint32_t a0 = pa[0], b0 = pb[0];
             uint64_t h[3] = {0ull, 0ull, 0ull};                // (+0.0f, +0.0f)
-            area_group2(pa, pb, a0, b0, shift, wa, nwa, h);
-            for (int g = 1; g < groups - 1; ++g) area_group2(pa, pb, a0, b0, shift, wm, nwm, h);
-            if (groups > 1) area_group2(pa, pb, a0, b0, shift, wz, nwz, h);
-            const float beta_a = row_weight(2 * p), beta_b = two ? row_weight(2 * p + 1) : 0.0f;
+            if (has_first) area_group2(pa, pb, a0, b0, shift, wa, nwa, h);
+            for (int g = 0; g < mid; ++g) area_group2(pa, pb, a0, b0, shift, wm, nwm, h);
+            if (tail_halves == 2) area_group2(pa, pb, a0, b0, shift, wz, nwz, h);
+            else area_half2(pa, pb, a0, b0, shift, wz, nwz, h);
+            // sum over rows: acc += beta_a * h_a, then += beta_b * h_b (the pad row of an odd count re-reads row a with weight 0)
+            const float beta_a = __shfl_sync(0xFFFFFFFFu, my_beta_a, p & 31), beta_b = __shfl_sync(0xFFFFFFFFu, my_beta_b, p & 31);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 float ha, hb;
                 f2_unpack(h[c], ha, hb);
-                const float ba = __fmul_rn(beta_a, ha);
-                acc[c] = (p == 0) ? ba : __fadd_rn(acc[c], ba);
-                if (two) acc[c] = __fadd_rn(acc[c], __fmul_rn(beta_b, hb));
+                acc[c] = __fadd_rn(__fadd_rn(acc[c], __fmul_rn(beta_a, ha)), __fmul_rn(beta_b, hb));
             }
         }
         __syncthreads();          // the buffers are refilled two iterations later
@@ -304,6 +365,24 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
 #pragma unroll
         for (int c = 0; c < 3; ++c) emit_value(sat_rint_u8(acc[c]), c, i + c, norm_mode, out, out_u8);
     }
+}
+
+struct ResizeRowsLaunch {
+    ResizeTables t; int out_h, out_w, norm_mode; float* out; uint8_t* out_u8; int buf_bytes; dim3 grid; int threads; size_t smem;
+    cudaStream_t stream;
+};
+template <int kMaxRegs>
+cudaError_t launch_rows(const ResizeRowsLaunch& a) {
+    static thread_local int configured_dev = -1;            // the opt-in shared-memory size is set once per (thread, device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(resize_area_rows_kernel<kMaxRegs>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        configured_dev = dev;
+    }
+    resize_area_rows_kernel<kMaxRegs><<<a.grid, a.threads, a.smem, a.stream>>>(a.t, a.out_h, a.out_w, a.norm_mode, a.out, a.out_u8, a.buf_bytes);
+    return cudaGetLastError();
 }
 
 // max_src_w: widest source of the batch; n_area / n_other: how many images are / are not in the
@@ -330,16 +409,8 @@ cudaError_t launch_resize_norm(const ResizeTables& t, int n, int out_h, int out_
     const size_t smem = (size_t)4 * buf_bytes;                // two pairs of source rows in flight
     const bool rows_ok = n_area > 0 && out_w <= kRowsMaxThreads && smem <= 200 * 1024 && n <= 65535 && segs <= 65535;
     if (rows_ok) {
-        static thread_local int configured_dev = -1;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (configured_dev != dev) {
-            cudaError_t e = cudaFuncSetAttribute(resize_area_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e != cudaSuccess) return e;
-            configured_dev = dev;
-        }
-        resize_area_rows_kernel<<<dim3(out_h, n, segs), seg_w, smem, stream>>>(t, out_h, out_w, norm_mode, d_out, d_out_u8, buf_bytes);
-        cudaError_t e = cudaGetLastError();
+        const ResizeRowsLaunch a{t, out_h, out_w, norm_mode, d_out, d_out_u8, buf_bytes, dim3(out_h, n, segs), seg_w, smem, stream};
+        cudaError_t e = seg_w <= 256 ? launch_rows<64>(a) : seg_w <= 320 ? launch_rows<48>(a) : launch_rows<40>(a);
         if (e != cudaSuccess) return e;
         if (n_other == 0) return cudaSuccess;
     }
