@@ -170,3 +170,41 @@ def test_classifier_batches_multi_rejects_bad_arguments(coder):
         coder.classifier_batches_multi([img], [0], [((224, 224), "tf")])
     with pytest.raises(ValueError):
         coder.classifier_batches_multi([img], [2], [])
+
+
+@pytest.mark.parametrize("target", [64, 224, 299, 331, 500])
+def test_area_tap_run_shapes_sweep(coder, target):
+    """The row kernel walks a tap run as [first group] + whole groups + [whole or half group], decided per warp, with one
+    of three register-capped instantiations by CTA size: sweep the x scale from just above 1 (runs of two or three taps)
+    to 21 (runs of 23) so that every tail form, mixed warps included, and every instantiation meets the oracle."""
+    rng = np.random.default_rng(target)
+    widths = sorted({int(target * s) + int(rng.integers(0, 7)) for s in np.linspace(1.02, 21.0, 36)})
+    icons = [rng.integers(0, 256, (int(rng.integers(40, 90)), w, 3), dtype=np.uint8) for w in widths]
+    _, u8 = coder.icons_to_batch(icons, (target, 17), "identity", return_uint8=True)
+    for i, ic in enumerate(icons):
+        assert np.array_equal(u8[i], ro.resize_area(ic, target, 17)), (ic.shape, target)
+
+
+def test_area_rows_unaligned_pitch_device_api(coder):
+    """Rows that cannot be bulk-copied (pitch and base not multiples of 16 bytes) take the cooperative copy path."""
+    import ctypes as C
+    import torch
+    from wicca_b200 import _capi
+    rng = np.random.default_rng(5)
+    H, W, pitch = 301, 1777, 1777 * 3 + 5
+    imgs = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(2)]
+    flat = torch.zeros(2 * H * pitch + 3, dtype=torch.uint8, device="cuda:0")
+    ptrs = []
+    for k, im in enumerate(imgs):
+        view = flat[3 + k * H * pitch: 3 + (k + 1) * H * pitch].view(H, pitch)
+        view[:, : W * 3].copy_(torch.from_numpy(im.reshape(H, -1)))
+        ptrs.append(view.data_ptr())
+    for target in (224, 331):
+        o8 = torch.empty((2, target, target, 3), dtype=torch.uint8, device="cuda:0")
+        of = torch.empty((2, target, target, 3), dtype=torch.float32, device="cuda:0")
+        rc = _capi.load().wicca_resize_norm_dev((C.c_void_p * 2)(*ptrs), (C.c_int * 2)(H, H), (C.c_int * 2)(W, W), (C.c_int64 * 2)(pitch, pitch),
+                                                2, target, target, 0, of.data_ptr(), o8.data_ptr(), 0,
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _capi.check(rc, "wicca_resize_norm_dev")
+        torch.cuda.synchronize()
+        assert np.array_equal(o8.cpu().numpy(), np.stack([ro.resize_area(im, target, target) for im in imgs])), target
