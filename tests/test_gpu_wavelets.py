@@ -80,3 +80,15 @@ def test_long_custom_filter_and_two_channels_take_the_general_kernels():
         assert np.array_equal(db2.get_small_copy(img2, 2), fo.wavelet_icon(img2, 2, "db2"))
     finally:
         del fo.DEC_LO["_custom10"]
+
+
+@pytest.mark.parametrize("name,side", [("db2", 2048), ("db4", 1024), ("coif1", 1536)])
+def test_millions_of_elements_catch_rare_rounding_events(name, side):
+    """A fused multiply-add in place of a rounded product followed by a rounded sum changes a few results per million
+    (ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 whatever the modifiers say; the column pass once did that):
+    small images pass by luck, so compare every byte of images with millions of elements, at depths 1 and 3."""
+    from wicca_b200 import OrthogonalWaveletCoder
+    coder = OrthogonalWaveletCoder(name)
+    img = np.random.default_rng(5).integers(0, 256, (side, side, 3), dtype=np.uint8)
+    for d in (1, 3):
+        assert np.array_equal(coder.get_small_copy(img, d), fo.wavelet_icon(img, d, name)), (name, side, d)

@@ -233,9 +233,12 @@ fir_tile_kernel(const TIn* __restrict__ src, int64_t pitch_elems, int H, int W, 
             for (int ch = 0; ch < C; ++ch) d[o * C + ch] = acc[o][ch];
     }
     __syncthreads();
-    // ---- columns: two neighbouring elements of an output row per work item - an 8-byte shared load feeds both halves
-    // of Blackwell's packed float32 pair instructions (mul.rn.f32x2 / add.rn.f32x2: two IEEE operations per issue slot,
-    // each half bit-identical to the scalar instruction), which halves the issue slots of this pass
+    // ---- columns: two neighbouring elements of an output row per work item - an 8-byte shared load feeds the pair, the
+    // two products are scalar (mul.rn.f32) and the running sums one packed add.rn.f32x2 (two IEEE additions per issue slot,
+    // each half bit-identical to the scalar instruction).  The products must NOT be a mul.rn.f32x2: ptxas 12.9 contracts
+    // mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 in spite of the .rn modifiers and of --fmad=false (seen in the SASS; also
+    // when the product is written fma(v, g, -0)), which skips the rounding of the product - a handful of icon bytes per
+    // million then differ from the definition (found by tools/bench_rows.py on a 1024 x 1024 image).
     constexpr int seg = kTileW * C, seg2 = seg / 2;                              // kTileW is even
     for (int e = threadIdx.x; e < kTileH * seg2; e += kTileThreads) {
         const int i = e / seg2, q = 2 * (e - i * seg2);
@@ -246,10 +249,9 @@ fir_tile_kernel(const TIn* __restrict__ src, int64_t pitch_elems, int H, int W, 
 #pragma unroll
         for (int m = 0; m < L; ++m) {
             const float2 v = *reinterpret_cast<const float2*>(p + m * G::kTPitch);
-            uint64_t v2, g2, pr;
-            asm("mov.b64 %0, {%1, %2};" : "=l"(v2) : "f"(v.x), "f"(v.y));
-            asm("mov.b64 %0, {%1, %1};" : "=l"(g2) : "f"(s_g[m]));
-            asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(v2), "l"(g2));
+            const float g = s_g[m];
+            uint64_t pr;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(pr) : "f"(__fmul_rn(v.x, g)), "f"(__fmul_rn(v.y, g)));
             if (m == 0) acc = pr;
             else asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc) : "l"(acc), "l"(pr));
         }
