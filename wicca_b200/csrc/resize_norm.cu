@@ -117,9 +117,9 @@ __global__ void resize_norm_kernel(ResizeTables t, int img0, int out_h, int out_
 // [left partial] + n_full whole pixels + [right partial].  The run is read as 32-bit words,
 // realigned with one funnel shift per word and consumed four taps (12 bytes) at a time, per channel
 // in OpenCV's order (three independent chains per thread).  The run always starts at pixel
-// s_first - 1 and is padded to whole groups with weight-0 taps: src * 0 = +0 and h + 0 = h exactly,
-// so a padded tap changes nothing, and only the first and the last group need per-tap weights
-// (kept in registers: they do not depend on the row).
+// s_first - 1 and ends in a group of four or of two taps, padded with weight-0 taps where needed:
+// src * 0 = +0 and h + 0 = h exactly, so a padded tap changes nothing, and only the first and the
+// last group need per-tap weights (kept in registers: they do not depend on the row).
 //
 // src * alpha costs two instructions per byte: PRMT builds the float 2^23 + src, and
 // fma(2^23 + src, alpha, -2^23 * alpha) rounds the exact product src * alpha once, i.e. it is
@@ -133,25 +133,10 @@ __device__ __forceinline__ uint32_t rs_smem_u32(const void* p) { return (uint32_
 __device__ __forceinline__ void rs_mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rs_smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void rs_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rs_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void rs_mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(rs_smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void rs_mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+__device__ __forceinline__ void rs_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void rs_mbar_wait_a(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void rs_mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -163,21 +148,10 @@ __device__ __forceinline__ void rs_mbar_wait_a(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar), "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void rs_bulk_load_a(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+__device__ __forceinline__ void rs_bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc),
                  "r"(bytes), "r"(bar)
                  : "memory");
-}
-__device__ __forceinline__ void rs_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     rs_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(rs_smem_u32(bar))
-                 : "memory");
-}
-
-// (float)byte_k(word) * w, exactly: see the note above.  nw = -2^23 * w.
-template <int K>
-__device__ __forceinline__ float byte_times(uint32_t word, float w, float nw) {
-    return __fmaf_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440 | K)), w, nw);
 }
 
 // Blackwell's packed float32 pair instructions (FFMA2 / FADD2): two independent IEEE operations per issue slot.  The
@@ -289,9 +263,9 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
         if (bulk) {
             if (threadIdx.x == 0) {
                 const uint32_t bar = bar0 + 8u * (p & 1), dst = rows0 + (2 * (p & 1)) * buf_bytes + kRowPadFront;
-                rs_mbar_expect_tx_a(bar, (uint32_t)(copy_bytes * n_here));
-                rs_bulk_load_a(dst, g, (uint32_t)copy_bytes, bar);
-                if (n_here == 2) rs_bulk_load_a(dst + buf_bytes, g + j.pitch, (uint32_t)copy_bytes, bar);
+                rs_mbar_expect_tx(bar, (uint32_t)(copy_bytes * n_here));
+                rs_bulk_load(dst, g, (uint32_t)copy_bytes, bar);
+                if (n_here == 2) rs_bulk_load(dst + buf_bytes, g + j.pitch, (uint32_t)copy_bytes, bar);
             }
         } else {
             for (int q = 0; q < n_here; ++q)
@@ -338,7 +312,7 @@ resize_area_rows_kernel(ResizeTables t, int out_h, int out_w, int norm_mode, flo
             my_beta_a = row_weight(2 * (p + lane)); my_beta_b = row_weight(2 * (p + lane) + 1);
         }
         if (p + 1 < n_pairs) fetch(p + 1);
-        if (bulk) rs_mbar_wait_a(bar0 + 8u * (p & 1), (uint32_t)(p >> 1) & 1u);
+        if (bulk) rs_mbar_wait(bar0 + 8u * (p & 1), (uint32_t)(p >> 1) & 1u);
         else __syncthreads();
         if (warp_active) {
             const uint32_t* pa = reinterpret_cast<const uint32_t*>(s_mine + (2 * (p & 1)) * buf_bytes);
