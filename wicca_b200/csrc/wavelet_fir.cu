@@ -207,22 +207,41 @@ fir_tile_kernel(const TIn* __restrict__ src, int64_t pitch_elems, int H, int W, 
     for (int e = threadIdx.x; e < rows * groups; e += kTileThreads) {
         const int r = e / groups, jg = e - r * groups;
         const TIn* p = reinterpret_cast<const TIn*>(s_raw + (size_t)r * kRowBytes + lead) + (size_t)(2 * kOutPerThread * jg) * C;
-        // the 2*4 + L - 2 pixels the four outputs share, converted once
+        // the 2*4 + L - 2 pixels the four outputs share, fetched once
         constexpr int kPix = 2 * kOutPerThread + L - 2;
         float px[kPix][C];
+        if (kU8) {
+            // Bytes: the run is read as aligned 32-bit words and byte k becomes the float 2^23 + byte with one PRMT (no
+            // LDS.U8, no I2F - the conversion pipe runs at a quarter of the rate and was as busy as the issue port).  The
+            // product is then fma(2^23 + byte, g, -2^23 * g): (2^23 + byte) * g is exact inside the fma and 2^23 * g is
+            // exact, so the one rounding is that of byte * g - bit-identical to __fmul_rn((float)byte, g).
+            constexpr int kBytes = kPix * C, kWords = ((kBytes - 1) >> 2) + 2;      // words that can hold a byte of the run
+            const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+            const uint32_t sh = (uint32_t)(a & 3) * 8;
+            uint32_t wd[kWords];
 #pragma unroll
-        for (int k = 0; k < kPix; ++k)
+            for (int k = 0; k < kWords; ++k) wd[k] = wp[k];
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) px[k][ch] = (float)p[k * C + ch];
+            for (int b = 0; b < kBytes; ++b) {
+                const uint32_t x = __funnelshift_r(wd[b >> 2], wd[(b >> 2) + 1], sh);          // hoisted: one per word
+                px[b / C][b % C] = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7440 | (b & 3)));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPix; ++k)
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) px[k][ch] = (float)p[k * C + ch];
+        }
         float acc[kOutPerThread][C];
 #pragma unroll
         for (int n = 0; n < L; ++n) {
-            const float g = s_g[n];
+            const float g = s_g[n], ng = -8388608.0f * g;
 #pragma unroll
             for (int o = 0; o < kOutPerThread; ++o)
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) {
-                    const float v = __fmul_rn(px[2 * o + n][ch], g);
+                    const float v = kU8 ? __fmaf_rn(px[2 * o + n][ch], g, ng) : __fmul_rn(px[2 * o + n][ch], g);
                     acc[o][ch] = n == 0 ? v : __fadd_rn(acc[o][ch], v);
                 }
         }
