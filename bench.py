@@ -215,10 +215,13 @@ def _peak():
         return 6650.0, "6650 GB/s (of fallback)"
 
 
-def host_link_ceiling(torch, dist, dev, world, host_flat, out_flat, h2d_bytes, d2h_bytes, barrier):
+def host_link_ceiling(torch, dist, dev, world, host_flats, out_flats, h2d_bytes, d2h_bytes, barrier):
     """What the host side of the PCIe links gives this job, measured with plain large copies on every rank at once:
     (i) H2D only, (ii) one e2e step's traffic - h2d_bytes up on one stream, d2h_bytes down on another - with no
-    kernels, no 2-D pitch, no per-image synchronisation.  An e2e step cannot finish faster than (ii)."""
+    kernels, no 2-D pitch, no per-image synchronisation.  An e2e step cannot finish faster than (ii).  The copies walk
+    the SAME page-locked buffers as the e2e leg (its distinct source images in turn, one output block per image), so the
+    host's caches see the same footprint: one 159 MB source copied thirty times would partly be served from them."""
+    host_flat, out_flat = host_flats[0], out_flats[0]
     n_up = max(1, round(h2d_bytes / host_flat.numel()))
     n_down = max(1, round(d2h_bytes / out_flat.numel()))
     d_up = torch.empty(host_flat.numel(), dtype=torch.uint8, device=dev)
@@ -236,14 +239,14 @@ def host_link_ceiling(torch, dist, dev, world, host_flat, out_flat, h2d_bytes, d
             ev = None
             if up and i < n_up:
                 with torch.cuda.stream(s_up):
-                    d_up.copy_(host_flat, non_blocking=True)
+                    d_up.copy_(host_flats[i % len(host_flats)], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(s_up)
             if down and i < n_down:
                 with torch.cuda.stream(s_down):
                     if up and prev[0] is not None:
                         s_down.wait_event(prev[0])
-                    out_flat.copy_(d_down, non_blocking=True)
+                    out_flats[i % len(out_flats)].copy_(d_down, non_blocking=True)
             prev[0] = ev
         s_up.synchronize(); s_down.synchronize()
         prev[0] = None
@@ -262,8 +265,9 @@ def host_link_ceiling(torch, dist, dev, world, host_flat, out_flat, h2d_bytes, d
             "h2d_GBps_with_d2h": world * up_b / t_both / 1e9, "d2h_GBps_with_h2d": world * down_b / t_both / 1e9,
             "note": "a probe of the same traffic with plain copies, best of two; run-to-run spread of either side is a few per "
                     "cent, so frac_of_ceiling reads 0.94-1.04",
-            "method": f"every rank at once, page-locked buffers: {n_up} x {host_flat.numel() / 1e6:.0f} MB cudaMemcpyAsync up on one "
-                      f"stream + {n_down} x {out_flat.numel() / 1e6:.0f} MB down on another (the byte counts of one e2e step), max over ranks"}
+            "method": f"every rank at once, the e2e leg's page-locked buffers ({len(host_flats)} sources in turn, {len(out_flats)} output "
+                      f"blocks): {n_up} x {host_flat.numel() / 1e6:.0f} MB cudaMemcpyAsync up on one stream + {n_down} x "
+                      f"{out_flat.numel() / 1e6:.0f} MB down on another (the byte counts of one e2e step), max over ranks"}
 
 
 def extra_subbands(torch, lib, _capi, dev, local, stream, all_max, peak):
@@ -620,9 +624,10 @@ def run_ours(args) -> int:
                 e2e_checked += 1
         del expected
     # the host's measured limit for the same traffic, all ranks at once
-    # (after the parity check: the probe's downward copies overwrite the first image's icons)
-    out_flat_t = torch.from_numpy(np.ctypeslib.as_array((C.c_uint8 * sum(icon_sizes)).from_address(out_ptrs[0].value)))
-    ceiling = host_link_ceiling(torch, dist, dev, world, torch.from_numpy(host_flats[0]), out_flat_t, h2d_bytes, d2h_bytes, barrier)
+    # (after the parity check: the probe's downward copies overwrite the icons)
+    out_flat_t = [torch.from_numpy(np.ctypeslib.as_array((C.c_uint8 * sum(icon_sizes)).from_address(q.value))) for q in out_ptrs]
+    ceiling = host_link_ceiling(torch, dist, dev, world, [torch.from_numpy(f) for f in host_flats], out_flat_t, h2d_bytes, d2h_bytes,
+                                barrier)
     ceiling_value = world * BATCH * MP_PER_IMAGE / ceiling["step_traffic_s"]
 
     for p in host_ptrs + out_ptrs:

@@ -93,3 +93,45 @@ def test_batch_writes_into_caller_arrays_and_registered_memory():
         coder.get_small_copies_batch(imgs[:1], depths, out=[[np.empty((3, 3, 3), np.uint8)] * 3])
     del out, row, ic, view
     arena.close()
+
+
+def test_batch_page_locked_buffers_take_the_flat_link_copies():
+    """Batch workers move large page-locked images and icons over the link as flat copies and re-pitch them on the
+    device (copy_rows_kernel): rows whose byte count is odd, a multiple of 2 or of 4, page-locked outputs through
+    ``out=``, a strided page-locked source (which keeps the 2-D copy), all against the oracle."""
+    import ctypes as C
+    lib = _capi.load()
+    coder = HaarCoder()
+    blocks = []
+
+    def pinned(shape):
+        n = int(np.prod(shape))
+        p = C.c_void_p()
+        _capi.check(lib.wicca_host_alloc(C.byref(p), max(1, n)), "wicca_host_alloc")
+        blocks.append(p)
+        return np.ctypeslib.as_array((C.c_uint8 * max(1, n)).from_address(p.value)).reshape(shape)
+
+    try:
+        rng = np.random.default_rng(8)
+        imgs = []
+        for (h, w) in [(700, 1001), (640, 1002), (900, 1004), (513, 2047), (300, 299)]:      # the last one is below the flat threshold
+            a = pinned((h, w, 3))
+            a[:] = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            imgs.append(a)
+        wide = pinned((600, 1500, 3))
+        wide[:] = rng.integers(0, 256, wide.shape, dtype=np.uint8)
+        imgs.append(wide[:, 100:1101])                                                       # strided rows, still page-locked
+        depths = [1, 2, 3, 6]
+        outs = [[pinned((-(-im.shape[0] // (1 << d)), -(-im.shape[1] // (1 << d)), 3)) for d in depths] for im in imgs]
+        for row in outs:
+            for o in row:
+                o[:] = 0xAB
+        got = coder.get_small_copies_batch(imgs, depths, devices=[0], out=outs)
+        for im, row, row_out in zip(imgs, got, outs):
+            for d, ic, o in zip(depths, row, row_out):
+                exp = ho.haar_icon_blocksum(np.ascontiguousarray(im), d)
+                assert np.array_equal(ic, exp), (im.shape, d)
+                assert np.array_equal(o, exp), (im.shape, d, "page-locked destination")
+    finally:
+        for p in blocks:
+            lib.wicca_host_free(p)

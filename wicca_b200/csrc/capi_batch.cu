@@ -51,6 +51,7 @@ int upload_slots() {
 
 int worker_body(const BatchArgs& a, int device, int first, int step, WorkerResult& res) {
     ScopedAffinity bind(device);         // this worker (and the buffers it allocates) stays on the GPU's NUMA node
+    ScopedLinkShared shared;             // uploads and read-backs of different images overlap: flat copies over the link
     const int n_slots = upload_slots();
     CtxLease slot[4];
     bool busy[4] = {false, false, false, false};
@@ -60,10 +61,15 @@ int worker_body(const BatchArgs& a, int device, int first, int step, WorkerResul
     }
     // one allocation per slot, sized for the largest image of this worker (ragged batches would
     // otherwise grow the buffer - and synchronise the device - several times)
-    size_t max_src = 0;
-    for (int i = first; i < a.n_images; i += step)
+    size_t max_src = 0, max_tight = 0;
+    for (int i = first; i < a.n_images; i += step) {
         max_src = std::max(max_src, (size_t)wicca_pitch_bytes(a.Ws[i], a.C) * a.Hs[i] + 256);
-    for (int s = 0; s < n_slots; ++s) WICCA_CUDA(slot[s].c->d_src.reserve(max_src));
+        if (is_pinned_host(a.srcs[i])) max_tight = std::max(max_tight, (size_t)a.Ws[i] * a.C * a.Hs[i]);   // lands flat in d_stage first
+    }
+    for (int s = 0; s < n_slots; ++s) {
+        WICCA_CUDA(slot[s].c->d_src.reserve(max_src));
+        if (max_tight) WICCA_CUDA(slot[s].c->d_stage.reserve(max_tight));
+    }
     int j = 0;
     for (int i = first; i < a.n_images; i += step) {
         const int H = a.Hs[i], W = a.Ws[i];
@@ -170,15 +176,18 @@ struct ClsArgs {
 
 int cls_worker(const ClsArgs& a, int device, int first, int step, WorkerResult& res) {
     ScopedAffinity bind(device);
+    ScopedLinkShared shared;
     CtxLease slot[2];
     bool busy[2] = {false, false};
     for (int s = 0; s < 2; ++s) {
         int rc = acquire_ctx(device, &slot[s].c);
         if (rc) return rc;
     }
-    size_t max_src = 0;
-    for (int i = first; i < a.n_images; i += step)
+    size_t max_src = 0, max_tight = 0;
+    for (int i = first; i < a.n_images; i += step) {
         max_src = std::max(max_src, (size_t)wicca_pitch_bytes(a.Ws[i], 3) * a.Hs[i] + 256);
+        if (!a.jpeg_lens && is_pinned_host(a.srcs[i])) max_tight = std::max(max_tight, (size_t)a.Ws[i] * 3 * a.Hs[i]);
+    }
     // per image and target: n_depths icon slots followed by the source-image slot
     const int n_out = a.n_depths + (a.dst_images ? 1 : 0);
     std::vector<size_t> slot_elems(a.n_targets), out_off(a.n_targets + 1, 0);
@@ -190,6 +199,7 @@ int cls_worker(const ClsArgs& a, int device, int first, int step, WorkerResult& 
     for (int s = 0; s < 2; ++s) {
         Ctx& c = *slot[s].c;
         WICCA_CUDA(c.d_src.reserve(max_src));
+        if (max_tight) WICCA_CUDA(c.d_stage.reserve(max_tight));
         WICCA_CUDA(c.d_f32a.reserve(out_bytes));
         WICCA_CUDA(c.h_out.reserve(out_bytes));
     }

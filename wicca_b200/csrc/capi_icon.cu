@@ -290,7 +290,11 @@ int icons_from_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int* d
         c.flush_pending();                           // never reallocate under copies that are still owed
         WICCA_CUDA(c.h_bounce.reserve(bounce));
     }
-    size_t boff = 0;
+    size_t boff = 0, pack_bytes = 0, pack_off = 0;
+    for (int i = 0; i < n_depths; ++i)             // large icons are packed tight on the device and cross the link flat
+        if (c.link_shared && depths[i] > 0 && (size_t)outs[i].w * C * outs[i].h >= kFlatCopyMin && outs[i].pitch != (int64_t)outs[i].w * C)
+            pack_bytes += (size_t)align_up((int64_t)outs[i].w * C * outs[i].h, 256);
+    if (pack_bytes) WICCA_CUDA(c.d_pack.reserve(pack_bytes));
     for (int i = 0; i < n_depths; ++i) {
         if (depths[i] <= 0) continue;
         const size_t rowb = (size_t)outs[i].w * C;
@@ -300,8 +304,8 @@ int icons_from_resident(Ctx& c, int H, int W, int C, int64_t pitch, const int* d
             c.pending.push_back({dsts[i], target, rowb * outs[i].h});
             boff += rowb * outs[i].h;
         }
-        WICCA_CUDA(cudaMemcpy2DAsync(target, rowb, outs[i].d_ptr, (size_t)outs[i].pitch, rowb, (size_t)outs[i].h,
-                                     cudaMemcpyDeviceToHost, c.stream));
+        int rc = download_rows_async(c, target, outs[i].d_ptr, outs[i].pitch, (int64_t)rowb, outs[i].h, &pack_off);
+        if (rc) return rc;
     }
     WICCA_CUDA(cudaEventRecord(c.ev[3], c.stream));
     return 0;

@@ -407,6 +407,7 @@ int wicca_batch_icons_from_jpeg(const uint8_t* const* datas, const size_t* lens,
     std::vector<std::string> msgs(n_threads);
     std::vector<float> host_ms(n_threads, 0.f);
     auto work = [&](int tix) {
+        ScopedLinkShared shared;                  // the icons of many files flow back at once: flat copies over the link
         for (;;) {
             const int i = next.fetch_add(1);
             if (i >= n_images) return;

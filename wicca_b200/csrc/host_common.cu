@@ -1,5 +1,6 @@
 // host_common.cu - error strings, device/context pool, TMA descriptor encoding.
 #include "host_common.h"
+#include "kernels.h"
 
 #include <math.h>
 #include <ctype.h>
@@ -130,6 +131,7 @@ void Ctx::destroy() {
     cudaSetDevice(device);
     d_src.release(); d_icons.release(); d_desc.release(); d_strip.release();
     d_f32a.release(); d_f32b.release(); d_misc.release(); d_tmp.release(); d_sum6.release();
+    d_stage.release(); d_pack.release();
     h_desc.release(); h_bounce.release(); h_in.release(); h_out.release(); h_jpeg.release();
     for (auto& x : ev) if (x) { cudaEventDestroy(x); x = nullptr; }
     if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
@@ -200,6 +202,10 @@ const DeviceInfo& device_info(int device) {
     return di;
 }
 
+static thread_local bool tl_link_shared = false;
+ScopedLinkShared::ScopedLinkShared() : prev(tl_link_shared) { tl_link_shared = true; }
+ScopedLinkShared::~ScopedLinkShared() { tl_link_shared = prev; }
+
 int acquire_ctx(int device, Ctx** out) {
     int rc = check_device(device);
     if (rc) return rc;
@@ -210,6 +216,7 @@ int acquire_ctx(int device, Ctx** out) {
         if (!pool->idle.empty()) {
             *out = pool->idle.back();
             pool->idle.pop_back();
+            (*out)->link_shared = tl_link_shared;
             return 0;
         }
     }
@@ -220,6 +227,7 @@ int acquire_ctx(int device, Ctx** out) {
         std::lock_guard<std::mutex> lk(pool->mu);
         pool->all.push_back(c);
     }
+    c->link_shared = tl_link_shared;
     *out = c;
     return 0;
 }
@@ -308,6 +316,18 @@ ScopedAffinity::~ScopedAffinity() {
 int upload_image_async(Ctx& c, const uint8_t* src, int H, int64_t row_bytes, int64_t stride, int64_t pitch) {
     const size_t total = (size_t)row_bytes * H;
     if (total < ((size_t)4 << 20) || is_pinned_host(src)) {
+        if (c.link_shared && stride == row_bytes && total >= kFlatCopyMin) {
+            if (pitch == row_bytes) {          // already the device layout
+                WICCA_CUDA(cudaMemcpyAsync(c.d_src.p, src, total, cudaMemcpyHostToDevice, c.stream));
+                return 0;
+            }
+            if (is_pinned_host(src)) {         // flat over the link, spread to the pitch on the device
+                WICCA_CUDA(c.d_stage.reserve(total));
+                WICCA_CUDA(cudaMemcpyAsync(c.d_stage.p, src, total, cudaMemcpyHostToDevice, c.stream));
+                WICCA_CUDA(launch_copy_rows(c.d_src.p, pitch, c.d_stage.p, row_bytes, row_bytes, H, c.stream));
+                return 0;
+            }
+        }
         WICCA_CUDA(cudaMemcpy2DAsync(c.d_src.p, (size_t)pitch, src, (size_t)stride, (size_t)row_bytes, (size_t)H,
                                      cudaMemcpyHostToDevice, c.stream));
         return 0;
@@ -338,6 +358,22 @@ int upload_image_async(Ctx& c, const uint8_t* src, int H, int64_t row_bytes, int
     for (auto& th : threads) th.join();
     for (cudaError_t e : errs)
         if (e != cudaSuccess) return cuda_fail(e, "staged image upload");
+    return 0;
+}
+
+int download_rows_async(Ctx& c, void* h_dst, const void* d_src, int64_t d_pitch, int64_t row_bytes, int rows, size_t* pack_off) {
+    const size_t total = (size_t)row_bytes * rows;
+    if (d_pitch == row_bytes) {
+        WICCA_CUDA(cudaMemcpyAsync(h_dst, d_src, total, cudaMemcpyDeviceToHost, c.stream));
+    } else if (c.link_shared && total >= kFlatCopyMin && pack_off && *pack_off + total <= c.d_pack.cap) {
+        uint8_t* tight = (uint8_t*)c.d_pack.p + *pack_off;
+        *pack_off += (size_t)align_up((int64_t)total, 256);
+        WICCA_CUDA(launch_copy_rows(tight, row_bytes, d_src, d_pitch, row_bytes, rows, c.stream));
+        WICCA_CUDA(cudaMemcpyAsync(h_dst, tight, total, cudaMemcpyDeviceToHost, c.stream));
+    } else {
+        WICCA_CUDA(cudaMemcpy2DAsync(h_dst, (size_t)row_bytes, d_src, (size_t)d_pitch, (size_t)row_bytes, (size_t)rows,
+                                     cudaMemcpyDeviceToHost, c.stream));
+    }
     return 0;
 }
 

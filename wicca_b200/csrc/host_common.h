@@ -53,6 +53,8 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};                // start, h2d done, kernels done, d2h done, spare x2
     DevBuf d_src, d_icons, d_desc, d_strip, d_f32a, d_f32b, d_misc, d_tmp, d_sum6;
+    DevBuf d_stage, d_pack;                // tight-row staging of an upload / of results on their way to the host (see below)
+    bool link_shared = false;              // set by the batch workers: uploads and read-backs of other images share the link
     PinBuf h_desc, h_bounce, h_in, h_out, h_jpeg;
     // Results bound for pageable host memory are DMA'd into h_bounce (so the copy is truly
     // asynchronous) and moved to their destination after the stream has been synchronised.
@@ -73,6 +75,13 @@ int device_count_cached();
 int check_device(int device);                       // 0 or WICCA_EDEVICE / cuda error
 const DeviceInfo& device_info(int device);
 int acquire_ctx(int device, Ctx** out);             // sets the calling thread's current device
+// Batch workers declare that the host link is shared with other images' traffic for as long as the guard lives: every
+// context the thread acquires meanwhile has link_shared set (upload_image_async / download_rows_async read it).
+struct ScopedLinkShared {
+    ScopedLinkShared();
+    ~ScopedLinkShared();
+    bool prev;
+};
 void release_ctx(Ctx* c);
 void destroy_all_ctx();
 void resize_table_cache_clear();                        // capi_resize.cu: cached tap tables of wicca_resize_norm_dev
@@ -105,7 +114,16 @@ struct ScopedAffinity {
 // Page-locked sources are DMA'd directly; pageable ones are staged band by band through the pinned
 // buffer c.h_in by a few helper threads, so the CPU copy of band k+1 overlaps the DMA of band k.
 // c.d_src must already be reserved.
+// In a batch worker (c.link_shared) everything large crosses the link as ONE FLAT copy: a pitched 2-D copy costs nothing
+// on an idle link (55.0 vs 55.4 GB/s) but 6 % of the end-to-end rate once uploads and read-backs share it (measured:
+// 16.4-16.5 k -> 17.5 k MP/s, 0.92 -> 0.98 of the plain-copy ceiling).  So a tight page-locked image lands in c.d_stage and
+// copy_rows_kernel (0.1 ms for 159 MB, off the link) spreads it to the pitch; results take the mirror path through
+// c.d_pack.  One-shot calls have the link to themselves and keep the direct 2-D copies (0.1 ms less latency).
 int upload_image_async(Ctx& c, const uint8_t* src, int H, int64_t row_bytes, int64_t stride, int64_t pitch);
+// Pitched device rows -> tight host rows on c.stream (page-locked or bounce target): flat over the link when the block
+// is large, through c.d_pack at offset *pack_off (advanced); the caller reserves c.d_pack for everything it sends.
+int download_rows_async(Ctx& c, void* h_dst, const void* d_src, int64_t d_pitch, int64_t row_bytes, int rows, size_t* pack_off);
+constexpr size_t kFlatCopyMin = (size_t)256 << 10;      // below this a 2-D copy straight over the link is cheaper
 
 int icon_variant_from_env();
 

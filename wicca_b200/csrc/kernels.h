@@ -52,6 +52,10 @@ struct ResizeTables {
 cudaError_t launch_resize_norm(const ResizeTables& t, int n, int out_h, int out_w, int norm_mode, float* d_out,
                                uint8_t* d_out_u8, int max_src_w, int n_area, int n_other, cudaStream_t stream);
 
+// ---- copy_rows.cu: device-to-device copy between row pitches (the device side of the flat host-link copies)
+cudaError_t launch_copy_rows(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t row_bytes, int rows,
+                             cudaStream_t stream);
+
 // ---- other orthogonal wavelets (wavelet_fir.cu): LL pyramid with a longer low-pass filter, periodic per level
 struct FirTaps { float g[16]; int n, c; };     // taps (sum 1), their count (even, <= 16), centre offset n/2 - 1
 cudaError_t launch_wavelet_fir(const uint8_t* d_src, int64_t pitch, int H, int W, int C, int depth, int border_type,
