@@ -59,6 +59,26 @@ def test_resize_oracle_live_cv2():
             assert np.array_equal(ro.resize_area(src, t, t), cv2.resize(src, (t, t), interpolation=cv2.INTER_AREA))
 
 
+def test_resize_oracle_live_cv2_headline_sizes_and_random_pairs():
+    """The pin of row A5 at scale: the depth-1 icon of the headline image (3197 x 4142) to both classifier sizes, and 60
+    random (source, target) pairs over all three regimes incl. non-square targets - the restatement must equal the
+    installed cv2 bit for bit (SURVEY.md Appendix A probed 88 pairs the same way)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(2026)
+    big = rng.integers(0, 256, (3197, 4142, 3), dtype=np.uint8)
+    for t in (224, 331):
+        assert np.array_equal(ro.resize_area(big, t, t), cv2.resize(big, (t, t), interpolation=cv2.INTER_AREA)), t
+    seen = set()
+    for _ in range(60):
+        sh, sw = int(rng.integers(2, 1700)), int(rng.integers(2, 2200))
+        tw = int(rng.choice([224, 240, 299, 331, int(rng.integers(3, 400))]))
+        th = int(rng.choice([224, 299, 331, int(rng.integers(3, 400))]))
+        src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        seen.add(ro.regime(sw, sh, tw, th))
+        assert np.array_equal(ro.resize_area(src, tw, th), cv2.resize(src, (tw, th), interpolation=cv2.INTER_AREA)), (sh, sw, tw, th)
+    assert {"generic", "bilinear"} <= seen
+
+
 def test_preprocess_modes():
     x = gen_input("noise", 2, 8, 8, 3)[None]
     assert np.array_equal(ro.preprocess_input(x, "identity"), x.astype(np.float32))
